@@ -1,0 +1,143 @@
+/*
+ * tgt_b200 C ABI  --  hand-written sm_100a kernels for the TGT hot path.
+ *
+ * The reference (shamim-hussain/tgt) has no FFI / plugin layer: its boundary is the
+ * Python nn.Module surface of lib.tgt (lib/tgt/__init__.py:1, lib/tgt/layers/__init__.py:1).
+ * This header is the C-ABI *under* that surface: each entry point replaces the ATen/cuBLAS
+ * launches the cited reference lines produce.  tgt_b200/_C.py binds it with ctypes and
+ * tgt_b200/ops.py wraps it in torch.autograd.Function objects.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (PyTorch caching allocator);
+ *    the library never allocates, frees or retains memory, and never synchronises.
+ *  - every call launches asynchronously on `stream` (a cudaStream_t passed as void*).
+ *  - return value: 0 = ok; non-zero = error, message via tgt_last_error() (thread local).
+ *    Unsupported shapes / dtypes are errors -- there is no fallback path.
+ *  - dtype codes: 0 = float32, 1 = bfloat16, 2 = float16.  All accumulation is fp32.
+ *  - R = B*N*N edge rows.  "head-major" means channel c = h*d + dd inside a block of H*d
+ *    channels (the Python layer permutes the reference's d-major weights once per call).
+ */
+#ifndef TGT_B200_H
+#define TGT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TGT_F32  0
+#define TGT_BF16 1
+#define TGT_F16  2
+
+/* ---- library ------------------------------------------------------------------------- */
+int         tgt_version(void);
+const char *tgt_last_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+uint64_t    tgt_launch_count(void);
+/* 0 = pick the fastest kernel that supports the shape (default); 1 = force the generic
+ * SIMT kernels (used by the tests to cross-check the tensor-core kernels). */
+void        tgt_set_kernel_policy(int policy);
+
+/* ---- LayerNorm over the channel dim of edge rows ---------------------------------------
+ * replaces nn.LayerNorm calls at lib/tgt/layers/triplet.py:47,207; layers.py:49,112,156.
+ * x:[rows,W] (x_dtype)  y:[rows,W] (y_dtype)  gamma,beta:[W] f32  mean,rstd:[rows] f32.   */
+int tgt_layernorm_fwd(const void *x, const float *gamma, const float *beta, void *y,
+                      float *mean, float *rstd, int64_t rows, int W, float eps,
+                      int x_dtype, int y_dtype, void *stream);
+/* dgamma,dbeta:[W] f32 must be ZERO on entry (accumulated with atomics).
+ * dy has y_dtype, dx has x_dtype.  If `dres` is non-null it is added to dx (fused residual
+ * gradient: dx = LN'(dy) + dres), dres has x_dtype.                                        */
+int tgt_layernorm_bwd(const void *dy, const void *x, const float *gamma, const float *mean,
+                      const float *rstd, const void *dres, void *dx, float *dgamma, float *dbeta,
+                      int64_t rows, int W, int x_dtype, int y_dtype, void *stream);
+
+/* ---- triplet attention core -------------------------------------------------------------
+ * replaces lib/tgt/layers/triplet.py:213-227 and 232-246 (both einsums, bias add, masked
+ * softmax, sigmoid gate) for TripletAttention, TripletAttentionUngated and AxialAttention.
+ * The O(N^3 H) tensor is never written to memory.
+ *
+ * proj : [R, ld]  row (b,i,j) holds the projections of LN(e)[b,i,j,:]; column blocks
+ *        (head-major, H*d wide) at off_q/off_k/off_v[dir], and H-wide bias / gate blocks at
+ *        off_e/off_g[dir] (dir 0 = inward, 1 = outward; -1 = block absent -> no bias / gate)
+ * mask : [B,N,N] f32 additive (0 or finfo.min; -inf allowed)
+ * va   : [R, 2*H*d] out, channel = dir*H*d + h*d + dd
+ * stats: [B,2,H,N(j),N(i),2] f32 out: row max m and 1/l of the masked softmax            */
+typedef struct {
+  int32_t B, N, H, d;
+  int64_t ld;
+  int32_t off_q[2], off_k[2], off_v[2], off_e[2], off_g[2];
+  float   scale;          /* d^-0.5 (triplet.py:190) */
+  int32_t dtype;          /* dtype of proj / va / dva / dproj */
+} tgt_triplet_attn_desc;
+
+int tgt_triplet_attn_fwd(const tgt_triplet_attn_desc *desc, const void *proj, const float *mask,
+                         void *va, float *stats, void *stream);
+/* dproj: [R, ld] out, same column layout as proj; every column named in desc is written.   */
+int tgt_triplet_attn_bwd(const tgt_triplet_attn_desc *desc, const void *proj, const float *mask,
+                         const void *va, const void *dva, const float *stats, void *dproj,
+                         void *stream);
+
+/* ---- triplet aggregate core ---------------------------------------------------------------
+ * replaces lib/tgt/layers/triplet.py:56-68 (TripletAggregate) and 106-120 (…Ungated).
+ * proj column blocks: off_v[dir] (H*d, head-major), off_e[dir], off_g[dir] (H; off_g = -1 ->
+ * ungated).  mask_dir[dir] != 0 -> add the mask in that direction (the gated reference masks
+ * only the inward direction, triplet.py:56-57 vs 63-64).
+ * aw : [B,2,H,N,N] f32 workspace/out, aw[b,dir,h,i,k] = attention weight A (query i, key k) */
+typedef struct {
+  int32_t B, N, H, d;
+  int64_t ld;
+  int32_t off_v[2], off_e[2], off_g[2];
+  int32_t mask_dir[2];
+  int32_t dtype;
+} tgt_triplet_aggr_desc;
+
+int tgt_triplet_aggr_fwd(const tgt_triplet_aggr_desc *desc, const void *proj, const float *mask,
+                         void *va, float *aw, void *stream);
+/* daw: [B,2,H,N,N] f32 scratch (written by the call).                                        */
+int tgt_triplet_aggr_bwd(const tgt_triplet_aggr_desc *desc, const void *proj, const float *mask,
+                         const void *dva, const float *aw, float *daw, void *dproj, void *stream);
+
+/* ---- EGT node/edge attention core ---------------------------------------------------------
+ * replaces lib/tgt/layers/layers.py:62-78 (EGT_Attention) and 121-125 (EdgeUpdate).
+ * Reference-native d-major channel layout: channel c = dd*H + h.
+ * qkv  : [B*N, ld_qkv]; Q at column 0, K at column H*d, V at 2*H*d (absent when attend==0)
+ * eg   : [R, ld_eg];    E at column 0, G at column H (absent when attend==0)
+ * mask : [B,N,N] f32 ; src_mask: [B,N] f32 additive column mask or NULL (layers.py:55-59)
+ * hhat : [R,H] out  (pre-mask logits, layers.py:69)
+ * vatt : [B*N, H*d] out (after the degree scaler when scale_degree)  -- attend only
+ * stats: [B*N, H, 3] f32 out: m, 1/l, sum of gates                   -- attend only         */
+typedef struct {
+  int32_t B, N, H, d;
+  int64_t ld_qkv, ld_eg;
+  float   scale;
+  int32_t attend;         /* 1 = EGT_Attention, 0 = EdgeUpdate (logits only) */
+  int32_t scale_degree;
+  int32_t dtype;
+} tgt_egt_desc;
+
+int tgt_egt_attn_fwd(const tgt_egt_desc *desc, const void *qkv, const void *eg, const float *mask,
+                     const float *src_mask, void *hhat, void *vatt, float *stats, void *stream);
+/* dhhat may be NULL (edge_update=False).  dqkv:[B*N, ld_qkv], deg:[R, ld_eg] out.            */
+int tgt_egt_attn_bwd(const tgt_egt_desc *desc, const void *qkv, const void *eg, const float *mask,
+                     const float *src_mask, const float *stats, const void *dhhat,
+                     const void *dvatt, void *dqkv, void *deg, void *stream);
+
+/* ---- FFN activation: y = dropout(gelu(u)) (exact erf GELU) -----------------------------------
+ * replaces F.gelu + nn.Dropout at lib/tgt/layers/layers.py:157-158.  The keep mask is a
+ * counter-based hash of (seed, element index): nothing is stored, backward regenerates it. */
+int tgt_gelu_dropout_fwd(const void *u, void *y, int64_t n, float p_drop, uint64_t seed,
+                         int dtype, void *stream);
+int tgt_gelu_dropout_bwd(const void *u, const void *dy, void *du, int64_t n, float p_drop,
+                         uint64_t seed, int dtype, void *stream);
+
+/* ---- residual: out = res + scale[b] * x  (per-sample DropPath + in-place add) --------------
+ * replaces DropPath + add_ at lib/tgt/layers/layers.py:163-177, 269-290.
+ * x,out: [B, inner] (dtype) ; res: [B, inner] (res_dtype) ; scale: [B] f32 or NULL (=1).     */
+int tgt_scaled_residual(const void *x, const void *res, const float *scale, void *out,
+                        int64_t B, int64_t inner, int dtype, int res_dtype, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TGT_B200_H */

@@ -1,0 +1,336 @@
+"""GPU parity tests: tgt_b200 CUDA path (through the C ABI) vs the golden vectors of the real reference and vs
+the CPU oracle.  Tolerances (stated per BASELINE.json north_star):
+  fp32 : max |ours - ref| / max |ref| <= 1e-5          (TF32 is off: torch default for matmul)
+  bf16 : relative L2 error <= 1e-2 on module outputs/grads, AND <= 1.5x the error the reference's own
+         bf16-autocast path makes on the same inputs (+1e-3 slack); bf16 storage alone costs ~1.1e-3.
+"""
+import glob
+import os
+
+import pytest
+import torch
+
+from conftest import GOLDEN, load_golden, max_rel, rel_err
+from oracle import tgt_oracle as O
+from tgt_b200 import TGT_Encoder, Graph, _C, ops
+from tgt_b200 import layers as L
+from tgt_b200.harness import models as HM
+from tgt_b200.harness.synthetic import make_edge_inputs, make_batch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+FP32_TOL = 1e-5
+BF16_TOL = 1e-2
+
+TRIPLET_FIX = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "triplet_*.pt"))
+                     if "tiangular" not in p)
+
+
+def _module_from_fixture(fx):
+    mod = L.get_triplet_layer(fx["kind"])(fx["edge_width"], fx["num_heads"])
+    mod.load_state_dict(fx["state"], strict=True)
+    return mod.to(DEV)
+
+
+def _run_triplet(mod, fx, autocast=None):
+    e = fx["e"].to(DEV).requires_grad_(True)
+    mask = fx["mask"].to(DEV)
+    mod.zero_grad(set_to_none=True)
+    if autocast is not None:
+        with torch.autocast("cuda", dtype=autocast):
+            out = mod(e, mask)
+    else:
+        out = mod(e, mask)
+    out.backward(fx["dout"].to(DEV).to(out.dtype))
+    return out, e.grad, {k: p.grad for k, p in mod.named_parameters()}
+
+
+@pytest.mark.parametrize("name", TRIPLET_FIX)
+def test_triplet_fp32_vs_golden(name):
+    fx = load_golden(name)
+    mod = _module_from_fixture(fx)
+    out, de, grads = _run_triplet(mod, fx)
+    assert out.dtype == torch.float32
+    assert max_rel(out.cpu(), fx["out"]) < FP32_TOL
+    assert max_rel(de.cpu(), fx["de"]) < FP32_TOL
+    for k, g in fx["grads"].items():
+        assert max_rel(grads[k].cpu(), g) < 2 * FP32_TOL, k
+
+
+def _oracle_autocast_error(fx, dtype):
+    """Error of the reference algorithm (oracle restatement) run on CUDA under autocast, vs the golden."""
+    p = {k: v.to(DEV).requires_grad_(True) for k, v in fx["state"].items()}
+    e = fx["e"].to(DEV).requires_grad_(True)
+    with torch.autocast("cuda", dtype=dtype):
+        out = O.TRIPLET_FNS[fx["kind"]](p, e, fx["mask"].to(DEV), fx["num_heads"])
+    out.backward(fx["dout"].to(DEV).to(out.dtype))
+    return rel_err(out.float().cpu(), fx["out"]), rel_err(e.grad.cpu(), fx["de"])
+
+
+@pytest.mark.parametrize("policy", [0, 1])
+@pytest.mark.parametrize("name", TRIPLET_FIX)
+def test_triplet_bf16_vs_golden(name, policy):
+    fx = load_golden(name)
+    mod = _module_from_fixture(fx)
+    _C.set_kernel_policy(policy)
+    try:
+        out, de, grads = _run_triplet(mod, fx, autocast=torch.bfloat16)
+    finally:
+        _C.set_kernel_policy(0)
+    assert out.dtype == torch.bfloat16
+    ref_eo, ref_ed = _oracle_autocast_error(fx, torch.bfloat16)
+    eo, ed = rel_err(out.float().cpu(), fx["out"]), rel_err(de.cpu(), fx["de"])
+    assert eo < BF16_TOL and eo < 1.5 * ref_eo + 1e-3, (eo, ref_eo)
+    assert ed < 2 * BF16_TOL and ed < 1.5 * ref_ed + 1e-3, (ed, ref_ed)
+    for k, g in fx["grads"].items():
+        assert rel_err(grads[k].cpu(), g) < 3 * BF16_TOL, k
+
+
+@pytest.mark.parametrize("name", ["triplet_attention_a.pt", "triplet_aggregate_a.pt"])
+def test_triplet_fp16_vs_golden(name):
+    fx = load_golden(name)
+    mod = _module_from_fixture(fx)
+    out, de, grads = _run_triplet(mod, fx, autocast=torch.float16)
+    assert out.dtype == torch.float16
+    assert rel_err(out.float().cpu(), fx["out"]) < 3e-3
+    assert rel_err(de.cpu(), fx["de"]) < 6e-3
+
+
+@pytest.mark.parametrize("name", ["egt.pt", "egt_noscale_noedge.pt", "edge_update.pt"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_egt_vs_golden(name, mode):
+    fx = load_golden(name)
+    if fx["kind"] == "edge_update":
+        mod = L.EdgeUpdate(fx["node_width"], fx["edge_width"], fx["num_heads"])
+    else:
+        mod = L.EGT_Attention(fx["node_width"], fx["edge_width"], fx["num_heads"], **fx["kwargs"])
+    mod.load_state_dict(fx["state"], strict=True)
+    mod = mod.to(DEV).eval()
+    h = fx["h"].to(DEV).requires_grad_(True)
+    e = fx["e"].to(DEV).requires_grad_(True)
+    mask = fx["mask"].to(DEV)
+    if mode == "bf16":
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            ho, eo = mod(h, e, mask)
+    else:
+        ho, eo = mod(h, e, mask)
+    loss = (ho.float() * fx["dh_out"].to(DEV)).sum()
+    if fx["de"] is not None or eo is e:
+        loss = loss + (eo.float() * fx["de_out"].to(DEV)).sum()
+    loss.backward()
+    if mode == "fp32":
+        chk = lambda a, b, k="": (max_rel(a.cpu(), b) < 2 * FP32_TOL) or pytest.fail(f"{k}: {max_rel(a.cpu(), b)}")
+    else:
+        chk = lambda a, b, k="": (rel_err(a.float().cpu(), b) < 2 * BF16_TOL) or pytest.fail(f"{k}: {rel_err(a.float().cpu(), b)}")
+    chk(ho, fx["h_out"], "h_out")
+    chk(eo, fx["e_out"], "e_out")
+    if fx["dh"] is not None:
+        chk(h.grad, fx["dh"], "dh")
+    if fx["de"] is not None:
+        chk(e.grad, fx["de"], "de")
+    for k, g in fx["grads"].items():
+        chk(dict(mod.named_parameters())[k].grad, g, k)
+
+
+@pytest.mark.parametrize("name,cls", [("model_multi_at.pt", HM.TGT_Multi), ("model_gap_agx2.pt", HM.TGT_Gap),
+                                      ("model_dist_at.pt", HM.TGT_Distance)])
+def test_whole_model_fp32_vs_golden(name, cls):
+    """Reference task models (lib/models/pcqm) on top of our encoder: eval-mode forward equals the reference's."""
+    fx = load_golden(name)
+    model = cls(**fx["cfg"], **fx["extra"])
+    model.load_state_dict(fx["state"], strict=True)
+    model = model.to(DEV).eval()
+    batch = {k: v.to(DEV) for k, v in fx["batch"].items()}
+    with torch.no_grad():
+        out = model(batch)
+    outs = out if isinstance(out, tuple) else (out,)
+    for o, g in zip(outs, fx["outs"]):
+        assert max_rel(o.cpu(), g) < 5 * FP32_TOL
+
+
+def test_config1_triplet_attention_vs_oracle():
+    """BASELINE.json configs[0]: TripletAttention(512, 8), B=4, N=16 (d=64), seed 0; fwd + all grads, fp32."""
+    torch.manual_seed(0)
+    mod = L.TripletAttention(512, 8)
+    e, mask = make_edge_inputs(4, 16, 512, [16, 12, 9, 5], seed=0)
+    p = {k: v.double().requires_grad_(True) for k, v in mod.state_dict().items()}
+    ed = e.double().requires_grad_(True)
+    ref = O.triplet_attention(p, ed, mask.double(), 8)
+    dout = torch.randn(ref.shape, generator=torch.Generator().manual_seed(1), dtype=torch.float64)
+    ref.backward(dout)
+    mod = mod.to(DEV)
+    eg = e.to(DEV).requires_grad_(True)
+    out = mod(eg, mask.to(DEV))
+    out.backward(dout.float().to(DEV))
+    assert max_rel(out.cpu(), ref) < FP32_TOL
+    assert max_rel(eg.grad.cpu(), ed.grad) < FP32_TOL
+    for k, prm in mod.named_parameters():
+        assert max_rel(prm.grad.cpu(), p[k].grad) < 2 * FP32_TOL, k
+    import json
+    kat = json.load(open(os.path.join(GOLDEN, "config1_kat.json")))       # checksum produced by the real reference
+    assert abs(float(out.double().sum()) - kat["sum"]) < 1e-4 * kat["abs_sum"]
+    for (b, i, j, c), v in zip([(0, 0, 0, 0), (1, 3, 7, 100), (2, 8, 8, 511), (3, 4, 2, 17)], kat["samples"]):
+        assert abs(float(out[b, i, j, c]) - v) < 1e-5 * max(1.0, abs(v))
+
+
+@pytest.mark.parametrize("kind,N,nn_", [("attention", 64, [64, 37]), ("attention", 48, [48, 25]),
+                                        ("attention", 33, [33, 1]), ("aggregate", 32, [32, 17]),
+                                        ("attention", 1, [1, 1]), ("aggregate", 64, [64, 40])])
+def test_shipped_width_bf16_vs_oracle(kind, N, nn_):
+    """Shipped head geometry (We=256, Ht=16, d=16) at ragged N up to the 64 maximum, bf16 tensor-core path vs the
+    fp64 oracle, and the tensor-core kernels vs the generic kernels (policy 1) on identical inputs."""
+    torch.manual_seed(3)
+    mod = L.get_triplet_layer(kind)(256, 16)
+    e, mask = make_edge_inputs(2, N, 256, nn_, seed=5)
+    p = {k: v.double().requires_grad_(True) for k, v in mod.state_dict().items()}
+    ed = e.double().requires_grad_(True)
+    ref = O.TRIPLET_FNS[kind](p, ed, mask.double(), 16)
+    dout = torch.randn(ref.shape, generator=torch.Generator().manual_seed(1), dtype=torch.float64)
+    ref.backward(dout)
+    mod = mod.to(DEV)
+    res = {}
+    for policy in (0, 1):
+        _C.set_kernel_policy(policy)
+        try:
+            mod.zero_grad(set_to_none=True)
+            eg = e.to(DEV).requires_grad_(True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out = mod(eg, mask.to(DEV))
+            out.backward(dout.to(DEV).to(out.dtype))
+            res[policy] = (out.float().cpu(), eg.grad.cpu(), {k: v.grad.cpu() for k, v in mod.named_parameters()})
+        finally:
+            _C.set_kernel_policy(0)
+        assert rel_err(res[policy][0], ref) < BF16_TOL
+        assert rel_err(res[policy][1], ed.grad) < 2 * BF16_TOL
+        for k in p:
+            assert rel_err(res[policy][2][k], p[k].grad) < 3 * BF16_TOL, (policy, k)
+    assert rel_err(res[0][0], res[1][0]) < BF16_TOL
+
+
+def test_outputs_survive_inplace_residual_add():
+    """TGT_Layer adds residuals in place to our outputs (layers.py:270-290): nothing saved may alias them."""
+    torch.manual_seed(0)
+    mod = L.TripletAttention(32, 2).to(DEV)
+    e, mask = make_edge_inputs(2, 6, 32, [6, 3], seed=1)
+    e = e.to(DEV).requires_grad_(True)
+    out = mod(e, mask.to(DEV))
+    out.add_(e.detach())
+    out.mul_(2.0)
+    out.sum().backward()
+    assert torch.isfinite(e.grad).all()
+
+
+def test_unsupported_inputs_raise():
+    mod = L.TripletAttention(32, 2).to(DEV)
+    e, mask = make_edge_inputs(1, 65, 32, [65], seed=1)
+    with pytest.raises(RuntimeError, match="N=65"):
+        mod(e.to(DEV), mask.to(DEV))
+    mod2 = L.TripletAttention(32, 2, attention_dropout=0.1).to(DEV).train()
+    e, mask = make_edge_inputs(1, 4, 32, [4], seed=1)
+    with pytest.raises(NotImplementedError):
+        mod2(e.to(DEV), mask.to(DEV))
+    mod2.eval()
+    mod2(e.to(DEV), mask.to(DEV))          # dropout inactive in eval: fine
+    with pytest.raises(NotImplementedError):
+        L.TriangularUpdate(32, 2).to(DEV)(e.to(DEV), mask.to(DEV))
+
+
+def test_padding_leak_of_aggregate_is_reproduced():
+    """TripletAggregate's outward softmax is unmasked (triplet.py:63-64): perturbing PADDED entries of e changes
+    real outputs in the reference; ours must reproduce that, not 'fix' it."""
+    torch.manual_seed(0)
+    mod = L.TripletAggregate(32, 2).to(DEV)
+    e, mask = make_edge_inputs(1, 8, 32, [5], seed=1)
+    e2 = e.clone()
+    e2[:, 5:, :, :] += 1.0
+    o1 = mod(e.to(DEV), mask.to(DEV))
+    o2 = mod(e2.to(DEV), mask.to(DEV))
+    assert (o1[:, :5, :5] - o2[:, :5, :5]).abs().max() > 1e-3
+    moda = L.TripletAttention(32, 2).to(DEV)
+    o1 = moda(e.to(DEV), mask.to(DEV))
+    o2 = moda(e2.to(DEV), mask.to(DEV))
+    assert (o1[:, :5, :5] - o2[:, :5, :5]).abs().max() < 1e-5
+
+
+def test_rowwise_kernels():
+    torch.manual_seed(0)
+    for W, xdt, ydt in [(256, torch.float32, torch.float32), (256, torch.bfloat16, torch.bfloat16),
+                        (768, torch.float32, torch.bfloat16), (36, torch.float32, torch.float32)]:
+        x = torch.randn(1000, W, device=DEV).to(xdt)
+        g = torch.rand(W, device=DEV) + 0.5
+        b = torch.randn(W, device=DEV)
+        y, mean, rstd = ops.layernorm_fwd(x, g, b, ydt)
+        ref = torch.nn.functional.layer_norm(x.float(), (W,), g, b)
+        tol = 1e-5 if ydt == torch.float32 else 1e-2
+        assert max_rel(y.float(), ref) < tol
+        dy = torch.randn(1000, W, device=DEV).to(ydt)
+        xr = x.float().requires_grad_(True)
+        gr, br = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        torch.nn.functional.layer_norm(xr, (W,), gr, br).backward(dy.float())
+        dx, dg, db = ops.layernorm_bwd(dy, x, g, mean, rstd)
+        assert max_rel(dx.float(), xr.grad) < (1e-5 if xdt == torch.float32 else 2e-2)
+        assert max_rel(dg, gr.grad) < 1e-4 and max_rel(db, br.grad) < 1e-4
+    # gelu + dropout: p=0 equals F.gelu; p>0 keeps ~(1-p), scales by 1/(1-p), fwd/bwd masks agree
+    u = torch.randn(4096, 256, device=DEV)
+    y = torch.empty_like(u)
+    _C.check(_C.lib().tgt_gelu_dropout_fwd(_C.ptr(u), _C.ptr(y), u.numel(), 0.0, 0, 0, _C.stream_ptr()), "gelu")
+    assert max_rel(y, torch.nn.functional.gelu(u)) < 1e-6
+    _C.check(_C.lib().tgt_gelu_dropout_fwd(_C.ptr(u), _C.ptr(y), u.numel(), 0.25, 1234, 0, _C.stream_ptr()), "gelu")
+    keep = (y != 0) | (u == 0)
+    assert abs(float(keep.float().mean()) - 0.75) < 0.01
+    assert max_rel(y[keep], torch.nn.functional.gelu(u)[keep] / 0.75) < 1e-6
+    du = torch.empty_like(u)
+    ones = torch.ones_like(u)
+    _C.check(_C.lib().tgt_gelu_dropout_bwd(_C.ptr(u), _C.ptr(ones), _C.ptr(du), u.numel(), 0.25, 1234, 0,
+                                           _C.stream_ptr()), "gelu_bwd")
+    assert bool(((du != 0) == (y != 0)).float().mean() > 0.999)
+    ur = u.clone().requires_grad_(True)
+    torch.nn.functional.gelu(ur).sum().backward()
+    assert max_rel(du[keep], ur.grad[keep] / 0.75) < 1e-5
+    # scaled residual
+    x = torch.randn(4, 8, 8, 32, device=DEV).bfloat16()
+    r = torch.randn(4, 8, 8, 32, device=DEV)
+    s = torch.tensor([0., 1.25, 1.25, 0.], device=DEV)
+    out = ops.scaled_residual(x, r, s)
+    assert out.dtype == torch.bfloat16
+    assert max_rel(out.float(), r + s.view(4, 1, 1, 1) * x.float()) < 1e-2
+
+
+def test_layer_train_mode_statistics_and_grads():
+    """Train mode with all dropouts on: runs, finite, and drop_path=1-eps style sanity (p=0 equals eval)."""
+    torch.manual_seed(0)
+    kw = dict(node_width=48, edge_width=32, num_heads=4, triplet_heads=2, triplet_type="attention")
+    layer = L.TGT_Layer(**kw, source_dropout=0.3, drop_path=0.2, node_act_dropout=0.1, edge_act_dropout=0.1).to(DEV)
+    e, mask = make_edge_inputs(4, 10, 32, [10, 7, 5, 2], seed=1)
+    h = torch.randn(4, 10, 48, device=DEV)
+    g = Graph(h=h.requires_grad_(True), e=e.to(DEV).requires_grad_(True), mask=mask.to(DEV), node_mask=None)
+    layer.train()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = layer(g)
+    (out.h.float().sum() + out.e.float().sum()).backward()
+    assert out.e.dtype == torch.bfloat16 and out.h.dtype == torch.bfloat16      # SURVEY 5.8 residual-stream dtype
+    assert torch.isfinite(g.h.grad).all() and torch.isfinite(g.e.grad).all()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in layer.parameters())
+    assert "node_mask" in out
+
+
+def test_encoder_fp32_train_vs_oracle_grads():
+    """3-layer encoder (attention + a last layer without edge branch), fp32, dropouts off but train mode:
+    output and parameter gradients vs the fp64 oracle."""
+    torch.manual_seed(4)
+    cfg = dict(node_width=48, edge_width=32, num_heads=4, triplet_heads=2, triplet_type="attention")
+    enc = TGT_Encoder(model_height=3, node_ended=True, edge_ended=False, **cfg)
+    e, mask = make_edge_inputs(2, 9, 32, [9, 5], seed=3)
+    h = torch.randn(2, 9, 48)
+    p = {k: v.double().requires_grad_(True) for k, v in enc.state_dict().items()}
+    ocfg = dict(cfg)
+    ocfg.pop("node_width"), ocfg.pop("edge_width")
+    ho, eo = O.encoder(p, h.double(), e.double(), mask.double(), model_height=3, node_ended=True,
+                       edge_ended=False, **ocfg)
+    (ho.sum() + 0.5 * eo.sum()).backward()
+    enc = enc.to(DEV).train()
+    g = enc(Graph(h=h.to(DEV), e=e.to(DEV), mask=mask.to(DEV)))
+    (g.h.sum() + 0.5 * g.e.sum()).backward()
+    assert max_rel(g.h.cpu(), ho) < 5 * FP32_TOL and max_rel(g.e.cpu(), eo) < 5 * FP32_TOL
+    for k, prm in enc.named_parameters():
+        assert max_rel(prm.grad.cpu(), p[k].grad, floor=1e-4) < 1e-4, k

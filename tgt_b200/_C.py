@@ -1,0 +1,115 @@
+"""ctypes binding of libtgt_b200.so (the C ABI declared in include/tgt_b200.h).
+
+There is deliberately no fallback: if the shared library is missing the first kernel call
+raises, and every non-zero return code becomes a RuntimeError carrying tgt_last_error().
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libtgt_b200.so")
+
+F32, BF16, F16 = 0, 1, 2
+_DTYPE_CODE = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    try:
+        return _DTYPE_CODE[dt]
+    except KeyError:
+        raise RuntimeError(f"tgt_b200: unsupported dtype {dt}") from None
+
+
+class TripletAttnDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("N", C.c_int32), ("H", C.c_int32), ("d", C.c_int32),
+                ("ld", C.c_int64),
+                ("off_q", C.c_int32 * 2), ("off_k", C.c_int32 * 2), ("off_v", C.c_int32 * 2),
+                ("off_e", C.c_int32 * 2), ("off_g", C.c_int32 * 2),
+                ("scale", C.c_float), ("dtype", C.c_int32)]
+
+
+class TripletAggrDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("N", C.c_int32), ("H", C.c_int32), ("d", C.c_int32),
+                ("ld", C.c_int64),
+                ("off_v", C.c_int32 * 2), ("off_e", C.c_int32 * 2), ("off_g", C.c_int32 * 2),
+                ("mask_dir", C.c_int32 * 2), ("dtype", C.c_int32)]
+
+
+class EgtDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("N", C.c_int32), ("H", C.c_int32), ("d", C.c_int32),
+                ("ld_qkv", C.c_int64), ("ld_eg", C.c_int64),
+                ("scale", C.c_float), ("attend", C.c_int32), ("scale_degree", C.c_int32),
+                ("dtype", C.c_int32)]
+
+
+_P = C.c_void_p
+_SIGNATURES = {
+    "tgt_version": (C.c_int, []),
+    "tgt_last_error": (C.c_char_p, []),
+    "tgt_launch_count": (C.c_uint64, []),
+    "tgt_set_kernel_policy": (None, [C.c_int]),
+    "tgt_layernorm_fwd": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_float, C.c_int, C.c_int, _P]),
+    "tgt_layernorm_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, _P]),
+    "tgt_triplet_attn_fwd": (C.c_int, [C.POINTER(TripletAttnDesc), _P, _P, _P, _P, _P]),
+    "tgt_triplet_attn_bwd": (C.c_int, [C.POINTER(TripletAttnDesc), _P, _P, _P, _P, _P, _P, _P]),
+    "tgt_triplet_aggr_fwd": (C.c_int, [C.POINTER(TripletAggrDesc), _P, _P, _P, _P, _P]),
+    "tgt_triplet_aggr_bwd": (C.c_int, [C.POINTER(TripletAggrDesc), _P, _P, _P, _P, _P, _P, _P]),
+    "tgt_egt_attn_fwd": (C.c_int, [C.POINTER(EgtDesc), _P, _P, _P, _P, _P, _P, _P, _P]),
+    "tgt_egt_attn_bwd": (C.c_int, [C.POINTER(EgtDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "tgt_gelu_dropout_fwd": (C.c_int, [_P, _P, C.c_int64, C.c_float, C.c_uint64, C.c_int, _P]),
+    "tgt_gelu_dropout_bwd": (C.c_int, [_P, _P, _P, C.c_int64, C.c_float, C.c_uint64, C.c_int, _P]),
+    "tgt_scaled_residual": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int, C.c_int, _P]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the shared library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        f"tgt_b200: CUDA library {LIB_PATH} is missing -- run "
+                        "`python -c 'import __graft_entry__ as g; g.build()'` (there is no fallback path)")
+                handle = C.CDLL(LIB_PATH)
+                for name, (res, args) in _SIGNATURES.items():
+                    fn = getattr(handle, name)
+                    fn.restype = res
+                    fn.argtypes = args
+                _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"tgt_b200.{what} failed: {lib().tgt_last_error().decode()}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def launch_count() -> int:
+    return int(lib().tgt_launch_count())
+
+
+def set_kernel_policy(policy: int) -> None:
+    """0 = fastest supported kernel (default), 1 = force the generic SIMT kernels."""
+    lib().tgt_set_kernel_policy(int(policy))

@@ -1,0 +1,84 @@
+// C-ABI entry points that dispatch between the tensor-core and the generic kernels, plus library state.
+#include "common.cuh"
+
+namespace tgt {
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_policy{0};
+
+// triplet_simt.cu
+int triplet_attn_fwd_simt(const tgt_triplet_attn_desc &, const void *, const float *, void *, float *, cudaStream_t);
+int triplet_attn_bwd_simt(const tgt_triplet_attn_desc &, const void *, const float *, const void *, const void *,
+                          const float *, void *, cudaStream_t);
+int triplet_aggr_fwd_simt(const tgt_triplet_aggr_desc &, const void *, const float *, void *, float *, cudaStream_t);
+int triplet_aggr_bwd_simt(const tgt_triplet_aggr_desc &, const void *, const float *, const void *, const float *,
+                          float *, void *, cudaStream_t);
+// triplet_mma.cu
+bool triplet_attn_mma_supported(const tgt_triplet_attn_desc &);
+int triplet_attn_fwd_mma(const tgt_triplet_attn_desc &, const void *, const float *, void *, float *, cudaStream_t);
+int triplet_attn_bwd_mma(const tgt_triplet_attn_desc &, const void *, const float *, const void *, const void *,
+                         const float *, void *, cudaStream_t);
+}  // namespace tgt
+
+using namespace tgt;
+
+extern "C" int tgt_version(void) { return 100; }
+extern "C" const char *tgt_last_error(void) { return g_err; }
+extern "C" uint64_t tgt_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+extern "C" void tgt_set_kernel_policy(int policy) { g_policy.store(policy); }
+
+static int attn_check(const tgt_triplet_attn_desc *D) {
+  if (!D) return fail("triplet_attn: null descriptor");
+  if (D->B <= 0 || D->N <= 0 || D->H <= 0 || D->d <= 0)
+    return fail("triplet_attn: bad shape B=%d N=%d H=%d d=%d", D->B, D->N, D->H, D->d);
+  if (D->N > 64) return fail("triplet_attn: N=%d > 64 unsupported", D->N);
+  if (D->d > 64) return fail("triplet_attn: head dim %d > 64 unsupported", D->d);
+  if (D->B > 65535 || D->H > 65535) return fail("triplet_attn: B or H > 65535 unsupported");
+  for (int dir = 0; dir < 2; ++dir) {
+    if (D->off_q[dir] < 0 || D->off_k[dir] < 0 || D->off_v[dir] < 0)
+      return fail("triplet_attn: q/k/v column blocks are mandatory");
+    if ((D->off_g[dir] >= 0) && (D->off_e[dir] < 0)) return fail("triplet_attn: gate without bias unsupported");
+  }
+  return 0;
+}
+
+extern "C" int tgt_triplet_attn_fwd(const tgt_triplet_attn_desc *D, const void *proj, const float *mask, void *va,
+                                    float *stats, void *stream) {
+  if (int e = attn_check(D)) return e;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (g_policy.load() == 0 && triplet_attn_mma_supported(*D)) return triplet_attn_fwd_mma(*D, proj, mask, va, stats, st);
+  return triplet_attn_fwd_simt(*D, proj, mask, va, stats, st);
+}
+
+extern "C" int tgt_triplet_attn_bwd(const tgt_triplet_attn_desc *D, const void *proj, const float *mask,
+                                    const void *va, const void *dva, const float *stats, void *dproj, void *stream) {
+  if (int e = attn_check(D)) return e;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (g_policy.load() == 0 && triplet_attn_mma_supported(*D))
+    return triplet_attn_bwd_mma(*D, proj, mask, va, dva, stats, dproj, st);
+  return triplet_attn_bwd_simt(*D, proj, mask, va, dva, stats, dproj, st);
+}
+
+static int aggr_check(const tgt_triplet_aggr_desc *D) {
+  if (!D) return fail("triplet_aggr: null descriptor");
+  if (D->B <= 0 || D->N <= 0 || D->H <= 0 || D->d <= 0)
+    return fail("triplet_aggr: bad shape B=%d N=%d H=%d d=%d", D->B, D->N, D->H, D->d);
+  if (D->N > 64) return fail("triplet_aggr: N=%d > 64 unsupported", D->N);
+  if (D->d > 64) return fail("triplet_aggr: head dim %d > 64 unsupported", D->d);
+  if (D->B > 65535) return fail("triplet_aggr: B > 65535 unsupported");
+  for (int dir = 0; dir < 2; ++dir)
+    if (D->off_v[dir] < 0 || D->off_e[dir] < 0) return fail("triplet_aggr: v/e column blocks are mandatory");
+  return 0;
+}
+
+extern "C" int tgt_triplet_aggr_fwd(const tgt_triplet_aggr_desc *D, const void *proj, const float *mask, void *va,
+                                    float *aw, void *stream) {
+  if (int e = aggr_check(D)) return e;
+  return triplet_aggr_fwd_simt(*D, proj, mask, va, aw, (cudaStream_t)stream);
+}
+
+extern "C" int tgt_triplet_aggr_bwd(const tgt_triplet_aggr_desc *D, const void *proj, const float *mask,
+                                    const void *dva, const float *aw, float *daw, void *dproj, void *stream) {
+  if (int e = aggr_check(D)) return e;
+  return triplet_aggr_bwd_simt(*D, proj, mask, dva, aw, daw, dproj, (cudaStream_t)stream);
+}

@@ -1,0 +1,411 @@
+// Row-wise HBM-bound kernels: LayerNorm fwd/bwd over edge rows, GELU+dropout, scaled residual.
+// All are one-pass streaming kernels: 16-byte vector loads/stores, one warp per row for LN
+// (W = 256 bf16 -> exactly one 16B vector per lane), grid-stride over rows so the grid can be
+// sized to the 148 SMs.
+#include "common.cuh"
+
+namespace tgt {
+
+constexpr int LN_MAX_ITERS = 8;   // supports W up to 8*32*(16/sizeof(T)) channels
+
+template <typename XT, typename YT>
+__global__ void __launch_bounds__(256)
+ln_fwd_kernel(const XT *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ beta,
+              YT *__restrict__ y, float *__restrict__ mean, float *__restrict__ rstd,
+              int64_t rows, int W, float eps) {
+  constexpr int V = 4;                       // process 4 channels per lane per iteration (16B fp32 / 8B bf16)
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int iters = (W + 32 * V - 1) / (32 * V);
+  for (int64_t r = warp0; r < rows; r += nwarps) {
+    const XT *xr = x + r * W;
+    float v[LN_MAX_ITERS][V];
+    float s = 0.f;
+#pragma unroll
+    for (int it = 0; it < LN_MAX_ITERS; ++it) {
+      if (it < iters) {
+        const int c = (it * 32 + lane) * V;
+        if (c < W) {
+          if constexpr (sizeof(XT) == 4) {
+            float4 t = *reinterpret_cast<const float4 *>(xr + c);
+            v[it][0] = t.x; v[it][1] = t.y; v[it][2] = t.z; v[it][3] = t.w;
+          } else {
+            uint2 raw = *reinterpret_cast<const uint2 *>(xr + c);
+            const XT *e = reinterpret_cast<const XT *>(&raw);
+#pragma unroll
+            for (int q = 0; q < V; ++q) v[it][q] = to_f(e[q]);
+          }
+#pragma unroll
+          for (int q = 0; q < V; ++q) s += v[it][q];
+        } else {
+#pragma unroll
+          for (int q = 0; q < V; ++q) v[it][q] = 0.f;
+        }
+      }
+    }
+    const float mu = warp_sum(s) / (float)W;
+    float ss = 0.f;
+#pragma unroll
+    for (int it = 0; it < LN_MAX_ITERS; ++it) {
+      if (it < iters) {
+        const int c = (it * 32 + lane) * V;
+        if (c < W) {
+#pragma unroll
+          for (int q = 0; q < V; ++q) { const float dlt = v[it][q] - mu; ss += dlt * dlt; }
+        }
+      }
+    }
+    const float rs = rsqrtf(warp_sum(ss) / (float)W + eps);
+    if (lane == 0) { mean[r] = mu; rstd[r] = rs; }
+    YT *yr = y + r * W;
+#pragma unroll
+    for (int it = 0; it < LN_MAX_ITERS; ++it) {
+      if (it < iters) {
+        const int c = (it * 32 + lane) * V;
+        if (c < W) {
+          const float4 g = *reinterpret_cast<const float4 *>(gamma + c);
+          const float4 b = *reinterpret_cast<const float4 *>(beta + c);
+          float o[V];
+          o[0] = (v[it][0] - mu) * rs * g.x + b.x;
+          o[1] = (v[it][1] - mu) * rs * g.y + b.y;
+          o[2] = (v[it][2] - mu) * rs * g.z + b.z;
+          o[3] = (v[it][3] - mu) * rs * g.w + b.w;
+          if constexpr (sizeof(YT) == 4) {
+            *reinterpret_cast<float4 *>(yr + c) = make_float4(o[0], o[1], o[2], o[3]);
+          } else {
+            uint2 raw;
+            YT *e = reinterpret_cast<YT *>(&raw);
+#pragma unroll
+            for (int q = 0; q < V; ++q) e[q] = from_f<YT>(o[q]);
+            *reinterpret_cast<uint2 *>(yr + c) = raw;
+          }
+        }
+      }
+    }
+  }
+}
+
+// dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)) (+ dres);  dgamma += dy*xhat; dbeta += dy
+template <typename XT, typename YT>
+__global__ void __launch_bounds__(256)
+ln_bwd_kernel(const YT *__restrict__ dy, const XT *__restrict__ x, const float *__restrict__ gamma,
+              const float *__restrict__ mean, const float *__restrict__ rstd,
+              const XT *__restrict__ dres, XT *__restrict__ dx,
+              float *__restrict__ dgamma, float *__restrict__ dbeta, int64_t rows, int W) {
+  constexpr int V = 4;
+  extern __shared__ float sm[];              // [2][W] block partials
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int iters = (W + 32 * V - 1) / (32 * V);
+  for (int c = threadIdx.x; c < 2 * W; c += blockDim.x) sm[c] = 0.f;
+  __syncthreads();
+  float ag[LN_MAX_ITERS][V], ab[LN_MAX_ITERS][V];
+#pragma unroll
+  for (int it = 0; it < LN_MAX_ITERS; ++it)
+#pragma unroll
+    for (int q = 0; q < V; ++q) { ag[it][q] = 0.f; ab[it][q] = 0.f; }
+
+  for (int64_t r = warp0; r < rows; r += nwarps) {
+    const XT *xr = x + r * W;
+    const YT *dyr = dy + r * W;
+    const float mu = mean[r], rs = rstd[r];
+    float xh[LN_MAX_ITERS][V], gd[LN_MAX_ITERS][V];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int it = 0; it < LN_MAX_ITERS; ++it) {
+      if (it < iters) {
+        const int c = (it * 32 + lane) * V;
+        if (c < W) {
+          float xv[V], dv[V];
+          if constexpr (sizeof(XT) == 4) {
+            float4 t = *reinterpret_cast<const float4 *>(xr + c);
+            xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
+          } else {
+            uint2 raw = *reinterpret_cast<const uint2 *>(xr + c);
+            const XT *e = reinterpret_cast<const XT *>(&raw);
+#pragma unroll
+            for (int q = 0; q < V; ++q) xv[q] = to_f(e[q]);
+          }
+          if constexpr (sizeof(YT) == 4) {
+            float4 t = *reinterpret_cast<const float4 *>(dyr + c);
+            dv[0] = t.x; dv[1] = t.y; dv[2] = t.z; dv[3] = t.w;
+          } else {
+            uint2 raw = *reinterpret_cast<const uint2 *>(dyr + c);
+            const YT *e = reinterpret_cast<const YT *>(&raw);
+#pragma unroll
+            for (int q = 0; q < V; ++q) dv[q] = to_f(e[q]);
+          }
+          const float4 g = *reinterpret_cast<const float4 *>(gamma + c);
+          const float gg[V] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+          for (int q = 0; q < V; ++q) {
+            xh[it][q] = (xv[q] - mu) * rs;
+            gd[it][q] = gg[q] * dv[q];
+            s1 += gd[it][q];
+            s2 += gd[it][q] * xh[it][q];
+            ag[it][q] += dv[q] * xh[it][q];
+            ab[it][q] += dv[q];
+          }
+        }
+      }
+    }
+    s1 = warp_sum(s1) / (float)W;
+    s2 = warp_sum(s2) / (float)W;
+    XT *dxr = dx + r * W;
+#pragma unroll
+    for (int it = 0; it < LN_MAX_ITERS; ++it) {
+      if (it < iters) {
+        const int c = (it * 32 + lane) * V;
+        if (c < W) {
+          float o[V];
+#pragma unroll
+          for (int q = 0; q < V; ++q) o[q] = rs * (gd[it][q] - s1 - xh[it][q] * s2);
+          if (dres != nullptr) {
+            if constexpr (sizeof(XT) == 4) {
+              float4 t = *reinterpret_cast<const float4 *>(dres + r * W + c);
+              o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w;
+            } else {
+              uint2 raw = *reinterpret_cast<const uint2 *>(dres + r * W + c);
+              const XT *e = reinterpret_cast<const XT *>(&raw);
+#pragma unroll
+              for (int q = 0; q < V; ++q) o[q] += to_f(e[q]);
+            }
+          }
+          if constexpr (sizeof(XT) == 4) {
+            *reinterpret_cast<float4 *>(dxr + c) = make_float4(o[0], o[1], o[2], o[3]);
+          } else {
+            uint2 raw;
+            XT *e = reinterpret_cast<XT *>(&raw);
+#pragma unroll
+            for (int q = 0; q < V; ++q) e[q] = from_f<XT>(o[q]);
+            *reinterpret_cast<uint2 *>(dxr + c) = raw;
+          }
+        }
+      }
+    }
+  }
+  // block reduce the per-lane channel partials through shared memory, then one atomic per channel
+#pragma unroll
+  for (int it = 0; it < LN_MAX_ITERS; ++it) {
+    if (it < iters) {
+      const int c = (it * 32 + lane) * V;
+      if (c < W) {
+#pragma unroll
+        for (int q = 0; q < V; ++q) {
+          atomicAdd(&sm[c + q], ag[it][q]);
+          atomicAdd(&sm[W + c + q], ab[it][q]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < W; c += blockDim.x) {
+    atomicAdd(&dgamma[c], sm[c]);
+    atomicAdd(&dbeta[c], sm[W + c]);
+  }
+}
+
+// ------------------------------------------------------------------ gelu + dropout
+__device__ __forceinline__ uint32_t mix_hash(uint64_t seed, uint64_t idx) {
+  // splitmix64 finaliser over (seed + idx * golden); good avalanche, stateless
+  uint64_t z = seed + idx * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (uint32_t)(z >> 32);
+}
+__device__ __forceinline__ float gelu_f(float u) { return 0.5f * u * (1.f + erff(u * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad(float u) {
+  const float cdf = 0.5f * (1.f + erff(u * 0.70710678118654752f));
+  const float pdf = 0.39894228040143268f * __expf(-0.5f * u * u);
+  return cdf + u * pdf;
+}
+
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(256)
+gelu_dropout_kernel(const T *__restrict__ u, const T *__restrict__ dy, T *__restrict__ out, int64_t n,
+                    float p_drop, uint64_t seed) {
+  constexpr int NV = 16 / sizeof(T);
+  const uint32_t thresh = p_drop > 0.f ? (uint32_t)fminf(p_drop * 4294967296.f, 4294967295.f) : 0u;
+  const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  const int64_t nvec = n / NV;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    float a[NV], o[NV];
+    load_vec<T, NV>(u + i * NV, a);
+    float g[NV];
+    if constexpr (BWD) load_vec<T, NV>(dy + i * NV, g);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      float m = keep_scale;
+      if (p_drop > 0.f && mix_hash(seed, (uint64_t)(i * NV + q)) < thresh) m = 0.f;
+      if constexpr (BWD) o[q] = g[q] * m * gelu_grad(a[q]);
+      else o[q] = gelu_f(a[q]) * m;
+    }
+    store_vec<T, NV>(out + i * NV, o);
+  }
+  // tail
+  if (blockIdx.x == 0) {
+    for (int64_t e = nvec * NV + threadIdx.x; e < n; e += blockDim.x) {
+      float m = keep_scale;
+      if (p_drop > 0.f && mix_hash(seed, (uint64_t)e) < thresh) m = 0.f;
+      const float a = to_f(u[e]);
+      out[e] = from_f<T>(BWD ? to_f(dy[e]) * m * gelu_grad(a) : gelu_f(a) * m);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ out = res + scale[b]*x
+template <typename T, typename RT>
+__global__ void __launch_bounds__(256)
+scaled_residual_kernel(const T *__restrict__ x, const RT *__restrict__ res, const float *__restrict__ scale,
+                       T *__restrict__ out, int64_t B, int64_t inner) {
+  constexpr int NV = 4;
+  const int64_t per = inner / NV;
+  const int64_t total = B * per;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t b = i / per;
+    const float s = scale ? scale[b] : 1.f;
+    const int64_t off = i * NV;
+    float xv[NV], rv[NV];
+    if constexpr (sizeof(T) == 4) {
+      float4 t = *reinterpret_cast<const float4 *>(x + off);
+      xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
+    } else {
+      uint2 raw = *reinterpret_cast<const uint2 *>(x + off);
+      const T *e = reinterpret_cast<const T *>(&raw);
+#pragma unroll
+      for (int q = 0; q < NV; ++q) xv[q] = to_f(e[q]);
+    }
+    if constexpr (sizeof(RT) == 4) {
+      float4 t = *reinterpret_cast<const float4 *>(res + off);
+      rv[0] = t.x; rv[1] = t.y; rv[2] = t.z; rv[3] = t.w;
+    } else {
+      uint2 raw = *reinterpret_cast<const uint2 *>(res + off);
+      const RT *e = reinterpret_cast<const RT *>(&raw);
+#pragma unroll
+      for (int q = 0; q < NV; ++q) rv[q] = to_f(e[q]);
+    }
+    float o[NV];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) o[q] = rv[q] + s * xv[q];
+    if constexpr (sizeof(T) == 4) {
+      *reinterpret_cast<float4 *>(out + off) = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+      uint2 raw;
+      T *e = reinterpret_cast<T *>(&raw);
+#pragma unroll
+      for (int q = 0; q < NV; ++q) e[q] = from_f<T>(o[q]);
+      *reinterpret_cast<uint2 *>(out + off) = raw;
+    }
+  }
+}
+
+static int grid_for(int64_t work_items, int per_block) {
+  int64_t g = (work_items + per_block - 1) / per_block;
+  const int64_t cap = 148 * 16;       // a few resident CTAs per SM, multiple of the SM count
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+template <typename XT, typename YT>
+static int ln_fwd_launch(const void *x, const float *gamma, const float *beta, void *y, float *mean,
+                         float *rstd, int64_t rows, int W, float eps, cudaStream_t st) {
+  ln_fwd_kernel<XT, YT><<<grid_for(rows, 8), 256, 0, st>>>((const XT *)x, gamma, beta, (YT *)y, mean, rstd,
+                                                            rows, W, eps);
+  return check_launch("ln_fwd_kernel");
+}
+template <typename XT, typename YT>
+static int ln_bwd_launch(const void *dy, const void *x, const float *gamma, const float *mean,
+                         const float *rstd, const void *dres, void *dx, float *dgamma, float *dbeta,
+                         int64_t rows, int W, cudaStream_t st) {
+  int g = grid_for(rows, 8 * 16);
+  if (g > 148 * 4) g = 148 * 4;
+  ln_bwd_kernel<XT, YT><<<g, 256, 2 * W * sizeof(float), st>>>((const YT *)dy, (const XT *)x, gamma, mean, rstd,
+                                                               (const XT *)dres, (XT *)dx, dgamma, dbeta, rows, W);
+  return check_launch("ln_bwd_kernel");
+}
+
+}  // namespace tgt
+
+using namespace tgt;
+
+#define LN_COMBOS(X)                                    \
+  X(TGT_F32, TGT_F32, float, float)                     \
+  X(TGT_F32, TGT_BF16, float, __nv_bfloat16)            \
+  X(TGT_BF16, TGT_BF16, __nv_bfloat16, __nv_bfloat16)   \
+  X(TGT_F32, TGT_F16, float, __half)                    \
+  X(TGT_F16, TGT_F16, __half, __half)
+
+extern "C" int tgt_layernorm_fwd(const void *x, const float *gamma, const float *beta, void *y, float *mean,
+                                 float *rstd, int64_t rows, int W, float eps, int x_dtype, int y_dtype,
+                                 void *stream) {
+  if (W % 4 != 0 || W > LN_MAX_ITERS * 128) return fail("layernorm: W=%d unsupported (need W%%4==0, W<=%d)", W, LN_MAX_ITERS * 128);
+  if (rows <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+#define X(xc, yc, XT, YT) \
+  if (x_dtype == xc && y_dtype == yc) return ln_fwd_launch<XT, YT>(x, gamma, beta, y, mean, rstd, rows, W, eps, st);
+  LN_COMBOS(X)
+#undef X
+  return fail("layernorm_fwd: unsupported dtype combination x=%d y=%d", x_dtype, y_dtype);
+}
+
+extern "C" int tgt_layernorm_bwd(const void *dy, const void *x, const float *gamma, const float *mean,
+                                 const float *rstd, const void *dres, void *dx, float *dgamma, float *dbeta,
+                                 int64_t rows, int W, int x_dtype, int y_dtype, void *stream) {
+  if (W % 4 != 0 || W > LN_MAX_ITERS * 128) return fail("layernorm: W=%d unsupported", W);
+  if (rows <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+#define X(xc, yc, XT, YT) \
+  if (x_dtype == xc && y_dtype == yc) return ln_bwd_launch<XT, YT>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, rows, W, st);
+  LN_COMBOS(X)
+#undef X
+  return fail("layernorm_bwd: unsupported dtype combination x=%d y=%d", x_dtype, y_dtype);
+}
+
+extern "C" int tgt_gelu_dropout_fwd(const void *u, void *y, int64_t n, float p_drop, uint64_t seed, int dtype,
+                                    void *stream) {
+  if (n <= 0) return 0;
+  if (p_drop < 0.f || p_drop >= 1.f) return fail("gelu_dropout: p_drop=%f out of range", p_drop);
+  cudaStream_t st = (cudaStream_t)stream;
+  TGT_DISPATCH_DTYPE(dtype, T, {
+    gelu_dropout_kernel<T, false><<<grid_for(n / (16 / sizeof(T)) + 1, 256 * 4), 256, 0, st>>>(
+        (const T *)u, nullptr, (T *)y, n, p_drop, seed);
+  });
+  return check_launch("gelu_dropout_fwd");
+}
+extern "C" int tgt_gelu_dropout_bwd(const void *u, const void *dy, void *du, int64_t n, float p_drop, uint64_t seed,
+                                    int dtype, void *stream) {
+  if (n <= 0) return 0;
+  if (p_drop < 0.f || p_drop >= 1.f) return fail("gelu_dropout: p_drop=%f out of range", p_drop);
+  cudaStream_t st = (cudaStream_t)stream;
+  TGT_DISPATCH_DTYPE(dtype, T, {
+    gelu_dropout_kernel<T, true><<<grid_for(n / (16 / sizeof(T)) + 1, 256 * 4), 256, 0, st>>>(
+        (const T *)u, (const T *)dy, (T *)du, n, p_drop, seed);
+  });
+  return check_launch("gelu_dropout_bwd");
+}
+
+extern "C" int tgt_scaled_residual(const void *x, const void *res, const float *scale, void *out, int64_t B,
+                                   int64_t inner, int dtype, int res_dtype, void *stream) {
+  if (B <= 0 || inner <= 0) return 0;
+  if (inner % 4 != 0) return fail("scaled_residual: inner=%lld must be a multiple of 4", (long long)inner);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int g = grid_for(B * inner / 4, 256 * 4);
+  if (dtype == res_dtype) {
+    TGT_DISPATCH_DTYPE(dtype, T, {
+      scaled_residual_kernel<T, T><<<g, 256, 0, st>>>((const T *)x, (const T *)res, scale, (T *)out, B, inner);
+    });
+  } else if (res_dtype == TGT_F32) {
+    TGT_DISPATCH_DTYPE(dtype, T, {
+      scaled_residual_kernel<T, float><<<g, 256, 0, st>>>((const T *)x, (const float *)res, scale, (T *)out, B, inner);
+    });
+  } else {
+    return fail("scaled_residual: unsupported dtype combination %d/%d", dtype, res_dtype);
+  }
+  return check_launch("scaled_residual");
+}

@@ -1,0 +1,170 @@
+"""Task models for the bench harness: input embedding + TGT encoder + heads.
+
+Functionally equivalent to (and state-dict compatible with) the reference's lib/models/pcqm
+{layers.py:11-173, multitask.py:10-68, gap_predictor.py:10-60, distance_predictor.py:9-54}; written as
+plain PyTorch because these O(N^2) pieces are outside the hot path ("reused unchanged").
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .. import TGT_Encoder, Graph
+from .synthetic import (NODE_FEATURES_OFFSET, NUM_NODE_FEATURES, EDGE_FEATURES_OFFSET, NUM_EDGE_FEATURES)
+
+HL_MEAN = 5.6894608
+
+
+class _GaussianBasis(nn.Module):
+    def __init__(self, K, edge_types):
+        super().__init__()
+        self.K = K
+        self.means = nn.Embedding(1, K)
+        self.stds = nn.Embedding(1, K)
+        self.mul = nn.Embedding(edge_types, 1, padding_idx=0)
+        self.bias = nn.Embedding(edge_types, 1, padding_idx=0)
+        nn.init.uniform_(self.means.weight, 0, 3)
+        nn.init.uniform_(self.stds.weight, 0, 3)
+        nn.init.constant_(self.bias.weight, 0)
+        nn.init.constant_(self.mul.weight, 1)
+
+    def forward(self, dist, types):
+        scale = self.mul(types).sum(dim=-2)
+        shift = self.bias(types).sum(dim=-2)
+        x = (scale * dist.unsqueeze(-1) + shift).expand(-1, -1, -1, self.K).float()
+        mu = self.means.weight.float().view(-1)
+        sd = self.stds.weight.float().view(-1).abs() + 1e-2
+        norm = (2 * 3.14159) ** 0.5
+        return (torch.exp(-0.5 * ((x - mu) / sd) ** 2) / (norm * sd)).type_as(self.means.weight)
+
+
+class _TwoLayer(nn.Module):
+    def __init__(self, n_in, n_out):
+        super().__init__()
+        self.layer1 = nn.Linear(n_in, n_in)
+        self.layer2 = nn.Linear(n_in, n_out)
+
+    def forward(self, x):
+        return self.layer2(F.gelu(self.layer1(x)))
+
+
+class _Gaussian3D(nn.Module):
+    def __init__(self, width, edge_types, K):
+        super().__init__()
+        self.gbf = _GaussianBasis(K, edge_types)
+        self.gbf_proj = _TwoLayer(K, width)
+
+    def forward(self, dist, types):
+        return self.gbf_proj(self.gbf(dist, types.long()))
+
+
+class EmbedInput(nn.Module):
+    def __init__(self, node_width, edge_width, upto_hop=32, embed_3d_type='gaussian', num_3d_kernels=128):
+        super().__init__()
+        if embed_3d_type not in ('gaussian', 'none'):
+            raise ValueError('harness supports embed_3d_type gaussian|none')
+        self.upto_hop = upto_hop
+        self.nodef_embed = nn.Embedding(NUM_NODE_FEATURES * NODE_FEATURES_OFFSET + 1, node_width, padding_idx=0)
+        self.dist_embed = nn.Embedding(upto_hop + 2, edge_width)
+        self.featm_embed = nn.Embedding(NUM_EDGE_FEATURES * EDGE_FEATURES_OFFSET + 1, edge_width, padding_idx=0)
+        self.uses_3d = embed_3d_type == 'gaussian'
+        if self.uses_3d:
+            self.m3d_embed = _Gaussian3D(edge_width, 2 * NODE_FEATURES_OFFSET + 1, num_3d_kernels)
+
+    def forward(self, inputs):
+        g = Graph(inputs)
+        nf = g.node_features.long()
+        h = self.nodef_embed(nf).sum(dim=2)
+        hops = g.distance_matrix.long().clamp(max=self.upto_hop + 1)
+        e = self.dist_embed(hops) + self.featm_embed(g.feature_matrix.long()).sum(dim=-2)
+        if self.uses_3d:
+            n = nf.size(1)
+            a = nf[:, :, 0]
+            types = torch.stack([a.unsqueeze(2).expand(-1, -1, n),
+                                 (a + NODE_FEATURES_OFFSET).unsqueeze(1).expand(-1, n, -1)], dim=-1)
+            e = e + self.m3d_embed(g.dist_input, types)
+        em = g.edge_mask.unsqueeze(-1).to(e.dtype)
+        g.h, g.e, g.mask = h, e, (1 - em) * torch.finfo(e.dtype).min
+        return g
+
+
+class _TaskModel(nn.Module):
+    node_ended, edge_ended = True, True
+
+    def __init__(self, model_height, layer_multiplier=1, upto_hop=32, embed_3d_type='gaussian',
+                 num_3d_kernels=128, num_dist_bins=None, **layer_configs):
+        super().__init__()
+        nw, ew = layer_configs['node_width'], layer_configs['edge_width']
+        self.encoder = TGT_Encoder(model_height=model_height, layer_multiplier=layer_multiplier,
+                                   node_ended=self.node_ended, edge_ended=self.edge_ended, egt_simple=False,
+                                   **layer_configs)
+        self.input_embed = EmbedInput(nw, ew, upto_hop, embed_3d_type, num_3d_kernels)
+        if self.node_ended:
+            self.final_ln_node = nn.LayerNorm(nw)
+            self.pred = nn.Linear(nw, 1)
+            nn.init.constant_(self.pred.bias, HL_MEAN)
+        if self.edge_ended:
+            self.final_ln_edge = nn.LayerNorm(ew)
+            self.dist_pred = nn.Linear(ew, num_dist_bins)
+
+    def _gap(self, g):
+        h = self.final_ln_node(g.h)
+        m = g.node_mask.float().unsqueeze(-1)
+        return self.pred((h * m).sum(dim=1) / (m.sum(dim=1) + 1e-9)).squeeze(-1)
+
+    def _bins(self, g):
+        return self.dist_pred(self.final_ln_edge(g.e))
+
+
+class TGT_Multi(_TaskModel):
+    node_ended, edge_ended = True, True
+
+    def __init__(self, model_height, num_dist_bins=128, **kw):
+        super().__init__(model_height, num_dist_bins=num_dist_bins, **kw)
+
+    def forward(self, inputs):
+        g = self.encoder(self.input_embed(inputs))
+        return self._gap(g), self._bins(g)
+
+
+class TGT_Gap(_TaskModel):
+    node_ended, edge_ended = True, False
+
+    def forward(self, inputs):
+        return self._gap(self.encoder(self.input_embed(inputs)))
+
+
+class TGT_Distance(_TaskModel):
+    node_ended, edge_ended = False, True
+
+    def __init__(self, model_height, num_dist_bins=128, **kw):
+        super().__init__(model_height, num_dist_bins=num_dist_bins, **kw)
+
+    def forward(self, inputs):
+        return self._bins(self.encoder(self.input_embed(inputs)))
+
+
+def coords2dist(x):
+    return torch.norm(x.unsqueeze(-2) - x.unsqueeze(-3), dim=-1)
+
+
+def pretrain_loss(gap, logits, batch, num_bins, range_bins=8.0, dist_loss_weight=0.1):
+    """L1(gap) + w * masked cross-entropy over distance bins (pretrain/scheme.py:78-88, commons.py:19-48)."""
+    prim = F.l1_loss(gap, batch['target'].to(gap.dtype))
+    tgt = (coords2dist(batch['dft_coords']) * ((num_bins - 1) / range_bins)).long().clamp(0, num_bins - 1)
+    xent = F.cross_entropy(logits.reshape(-1, num_bins), tgt.reshape(-1), reduction='none')
+    bsz = logits.size(0)
+    m = batch['edge_mask'].to(xent.dtype).view(bsz, -1)
+    dist = (xent.view(bsz, -1) * m).sum() / (m.sum() + 1e-9)
+    return prim + dist_loss_weight * dist
+
+
+TGT_AT_CONFIG = dict(       # configs/pcqm/tgt_at_200m/pretrain/tgt_at_tp.yaml
+    model_height=24, node_width=768, edge_width=256, num_heads=64, triplet_heads=16, triplet_type='attention',
+    source_dropout=0.3, drop_path=0.2, node_act_dropout=0.1, edge_act_dropout=0.1, activation='gelu',
+    scale_degree=True, node_ffn_multiplier=1.0, edge_ffn_multiplier=1.0, upto_hop=32, num_dist_bins=512)
+TGT_AGX2_CONFIG = dict(     # configs/pcqm/tgt_agx2_100m/gap_pred/tgt_agx2_tp_rdkit.yaml
+    model_height=12, layer_multiplier=2, node_width=768, edge_width=256, num_heads=64, triplet_heads=16,
+    triplet_type='aggregate', source_dropout=0.3, drop_path=0.2, node_act_dropout=0.1, edge_act_dropout=0.1,
+    activation='gelu', scale_degree=True, node_ffn_multiplier=1.0, edge_ffn_multiplier=1.0, upto_hop=32)

@@ -1,0 +1,227 @@
+"""EGT attention, edge update, FFN, DropPath and the TGT layer -- API surface of the reference's
+lib/tgt/layers/layers.py with the hot ops running on tgt_b200's CUDA kernels.
+
+State-dict keys / shapes, constructor signatures, sub-module names (update, node_ffn, tria, edge_ffn,
+drop_path) and parameter creation order are the reference's (layers.py:15-260).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .. import ops
+from .activations import get_activation
+from .triplet import get_triplet_layer
+
+
+class EGT_Attention(nn.Module):
+    """Reference: layers.py:15-84."""
+
+    def __init__(self, node_width, edge_width, num_heads, source_dropout=0, scale_degree=True, edge_update=True):
+        super().__init__()
+        self.node_width = node_width
+        self.edge_width = edge_width
+        self.num_heads = num_heads
+        self.source_dropout = source_dropout
+        self.scale_degree = scale_degree
+        self.edge_update = edge_update
+
+        assert not (self.node_width % self.num_heads), "node_width must be divisible by num_heads"
+        self._dot_dim = self.node_width // self.num_heads
+        self._scale_factor = self._dot_dim ** -0.5
+
+        self.mha_ln_h = nn.LayerNorm(self.node_width)
+        self.mha_ln_e = nn.LayerNorm(self.edge_width)
+        self.lin_QKV = nn.Linear(self.node_width, self.node_width * 3)
+        self.lin_EG = nn.Linear(self.edge_width, self.num_heads * 2)
+        self.lin_O_h = nn.Linear(self.node_width, self.node_width)
+        if self.edge_update:
+            self.lin_O_e = nn.Linear(self.num_heads, self.edge_width)
+
+    def forward(self, h, e, mask):
+        cd = ops.compute_dtype(e)
+        # node side: small [B*N, Wn] GEMMs -- plain library calls
+        qkv = self.lin_QKV(self.mha_ln_h(h))
+        # edge side: LN + projection to 2H channels (LN output recomputed in backward)
+        eg = ops.LNLinearFn.apply(e, self.mha_ln_e.weight, self.mha_ln_e.bias, self.lin_EG.weight,
+                                  self.lin_EG.bias, cd)
+        src = None
+        if self.source_dropout > 0 and self.training:       # layers.py:55-59; RNG stays in PyTorch
+            src = torch.empty((h.shape[0], h.shape[1]), dtype=torch.float32, device=h.device) \
+                       .bernoulli_(self.source_dropout) * torch.finfo(torch.float32).min
+        hhat, vatt = ops.EGTCoreFn.apply(qkv, eg, mask, src, self.num_heads, True, self.scale_degree, cd)
+        h = self.lin_O_h(vatt)
+        if self.edge_update:
+            e = self.lin_O_e(hhat)
+        return h, e
+
+
+class EdgeUpdate(nn.Module):
+    """Reference: layers.py:87-130."""
+
+    def __init__(self, node_width, edge_width, num_heads):
+        super().__init__()
+        self.node_width = node_width
+        self.edge_width = edge_width
+        self.num_heads = num_heads
+
+        assert not (self.node_width % self.num_heads), "node_width must be divisible by num_heads"
+        self._dot_dim = self.node_width // self.num_heads
+        self._scale_factor = self._dot_dim ** -0.5
+
+        self.mha_ln_h = nn.LayerNorm(self.node_width)
+        self.mha_ln_e = nn.LayerNorm(self.edge_width)
+        self.lin_QK = nn.Linear(self.node_width, self.node_width * 2)
+        self.lin_E = nn.Linear(self.edge_width, self.num_heads)
+        self.lin_O_e = nn.Linear(self.num_heads, self.edge_width)
+
+    def forward(self, h, e, mask):
+        cd = ops.compute_dtype(e)
+        qk = self.lin_QK(self.mha_ln_h(h))
+        eb = ops.LNLinearFn.apply(e, self.mha_ln_e.weight, self.mha_ln_e.bias, self.lin_E.weight,
+                                  self.lin_E.bias, cd)
+        hhat = ops.EGTCoreFn.apply(qk, eb, mask, None, self.num_heads, False, False, cd)
+        e = self.lin_O_e(hhat)
+        return h, e
+
+
+class FFN(nn.Module):
+    """Reference: layers.py:134-160."""
+
+    def __init__(self, width, multiplier=1., act_dropout=0., activation='gelu'):
+        super().__init__()
+        self.width = width
+        self.multiplier = multiplier
+        self.act_dropout = act_dropout
+        self.activation = activation
+
+        self.ffn_fn, self.act_mul = get_activation(activation)
+        inner_dim = round(self.width * self.multiplier)
+
+        self.ffn_ln = nn.LayerNorm(self.width)
+        self.lin_W1 = nn.Linear(self.width, inner_dim * self.act_mul)
+        self.lin_W2 = nn.Linear(inner_dim, self.width)
+        self.dropout = nn.Dropout(self.act_dropout)
+
+    def forward(self, x):
+        if self.activation == 'gelu' and x.is_cuda:
+            p = self.act_dropout if self.training else 0.
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0 else 0      # CPU generator: no sync
+            return ops.FFNGeluFn.apply(x, self.ffn_ln.weight, self.ffn_ln.bias, self.lin_W1.weight,
+                                       self.lin_W1.bias, self.lin_W2.weight, self.lin_W2.bias, p, seed,
+                                       ops.compute_dtype(x))
+        # gated activations (geglu/glu/swiglu) are not used by any shipped config: plain library ops
+        x_ln = self.ffn_ln(x)
+        x = self.ffn_fn(self.lin_W1(x_ln))
+        x = self.dropout(x)
+        return self.lin_W2(x)
+
+
+class DropPath(nn.Module):
+    """Reference: layers.py:163-177 (per-sample stochastic depth)."""
+
+    def __init__(self, drop_path=0.):
+        super().__init__()
+        self.drop_path = drop_path
+        self._keep_prob = 1 - self.drop_path
+
+    def sample_scale(self, x):
+        """[B] fp32 vector mask/keep_prob, or None when inactive."""
+        if self.drop_path > 0 and self.training:
+            m = torch.empty(x.size(0), dtype=torch.float32, device=x.device).bernoulli_(self._keep_prob)
+            return m / self._keep_prob
+        return None
+
+    def forward(self, x):
+        s = self.sample_scale(x)
+        if s is not None:
+            x = x * s.view(-1, *([1] * (x.ndim - 1))).to(x.dtype)
+        return x
+
+    def __repr__(self):
+        return f'{self.__class__.__name__}(drop_path={self.drop_path})'
+
+
+class TGT_Layer(nn.Module):
+    """Reference: layers.py:180-302."""
+
+    def __init__(self, node_width, edge_width, num_heads, activation='gelu', scale_degree=True,
+                 node_update=True, edge_update=True, triplet_heads=0, triplet_type='aggregate',
+                 triplet_dropout=0, node_ffn_multiplier=1., edge_ffn_multiplier=1., source_dropout=0,
+                 drop_path=0, node_act_dropout=0, edge_act_dropout=0):
+        super().__init__()
+        self.node_width = node_width
+        self.edge_width = edge_width
+        self.num_heads = num_heads
+        self.activation = activation
+        self.node_ffn_multiplier = node_ffn_multiplier
+        self.edge_ffn_multiplier = edge_ffn_multiplier
+        self.node_act_dropout = node_act_dropout
+        self.edge_act_dropout = edge_act_dropout
+        self.source_dropout = source_dropout
+        self.drop_path = drop_path
+        self.scale_degree = scale_degree
+        self.node_update = node_update
+        self.edge_update = edge_update
+        self.triplet_heads = triplet_heads
+        self.triplet_type = triplet_type
+        self.triplet_dropout = triplet_dropout
+
+        self._triplet_update = self.triplet_heads > 0
+
+        if self.node_update:
+            self.update = EGT_Attention(node_width=self.node_width, edge_width=self.edge_width,
+                                        num_heads=self.num_heads, source_dropout=self.source_dropout,
+                                        scale_degree=self.scale_degree, edge_update=self.edge_update)
+        elif self.edge_update:
+            self.update = EdgeUpdate(node_width=self.node_width, edge_width=self.edge_width,
+                                     num_heads=self.num_heads)
+        else:
+            raise ValueError('At least one of node_update and edge_update must be True')
+
+        if self.node_update:
+            self.node_ffn = FFN(width=self.node_width, multiplier=self.node_ffn_multiplier,
+                                act_dropout=self.node_act_dropout, activation=self.activation)
+        if self.edge_update:
+            if self._triplet_update:
+                TripletLayer = get_triplet_layer(self.triplet_type)
+                self.tria = TripletLayer(edge_width=self.edge_width, num_heads=self.triplet_heads,
+                                         attention_dropout=self.triplet_dropout)
+            self.edge_ffn = FFN(width=self.edge_width, multiplier=self.edge_ffn_multiplier,
+                                act_dropout=self.edge_act_dropout, activation=self.activation)
+
+        self.drop_path = DropPath(self.drop_path)
+
+    def _residual(self, x, res):
+        """drop_path(x) then add the residual (layers.py:269-290), as one fused kernel on CUDA."""
+        scale = self.drop_path.sample_scale(x)
+        if x.is_cuda:
+            return ops.scaled_residual(x, res, scale)
+        if scale is not None:
+            x = x * scale.view(-1, *([1] * (x.ndim - 1))).to(x.dtype)
+        return x + res
+
+    def forward(self, g):
+        h, e, mask = g.h, g.e, g.mask
+
+        h_r1, e_r1 = h, e
+        h, e = self.update(h, e, mask)
+
+        if self.node_update:
+            h = self._residual(h, h_r1)
+            h = self._residual(self.node_ffn(h), h)
+
+        if self.edge_update:
+            e = self._residual(e, e_r1)
+            if self._triplet_update:
+                e = self._residual(self.tria(e, mask), e)
+            e = self._residual(self.edge_ffn(e), e)
+
+        g = g.copy()
+        g.h, g.e = h, e
+        return g
+
+    def __repr__(self):
+        rep = super().__repr__()
+        return rep + f' (activation: {self.activation}, source_dropout: {self.source_dropout})'

@@ -1,0 +1,371 @@
+"""torch.autograd.Function wrappers over the C ABI (include/tgt_b200.h).
+
+Design rules:
+  * outputs are never saved for backward -- the caller (TGT_Layer) adds residuals to them;
+  * nothing O(N^3) and no LayerNorm output / projection buffer is kept between forward and
+    backward: the backward recomputes LN(e) and the projection GEMM, so a 24-layer TGT-At step
+    at B=256, N=64 fits in one B200's HBM;
+  * plain projection GEMMs go through cuBLAS (torch.addmm / torch.mm); everything else on the
+    path is one of our kernels;
+  * no fallback: CPU tensors or a missing library raise.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch.autograd import Function
+
+from . import _C
+
+Tensor = torch.Tensor
+
+
+def compute_dtype(t: Tensor) -> torch.dtype:
+    """dtype the kernels run in: the autocast dtype when autocast is on, else the tensor's."""
+    if t.is_cuda and torch.is_autocast_enabled("cuda"):
+        return torch.get_autocast_dtype("cuda")
+    return t.dtype
+
+
+def _require_cuda(*ts: Optional[Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("tgt_b200 kernels need CUDA tensors (there is no CPU fallback)")
+
+
+def _f32c(t: Tensor) -> Tensor:
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------
+# raw kernel wrappers (no autograd)
+# ------------------------------------------------------------------------------------------
+def layernorm_fwd(x2: Tensor, gamma: Tensor, beta: Tensor, out_dtype: torch.dtype, eps: float = 1e-5):
+    rows, W = x2.shape
+    y = torch.empty((rows, W), dtype=out_dtype, device=x2.device)
+    mean = torch.empty(rows, dtype=torch.float32, device=x2.device)
+    rstd = torch.empty(rows, dtype=torch.float32, device=x2.device)
+    _C.check(_C.lib().tgt_layernorm_fwd(_C.ptr(x2), _C.ptr(gamma), _C.ptr(beta), _C.ptr(y), _C.ptr(mean),
+                                        _C.ptr(rstd), rows, W, eps, _C.dtype_code(x2.dtype),
+                                        _C.dtype_code(out_dtype), _C.stream_ptr()), "layernorm_fwd")
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy: Tensor, x2: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor,
+                  dres: Optional[Tensor] = None):
+    rows, W = x2.shape
+    dx = torch.empty_like(x2)
+    dgb = torch.zeros((2, W), dtype=torch.float32, device=x2.device)
+    _C.check(_C.lib().tgt_layernorm_bwd(_C.ptr(dy), _C.ptr(x2), _C.ptr(gamma), _C.ptr(mean), _C.ptr(rstd),
+                                        _C.ptr(dres), _C.ptr(dx), _C.ptr(dgb[0]), _C.ptr(dgb[1]), rows, W,
+                                        _C.dtype_code(x2.dtype), _C.dtype_code(dy.dtype), _C.stream_ptr()),
+             "layernorm_bwd")
+    return dx, dgb[0], dgb[1]
+
+
+def _x_for_ln(e: Tensor, cdtype: torch.dtype) -> Tensor:
+    """LN kernels take x in fp32 or in the compute dtype."""
+    if e.dtype != torch.float32 and e.dtype != cdtype:
+        e = e.to(cdtype)
+    return e.contiguous()
+
+
+# ------------------------------------------------------------------------------------------
+# LayerNorm -> Linear with LN recompute in backward  (EGT lin_EG / lin_E)
+# ------------------------------------------------------------------------------------------
+class LNLinearFn(Function):
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, W, b, cdtype):
+        _require_cuda(x, W)
+        with torch.autocast("cuda", enabled=False):
+            shape = x.shape
+            x2 = _x_for_ln(x, cdtype).view(-1, shape[-1])
+            g, bt = _f32c(ln_w), _f32c(ln_b)
+            y, mean, rstd = layernorm_fwd(x2, g, bt, cdtype)
+            Wc = W.detach().to(cdtype)
+            out = torch.addmm(b.detach().to(cdtype), y, Wc.t())
+            ctx.save_for_backward(x2, g, bt, Wc, mean, rstd)
+            ctx.cdtype = cdtype
+            ctx.in_dtype = x.dtype
+            ctx.pdt = (ln_w.dtype, W.dtype, b.dtype)
+        return out.view(*shape[:-1], W.shape[0])
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, g, bt, Wc, mean, rstd = ctx.saved_tensors
+        cd = ctx.cdtype
+        with torch.autocast("cuda", enabled=False):
+            do = dout.reshape(-1, dout.shape[-1]).to(cd).contiguous()
+            y, _, _ = layernorm_fwd(x2, g, bt, cd)
+            dW = torch.mm(do.t(), y)
+            db = do.sum(0, dtype=torch.float32)
+            dy = torch.mm(do, Wc)
+            del y
+            dx, dg, dbt = layernorm_bwd(dy, x2, g, mean, rstd)
+        return (dx.view(*dout.shape[:-1], x2.shape[-1]).to(ctx.in_dtype), dg.to(ctx.pdt[0]), dbt.to(ctx.pdt[0]),
+                dW.to(ctx.pdt[1]), db.to(ctx.pdt[2]), None)
+
+
+# ------------------------------------------------------------------------------------------
+# triplet attention module: LN -> [QKV_in|QKV_out|EG_in|EG_out] GEMM -> core -> lin_O
+# ------------------------------------------------------------------------------------------
+class TripletAttentionFn(Function):
+    """e:[B,N,N,W]; Wcat:[C,W] rows in kernel order (head-major q/k/v blocks, then bias/gate blocks);
+    Wo:[W,2W] with columns in kernel order (dir, h, dd).  `layout` = (H, d, off_q, off_k, off_v, off_e, off_g)."""
+
+    @staticmethod
+    def forward(ctx, e, mask, ln_w, ln_b, Wcat, bcat, Wo, bo, layout, cdtype):
+        _require_cuda(e, mask, Wcat)
+        H, d, off_q, off_k, off_v, off_e, off_g = layout
+        B, N, _, W = e.shape
+        R = B * N * N
+        with torch.autocast("cuda", enabled=False):
+            x2 = _x_for_ln(e, cdtype).view(R, W)
+            g, bt = _f32c(ln_w), _f32c(ln_b)
+            Wc, bc = Wcat.detach().to(cdtype).contiguous(), bcat.detach().to(cdtype).contiguous()
+            Woc, boc = Wo.detach().to(cdtype).contiguous(), bo.detach().to(cdtype).contiguous()
+            m3 = _f32c(mask).view(B, N, N)
+            y, mean, rstd = layernorm_fwd(x2, g, bt, cdtype)
+            proj = torch.addmm(bc, y, Wc.t())
+            del y
+            desc = _C.TripletAttnDesc(B, N, H, d, proj.shape[1], off_q, off_k, off_v, off_e, off_g,
+                                      float(d) ** -0.5, _C.dtype_code(cdtype))
+            va = torch.empty((R, 2 * H * d), dtype=cdtype, device=e.device)
+            stats = torch.empty((B, 2, H, N, N, 2), dtype=torch.float32, device=e.device)
+            _C.check(_C.lib().tgt_triplet_attn_fwd(desc, _C.ptr(proj), _C.ptr(m3), _C.ptr(va), _C.ptr(stats),
+                                                   _C.stream_ptr()), "triplet_attn_fwd")
+            del proj
+            out = torch.addmm(boc, va, Woc.t())
+            ctx.save_for_backward(x2, m3, g, bt, Wc, bc, Woc, mean, rstd, stats, va)
+            ctx.desc = desc
+            ctx.cdtype = cdtype
+            ctx.in_dtype = e.dtype
+            ctx.pdt = (ln_w.dtype, Wcat.dtype, bcat.dtype, Wo.dtype, bo.dtype)
+        return out.view(B, N, N, W)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, m3, g, bt, Wc, bc, Woc, mean, rstd, stats, va = ctx.saved_tensors
+        cd, desc = ctx.cdtype, ctx.desc
+        B, N, W = desc.B, desc.N, x2.shape[1]
+        with torch.autocast("cuda", enabled=False):
+            do = dout.reshape(-1, W).to(cd).contiguous()
+            dWo = torch.mm(do.t(), va)
+            dbo = do.sum(0, dtype=torch.float32)
+            dva = torch.mm(do, Woc)
+            del do
+            y, _, _ = layernorm_fwd(x2, g, bt, cd)
+            proj = torch.addmm(bc, y, Wc.t())
+            dproj = torch.empty_like(proj)
+            _C.check(_C.lib().tgt_triplet_attn_bwd(desc, _C.ptr(proj), _C.ptr(m3), _C.ptr(va), _C.ptr(dva),
+                                                   _C.ptr(stats), _C.ptr(dproj), _C.stream_ptr()),
+                     "triplet_attn_bwd")
+            del proj, dva
+            dWc = torch.mm(dproj.t(), y)
+            dbc = dproj.sum(0, dtype=torch.float32)
+            del y
+            dy = torch.mm(dproj, Wc)
+            del dproj
+            dx, dg, dbt = layernorm_bwd(dy, x2, g, mean, rstd)
+        p = ctx.pdt
+        return (dx.view(B, N, N, W).to(ctx.in_dtype), None, dg.to(p[0]), dbt.to(p[0]), dWc.to(p[1]), dbc.to(p[2]),
+                dWo.to(p[3]), dbo.to(p[4]), None, None)
+
+
+class TripletAggregateFn(Function):
+    """`layout` = (H, d, off_v, off_e, off_g, mask_dir)."""
+
+    @staticmethod
+    def forward(ctx, e, mask, ln_w, ln_b, Wcat, bcat, Wo, bo, layout, cdtype):
+        _require_cuda(e, mask, Wcat)
+        H, d, off_v, off_e, off_g, mask_dir = layout
+        B, N, _, W = e.shape
+        R = B * N * N
+        with torch.autocast("cuda", enabled=False):
+            x2 = _x_for_ln(e, cdtype).view(R, W)
+            g, bt = _f32c(ln_w), _f32c(ln_b)
+            Wc, bc = Wcat.detach().to(cdtype).contiguous(), bcat.detach().to(cdtype).contiguous()
+            Woc, boc = Wo.detach().to(cdtype).contiguous(), bo.detach().to(cdtype).contiguous()
+            m3 = _f32c(mask).view(B, N, N)
+            y, mean, rstd = layernorm_fwd(x2, g, bt, cdtype)
+            proj = torch.addmm(bc, y, Wc.t())
+            del y
+            desc = _C.TripletAggrDesc(B, N, H, d, proj.shape[1], off_v, off_e, off_g, mask_dir,
+                                      _C.dtype_code(cdtype))
+            va = torch.empty((R, 2 * H * d), dtype=cdtype, device=e.device)
+            aw = torch.empty((B, 2, H, N, N), dtype=torch.float32, device=e.device)
+            _C.check(_C.lib().tgt_triplet_aggr_fwd(desc, _C.ptr(proj), _C.ptr(m3), _C.ptr(va), _C.ptr(aw),
+                                                   _C.stream_ptr()), "triplet_aggr_fwd")
+            del proj
+            out = torch.addmm(boc, va, Woc.t())
+            ctx.save_for_backward(x2, m3, g, bt, Wc, bc, Woc, mean, rstd, aw, va)
+            ctx.desc = desc
+            ctx.cdtype = cdtype
+            ctx.in_dtype = e.dtype
+            ctx.pdt = (ln_w.dtype, Wcat.dtype, bcat.dtype, Wo.dtype, bo.dtype)
+        return out.view(B, N, N, W)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, m3, g, bt, Wc, bc, Woc, mean, rstd, aw, va = ctx.saved_tensors
+        cd, desc = ctx.cdtype, ctx.desc
+        B, N, W = desc.B, desc.N, x2.shape[1]
+        with torch.autocast("cuda", enabled=False):
+            do = dout.reshape(-1, W).to(cd).contiguous()
+            dWo = torch.mm(do.t(), va)
+            dbo = do.sum(0, dtype=torch.float32)
+            dva = torch.mm(do, Woc)
+            del do
+            y, _, _ = layernorm_fwd(x2, g, bt, cd)
+            proj = torch.addmm(bc, y, Wc.t())
+            dproj = torch.empty_like(proj)
+            daw = torch.empty_like(aw)
+            _C.check(_C.lib().tgt_triplet_aggr_bwd(desc, _C.ptr(proj), _C.ptr(m3), _C.ptr(dva), _C.ptr(aw),
+                                                   _C.ptr(daw), _C.ptr(dproj), _C.stream_ptr()), "triplet_aggr_bwd")
+            del proj, dva, daw
+            dWc = torch.mm(dproj.t(), y)
+            dbc = dproj.sum(0, dtype=torch.float32)
+            del y
+            dy = torch.mm(dproj, Wc)
+            del dproj
+            dx, dg, dbt = layernorm_bwd(dy, x2, g, mean, rstd)
+        p = ctx.pdt
+        return (dx.view(B, N, N, W).to(ctx.in_dtype), None, dg.to(p[0]), dbt.to(p[0]), dWc.to(p[1]), dbc.to(p[2]),
+                dWo.to(p[3]), dbo.to(p[4]), None, None)
+
+
+# ------------------------------------------------------------------------------------------
+# EGT node/edge attention core
+# ------------------------------------------------------------------------------------------
+class EGTCoreFn(Function):
+    """qkv:[B,N,3*Wn] (or [B,N,2*Wn] when attend=False), eg:[B,N,N,2H] (or [..,H]); returns (hhat, vatt)."""
+
+    @staticmethod
+    def forward(ctx, qkv, eg, mask, src_mask, H, attend, scale_degree, cdtype):
+        _require_cuda(qkv, eg, mask)
+        B, N = qkv.shape[0], qkv.shape[1]
+        Wn = qkv.shape[2] // (3 if attend else 2)
+        d = Wn // H
+        with torch.autocast("cuda", enabled=False):
+            q2 = qkv.detach().to(cdtype).contiguous()
+            eg2 = eg.detach().to(cdtype).contiguous()
+            m3 = _f32c(mask).view(B, N, N)
+            src = _f32c(src_mask).view(B, N) if src_mask is not None else None
+            desc = _C.EgtDesc(B, N, H, d, q2.shape[2], eg2.shape[3], float(d) ** -0.5, int(attend),
+                              int(scale_degree), _C.dtype_code(cdtype))
+            hhat = torch.empty((B, N, N, H), dtype=cdtype, device=qkv.device)
+            vatt = torch.empty((B, N, Wn), dtype=cdtype, device=qkv.device) if attend else None
+            stats = torch.empty((B, N, H, 3), dtype=torch.float32, device=qkv.device) if attend else None
+            _C.check(_C.lib().tgt_egt_attn_fwd(desc, _C.ptr(q2), _C.ptr(eg2), _C.ptr(m3), _C.ptr(src),
+                                               _C.ptr(hhat), _C.ptr(vatt), _C.ptr(stats), _C.stream_ptr()),
+                     "egt_attn_fwd")
+            ctx.save_for_backward(q2, eg2, m3, src, stats)
+            ctx.desc = desc
+            ctx.dts = (qkv.dtype, eg.dtype)
+            ctx.set_materialize_grads(False)
+        if attend:
+            return hhat, vatt
+        return hhat
+
+    @staticmethod
+    def backward(ctx, dhhat, dvatt=None):
+        q2, eg2, m3, src, stats = ctx.saved_tensors
+        desc = ctx.desc
+        cd = q2.dtype
+        with torch.autocast("cuda", enabled=False):
+            if desc.attend and dvatt is None:
+                dvatt = torch.zeros((desc.B, desc.N, desc.H * desc.d), dtype=cd, device=q2.device)
+            dh = dhhat.to(cd).contiguous() if dhhat is not None else None
+            dv = dvatt.to(cd).contiguous() if dvatt is not None else None
+            dqkv = torch.empty_like(q2)
+            deg = torch.empty_like(eg2)
+            _C.check(_C.lib().tgt_egt_attn_bwd(desc, _C.ptr(q2), _C.ptr(eg2), _C.ptr(m3), _C.ptr(src),
+                                               _C.ptr(stats), _C.ptr(dh), _C.ptr(dv), _C.ptr(dqkv), _C.ptr(deg),
+                                               _C.stream_ptr()), "egt_attn_bwd")
+        return dqkv.to(ctx.dts[0]), deg.to(ctx.dts[1]), None, None, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------
+# FFN: LN -> W1 -> gelu -> dropout -> W2   (saves the input, LN stats and the pre-activation only)
+# ------------------------------------------------------------------------------------------
+class FFNGeluFn(Function):
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, W1, b1, W2, b2, p_drop, seed, cdtype):
+        _require_cuda(x, W1)
+        with torch.autocast("cuda", enabled=False):
+            shape = x.shape
+            x2 = _x_for_ln(x, cdtype).view(-1, shape[-1])
+            g, bt = _f32c(ln_w), _f32c(ln_b)
+            W1c, W2c = W1.detach().to(cdtype).contiguous(), W2.detach().to(cdtype).contiguous()
+            y, mean, rstd = layernorm_fwd(x2, g, bt, cdtype)
+            u = torch.addmm(b1.detach().to(cdtype), y, W1c.t())
+            del y
+            a = torch.empty_like(u)
+            _C.check(_C.lib().tgt_gelu_dropout_fwd(_C.ptr(u), _C.ptr(a), u.numel(), float(p_drop), int(seed),
+                                                   _C.dtype_code(cdtype), _C.stream_ptr()), "gelu_dropout_fwd")
+            out = torch.addmm(b2.detach().to(cdtype), a, W2c.t())
+            ctx.save_for_backward(x2, g, bt, W1c, W2c, mean, rstd, u)
+            ctx.meta = (float(p_drop), int(seed), cdtype, x.dtype,
+                        (ln_w.dtype, W1.dtype, b1.dtype, W2.dtype, b2.dtype))
+        return out.view(*shape[:-1], W2.shape[0])
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, g, bt, W1c, W2c, mean, rstd, u = ctx.saved_tensors
+        p_drop, seed, cd, in_dtype, p = ctx.meta
+        with torch.autocast("cuda", enabled=False):
+            do = dout.reshape(-1, dout.shape[-1]).to(cd).contiguous()
+            a = torch.empty_like(u)
+            _C.check(_C.lib().tgt_gelu_dropout_fwd(_C.ptr(u), _C.ptr(a), u.numel(), p_drop, seed,
+                                                   _C.dtype_code(cd), _C.stream_ptr()), "gelu_dropout_fwd")
+            dW2 = torch.mm(do.t(), a)
+            db2 = do.sum(0, dtype=torch.float32)
+            da = torch.mm(do, W2c)
+            du = a  # reuse the buffer
+            _C.check(_C.lib().tgt_gelu_dropout_bwd(_C.ptr(u), _C.ptr(da), _C.ptr(du), u.numel(), p_drop, seed,
+                                                   _C.dtype_code(cd), _C.stream_ptr()), "gelu_dropout_bwd")
+            del da
+            y, _, _ = layernorm_fwd(x2, g, bt, cd)
+            dW1 = torch.mm(du.t(), y)
+            db1 = du.sum(0, dtype=torch.float32)
+            del y
+            dy = torch.mm(du, W1c)
+            dx, dg, dbt = layernorm_bwd(dy, x2, g, mean, rstd)
+        return (dx.view(*dout.shape[:-1], x2.shape[-1]).to(in_dtype), dg.to(p[0]), dbt.to(p[0]), dW1.to(p[1]),
+                db1.to(p[2]), dW2.to(p[3]), db2.to(p[4]), None, None, None)
+
+
+# ------------------------------------------------------------------------------------------
+# out = res + scale[b] * x      (DropPath + residual add, layers.py:163-177 / 269-290)
+# ------------------------------------------------------------------------------------------
+class ScaledResidualFn(Function):
+    @staticmethod
+    def forward(ctx, x, res, scale):
+        _require_cuda(x, res)
+        B = x.shape[0]
+        xc = x.contiguous()
+        rc = res.contiguous()
+        out = torch.empty_like(xc)
+        sc = _f32c(scale).view(B) if scale is not None else None
+        _C.check(_C.lib().tgt_scaled_residual(_C.ptr(xc), _C.ptr(rc), _C.ptr(sc), _C.ptr(out), B,
+                                              xc.numel() // B, _C.dtype_code(xc.dtype), _C.dtype_code(rc.dtype),
+                                              _C.stream_ptr()), "scaled_residual")
+        ctx.scale = sc
+        ctx.res_dtype = res.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dres = dout if dout.dtype == ctx.res_dtype else dout.to(ctx.res_dtype)
+        if ctx.scale is None:
+            return dout, dres, None
+        sc = ctx.scale.view(-1, *([1] * (dout.dim() - 1)))
+        return (dout * sc).to(dout.dtype), dres, None
+
+
+def scaled_residual(x: Tensor, res: Tensor, scale: Optional[Tensor]) -> Tensor:
+    return ScaledResidualFn.apply(x, res, scale)

@@ -51,3 +51,17 @@ def max_rel(a, b, floor=1e-6):
     """max |a-b| normalised by max |b| (the 'max-rel' figure the fp32 tolerance is stated on)."""
     a, b = a.detach().double(), b.detach().double()
     return float((a - b).abs().max() / (b.abs().max() + floor))
+
+
+def assert_grads_close(ours, ref, tol, metric="max"):
+    """Compare dicts of parameter gradients.  Gradients that are analytically zero in the reference (a bias that
+    feeds a softmax is shift-invariant, so its gradient is round-off only) are checked on the scale of the largest
+    gradient of the set instead of on their own (meaningless) magnitude."""
+    scale = max(float(g.detach().double().abs().max()) for g in ref.values())
+    for k, g in ref.items():
+        a, b = ours[k].detach().double().cpu(), g.detach().double().cpu()
+        if float(b.abs().max()) < 1e-6 * scale:
+            assert float((a - b).abs().max()) < tol * scale, f"{k}: zero-grad noise {float((a - b).abs().max())}"
+            continue
+        err = max_rel(a, b) if metric == "max" else rel_err(a, b)
+        assert err < tol, f"{k}: {err}"

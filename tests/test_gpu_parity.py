@@ -10,7 +10,7 @@ import os
 import pytest
 import torch
 
-from conftest import GOLDEN, load_golden, max_rel, rel_err
+from conftest import GOLDEN, load_golden, max_rel, rel_err, assert_grads_close
 from oracle import tgt_oracle as O
 from tgt_b200 import TGT_Encoder, Graph, _C, ops
 from tgt_b200 import layers as L
@@ -53,8 +53,7 @@ def test_triplet_fp32_vs_golden(name):
     assert out.dtype == torch.float32
     assert max_rel(out.cpu(), fx["out"]) < FP32_TOL
     assert max_rel(de.cpu(), fx["de"]) < FP32_TOL
-    for k, g in fx["grads"].items():
-        assert max_rel(grads[k].cpu(), g) < 2 * FP32_TOL, k
+    assert_grads_close(grads, fx["grads"], 2 * FP32_TOL, "max")
 
 
 def _oracle_autocast_error(fx, dtype):
@@ -82,8 +81,7 @@ def test_triplet_bf16_vs_golden(name, policy):
     eo, ed = rel_err(out.float().cpu(), fx["out"]), rel_err(de.cpu(), fx["de"])
     assert eo < BF16_TOL and eo < 1.5 * ref_eo + 1e-3, (eo, ref_eo)
     assert ed < 2 * BF16_TOL and ed < 1.5 * ref_ed + 1e-3, (ed, ref_ed)
-    for k, g in fx["grads"].items():
-        assert rel_err(grads[k].cpu(), g) < 3 * BF16_TOL, k
+    assert_grads_close(grads, fx["grads"], 3 * BF16_TOL, "l2")
 
 
 @pytest.mark.parametrize("name", ["triplet_attention_a.pt", "triplet_aggregate_a.pt"])
@@ -128,8 +126,8 @@ def test_egt_vs_golden(name, mode):
         chk(h.grad, fx["dh"], "dh")
     if fx["de"] is not None:
         chk(e.grad, fx["de"], "de")
-    for k, g in fx["grads"].items():
-        chk(dict(mod.named_parameters())[k].grad, g, k)
+    assert_grads_close({k: v.grad for k, v in mod.named_parameters() if k in fx["grads"]}, fx["grads"],
+                       2 * FP32_TOL if mode == "fp32" else 2 * BF16_TOL, "max" if mode == "fp32" else "l2")
 
 
 @pytest.mark.parametrize("name,cls", [("model_multi_at.pt", HM.TGT_Multi), ("model_gap_agx2.pt", HM.TGT_Gap),
@@ -164,8 +162,8 @@ def test_config1_triplet_attention_vs_oracle():
     out.backward(dout.float().to(DEV))
     assert max_rel(out.cpu(), ref) < FP32_TOL
     assert max_rel(eg.grad.cpu(), ed.grad) < FP32_TOL
-    for k, prm in mod.named_parameters():
-        assert max_rel(prm.grad.cpu(), p[k].grad) < 2 * FP32_TOL, k
+    assert_grads_close({k: v.grad for k, v in mod.named_parameters()}, {k: v.grad for k, v in p.items()},
+                       2 * FP32_TOL, "max")
     import json
     kat = json.load(open(os.path.join(GOLDEN, "config1_kat.json")))       # checksum produced by the real reference
     assert abs(float(out.double().sum()) - kat["sum"]) < 1e-4 * kat["abs_sum"]
@@ -202,8 +200,7 @@ def test_shipped_width_bf16_vs_oracle(kind, N, nn_):
             _C.set_kernel_policy(0)
         assert rel_err(res[policy][0], ref) < BF16_TOL
         assert rel_err(res[policy][1], ed.grad) < 2 * BF16_TOL
-        for k in p:
-            assert rel_err(res[policy][2][k], p[k].grad) < 3 * BF16_TOL, (policy, k)
+        assert_grads_close(res[policy][2], {k: v.grad for k, v in p.items()}, 3 * BF16_TOL, "l2")
     assert rel_err(res[0][0], res[1][0]) < BF16_TOL
 
 
@@ -332,5 +329,5 @@ def test_encoder_fp32_train_vs_oracle_grads():
     g = enc(Graph(h=h.to(DEV), e=e.to(DEV), mask=mask.to(DEV)))
     (g.h.sum() + 0.5 * g.e.sum()).backward()
     assert max_rel(g.h.cpu(), ho) < 5 * FP32_TOL and max_rel(g.e.cpu(), eo) < 5 * FP32_TOL
-    for k, prm in enc.named_parameters():
-        assert max_rel(prm.grad.cpu(), p[k].grad, floor=1e-4) < 1e-4, k
+    assert_grads_close({k: v.grad for k, v in enc.named_parameters()}, {k: v.grad for k, v in p.items()},
+                       1e-4, "max")

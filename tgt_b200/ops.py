@@ -21,6 +21,41 @@ from . import _C
 Tensor = torch.Tensor
 
 
+class KernelTimer:
+    """Optional per-kernel timing with CUDA events on the launching (current) stream; used by bench.py to
+    measure each of our kernels INSIDE the real step.  Disabled (zero overhead) by default."""
+    enabled = False
+    records = {}
+
+    @classmethod
+    def reset(cls, enabled: bool) -> None:
+        cls.enabled = enabled
+        cls.records = {}
+
+    @classmethod
+    def summary(cls):
+        """name -> (launches, total_ms); call after torch.cuda.synchronize()."""
+        return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in cls.records.items()}
+
+
+class timed:
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if KernelTimer.enabled:
+            self.ev0 = torch.cuda.Event(enable_timing=True)
+            self.ev0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if KernelTimer.enabled:
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev1.record()
+            KernelTimer.records.setdefault(self.name, []).append((self.ev0, ev1))
+        return False
+
+
 def compute_dtype(t: Tensor) -> torch.dtype:
     """dtype the kernels run in: the autocast dtype when autocast is on, else the tensor's."""
     if t.is_cuda and torch.is_autocast_enabled("cuda"):
@@ -49,9 +84,10 @@ def layernorm_fwd(x2: Tensor, gamma: Tensor, beta: Tensor, out_dtype: torch.dtyp
     y = torch.empty((rows, W), dtype=out_dtype, device=x2.device)
     mean = torch.empty(rows, dtype=torch.float32, device=x2.device)
     rstd = torch.empty(rows, dtype=torch.float32, device=x2.device)
-    _C.check(_C.lib().tgt_layernorm_fwd(_C.ptr(x2), _C.ptr(gamma), _C.ptr(beta), _C.ptr(y), _C.ptr(mean),
-                                        _C.ptr(rstd), rows, W, eps, _C.dtype_code(x2.dtype),
-                                        _C.dtype_code(out_dtype), _C.stream_ptr()), "layernorm_fwd")
+    with timed(f"layernorm_fwd_W{W}"):
+        _C.check(_C.lib().tgt_layernorm_fwd(_C.ptr(x2), _C.ptr(gamma), _C.ptr(beta), _C.ptr(y), _C.ptr(mean),
+                                            _C.ptr(rstd), rows, W, eps, _C.dtype_code(x2.dtype),
+                                            _C.dtype_code(out_dtype), _C.stream_ptr()), "layernorm_fwd")
     return y, mean, rstd
 
 
@@ -60,10 +96,11 @@ def layernorm_bwd(dy: Tensor, x2: Tensor, gamma: Tensor, mean: Tensor, rstd: Ten
     rows, W = x2.shape
     dx = torch.empty_like(x2)
     dgb = torch.zeros((2, W), dtype=torch.float32, device=x2.device)
-    _C.check(_C.lib().tgt_layernorm_bwd(_C.ptr(dy), _C.ptr(x2), _C.ptr(gamma), _C.ptr(mean), _C.ptr(rstd),
-                                        _C.ptr(dres), _C.ptr(dx), _C.ptr(dgb[0]), _C.ptr(dgb[1]), rows, W,
-                                        _C.dtype_code(x2.dtype), _C.dtype_code(dy.dtype), _C.stream_ptr()),
-             "layernorm_bwd")
+    with timed(f"layernorm_bwd_W{W}"):
+        _C.check(_C.lib().tgt_layernorm_bwd(_C.ptr(dy), _C.ptr(x2), _C.ptr(gamma), _C.ptr(mean), _C.ptr(rstd),
+                                            _C.ptr(dres), _C.ptr(dx), _C.ptr(dgb[0]), _C.ptr(dgb[1]), rows, W,
+                                            _C.dtype_code(x2.dtype), _C.dtype_code(dy.dtype), _C.stream_ptr()),
+                 "layernorm_bwd")
     return dx, dgb[0], dgb[1]
 
 
@@ -136,8 +173,9 @@ class TripletAttentionFn(Function):
                                       float(d) ** -0.5, _C.dtype_code(cdtype))
             va = torch.empty((R, 2 * H * d), dtype=cdtype, device=e.device)
             stats = torch.empty((B, 2, H, N, N, 2), dtype=torch.float32, device=e.device)
-            _C.check(_C.lib().tgt_triplet_attn_fwd(desc, _C.ptr(proj), _C.ptr(m3), _C.ptr(va), _C.ptr(stats),
-                                                   _C.stream_ptr()), "triplet_attn_fwd")
+            with timed("triplet_attn_fwd"):
+                _C.check(_C.lib().tgt_triplet_attn_fwd(desc, _C.ptr(proj), _C.ptr(m3), _C.ptr(va), _C.ptr(stats),
+                                                       _C.stream_ptr()), "triplet_attn_fwd")
             del proj
             out = torch.addmm(boc, va, Woc.t())
             ctx.save_for_backward(x2, m3, g, bt, Wc, bc, Woc, mean, rstd, stats, va)
@@ -161,9 +199,10 @@ class TripletAttentionFn(Function):
             y, _, _ = layernorm_fwd(x2, g, bt, cd)
             proj = torch.addmm(bc, y, Wc.t())
             dproj = torch.empty_like(proj)
-            _C.check(_C.lib().tgt_triplet_attn_bwd(desc, _C.ptr(proj), _C.ptr(m3), _C.ptr(va), _C.ptr(dva),
-                                                   _C.ptr(stats), _C.ptr(dproj), _C.stream_ptr()),
-                     "triplet_attn_bwd")
+            with timed("triplet_attn_bwd"):
+                _C.check(_C.lib().tgt_triplet_attn_bwd(desc, _C.ptr(proj), _C.ptr(m3), _C.ptr(va), _C.ptr(dva),
+                                                       _C.ptr(stats), _C.ptr(dproj), _C.stream_ptr()),
+                         "triplet_attn_bwd")
             del proj, dva
             dWc = torch.mm(dproj.t(), y)
             dbc = dproj.sum(0, dtype=torch.float32)
@@ -198,8 +237,9 @@ class TripletAggregateFn(Function):
                                       _C.dtype_code(cdtype))
             va = torch.empty((R, 2 * H * d), dtype=cdtype, device=e.device)
             aw = torch.empty((B, 2, H, N, N), dtype=torch.float32, device=e.device)
-            _C.check(_C.lib().tgt_triplet_aggr_fwd(desc, _C.ptr(proj), _C.ptr(m3), _C.ptr(va), _C.ptr(aw),
-                                                   _C.stream_ptr()), "triplet_aggr_fwd")
+            with timed("triplet_aggr_fwd"):
+                _C.check(_C.lib().tgt_triplet_aggr_fwd(desc, _C.ptr(proj), _C.ptr(m3), _C.ptr(va), _C.ptr(aw),
+                                                       _C.stream_ptr()), "triplet_aggr_fwd")
             del proj
             out = torch.addmm(boc, va, Woc.t())
             ctx.save_for_backward(x2, m3, g, bt, Wc, bc, Woc, mean, rstd, aw, va)
@@ -224,8 +264,10 @@ class TripletAggregateFn(Function):
             proj = torch.addmm(bc, y, Wc.t())
             dproj = torch.empty_like(proj)
             daw = torch.empty_like(aw)
-            _C.check(_C.lib().tgt_triplet_aggr_bwd(desc, _C.ptr(proj), _C.ptr(m3), _C.ptr(dva), _C.ptr(aw),
-                                                   _C.ptr(daw), _C.ptr(dproj), _C.stream_ptr()), "triplet_aggr_bwd")
+            with timed("triplet_aggr_bwd"):
+                _C.check(_C.lib().tgt_triplet_aggr_bwd(desc, _C.ptr(proj), _C.ptr(m3), _C.ptr(dva), _C.ptr(aw),
+                                                       _C.ptr(daw), _C.ptr(dproj), _C.stream_ptr()),
+                         "triplet_aggr_bwd")
             del proj, dva, daw
             dWc = torch.mm(dproj.t(), y)
             dbc = dproj.sum(0, dtype=torch.float32)
@@ -260,9 +302,10 @@ class EGTCoreFn(Function):
             hhat = torch.empty((B, N, N, H), dtype=cdtype, device=qkv.device)
             vatt = torch.empty((B, N, Wn), dtype=cdtype, device=qkv.device) if attend else None
             stats = torch.empty((B, N, H, 3), dtype=torch.float32, device=qkv.device) if attend else None
-            _C.check(_C.lib().tgt_egt_attn_fwd(desc, _C.ptr(q2), _C.ptr(eg2), _C.ptr(m3), _C.ptr(src),
-                                               _C.ptr(hhat), _C.ptr(vatt), _C.ptr(stats), _C.stream_ptr()),
-                     "egt_attn_fwd")
+            with timed("egt_attn_fwd"):
+                _C.check(_C.lib().tgt_egt_attn_fwd(desc, _C.ptr(q2), _C.ptr(eg2), _C.ptr(m3), _C.ptr(src),
+                                                   _C.ptr(hhat), _C.ptr(vatt), _C.ptr(stats), _C.stream_ptr()),
+                         "egt_attn_fwd")
             ctx.save_for_backward(q2, eg2, m3, src, stats)
             ctx.desc = desc
             ctx.dts = (qkv.dtype, eg.dtype)
@@ -283,9 +326,10 @@ class EGTCoreFn(Function):
             dv = dvatt.to(cd).contiguous() if dvatt is not None else None
             dqkv = torch.empty_like(q2)
             deg = torch.empty_like(eg2)
-            _C.check(_C.lib().tgt_egt_attn_bwd(desc, _C.ptr(q2), _C.ptr(eg2), _C.ptr(m3), _C.ptr(src),
-                                               _C.ptr(stats), _C.ptr(dh), _C.ptr(dv), _C.ptr(dqkv), _C.ptr(deg),
-                                               _C.stream_ptr()), "egt_attn_bwd")
+            with timed("egt_attn_bwd"):
+                _C.check(_C.lib().tgt_egt_attn_bwd(desc, _C.ptr(q2), _C.ptr(eg2), _C.ptr(m3), _C.ptr(src),
+                                                   _C.ptr(stats), _C.ptr(dh), _C.ptr(dv), _C.ptr(dqkv), _C.ptr(deg),
+                                                   _C.stream_ptr()), "egt_attn_bwd")
         return dqkv.to(ctx.dts[0]), deg.to(ctx.dts[1]), None, None, None, None, None, None
 
 

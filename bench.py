@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- molecules/s of a TGT-At 24-layer training step (fwd + loss + bwd + Adam) at batch 256 x N=64
+(BASELINE.json configs[2]/[3]) on N x B200, plus the roofline of our dominant kernel and the CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for the definition of every field.
+
+  value        : molecules/s, inputs already resident in HBM, K steps timed with CUDA events, max over ranks
+  e2e          : same step driven from pinned HOST buffers (H2D copy of the raw batch + D2H read of the loss
+                 inside the timed region)
+  roofline     : our kernel with the largest share of the step, timed with CUDA events INSIDE the step
+  kernels      : the same for every one of our kernels (share of step, achieved vs bound)
+  cpu_baseline : the oracle port (oracle/tgt_oracle.py == the reference's PyTorch-CPU algorithm) on the host
+                 cores, on a bounded micro-batch of the same workload
+  --impl reference : only the CPU path, K steps of a bounded micro-batch each.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "molecules/sec TGT-At 24L fwd+bwd @ batch256 N=64"
+UNIT = "molecules/s"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=float(p["hbm_gbs"]), tc_burst=float(p["bf16_tflops"]),
+                    tc_sustained=float(p["bf16_tflops_sustained"]), source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tc_burst=1590.0, tc_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+# ------------------------------------------------------------------------------------------------ model config
+def model_cfg(args):
+    from tgt_b200.harness.models import TGT_AT_CONFIG
+    cfg = dict(TGT_AT_CONFIG)
+    cfg["model_height"] = args.layers
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline
+def cpu_step_fn(args, B):
+    """Reference algorithm on CPU (oracle port), fp32, all host threads: fwd + loss + bwd + Adam."""
+    from oracle import tgt_oracle as O                       # checker / baseline only
+    from tgt_b200.harness.models import TGT_Multi
+    from tgt_b200.harness.synthetic import make_batch
+    cfg = model_cfg(args)
+    torch.manual_seed(0)
+    model = TGT_Multi(**cfg)                                  # parameter container only (never called on CPU)
+    params = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in model.state_dict().items()}
+    opt = torch.optim.Adam([v for v in params.values() if v.requires_grad], lr=1e-5)
+    batch = make_batch(B, args.nodes, seed=1)
+    ocfg = {k: v for k, v in cfg.items() if k in ("num_heads", "triplet_heads", "triplet_type", "activation",
+                                                   "scale_degree")}
+
+    def step():
+        gap, logits = O.tgt_multi(params, batch, model_height=cfg["model_height"], upto_hop=cfg["upto_hop"], **ocfg)
+        loss = O.pretrain_loss(gap, logits, batch, cfg["num_dist_bins"])
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return float(loss.detach())
+    return step
+
+
+def cpu_baseline(args, B, steps, warmup):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = cpu_step_fn(args, B)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return dict(value=B / dt, unit=UNIT, cores=cores, kind="port",
+                sample=f"oracle port of lib.tgt + lib.models.pcqm (PyTorch-CPU fp32 eager), TGT-At {args.layers}L "
+                       f"N={args.nodes}, micro-batch {B} molecules/step, {steps} timed step(s) after {warmup} warm-up, "
+                       f"{dt:.2f} s/step"), dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = args.cpu_batch or 2
+    base, dt = cpu_baseline(args, B, args.steps, args.warmup)
+    out = dict(metric=METRIC, value=base["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+               ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+               data="synthetic", impl="reference",
+               config=dict(workload=f"TGT-At {args.layers}L training step (fwd+loss+bwd+Adam), N={args.nodes}, "
+                                    f"CPU micro-batch {B} (bounded sample of the batch-{args.batch} workload)",
+                           inputs="synthetic PCQM-shaped batch, random-init weights"),
+               cpu_baseline=base,
+               e2e=dict(value=base["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+               gpu_launches=0)
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.p is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                              ("sw_power_cap", 8)):
+                if len(r) > col and r[col].strip().lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------------ roofline model
+def kernel_models(B, N, We, Ht, Wn, Hn, s=2):
+    """Algorithmic bytes / flops per launch of each of our kernels at this shape (DESIGN.md 'Kernels')."""
+    R = B * N * N
+    d = {}
+    d["triplet_attn_fwd"] = dict(bytes=(8 * R * We + 4 * R * Ht) * s + 4 * R, flops=8 * B * N ** 3 * We)
+    d["triplet_attn_bwd"] = dict(bytes=(16 * R * We + 8 * R * Ht) * s + 4 * R, flops=20 * B * N ** 3 * We)
+    d["triplet_aggr_fwd"] = dict(bytes=(4 * R * We + 4 * R * Ht) * s + 4 * R, flops=4 * B * N ** 3 * We)
+    d["triplet_aggr_bwd"] = dict(bytes=(8 * R * We + 8 * R * Ht) * s + 4 * R, flops=8 * B * N ** 3 * We)
+    d["egt_attn_fwd"] = dict(bytes=(3 * R * Hn + 4 * B * N * Wn) * s + 4 * R, flops=4 * B * N * N * Wn)
+    d["egt_attn_bwd"] = dict(bytes=(5 * R * Hn + 8 * B * N * Wn) * s + 4 * R, flops=10 * B * N * N * Wn)
+    for W in (We, Wn):
+        rows = R if W == We else B * N
+        d[f"layernorm_fwd_W{W}"] = dict(bytes=2 * rows * W * s, flops=0)
+        d[f"layernorm_bwd_W{W}"] = dict(bytes=3 * rows * W * s, flops=0)
+    return d
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch.distributed as dist
+    from tgt_b200 import _C, ops
+    from tgt_b200.harness.models import TGT_Multi, pretrain_loss
+    from tgt_b200.harness.synthetic import make_batch, add_scheme_fields
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU path)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _C.lib()                                                   # fail loudly if the CUDA library is missing
+
+    cfg = model_cfg(args)
+    torch.manual_seed(0)
+    model = TGT_Multi(**cfg).to(dev).train()
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-5, fused=True)
+    B, N = args.batch, args.nodes
+    micro = args.micro_batch or B
+    assert B % micro == 0
+
+    raw_keys = ("num_nodes", "node_mask", "node_features", "distance_matrix", "feature_matrix", "dft_coords", "target")
+    host = make_batch(B, N, seed=1 + rank, with_3d=False)
+    host = {k: host[k].pin_memory() for k in raw_keys}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+    resident = {k: v.to(dev) for k, v in host.items()}
+
+    def step(raw):
+        total = None
+        for mb in range(0, B, micro):
+            part = {k: v[mb:mb + micro] for k, v in raw.items()} if micro != B else raw
+            batch = add_scheme_fields(part, with_3d=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                gap, logits = net(batch)
+                loss = pretrain_loss(gap.float(), logits.float() if args.fp32_logits else logits, batch,
+                                     cfg["num_dist_bins"]) * (micro / B)
+            loss.backward()
+            total = loss.detach() if total is None else total + loss.detach()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return total
+
+    def step_e2e():
+        raw = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        return float(step(raw).item())                          # D2H read of the loss (4 bytes) every step
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_region(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step(resident)
+    torch.cuda.reset_peak_memory_stats()
+    clocks = ClockSampler(local) if rank == 0 else None
+    n0 = _C.launch_count()
+    ms = timed_region(lambda: step(resident), args.steps)
+    launches = _C.launch_count() - n0
+    clk = clocks.stop() if clocks else None
+    ms_e2e = timed_region(step_e2e, args.steps)
+    peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
+
+    # per-kernel timing inside the real step (CUDA events on the launching stream)
+    ops.KernelTimer.reset(True)
+    barrier()
+    ksteps = max(1, min(args.steps, 2))
+    for _ in range(ksteps):
+        step(resident)
+    barrier()
+    ksum = ops.KernelTimer.summary()
+    ops.KernelTimer.reset(False)
+
+    if rank == 0:
+        pk = peaks()
+        km = kernel_models(micro, N, cfg["edge_width"], cfg["triplet_heads"], cfg["node_width"], cfg["num_heads"])
+        step_ms = ms / args.steps
+        kernels = {}
+        for name, (n, tot) in ksum.items():
+            per = tot / n
+            ent = dict(launches_per_step=n / ksteps, ms_per_launch=per, share_of_step=(tot / ksteps) / step_ms)
+            if name in km:
+                gbs = km[name]["bytes"] / (per * 1e-3) / 1e9
+                tfs = km[name]["flops"] / (per * 1e-3) / 1e12
+                ent.update(alg_bytes=km[name]["bytes"], alg_flops=km[name]["flops"], hbm_gbs=gbs,
+                           hbm_frac=gbs / pk["hbm"], tflops=tfs, tc_frac=tfs / pk["tc_sustained"])
+            kernels[name] = ent
+        cand = [k for k in kernels if k in km and k.startswith("triplet")] or [k for k in kernels if k in km]
+        top = max(cand, key=lambda k: kernels[k]["share_of_step"]) if cand else None
+        roofline = None
+        if top:
+            e = kernels[top]
+            roofline = dict(kernel=top, bound="hbm", achieved=e["hbm_gbs"], peak=pk["hbm"], unit="GB/s",
+                            frac=e["hbm_frac"], traffic=None, peak_source=pk["source"],
+                            ms_per_launch=e["ms_per_launch"], share_of_step=e["share_of_step"],
+                            tensor_tflops=e["tflops"], tensor_frac_of_sustained=e["tc_frac"])
+        base = None
+        if not args.no_cpu_baseline:
+            base, _ = cpu_baseline(args, args.cpu_batch or 4, 1, 1 if args.cpu_warm else 0)
+        out = dict(metric=METRIC, value=world * B / (step_ms * 1e-3), unit=UNIT, n_gpus=world, steps=args.steps,
+                   warmup=args.warmup, ms_per_step=step_ms, higher_is_better=True, scaling="weak", vs_baseline=None,
+                   dtype="bf16", data="synthetic",
+                   config=dict(workload=f"TGT-At {args.layers}L (TGT_Multi, pretrain loss) training step = fwd + loss + "
+                                        f"bwd + fused Adam, per-GPU batch {B} x N={N}, bf16 autocast, train mode "
+                                        f"(source_dropout .3, drop_path .2, act_dropout .1)",
+                               micro_batch=micro, parallelism=f"dp{world}",
+                               inputs="synthetic PCQM-shaped batch (tgt_b200/harness/synthetic.py), random-init weights",
+                               l2="inputs and activations per step (>10 GB) exceed the 126 MB L2; no explicit flush"),
+                   e2e=dict(value=world * B / (ms_e2e / args.steps * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d_bytes,
+                            d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps),
+                   gpu_launches=int(launches), clocks=clk, roofline=roofline, kernels=kernels,
+                   cpu_baseline=base, peak_mem_gib=peak_mem)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (BASELINE: 256)")
+    ap.add_argument("--micro-batch", type=int, default=0, help="gradient-accumulation micro-batch (0 = whole batch)")
+    ap.add_argument("--nodes", type=int, default=64)
+    ap.add_argument("--layers", type=int, default=24)
+    ap.add_argument("--cpu-batch", type=int, default=0)
+    ap.add_argument("--cpu-warm", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fp32-logits", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

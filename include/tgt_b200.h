@@ -20,6 +20,7 @@
 #ifndef TGT_B200_H
 #define TGT_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -71,12 +72,19 @@ typedef struct {
   int32_t dtype;          /* dtype of proj / va / dva / dproj */
 } tgt_triplet_attn_desc;
 
+/* workspace: caller-provided scratch of at least tgt_triplet_attn_workspace_bytes(desc, backward)
+ * bytes (0 for shapes only the generic kernels support); holds the [B,2,H,64,64] bias / gate
+ * tiles (and, backward, their gradients).  Contents are undefined after the call.
+ * stats written by the forward are private to the kernel family that wrote them: run the
+ * backward under the same kernel policy as the forward.                                     */
+size_t tgt_triplet_attn_workspace_bytes(const tgt_triplet_attn_desc *desc, int backward);
 int tgt_triplet_attn_fwd(const tgt_triplet_attn_desc *desc, const void *proj, const float *mask,
-                         void *va, float *stats, void *stream);
+                         void *va, float *stats, void *workspace, size_t workspace_bytes,
+                         void *stream);
 /* dproj: [R, ld] out, same column layout as proj; every column named in desc is written.   */
 int tgt_triplet_attn_bwd(const tgt_triplet_attn_desc *desc, const void *proj, const float *mask,
                          const void *va, const void *dva, const float *stats, void *dproj,
-                         void *stream);
+                         void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- triplet aggregate core ---------------------------------------------------------------
  * replaces lib/tgt/layers/triplet.py:56-68 (TripletAggregate) and 106-120 (…Ungated).
@@ -118,10 +126,14 @@ typedef struct {
 
 int tgt_egt_attn_fwd(const tgt_egt_desc *desc, const void *qkv, const void *eg, const float *mask,
                      const float *src_mask, void *hhat, void *vatt, float *stats, void *stream);
-/* dhhat may be NULL (edge_update=False).  dqkv:[B*N, ld_qkv], deg:[R, ld_eg] out.            */
+/* vatt: the forward output (attend only; delta = dvatt . vatt).  dhhat may be NULL
+ * (edge_update=False).  dqkv:[B*N, ld_qkv], deg:[R, ld_eg] out.  workspace: at least
+ * tgt_egt_attn_workspace_bytes(desc) bytes of caller-provided scratch ([R,H] attention weights). */
+size_t tgt_egt_attn_workspace_bytes(const tgt_egt_desc *desc);
 int tgt_egt_attn_bwd(const tgt_egt_desc *desc, const void *qkv, const void *eg, const float *mask,
-                     const float *src_mask, const float *stats, const void *dhhat,
-                     const void *dvatt, void *dqkv, void *deg, void *stream);
+                     const float *src_mask, const float *stats, const void *vatt, const void *dhhat,
+                     const void *dvatt, void *dqkv, void *deg, void *workspace, size_t workspace_bytes,
+                     void *stream);
 
 /* ---- FFN activation: y = dropout(gelu(u)) (exact erf GELU) -----------------------------------
  * replaces F.gelu + nn.Dropout at lib/tgt/layers/layers.py:157-158.  The keep mask is a

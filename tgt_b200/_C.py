@@ -55,12 +55,14 @@ _SIGNATURES = {
     "tgt_set_kernel_policy": (None, [C.c_int]),
     "tgt_layernorm_fwd": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_float, C.c_int, C.c_int, _P]),
     "tgt_layernorm_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, _P]),
-    "tgt_triplet_attn_fwd": (C.c_int, [C.POINTER(TripletAttnDesc), _P, _P, _P, _P, _P]),
-    "tgt_triplet_attn_bwd": (C.c_int, [C.POINTER(TripletAttnDesc), _P, _P, _P, _P, _P, _P, _P]),
+    "tgt_triplet_attn_workspace_bytes": (C.c_size_t, [C.POINTER(TripletAttnDesc), C.c_int]),
+    "tgt_triplet_attn_fwd": (C.c_int, [C.POINTER(TripletAttnDesc), _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "tgt_triplet_attn_bwd": (C.c_int, [C.POINTER(TripletAttnDesc), _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "tgt_triplet_aggr_fwd": (C.c_int, [C.POINTER(TripletAggrDesc), _P, _P, _P, _P, _P]),
     "tgt_triplet_aggr_bwd": (C.c_int, [C.POINTER(TripletAggrDesc), _P, _P, _P, _P, _P, _P, _P]),
     "tgt_egt_attn_fwd": (C.c_int, [C.POINTER(EgtDesc), _P, _P, _P, _P, _P, _P, _P, _P]),
-    "tgt_egt_attn_bwd": (C.c_int, [C.POINTER(EgtDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "tgt_egt_attn_workspace_bytes": (C.c_size_t, [C.POINTER(EgtDesc)]),
+    "tgt_egt_attn_bwd": (C.c_int, [C.POINTER(EgtDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "tgt_gelu_dropout_fwd": (C.c_int, [_P, _P, C.c_int64, C.c_float, C.c_uint64, C.c_int, _P]),
     "tgt_gelu_dropout_bwd": (C.c_int, [_P, _P, _P, C.c_int64, C.c_float, C.c_uint64, C.c_int, _P]),
     "tgt_scaled_residual": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int, C.c_int, _P]),

@@ -15,9 +15,11 @@ int triplet_aggr_bwd_simt(const tgt_triplet_aggr_desc &, const void *, const flo
                           float *, void *, cudaStream_t);
 // triplet_mma.cu
 bool triplet_attn_mma_supported(const tgt_triplet_attn_desc &);
-int triplet_attn_fwd_mma(const tgt_triplet_attn_desc &, const void *, const float *, void *, float *, cudaStream_t);
+size_t triplet_attn_mma_workspace(const tgt_triplet_attn_desc &, int backward);
+int triplet_attn_fwd_mma(const tgt_triplet_attn_desc &, const void *, const float *, void *, float *, void *, size_t,
+                         cudaStream_t);
 int triplet_attn_bwd_mma(const tgt_triplet_attn_desc &, const void *, const float *, const void *, const void *,
-                         const float *, void *, cudaStream_t);
+                         const float *, void *, void *, size_t, cudaStream_t);
 }  // namespace tgt
 
 using namespace tgt;
@@ -42,20 +44,28 @@ static int attn_check(const tgt_triplet_attn_desc *D) {
   return 0;
 }
 
+extern "C" size_t tgt_triplet_attn_workspace_bytes(const tgt_triplet_attn_desc *D, int backward) {
+  if (!D || attn_check(D)) return 0;
+  if (g_policy.load() == 0 && triplet_attn_mma_supported(*D)) return triplet_attn_mma_workspace(*D, backward);
+  return 0;
+}
+
 extern "C" int tgt_triplet_attn_fwd(const tgt_triplet_attn_desc *D, const void *proj, const float *mask, void *va,
-                                    float *stats, void *stream) {
+                                    float *stats, void *ws, size_t ws_bytes, void *stream) {
   if (int e = attn_check(D)) return e;
   cudaStream_t st = (cudaStream_t)stream;
-  if (g_policy.load() == 0 && triplet_attn_mma_supported(*D)) return triplet_attn_fwd_mma(*D, proj, mask, va, stats, st);
+  if (g_policy.load() == 0 && triplet_attn_mma_supported(*D))
+    return triplet_attn_fwd_mma(*D, proj, mask, va, stats, ws, ws_bytes, st);
   return triplet_attn_fwd_simt(*D, proj, mask, va, stats, st);
 }
 
 extern "C" int tgt_triplet_attn_bwd(const tgt_triplet_attn_desc *D, const void *proj, const float *mask,
-                                    const void *va, const void *dva, const float *stats, void *dproj, void *stream) {
+                                    const void *va, const void *dva, const float *stats, void *dproj, void *ws,
+                                    size_t ws_bytes, void *stream) {
   if (int e = attn_check(D)) return e;
   cudaStream_t st = (cudaStream_t)stream;
   if (g_policy.load() == 0 && triplet_attn_mma_supported(*D))
-    return triplet_attn_bwd_mma(*D, proj, mask, va, dva, stats, dproj, st);
+    return triplet_attn_bwd_mma(*D, proj, mask, va, dva, stats, dproj, ws, ws_bytes, st);
   return triplet_attn_bwd_simt(*D, proj, mask, va, dva, stats, dproj, st);
 }
 

@@ -44,8 +44,11 @@ __global__ void egt_fwd_kernel(const tgt_egt_desc D, const T *__restrict__ qkv, 
         const float g = ACC ? sigmoid_acc(to_f(eg[row * D.ld_eg + H + h]) + mk)
                             : sigmoidf_(to_f(eg[row * D.ld_eg + H + h]) + mk);
         s += mk;
+        // keys masked to -inf (padding + source dropout, layers.py:55-59) contribute exactly 0, also as the
+        // first key of the online softmax; a row whose keys are ALL -inf ends as 0 * inf = NaN like the reference
         const float mn = fmaxf(mx, s);
-        const float corr = expf(mx - mn), p = expf(s - mn);
+        const float corr = mx == -INFINITY ? 0.f : expf(mx - mn);
+        const float p = s == -INFINITY ? 0.f : expf(s - mn);
         lsum = lsum * corr + p;
         const float pg = p * g;
         const T *vp = kp + (int64_t)H * d;
@@ -240,6 +243,13 @@ static int egt_bwd_t(const tgt_egt_desc &D, const void *qkv, const void *eg, con
   return check_launch("egt_bwd_cols_kernel");
 }
 
+// egt_fast.cu
+bool egt_fast_supported(const tgt_egt_desc &);
+size_t egt_fast_workspace(const tgt_egt_desc &);
+int egt_fwd_fast_launch(const tgt_egt_desc &, const void *, const void *, const float *, const float *, void *, void *,
+                        float *, cudaStream_t);
+int egt_bwd_fast_launch(const tgt_egt_desc &, const void *, const void *, const float *, const float *, const float *,
+                        const void *, const void *, const void *, void *, void *, void *, size_t, cudaStream_t);
 }  // namespace tgt
 
 using namespace tgt;
@@ -252,17 +262,27 @@ static int egt_check(const tgt_egt_desc *D) {
   return 0;
 }
 
+extern "C" size_t tgt_egt_attn_workspace_bytes(const tgt_egt_desc *D) {
+  if (!D || egt_check(D)) return 0;
+  return (g_policy.load() == 0 && egt_fast_supported(*D)) ? egt_fast_workspace(*D) : 0;
+}
+
 extern "C" int tgt_egt_attn_fwd(const tgt_egt_desc *D, const void *qkv, const void *eg, const float *mask,
                                 const float *src_mask, void *hhat, void *vatt, float *stats, void *stream) {
   if (int e = egt_check(D)) return e;
+  if (g_policy.load() == 0 && egt_fast_supported(*D))
+    return egt_fwd_fast_launch(*D, qkv, eg, mask, src_mask, hhat, vatt, stats, (cudaStream_t)stream);
   TGT_DISPATCH_DTYPE(D->dtype, T, return egt_fwd_t<T>(*D, qkv, eg, mask, src_mask, hhat, vatt, stats, (cudaStream_t)stream));
   return 0;
 }
 
 extern "C" int tgt_egt_attn_bwd(const tgt_egt_desc *D, const void *qkv, const void *eg, const float *mask,
-                                const float *src_mask, const float *stats, const void *dhhat, const void *dvatt,
-                                void *dqkv, void *deg, void *stream) {
+                                const float *src_mask, const float *stats, const void *vatt, const void *dhhat,
+                                const void *dvatt, void *dqkv, void *deg, void *ws, size_t ws_bytes, void *stream) {
   if (int e = egt_check(D)) return e;
+  if (g_policy.load() == 0 && egt_fast_supported(*D))
+    return egt_bwd_fast_launch(*D, qkv, eg, mask, src_mask, stats, vatt, dhhat, dvatt, dqkv, deg, ws, ws_bytes,
+                               (cudaStream_t)stream);
   TGT_DISPATCH_DTYPE(D->dtype, T, return egt_bwd_t<T>(*D, qkv, eg, mask, src_mask, stats, dhhat, dvatt, dqkv, deg, (cudaStream_t)stream));
   return 0;
 }

@@ -104,6 +104,14 @@ def layernorm_bwd(dy: Tensor, x2: Tensor, gamma: Tensor, mean: Tensor, rstd: Ten
     return dx, dgb[0], dgb[1]
 
 
+def _workspace(nbytes: int, device):
+    """Scratch for one kernel call from PyTorch's caching allocator (the library never allocates)."""
+    nbytes = int(nbytes)
+    if nbytes == 0:
+        return None, 0
+    return torch.empty(nbytes, dtype=torch.uint8, device=device), nbytes
+
+
 def _x_for_ln(e: Tensor, cdtype: torch.dtype) -> Tensor:
     """LN kernels take x in fp32 or in the compute dtype."""
     if e.dtype != torch.float32 and e.dtype != cdtype:
@@ -124,12 +132,13 @@ class LNLinearFn(Function):
             g, bt = _f32c(ln_w), _f32c(ln_b)
             y, mean, rstd = layernorm_fwd(x2, g, bt, cdtype)
             Wc = W.detach().to(cdtype)
-            out = torch.addmm(b.detach().to(cdtype), y, Wc.t())
+            out = torch.empty((*shape[:-1], W.shape[0]), dtype=cdtype, device=x.device)
+            torch.addmm(b.detach().to(cdtype), y, Wc.t(), out=out.view(-1, W.shape[0]))
             ctx.save_for_backward(x2, g, bt, Wc, mean, rstd)
             ctx.cdtype = cdtype
             ctx.in_dtype = x.dtype
             ctx.pdt = (ln_w.dtype, W.dtype, b.dtype)
-        return out.view(*shape[:-1], W.shape[0])
+        return out                      # a fresh base tensor (never a view): callers add residuals in place
 
     @staticmethod
     def backward(ctx, dout):
@@ -173,17 +182,20 @@ class TripletAttentionFn(Function):
                                       float(d) ** -0.5, _C.dtype_code(cdtype))
             va = torch.empty((R, 2 * H * d), dtype=cdtype, device=e.device)
             stats = torch.empty((B, 2, H, N, N, 2), dtype=torch.float32, device=e.device)
+            ws, wsb = _workspace(_C.lib().tgt_triplet_attn_workspace_bytes(desc, 0), e.device)
             with timed("triplet_attn_fwd"):
                 _C.check(_C.lib().tgt_triplet_attn_fwd(desc, _C.ptr(proj), _C.ptr(m3), _C.ptr(va), _C.ptr(stats),
-                                                       _C.stream_ptr()), "triplet_attn_fwd")
+                                                       _C.ptr(ws), wsb, _C.stream_ptr()), "triplet_attn_fwd")
+            del ws
             del proj
-            out = torch.addmm(boc, va, Woc.t())
+            out = torch.empty((B, N, N, W), dtype=cdtype, device=e.device)
+            torch.addmm(boc, va, Woc.t(), out=out.view(R, W))
             ctx.save_for_backward(x2, m3, g, bt, Wc, bc, Woc, mean, rstd, stats, va)
             ctx.desc = desc
             ctx.cdtype = cdtype
             ctx.in_dtype = e.dtype
             ctx.pdt = (ln_w.dtype, Wcat.dtype, bcat.dtype, Wo.dtype, bo.dtype)
-        return out.view(B, N, N, W)
+        return out
 
     @staticmethod
     def backward(ctx, dout):
@@ -199,10 +211,12 @@ class TripletAttentionFn(Function):
             y, _, _ = layernorm_fwd(x2, g, bt, cd)
             proj = torch.addmm(bc, y, Wc.t())
             dproj = torch.empty_like(proj)
+            ws, wsb = _workspace(_C.lib().tgt_triplet_attn_workspace_bytes(desc, 1), x2.device)
             with timed("triplet_attn_bwd"):
                 _C.check(_C.lib().tgt_triplet_attn_bwd(desc, _C.ptr(proj), _C.ptr(m3), _C.ptr(va), _C.ptr(dva),
-                                                       _C.ptr(stats), _C.ptr(dproj), _C.stream_ptr()),
-                         "triplet_attn_bwd")
+                                                       _C.ptr(stats), _C.ptr(dproj), _C.ptr(ws), wsb,
+                                                       _C.stream_ptr()), "triplet_attn_bwd")
+            del ws
             del proj, dva
             dWc = torch.mm(dproj.t(), y)
             dbc = dproj.sum(0, dtype=torch.float32)
@@ -241,13 +255,14 @@ class TripletAggregateFn(Function):
                 _C.check(_C.lib().tgt_triplet_aggr_fwd(desc, _C.ptr(proj), _C.ptr(m3), _C.ptr(va), _C.ptr(aw),
                                                        _C.stream_ptr()), "triplet_aggr_fwd")
             del proj
-            out = torch.addmm(boc, va, Woc.t())
+            out = torch.empty((B, N, N, W), dtype=cdtype, device=e.device)
+            torch.addmm(boc, va, Woc.t(), out=out.view(R, W))
             ctx.save_for_backward(x2, m3, g, bt, Wc, bc, Woc, mean, rstd, aw, va)
             ctx.desc = desc
             ctx.cdtype = cdtype
             ctx.in_dtype = e.dtype
             ctx.pdt = (ln_w.dtype, Wcat.dtype, bcat.dtype, Wo.dtype, bo.dtype)
-        return out.view(B, N, N, W)
+        return out
 
     @staticmethod
     def backward(ctx, dout):
@@ -306,7 +321,7 @@ class EGTCoreFn(Function):
                 _C.check(_C.lib().tgt_egt_attn_fwd(desc, _C.ptr(q2), _C.ptr(eg2), _C.ptr(m3), _C.ptr(src),
                                                    _C.ptr(hhat), _C.ptr(vatt), _C.ptr(stats), _C.stream_ptr()),
                          "egt_attn_fwd")
-            ctx.save_for_backward(q2, eg2, m3, src, stats)
+            ctx.save_for_backward(q2, eg2, m3, src, stats, vatt)
             ctx.desc = desc
             ctx.dts = (qkv.dtype, eg.dtype)
             ctx.set_materialize_grads(False)
@@ -316,7 +331,7 @@ class EGTCoreFn(Function):
 
     @staticmethod
     def backward(ctx, dhhat, dvatt=None):
-        q2, eg2, m3, src, stats = ctx.saved_tensors
+        q2, eg2, m3, src, stats, vatt = ctx.saved_tensors
         desc = ctx.desc
         cd = q2.dtype
         with torch.autocast("cuda", enabled=False):
@@ -326,10 +341,12 @@ class EGTCoreFn(Function):
             dv = dvatt.to(cd).contiguous() if dvatt is not None else None
             dqkv = torch.empty_like(q2)
             deg = torch.empty_like(eg2)
+            ws, wsb = _workspace(_C.lib().tgt_egt_attn_workspace_bytes(desc), q2.device)
             with timed("egt_attn_bwd"):
                 _C.check(_C.lib().tgt_egt_attn_bwd(desc, _C.ptr(q2), _C.ptr(eg2), _C.ptr(m3), _C.ptr(src),
-                                                   _C.ptr(stats), _C.ptr(dh), _C.ptr(dv), _C.ptr(dqkv), _C.ptr(deg),
-                                                   _C.stream_ptr()), "egt_attn_bwd")
+                                                   _C.ptr(stats), _C.ptr(vatt), _C.ptr(dh), _C.ptr(dv), _C.ptr(dqkv),
+                                                   _C.ptr(deg), _C.ptr(ws), wsb, _C.stream_ptr()), "egt_attn_bwd")
+            del ws
         return dqkv.to(ctx.dts[0]), deg.to(ctx.dts[1]), None, None, None, None, None, None
 
 
@@ -351,11 +368,12 @@ class FFNGeluFn(Function):
             a = torch.empty_like(u)
             _C.check(_C.lib().tgt_gelu_dropout_fwd(_C.ptr(u), _C.ptr(a), u.numel(), float(p_drop), int(seed),
                                                    _C.dtype_code(cdtype), _C.stream_ptr()), "gelu_dropout_fwd")
-            out = torch.addmm(b2.detach().to(cdtype), a, W2c.t())
+            out = torch.empty((*shape[:-1], W2.shape[0]), dtype=cdtype, device=x.device)
+            torch.addmm(b2.detach().to(cdtype), a, W2c.t(), out=out.view(-1, W2.shape[0]))
             ctx.save_for_backward(x2, g, bt, W1c, W2c, mean, rstd, u)
             ctx.meta = (float(p_drop), int(seed), cdtype, x.dtype,
                         (ln_w.dtype, W1.dtype, b1.dtype, W2.dtype, b2.dtype))
-        return out.view(*shape[:-1], W2.shape[0])
+        return out
 
     @staticmethod
     def backward(ctx, dout):

@@ -16,3 +16,7 @@ try:
 except Exception as e:
     print("bench json unreadable:", e)
 PY
+if [ -n "$NCU_LIST" ]; then
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --layers 2 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench_$TAG.log 2>&1
+  python scripts/summarize_launches.py gpurun_out/launches_$TAG.csv > gpurun_out/launches_$TAG.md; head -45 gpurun_out/launches_$TAG.md | cut -c1-160
+fi

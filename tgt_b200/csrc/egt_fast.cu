@@ -16,7 +16,8 @@
 namespace tgt {
 
 constexpr int EF_ROWS = 8;       // rows (l or m) per CTA
-constexpr int EF_CHUNK = 16;     // staged rows per shared-memory chunk
+constexpr int EF_BROWS = 4;      // rows per CTA of the backward row pass (register-heavy: 3 CTAs x 4 warps per SM)
+constexpr int EF_CHUNK = 8;      // staged rows per shared-memory chunk
 constexpr int EF_DMAX = 16;
 
 __device__ __forceinline__ void ef_cp16(uint32_t dst, const void *src, bool valid) {
@@ -66,22 +67,23 @@ __device__ __forceinline__ void stage_rows(unsigned char *sm, const T *src, int6
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-template <typename T>
-__global__ void __launch_bounds__(EF_ROWS * 32)
+template <typename T, int HC, int DC, int ATT>
+__global__ void __launch_bounds__(EF_ROWS * 32, 2)
 egt_fwd_fast(const tgt_egt_desc D, const T *__restrict__ qkv, const T *__restrict__ eg, const float *__restrict__ mask,
              const float *__restrict__ src, T *__restrict__ hhat, T *__restrict__ vatt, float *__restrict__ stats) {
   extern __shared__ __align__(16) unsigned char sm[];           // [EF_CHUNK][2*Wn] K|V   (or [EF_CHUNK][Wn] K only)
-  const int N = D.N, H = D.H, d = D.d, Wn = H * d;
+  const int N = D.N, H = HC ? HC : D.H, d = DC ? DC : D.d, Wn = H * d;   // HC/DC: compile-time shape (0 = runtime)
+  constexpr int DL = DC ? DC : EF_DMAX;
   const int b = blockIdx.y, l = blockIdx.x * EF_ROWS + (threadIdx.x >> 5), hp = threadIdx.x & 31;
   const bool active = l < N && 2 * hp < H;
   const int la = l < N ? l : N - 1;
-  const bool attend = D.attend != 0;
+  const bool attend = ATT < 0 ? D.attend != 0 : ATT != 0;     // ATT: compile-time attend flag (-1 = runtime)
   const int kvw = attend ? 2 * Wn : Wn;
   const T *smT = reinterpret_cast<const T *>(sm);
 
-  float q0[EF_DMAX], q1[EF_DMAX], o0[EF_DMAX], o1[EF_DMAX];
+  float q0[DL], q1[DL], o0[DL], o1[DL];
 #pragma unroll
-  for (int dd = 0; dd < EF_DMAX; ++dd) {
+  for (int dd = 0; dd < DL; ++dd) {
     q0[dd] = q1[dd] = o0[dd] = o1[dd] = 0.f;
     if (dd < d && active) {
       const float2 v = Pair<T>::unpack(ldg32(qkv + (int64_t)(b * N + la) * D.ld_qkv + dd * H + 2 * hp));
@@ -121,7 +123,7 @@ egt_fwd_fast(const tgt_egt_desc D, const T *__restrict__ qkv, const T *__restric
         const T *kp = smT + mm * kvw + 2 * hp;
         float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-        for (int dd = 0; dd < EF_DMAX; ++dd)
+        for (int dd = 0; dd < DL; ++dd)
           if (dd < d) {
             const float2 kv = Pair<T>::unpack(*reinterpret_cast<const uint32_t *>(kp + dd * H));
             s0 = fmaf(q0[dd], kv.x, s0);
@@ -145,7 +147,7 @@ egt_fwd_fast(const tgt_egt_desc D, const T *__restrict__ qkv, const T *__restric
           const float a0 = p0 * g0, a1 = p1 * g1;
           const T *vp = kp + Wn;
 #pragma unroll
-          for (int dd = 0; dd < EF_DMAX; ++dd)
+          for (int dd = 0; dd < DL; ++dd)
             if (dd < d) {
               const float2 vv = Pair<T>::unpack(*reinterpret_cast<const uint32_t *>(vp + dd * H));
               o0[dd] = fmaf(o0[dd], c0, a0 * vv.x);
@@ -164,7 +166,7 @@ egt_fwd_fast(const tgt_egt_desc D, const T *__restrict__ qkv, const T *__restric
     const float sc0 = D.scale_degree ? log1pf(dg0) : 1.f, sc1 = D.scale_degree ? log1pf(dg1) : 1.f;
     T *op = vatt + (int64_t)(b * N + l) * Wn + 2 * hp;
 #pragma unroll
-    for (int dd = 0; dd < EF_DMAX; ++dd)
+    for (int dd = 0; dd < DL; ++dd)
       if (dd < d) stg32(op + dd * H, Pair<T>::pack(o0[dd] * i0 * sc0, o1[dd] * i1 * sc1));
     float *st = stats + ((int64_t)(b * N + l) * H + 2 * hp) * 3;
     st[0] = mx0; st[1] = i0; st[2] = dg0;
@@ -174,25 +176,26 @@ egt_fwd_fast(const tgt_egt_desc D, const T *__restrict__ qkv, const T *__restric
 
 // ------------------------------------------------------------------------------------------------ backward, row pass
 // vatt is the forward output (U * sc): delta = sum_m dP P = dV_att . U * sc = dV_att . V_att
-template <typename T>
-__global__ void __launch_bounds__(EF_ROWS * 32)
+template <typename T, int HC, int DC, int ATT>
+__global__ void __launch_bounds__(EF_BROWS * 32, 3)
 egt_bwd_rows_fast(const tgt_egt_desc D, const T *__restrict__ qkv, const T *__restrict__ eg,
                   const float *__restrict__ mask, const float *__restrict__ src, const float *__restrict__ stats,
                   const T *__restrict__ vatt, const T *__restrict__ dhhat, const T *__restrict__ dvatt,
                   T *__restrict__ dqkv, T *__restrict__ deg_out, T *__restrict__ aw) {
   extern __shared__ __align__(16) unsigned char sm[];
-  const int N = D.N, H = D.H, d = D.d, Wn = H * d;
-  const int b = blockIdx.y, l = blockIdx.x * EF_ROWS + (threadIdx.x >> 5), hp = threadIdx.x & 31;
+  const int N = D.N, H = HC ? HC : D.H, d = DC ? DC : D.d, Wn = H * d;   // HC/DC: compile-time shape (0 = runtime)
+  constexpr int DL = DC ? DC : EF_DMAX;
+  const int b = blockIdx.y, l = blockIdx.x * EF_BROWS + (threadIdx.x >> 5), hp = threadIdx.x & 31;
   const bool active = l < N && 2 * hp < H;
   const int la = l < N ? l : N - 1;
-  const bool attend = D.attend != 0;
+  const bool attend = ATT < 0 ? D.attend != 0 : ATT != 0;     // ATT: compile-time attend flag (-1 = runtime)
   const int kvw = attend ? 2 * Wn : Wn;
   const T *smT = reinterpret_cast<const T *>(sm);
 
-  float q0[EF_DMAX], q1[EF_DMAX], go0[EF_DMAX], go1[EF_DMAX], dq0[EF_DMAX], dq1[EF_DMAX];
+  float q0[DL], q1[DL], go0[DL], go1[DL], dq0[DL], dq1[DL];
   float dsc0 = 0.f, dsc1 = 0.f;
 #pragma unroll
-  for (int dd = 0; dd < EF_DMAX; ++dd) {
+  for (int dd = 0; dd < DL; ++dd) {
     q0[dd] = q1[dd] = go0[dd] = go1[dd] = dq0[dd] = dq1[dd] = 0.f;
     if (dd < d && active) {
       const float2 v = Pair<T>::unpack(ldg32(qkv + (int64_t)(b * N + la) * D.ld_qkv + dd * H + 2 * hp));
@@ -257,7 +260,7 @@ egt_bwd_rows_fast(const tgt_egt_desc D, const T *__restrict__ qkv, const T *__re
           const T *vp = kp + Wn;
           float s0 = 0.f, s1 = 0.f, dA0 = 0.f, dA1 = 0.f;
 #pragma unroll
-          for (int dd = 0; dd < EF_DMAX; ++dd)
+          for (int dd = 0; dd < DL; ++dd)
             if (dd < d) {
               const float2 kv = Pair<T>::unpack(*reinterpret_cast<const uint32_t *>(kp + dd * H));
               const float2 vv = Pair<T>::unpack(*reinterpret_cast<const uint32_t *>(vp + dd * H));
@@ -282,7 +285,7 @@ egt_bwd_rows_fast(const tgt_egt_desc D, const T *__restrict__ qkv, const T *__re
         }
         stg32(deg_out + (erow0 + m) * D.ld_eg + 2 * hp, Pair<T>::pack(dH0, dH1));
 #pragma unroll
-        for (int dd = 0; dd < EF_DMAX; ++dd)
+        for (int dd = 0; dd < DL; ++dd)
           if (dd < d) {
             const float2 kv = Pair<T>::unpack(*reinterpret_cast<const uint32_t *>(kp + dd * H));
             dq0[dd] = fmaf(dH0, kv.x, dq0[dd]);
@@ -294,29 +297,30 @@ egt_bwd_rows_fast(const tgt_egt_desc D, const T *__restrict__ qkv, const T *__re
   if (active) {
     T *op = dqkv + (int64_t)(b * N + l) * D.ld_qkv + 2 * hp;
 #pragma unroll
-    for (int dd = 0; dd < EF_DMAX; ++dd)
+    for (int dd = 0; dd < DL; ++dd)
       if (dd < d) stg32(op + dd * H, Pair<T>::pack(dq0[dd] * D.scale, dq1[dd] * D.scale));
   }
 }
 
 // ------------------------------------------------------------------------------------------------ backward, column pass
 // reads dH from deg_out (written by the row pass) and a*sc from aw;  dK = scale * sum_l dH q ; dV = sum_l (a sc) dV_att
-template <typename T>
-__global__ void __launch_bounds__(EF_ROWS * 32)
+template <typename T, int HC, int DC, int ATT>
+__global__ void __launch_bounds__(EF_ROWS * 32, 2)
 egt_bwd_cols_fast(const tgt_egt_desc D, const T *__restrict__ qkv, const T *__restrict__ dvatt,
                   const T *__restrict__ deg_out, const T *__restrict__ aw, T *__restrict__ dqkv) {
   extern __shared__ __align__(16) unsigned char sm[];           // [EF_CHUNK][2*Wn]  Q | dV_att
-  const int N = D.N, H = D.H, d = D.d, Wn = H * d;
+  const int N = D.N, H = HC ? HC : D.H, d = DC ? DC : D.d, Wn = H * d;   // HC/DC: compile-time shape (0 = runtime)
+  constexpr int DL = DC ? DC : EF_DMAX;
   const int b = blockIdx.y, m = blockIdx.x * EF_ROWS + (threadIdx.x >> 5), hp = threadIdx.x & 31;
   const bool active = m < N && 2 * hp < H;
   const int ma = m < N ? m : N - 1;
-  const bool attend = D.attend != 0;
+  const bool attend = ATT < 0 ? D.attend != 0 : ATT != 0;     // ATT: compile-time attend flag (-1 = runtime)
   const int qw = attend ? 2 * Wn : Wn;
   const T *smT = reinterpret_cast<const T *>(sm);
 
-  float dk0[EF_DMAX], dk1[EF_DMAX], dv0[EF_DMAX], dv1[EF_DMAX];
+  float dk0[DL], dk1[DL], dv0[DL], dv1[DL];
 #pragma unroll
-  for (int dd = 0; dd < EF_DMAX; ++dd) dk0[dd] = dk1[dd] = dv0[dd] = dv1[dd] = 0.f;
+  for (int dd = 0; dd < DL; ++dd) dk0[dd] = dk1[dd] = dv0[dd] = dv1[dd] = 0.f;
 
   for (int lc = 0; lc < N; lc += EF_CHUNK) {
     __syncthreads();
@@ -343,7 +347,7 @@ egt_bwd_cols_fast(const tgt_egt_desc D, const T *__restrict__ qkv, const T *__re
         const float2 dh = Pair<T>::unpack(hp_[ll]);
         const float2 av = Pair<T>::unpack(ap[ll]);
 #pragma unroll
-        for (int dd = 0; dd < EF_DMAX; ++dd)
+        for (int dd = 0; dd < DL; ++dd)
           if (dd < d) {
             const float2 qv = Pair<T>::unpack(*reinterpret_cast<const uint32_t *>(qp + dd * H));
             dk0[dd] = fmaf(dh.x, qv.x, dk0[dd]);
@@ -360,7 +364,7 @@ egt_bwd_cols_fast(const tgt_egt_desc D, const T *__restrict__ qkv, const T *__re
   if (active) {
     T *okp = dqkv + (int64_t)(b * N + m) * D.ld_qkv + Wn + 2 * hp;
 #pragma unroll
-    for (int dd = 0; dd < EF_DMAX; ++dd)
+    for (int dd = 0; dd < DL; ++dd)
       if (dd < d) {
         stg32(okp + dd * H, Pair<T>::pack(dk0[dd] * D.scale, dk1[dd] * D.scale));
         if (attend) stg32(okp + Wn + dd * H, Pair<T>::pack(dv0[dd], dv1[dd]));
@@ -385,10 +389,16 @@ template <typename T>
 static int fwd_t(const tgt_egt_desc &D, const void *qkv, const void *eg, const float *mask, const float *src, void *hhat,
                  void *vatt, float *stats, cudaStream_t st) {
   const size_t smem = (size_t)EF_CHUNK * (D.attend ? 2 : 1) * D.H * D.d * 2;
-  TGT_CUDA_OK(cudaFuncSetAttribute(egt_fwd_fast<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((D.N + EF_ROWS - 1) / EF_ROWS, D.B);
-  egt_fwd_fast<T><<<grid, EF_ROWS * 32, smem, st>>>(D, (const T *)qkv, (const T *)eg, mask, src, (T *)hhat, (T *)vatt,
-                                                    stats);
+#define L(HC, DC, AT)                                                                                                     \
+  do {                                                                                                                \
+    TGT_CUDA_OK(cudaFuncSetAttribute(egt_fwd_fast<T, HC, DC, AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    egt_fwd_fast<T, HC, DC, AT><<<grid, EF_ROWS * 32, smem, st>>>(D, (const T *)qkv, (const T *)eg, mask, src, (T *)hhat,   \
+                                                              (T *)vatt, stats);                                      \
+  } while (0)
+  // the shipped TGT geometry (Wn = 768, 64 heads) is fully specialised: all strides become immediates
+  if (D.H == 64 && D.d == 12 && D.attend) L(64, 12, 1); else if (D.H == 64 && D.d == 12) L(64, 12, 0); else L(0, 0, -1);
+#undef L
   return check_launch("egt_fwd_fast");
 }
 
@@ -397,16 +407,21 @@ static int bwd_t(const tgt_egt_desc &D, const void *qkv, const void *eg, const f
                  const float *stats, const void *vatt, const void *dhhat, const void *dvatt, void *dqkv, void *deg,
                  void *ws, cudaStream_t st) {
   const size_t smem = (size_t)EF_CHUNK * (D.attend ? 2 : 1) * D.H * D.d * 2;
-  TGT_CUDA_OK(cudaFuncSetAttribute(egt_bwd_rows_fast<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  TGT_CUDA_OK(cudaFuncSetAttribute(egt_bwd_cols_fast<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((D.N + EF_ROWS - 1) / EF_ROWS, D.B);
   T *aw = (T *)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
-  egt_bwd_rows_fast<T><<<grid, EF_ROWS * 32, smem, st>>>(D, (const T *)qkv, (const T *)eg, mask, src, stats,
-                                                         (const T *)vatt, (const T *)dhhat, (const T *)dvatt, (T *)dqkv,
-                                                         (T *)deg, aw);
-  if (int e = check_launch("egt_bwd_rows_fast")) return e;
-  egt_bwd_cols_fast<T><<<grid, EF_ROWS * 32, smem, st>>>(D, (const T *)qkv, (const T *)dvatt, (const T *)deg, aw,
-                                                         (T *)dqkv);
+#define L(HC, DC, AT)                                                                                                          \
+  do {                                                                                                                     \
+    TGT_CUDA_OK(cudaFuncSetAttribute(egt_bwd_rows_fast<T, HC, DC, AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    TGT_CUDA_OK(cudaFuncSetAttribute(egt_bwd_cols_fast<T, HC, DC, AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    egt_bwd_rows_fast<T, HC, DC, AT><<<dim3((D.N + EF_BROWS - 1) / EF_BROWS, D.B), EF_BROWS * 32, smem, st>>>(D, (const T *)qkv, (const T *)eg, mask, src, stats,       \
+                                                                   (const T *)vatt, (const T *)dhhat, (const T *)dvatt,    \
+                                                                   (T *)dqkv, (T *)deg, aw);                               \
+    if (int e = check_launch("egt_bwd_rows_fast")) return e;                                                               \
+    egt_bwd_cols_fast<T, HC, DC, AT><<<grid, EF_ROWS * 32, smem, st>>>(D, (const T *)qkv, (const T *)dvatt, (const T *)deg, aw,  \
+                                                                   (T *)dqkv);                                             \
+  } while (0)
+  if (D.H == 64 && D.d == 12 && D.attend) L(64, 12, 1); else if (D.H == 64 && D.d == 12) L(64, 12, 0); else L(0, 0, -1);
+#undef L
   return check_launch("egt_bwd_cols_fast");
 }
 

@@ -177,13 +177,12 @@ def run_ours(args):
     import torch.distributed as dist
     from tgt_b200 import _C, ops
     from tgt_b200.harness.models import TGT_Multi, pretrain_loss
-    from tgt_b200.harness.synthetic import make_batch, add_scheme_fields
+    from tgt_b200.harness.synthetic import add_scheme_fields
+    from tgt_b200.harness.dist import env_rank_world, max_over_ranks, rank_batch, wrap_ddp
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU path)")
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, local, world = env_rank_world()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -193,17 +192,13 @@ def run_ours(args):
     cfg = model_cfg(args)
     torch.manual_seed(0)
     model = TGT_Multi(**cfg).to(dev).train()
-    net = model
-    if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
+    net = wrap_ddp(model, world, device_ids=[local])
     opt = torch.optim.Adam(model.parameters(), lr=1e-5, fused=True)
     B, N = args.batch, args.nodes
     micro = args.micro_batch or B
     assert B % micro == 0
 
-    raw_keys = ("num_nodes", "node_mask", "node_features", "distance_matrix", "feature_matrix", "dft_coords", "target")
-    host = make_batch(B, N, seed=1 + rank, with_3d=False)
-    host = {k: host[k].pin_memory() for k in raw_keys}
+    host = {k: v.pin_memory() for k, v in rank_batch(B, N, rank).items()}
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
     resident = {k: v.to(dev) for k, v in host.items()}
 
@@ -239,10 +234,7 @@ def run_ours(args):
             fn()
         e1.record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        return max_over_ranks(e0.elapsed_time(e1), world, dev)
 
     for _ in range(args.warmup):
         step(resident)

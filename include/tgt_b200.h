@@ -42,9 +42,11 @@ void        tgt_set_kernel_policy(int policy);
 
 /* ---- LayerNorm over the channel dim of edge rows ---------------------------------------
  * replaces nn.LayerNorm calls at lib/tgt/layers/triplet.py:47,207; layers.py:49,112,156.
- * x:[rows,W] (x_dtype)  y:[rows,W] (y_dtype)  gamma,beta:[W] f32  mean,rstd:[rows] f32.   */
+ * x:[rows,W] (x_dtype)  y:[rows,ldy] (y_dtype)  gamma,beta:[W] f32  mean,rstd:[rows] f32.
+ * ldy >= W: when ldy > W the extra columns are written as [1, 0, 0, ...] ("augmented" LN output:
+ * a weight-gradient GEMM dY^T * [LN(x) | 1] then yields the bias gradient in the same pass).   */
 int tgt_layernorm_fwd(const void *x, const float *gamma, const float *beta, void *y,
-                      float *mean, float *rstd, int64_t rows, int W, float eps,
+                      float *mean, float *rstd, int64_t rows, int W, int64_t ldy, float eps,
                       int x_dtype, int y_dtype, void *stream);
 /* dgamma,dbeta:[W] f32 must be ZERO on entry (accumulated with atomics).
  * dy has y_dtype, dx has x_dtype.  If `dres` is non-null it is added to dx (fused residual
@@ -145,7 +147,7 @@ int tgt_gelu_dropout_bwd(const void *u, const void *dy, void *du, int64_t n, flo
 
 /* ---- residual: out = res + scale[b] * x  (per-sample DropPath + in-place add) --------------
  * replaces DropPath + add_ at lib/tgt/layers/layers.py:163-177, 269-290.
- * x,out: [B, inner] (dtype) ; res: [B, inner] (res_dtype) ; scale: [B] f32 or NULL (=1).     */
+ * x,out: [B, inner] (dtype) ; res: [B, inner] (res_dtype) or NULL (=0) ; scale: [B] f32 or NULL (=1). */
 int tgt_scaled_residual(const void *x, const void *res, const float *scale, void *out,
                         int64_t B, int64_t inner, int dtype, int res_dtype, void *stream);
 

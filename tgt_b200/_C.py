@@ -53,7 +53,7 @@ _SIGNATURES = {
     "tgt_last_error": (C.c_char_p, []),
     "tgt_launch_count": (C.c_uint64, []),
     "tgt_set_kernel_policy": (None, [C.c_int]),
-    "tgt_layernorm_fwd": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_float, C.c_int, C.c_int, _P]),
+    "tgt_layernorm_fwd": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int64, C.c_float, C.c_int, C.c_int, _P]),
     "tgt_layernorm_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, _P]),
     "tgt_triplet_attn_workspace_bytes": (C.c_size_t, [C.POINTER(TripletAttnDesc), C.c_int]),
     "tgt_triplet_attn_fwd": (C.c_int, [C.POINTER(TripletAttnDesc), _P, _P, _P, _P, _P, C.c_size_t, _P]),

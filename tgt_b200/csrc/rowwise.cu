@@ -13,7 +13,7 @@ template <typename XT, typename YT>
 __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const XT *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ beta,
               YT *__restrict__ y, float *__restrict__ mean, float *__restrict__ rstd,
-              int64_t rows, int W, float eps) {
+              int64_t rows, int W, float eps, int64_t ldy) {
   constexpr int V = 4;                       // process 4 channels per lane per iteration (16B fp32 / 8B bf16)
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -59,7 +59,8 @@ ln_fwd_kernel(const XT *__restrict__ x, const float *__restrict__ gamma, const f
     }
     const float rs = rsqrtf(warp_sum(ss) / (float)W + eps);
     if (lane == 0) { mean[r] = mu; rstd[r] = rs; }
-    YT *yr = y + r * W;
+    YT *yr = y + r * ldy;
+    if (lane < ldy - W) yr[W + lane] = from_f<YT>(lane == 0 ? 1.f : 0.f);      // augmentation columns [1, 0, ...]
 #pragma unroll
     for (int it = 0; it < LN_MAX_ITERS; ++it) {
       if (it < iters) {
@@ -230,7 +231,7 @@ template <typename T> struct V8 {
 template <typename T, int RU>
 __global__ void __launch_bounds__(256)
 ln_fwd_w256(const T *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ beta,
-            T *__restrict__ y, float *__restrict__ mean, float *__restrict__ rstd, int64_t rows, float eps) {
+            T *__restrict__ y, float *__restrict__ mean, float *__restrict__ rstd, int64_t rows, float eps, int64_t ldy) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -262,7 +263,11 @@ ln_fwd_w256(const T *__restrict__ x, const float *__restrict__ gamma, const floa
       if (lane == 0) { mean[r0 + u] = mu; rstd[r0 + u] = rs; }
 #pragma unroll
       for (int q = 0; q < 8; ++q) v[q] = v[q] * rs * g[q] + bt[q];
-      *reinterpret_cast<uint4 *>(y + (r0 + u) * 256 + lane * 8) = V8<T>::pack(v);
+      *reinterpret_cast<uint4 *>(y + (r0 + u) * ldy + lane * 8) = V8<T>::pack(v);
+      if (ldy > 256 && lane == 0) {                  // augmentation columns [1, 0, 0, 0, 0, 0, 0, 0]
+        const float one[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        *reinterpret_cast<uint4 *>(y + (r0 + u) * ldy + 256) = V8<T>::pack(one);
+      }
     }
   }
 }
@@ -413,7 +418,9 @@ scaled_residual_kernel(const T *__restrict__ x, const RT *__restrict__ res, cons
 #pragma unroll
       for (int q = 0; q < NV; ++q) xv[q] = to_f(e[q]);
     }
-    if constexpr (sizeof(RT) == 4) {
+    if (res == nullptr) {
+      rv[0] = rv[1] = rv[2] = rv[3] = 0.f;
+    } else if constexpr (sizeof(RT) == 4) {
       float4 t = *reinterpret_cast<const float4 *>(res + off);
       rv[0] = t.x; rv[1] = t.y; rv[2] = t.z; rv[3] = t.w;
     } else {
@@ -447,15 +454,16 @@ static int grid_for(int64_t work_items, int per_block) {
 
 template <typename XT, typename YT>
 static int ln_fwd_launch(const void *x, const float *gamma, const float *beta, void *y, float *mean,
-                         float *rstd, int64_t rows, int W, float eps, cudaStream_t st) {
+                         float *rstd, int64_t rows, int W, float eps, int64_t ldy, cudaStream_t st) {
   if constexpr (sizeof(XT) == 2 && std::is_same<XT, YT>::value) {
-    if (W == 256 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0) {
-      ln_fwd_w256<XT, 4><<<grid_for(rows, 8 * 4), 256, 0, st>>>((const XT *)x, gamma, beta, (YT *)y, mean, rstd, rows, eps);
+    if (W == 256 && (ldy == 256 || ldy == 264) && (((uintptr_t)x | (uintptr_t)y) & 15) == 0) {
+      ln_fwd_w256<XT, 4><<<grid_for(rows, 8 * 4), 256, 0, st>>>((const XT *)x, gamma, beta, (YT *)y, mean, rstd, rows, eps,
+                                                                 ldy);
       return check_launch("ln_fwd_w256");
     }
   }
   ln_fwd_kernel<XT, YT><<<grid_for(rows, 8), 256, 0, st>>>((const XT *)x, gamma, beta, (YT *)y, mean, rstd,
-                                                            rows, W, eps);
+                                                            rows, W, eps, ldy);
   return check_launch("ln_fwd_kernel");
 }
 template <typename XT, typename YT>
@@ -490,13 +498,14 @@ using namespace tgt;
   X(TGT_F16, TGT_F16, __half, __half)
 
 extern "C" int tgt_layernorm_fwd(const void *x, const float *gamma, const float *beta, void *y, float *mean,
-                                 float *rstd, int64_t rows, int W, float eps, int x_dtype, int y_dtype,
+                                 float *rstd, int64_t rows, int W, int64_t ldy, float eps, int x_dtype, int y_dtype,
                                  void *stream) {
   if (W % 4 != 0 || W > LN_MAX_ITERS * 128) return fail("layernorm: W=%d unsupported (need W%%4==0, W<=%d)", W, LN_MAX_ITERS * 128);
+  if (ldy < W || ldy > W + 32 || ldy % 4) return fail("layernorm: ldy=%lld must be in [W, W+32] and a multiple of 4", (long long)ldy);
   if (rows <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
 #define X(xc, yc, XT, YT) \
-  if (x_dtype == xc && y_dtype == yc) return ln_fwd_launch<XT, YT>(x, gamma, beta, y, mean, rstd, rows, W, eps, st);
+  if (x_dtype == xc && y_dtype == yc) return ln_fwd_launch<XT, YT>(x, gamma, beta, y, mean, rstd, rows, W, eps, ldy, st);
   LN_COMBOS(X)
 #undef X
   return fail("layernorm_fwd: unsupported dtype combination x=%d y=%d", x_dtype, y_dtype);

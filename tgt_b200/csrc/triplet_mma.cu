@@ -19,6 +19,7 @@
 //     (adding the mask, applying the sigmoid), a post kernel scatters dE/dG back.  Both live in the caller-provided
 //     workspace.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace tgt {
 
@@ -104,6 +105,35 @@ __device__ __forceinline__ void load_a_xt(uint32_t (&a)[4], uint32_t base, int m
   ldsm_x4_t(a, base + xch_off(r, c));
 }
 
+// Rows whose N keys are ALL masked (padding atoms as queries) do not depend on j.  The reference gives them a
+// uniform softmax (the -3.4e38 mask absorbs the logits).  Make that exact and lse-representable: zero the row's
+// logit scale and bias, so x = 0, P = 1/N, lse2 = log2(N).  Returns the per-row logit scale.
+__device__ __forceinline__ void fix_fully_masked_rows(float (&eb)[8][4], float c1, float &c1r0, float &c1r1) {
+  int fm0 = 1, fm1 = 1;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    fm0 &= (eb[nt][0] <= -1e37f) & (eb[nt][1] <= -1e37f);
+    fm1 &= (eb[nt][2] <= -1e37f) & (eb[nt][3] <= -1e37f);
+  }
+  fm0 &= __shfl_xor_sync(0xffffffffu, fm0, 1);
+  fm0 &= __shfl_xor_sync(0xffffffffu, fm0, 2);
+  fm1 &= __shfl_xor_sync(0xffffffffu, fm1, 1);
+  fm1 &= __shfl_xor_sync(0xffffffffu, fm1, 2);
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    if (fm0) {
+      eb[nt][0] = eb[nt][0] == -INFINITY ? -INFINITY : 0.f;
+      eb[nt][1] = eb[nt][1] == -INFINITY ? -INFINITY : 0.f;
+    }
+    if (fm1) {
+      eb[nt][2] = eb[nt][2] == -INFINITY ? -INFINITY : 0.f;
+      eb[nt][3] = eb[nt][3] == -INFINITY ? -INFINITY : 0.f;
+    }
+  }
+  c1r0 = fm0 ? 0.f : c1;
+  c1r1 = fm1 ? 0.f : c1;
+}
+
 struct RowMap {
   int64_t bN;      // b * N
   int N, j, dir;
@@ -180,7 +210,7 @@ constexpr int FWD_STAGES = 4;
 constexpr int FWD_STAGE_BYTES = 3 * TN * HD * 2;      // Q, K, V tiles: 6 KB
 
 template <typename T>
-__global__ void __launch_bounds__(128, 3)
+__global__ void __launch_bounds__(128, 4)
 tri_attn_fwd_mma(const tgt_triplet_attn_desc D, const T *__restrict__ proj, const float *__restrict__ ws_e,
                  const __half *__restrict__ ws_g, T *__restrict__ va, float *__restrict__ stats) {
   __shared__ __align__(128) unsigned char smem[FWD_STAGES * FWD_STAGE_BYTES];
@@ -207,7 +237,8 @@ tri_attn_fwd_mma(const tgt_triplet_attn_desc D, const T *__restrict__ proj, cons
       gt[nt][1] = *reinterpret_cast<const uint32_t *>(ws_g + tbase + (m0 + g + 8) * TN + col);
     }
   }
-  const float c1 = D.scale * LOG2E;
+  float c1r0, c1r1;
+  fix_fully_masked_rows(eb, D.scale * LOG2E, c1r0, c1r1);
 
   RowMap rm{(int64_t)b * N, N, 0, dir};
   const int lrow = tid >> 1, lchunk = tid & 1;        // this thread's cp.async slot in each 64x16 tile
@@ -256,10 +287,10 @@ tri_attn_fwd_mma(const tgt_triplet_attn_desc D, const T *__restrict__ proj, cons
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      s[nt][0] = fmaf(s[nt][0], c1, eb[nt][0]);
-      s[nt][1] = fmaf(s[nt][1], c1, eb[nt][1]);
-      s[nt][2] = fmaf(s[nt][2], c1, eb[nt][2]);
-      s[nt][3] = fmaf(s[nt][3], c1, eb[nt][3]);
+      s[nt][0] = fmaf(s[nt][0], c1r0, eb[nt][0]);
+      s[nt][1] = fmaf(s[nt][1], c1r0, eb[nt][1]);
+      s[nt][2] = fmaf(s[nt][2], c1r1, eb[nt][2]);
+      s[nt][3] = fmaf(s[nt][3], c1r1, eb[nt][3]);
       mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
       mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
     }
@@ -306,10 +337,10 @@ tri_attn_fwd_mma(const tgt_triplet_attn_desc D, const T *__restrict__ proj, cons
       *reinterpret_cast<uint32_t *>(dst) = Mma<T>::pack(o[0][2] * inv1, o[0][3] * inv1);
       *reinterpret_cast<uint32_t *>(dst + 8) = Mma<T>::pack(o[1][2] * inv1, o[1][3] * inv1);
     }
-    if (q == 0) {
-      float *stp = stats + ((((int64_t)(b * 2 + dir) * H + h) * N + j) * N) * 2;
-      if (i0 < N) *reinterpret_cast<float2 *>(stp + 2 * i0) = make_float2(mx0, inv0);
-      if (i1 < N) *reinterpret_cast<float2 *>(stp + 2 * i1) = make_float2(mx1, inv1);
+    if (q == 0) {          // one float per row: log2-domain log-sum-exp  (P = exp2(x - lse2))
+      float *stp = stats + (((int64_t)(b * 2 + dir) * H + h) * N + j) * N;
+      if (i0 < N) stp[i0] = mx0 + __log2f(l0);
+      if (i1 < N) stp[i1] = mx1 + __log2f(l1);
     }
   }
   cp_async_wait<0>();
@@ -321,8 +352,8 @@ constexpr int BWD_STAGE_BYTES = 4 * TN * HD * 2;      // Q, K, V, dO tiles: 8 KB
 constexpr int XCH_BYTES = TN * TN * 2;                // one 64x64 16-bit exchange tile: 8 KB
 constexpr int BWD_SMEM = BWD_STAGES * BWD_STAGE_BYTES + 4 * XCH_BYTES;   // 24 KB + 2 x (dS, A) = 56 KB
 
-template <typename T>
-__global__ void __launch_bounds__(128, 2)
+template <typename T, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 tri_attn_bwd_mma(const tgt_triplet_attn_desc D, const T *__restrict__ proj, const float *__restrict__ ws_e,
                  const __half *__restrict__ ws_g, const T *__restrict__ dva, const float *__restrict__ stats,
                  T *__restrict__ dproj, float *__restrict__ ws_de, float *__restrict__ ws_dg) {
@@ -354,7 +385,8 @@ tri_attn_bwd_mma(const tgt_triplet_attn_desc D, const T *__restrict__ proj, cons
 #pragma unroll
     for (int c = 0; c < 4; ++c) de[nt][c] = dg[nt][c] = 0.f;
 
-  const float c1 = D.scale * LOG2E;
+  float c1r0, c1r1;
+  fix_fully_masked_rows(eb, D.scale * LOG2E, c1r0, c1r1);
   RowMap rm{(int64_t)b * N, N, 0, dir};
   const int lrow = tid >> 1, lchunk = tid & 1;
   const bool lvalid = lrow < N;
@@ -363,7 +395,7 @@ tri_attn_bwd_mma(const tgt_triplet_attn_desc D, const T *__restrict__ proj, cons
   const int offo = dir * H * HD + h * HD;
   const uint32_t ldst = tile_off(lrow, lchunk);
   const int i0 = m0 + g, i1 = m0 + g + 8;
-  const float *stb = stats + (((int64_t)(b * 2 + dir) * H + h) * N) * N * 2;
+  const float *stb = stats + (((int64_t)(b * 2 + dir) * H + h) * N) * N;
 
   auto issue = [&](int j) {
     if (j < N) {
@@ -377,25 +409,26 @@ tri_attn_bwd_mma(const tgt_triplet_attn_desc D, const T *__restrict__ proj, cons
     }
     cp_async_commit();
   };
-  auto load_stats = [&](int j, float2 &a, float2 &c) {
-    a = make_float2(0.f, 0.f);
-    c = make_float2(0.f, 0.f);
+  // rows beyond N (tile padding) get lse2 = +inf  ->  P = exp2(-inf) = 0 for the whole row
+  auto load_stats = [&](int j, float &a, float &c) {
+    a = INFINITY;
+    c = INFINITY;
     if (j < N) {
-      if (i0 < N) a = *reinterpret_cast<const float2 *>(stb + ((int64_t)j * N + i0) * 2);
-      if (i1 < N) c = *reinterpret_cast<const float2 *>(stb + ((int64_t)j * N + i1) * 2);
+      if (i0 < N) a = stb[(int64_t)j * N + i0];
+      if (i1 < N) c = stb[(int64_t)j * N + i1];
     }
   };
 
 #pragma unroll
   for (int s = 0; s < BWD_STAGES - 1; ++s) issue(s);
-  float2 st0, st1;
+  float st0, st1;
   load_stats(0, st0, st1);
 
   for (int j = 0; j < N; ++j) {
     cp_async_wait<BWD_STAGES - 2>();
     __syncthreads();                                   // (A) stage j landed; everyone is done with iteration j-1
     issue(j + BWD_STAGES - 1);
-    const float m2_0 = st0.x, inv0 = st0.y, m2_1 = st1.x, inv1 = st1.y;
+    const float lse0 = st0, lse1 = st1;
     load_stats(j + 1, st0, st1);
     const uint32_t st = sbase + (j % BWD_STAGES) * BWD_STAGE_BYTES;
     const uint32_t sQ = st, sK = st + TN * HD * 2, sV = st + 2 * TN * HD * 2, sO = st + 3 * TN * HD * 2;
@@ -428,8 +461,7 @@ tri_attn_bwd_mma(const tgt_triplet_attn_desc D, const T *__restrict__ proj, cons
       const float gg[4] = {g0.x, g0.y, g1.x, g1.y};
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const float m2 = c < 2 ? m2_0 : m2_1, inv = c < 2 ? inv0 : inv1;
-        const float p = fast_exp2(fmaf(s[nt][c], c1, eb[nt][c]) - m2) * inv;
+        const float p = fast_exp2(fmaf(s[nt][c], c < 2 ? c1r0 : c1r1, eb[nt][c]) - (c < 2 ? lse0 : lse1));
         const float dap = da[nt][c] * p;
         dg[nt][c] += dap;
         s[nt][c] = p;                      // P
@@ -597,9 +629,15 @@ static int bwd_impl(const tgt_triplet_attn_desc &D, const void *proj, const floa
   const size_t psm = 2 * (size_t)D.H * 65 * sizeof(float);
   tri_prep_bias_gate<T><<<dim3(TN, 2, D.B), 256, psm, st>>>(D, (const T *)proj, mask, w.e, w.g);
   if (int e = check_launch("tri_prep_bias_gate")) return e;
-  TGT_CUDA_OK(cudaFuncSetAttribute(tri_attn_bwd_mma<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
-  tri_attn_bwd_mma<T><<<dim3(D.H, 2, D.B), 128, BWD_SMEM, st>>>(D, (const T *)proj, w.e, w.g, (const T *)dva, stats,
-                                                                (T *)dproj, w.de, w.dg);
+  static const int minb = [] { const char *v = getenv("TGT_TRI_BWD_MINB"); return v ? atoi(v) : 2; }();   // tuning knob
+#define L(MB)                                                                                                         \
+  do {                                                                                                                \
+    TGT_CUDA_OK(cudaFuncSetAttribute(tri_attn_bwd_mma<T, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM)); \
+    tri_attn_bwd_mma<T, MB><<<dim3(D.H, 2, D.B), 128, BWD_SMEM, st>>>(D, (const T *)proj, w.e, w.g, (const T *)dva,    \
+                                                                      stats, (T *)dproj, w.de, w.dg);                 \
+  } while (0)
+  if (minb == 3) L(3); else L(2);
+#undef L
   if (int e = check_launch("tri_attn_bwd_mma")) return e;
   tri_post_bias_gate<T><<<dim3(D.N, 2, D.B), 256, psm, st>>>(D, w.de, w.dg, (T *)dproj);
   return check_launch("tri_post_bias_gate");

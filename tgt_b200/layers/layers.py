@@ -40,12 +40,18 @@ class EGT_Attention(nn.Module):
             self.lin_O_e = nn.Linear(self.num_heads, self.edge_width)
 
     def forward(self, h, e, mask):
+        h, e, _ = self.forward_alias(h, e, mask)
+        return h, e
+
+    def forward_alias(self, h, e, mask):
+        """forward() plus an alias of the input `e` to be used for the caller's residual add (its gradient is
+        then folded into the LayerNorm-backward kernel, see ops.LNLinearFn)."""
         cd = ops.compute_dtype(e)
         # node side: small [B*N, Wn] GEMMs -- plain library calls
         qkv = self.lin_QKV(self.mha_ln_h(h))
         # edge side: LN + projection to 2H channels (LN output recomputed in backward)
-        eg = ops.LNLinearFn.apply(e, self.mha_ln_e.weight, self.mha_ln_e.bias, self.lin_EG.weight,
-                                  self.lin_EG.bias, cd)
+        eg, e_alias = ops.LNLinearFn.apply(e, self.mha_ln_e.weight, self.mha_ln_e.bias, self.lin_EG.weight,
+                                           self.lin_EG.bias, cd)
         src = None
         if self.source_dropout > 0 and self.training:       # layers.py:55-59; RNG stays in PyTorch
             src = torch.empty((h.shape[0], h.shape[1]), dtype=torch.float32, device=h.device) \
@@ -54,7 +60,7 @@ class EGT_Attention(nn.Module):
         h = self.lin_O_h(vatt)
         if self.edge_update:
             e = self.lin_O_e(hhat)
-        return h, e
+        return h, e, e_alias
 
 
 class EdgeUpdate(nn.Module):
@@ -77,13 +83,17 @@ class EdgeUpdate(nn.Module):
         self.lin_O_e = nn.Linear(self.num_heads, self.edge_width)
 
     def forward(self, h, e, mask):
+        h, e, _ = self.forward_alias(h, e, mask)
+        return h, e
+
+    def forward_alias(self, h, e, mask):
         cd = ops.compute_dtype(e)
         qk = self.lin_QK(self.mha_ln_h(h))
-        eb = ops.LNLinearFn.apply(e, self.mha_ln_e.weight, self.mha_ln_e.bias, self.lin_E.weight,
-                                  self.lin_E.bias, cd)
+        eb, e_alias = ops.LNLinearFn.apply(e, self.mha_ln_e.weight, self.mha_ln_e.bias, self.lin_E.weight,
+                                           self.lin_E.bias, cd)
         hhat = ops.EGTCoreFn.apply(qk, eb, mask, None, self.num_heads, False, False, cd)
         e = self.lin_O_e(hhat)
-        return h, e
+        return h, e, e_alias
 
 
 class FFN(nn.Module):
@@ -105,17 +115,23 @@ class FFN(nn.Module):
         self.dropout = nn.Dropout(self.act_dropout)
 
     def forward(self, x):
-        if self.activation == 'gelu' and x.is_cuda:
+        return self.forward_alias(x)[0]
+
+    def forward_alias(self, x):
+        """(FFN(x), alias of x for the caller's residual add -- see ops.LNLinearFn)."""
+        if self.activation == 'gelu':
             p = self.act_dropout if self.training else 0.
             seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0 else 0      # CPU generator: no sync
             return ops.FFNGeluFn.apply(x, self.ffn_ln.weight, self.ffn_ln.bias, self.lin_W1.weight,
                                        self.lin_W1.bias, self.lin_W2.weight, self.lin_W2.bias, p, seed,
                                        ops.compute_dtype(x))
-        # gated activations (geglu/glu/swiglu) are not used by any shipped config: plain library ops
+        # gated activations (geglu/glu/swiglu) are not used by any shipped config: plain library ops on the
+        # LayerNorm / GEMMs (still CUDA-only: the residual kernels around this module refuse CPU tensors)
+        ops._require_cuda(x)
         x_ln = self.ffn_ln(x)
-        x = self.ffn_fn(self.lin_W1(x_ln))
-        x = self.dropout(x)
-        return self.lin_W2(x)
+        y = self.ffn_fn(self.lin_W1(x_ln))
+        y = self.dropout(y)
+        return self.lin_W2(y), x
 
 
 class DropPath(nn.Module):
@@ -194,29 +210,30 @@ class TGT_Layer(nn.Module):
         self.drop_path = DropPath(self.drop_path)
 
     def _residual(self, x, res):
-        """drop_path(x) then add the residual (layers.py:269-290), as one fused kernel on CUDA."""
-        scale = self.drop_path.sample_scale(x)
-        if x.is_cuda:
-            return ops.scaled_residual(x, res, scale)
-        if scale is not None:
-            x = x * scale.view(-1, *([1] * (x.ndim - 1))).to(x.dtype)
-        return x + res
+        """drop_path(x) then add the residual (layers.py:269-290), as one fused kernel."""
+        return ops.scaled_residual(x, res, self.drop_path.sample_scale(x))
 
     def forward(self, g):
         h, e, mask = g.h, g.e, g.mask
 
-        h_r1, e_r1 = h, e
-        h, e = self.update(h, e, mask)
+        # every sub-module also hands back an alias of its edge/node input; adding the residual to THAT routes the
+        # residual gradient into the sub-module's LayerNorm-backward kernel (ops.LNLinearFn) -- same values as the
+        # reference's `x.add_(x_r)` (layers.py:269-290)
+        h_r1 = h
+        h, e_new, e_r1 = self.update.forward_alias(h, e, mask)
 
         if self.node_update:
             h = self._residual(h, h_r1)
-            h = self._residual(self.node_ffn(h), h)
+            d, h_r2 = self.node_ffn.forward_alias(h)
+            h = self._residual(d, h_r2)
 
         if self.edge_update:
-            e = self._residual(e, e_r1)
+            e = self._residual(e_new, e_r1)
             if self._triplet_update:
-                e = self._residual(self.tria(e, mask), e)
-            e = self._residual(self.edge_ffn(e), e)
+                d, e_rt = self.tria.forward_alias(e, mask)
+                e = self._residual(d, e_rt)
+            d, e_r2 = self.edge_ffn.forward_alias(e)
+            e = self._residual(d, e_r2)
 
         g = g.copy()
         g.h, g.e = h, e

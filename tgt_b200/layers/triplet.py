@@ -76,6 +76,10 @@ class _AttentionFamily(_TripletBase):
         self._scale_factor = self._dot_dim ** -0.5
 
     def forward(self, e, mask):
+        return self.forward_alias(e, mask)[0]
+
+    def forward_alias(self, e, mask):
+        """(module(e), alias of e for the caller's residual add -- see ops.LNLinearFn)."""
         self._common_checks(e, mask)
         W, H, d = self.edge_width, self.num_heads, self._dot_dim
         dev = e.device
@@ -167,6 +171,9 @@ class _AggregateFamily(_TripletBase):
         self._scale_factor = self._dot_dim ** -0.5
 
     def forward(self, e, mask):
+        return self.forward_alias(e, mask)[0]
+
+    def forward_alias(self, e, mask):
         self._common_checks(e, mask)
         W, H, d = self.edge_width, self.num_heads, self._dot_dim
         dev = e.device
@@ -238,3 +245,5 @@ class TriangularUpdate(_TripletBase):
 
     def forward(self, e, mask):
         raise NotImplementedError("tgt_b200: TriangularUpdate has no CUDA kernel yet (no fallback by design)")
+
+    forward_alias = forward

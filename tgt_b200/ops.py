@@ -79,14 +79,22 @@ def _f32c(t: Tensor) -> Tensor:
 # ------------------------------------------------------------------------------------------
 # raw kernel wrappers (no autograd)
 # ------------------------------------------------------------------------------------------
-def layernorm_fwd(x2: Tensor, gamma: Tensor, beta: Tensor, out_dtype: torch.dtype, eps: float = 1e-5):
+AUG = 8          # augmentation columns appended to LayerNorm outputs: [1, 0, 0, 0, 0, 0, 0, 0]
+
+
+def layernorm_fwd(x2: Tensor, gamma: Tensor, beta: Tensor, out_dtype: torch.dtype, eps: float = 1e-5,
+                  aug: bool = False):
+    """y = LN(x).  With aug=True y is [rows, W+8] = [LN(x) | 1 | 0...]: `y[:, :W]` feeds the projection GEMM
+    (strided A operand) and the weight-gradient GEMM dP^T @ y_aug yields the bias gradient as its column W, so no
+    separate column-sum pass over the (up to 6.25x edge-sized) projection gradient is needed."""
     rows, W = x2.shape
-    y = torch.empty((rows, W), dtype=out_dtype, device=x2.device)
+    ldy = W + AUG if aug else W
+    y = torch.empty((rows, ldy), dtype=out_dtype, device=x2.device)
     mean = torch.empty(rows, dtype=torch.float32, device=x2.device)
     rstd = torch.empty(rows, dtype=torch.float32, device=x2.device)
     with timed(f"layernorm_fwd_W{W}"):
         _C.check(_C.lib().tgt_layernorm_fwd(_C.ptr(x2), _C.ptr(gamma), _C.ptr(beta), _C.ptr(y), _C.ptr(mean),
-                                            _C.ptr(rstd), rows, W, eps, _C.dtype_code(x2.dtype),
+                                            _C.ptr(rstd), rows, W, ldy, eps, _C.dtype_code(x2.dtype),
                                             _C.dtype_code(out_dtype), _C.stream_ptr()), "layernorm_fwd")
     return y, mean, rstd
 
@@ -110,6 +118,16 @@ def _workspace(nbytes: int, device):
     if nbytes == 0:
         return None, 0
     return torch.empty(nbytes, dtype=torch.uint8, device=device), nbytes
+
+
+def _dres_for(dalias: Optional[Tensor], x2: Tensor) -> Optional[Tensor]:
+    """Residual gradient (w.r.t. the aliased input) in the layout / dtype the LayerNorm backward kernel adds."""
+    if dalias is None:
+        return None
+    d = dalias.reshape(x2.shape)
+    if d.dtype != x2.dtype:
+        d = d.to(x2.dtype)
+    return d.contiguous()
 
 
 def _x_for_ln(e: Tensor, cdtype: torch.dtype) -> Tensor:
@@ -138,20 +156,27 @@ class LNLinearFn(Function):
             ctx.cdtype = cdtype
             ctx.in_dtype = x.dtype
             ctx.pdt = (ln_w.dtype, W.dtype, b.dtype)
-        return out                      # a fresh base tensor (never a view): callers add residuals in place
+            ctx.set_materialize_grads(False)
+        # `out` is a fresh base tensor (never a view): callers may add residuals in place.  `x` is returned as a
+        # second output (an alias): when the caller uses THAT for its residual add, the residual gradient arrives
+        # here as `dalias` and is folded into the LayerNorm backward kernel (dx = LN'(dy) + dres) instead of
+        # costing autograd an extra read-read-write accumulation pass over an edge-sized tensor.
+        return out, x
 
     @staticmethod
-    def backward(ctx, dout):
+    def backward(ctx, dout, dalias=None):
         x2, g, bt, Wc, mean, rstd = ctx.saved_tensors
         cd = ctx.cdtype
+        if dout is None:
+            return (dalias, None, None, None, None, None)
         with torch.autocast("cuda", enabled=False):
             do = dout.reshape(-1, dout.shape[-1]).to(cd).contiguous()
-            y, _, _ = layernorm_fwd(x2, g, bt, cd)
-            dW = torch.mm(do.t(), y)
-            db = do.sum(0, dtype=torch.float32)
+            y, _, _ = layernorm_fwd(x2, g, bt, cd, aug=True)
+            dWa = torch.mm(do.t(), y)                     # [out, W+8]: weight gradient | bias gradient
+            dW, db = dWa[:, :x2.shape[1]], dWa[:, x2.shape[1]]
             dy = torch.mm(do, Wc)
             del y
-            dx, dg, dbt = layernorm_bwd(dy, x2, g, mean, rstd)
+            dx, dg, dbt = layernorm_bwd(dy, x2, g, mean, rstd, _dres_for(dalias, x2))
         return (dx.view(*dout.shape[:-1], x2.shape[-1]).to(ctx.in_dtype), dg.to(ctx.pdt[0]), dbt.to(ctx.pdt[0]),
                 dW.to(ctx.pdt[1]), db.to(ctx.pdt[2]), None)
 
@@ -195,11 +220,14 @@ class TripletAttentionFn(Function):
             ctx.cdtype = cdtype
             ctx.in_dtype = e.dtype
             ctx.pdt = (ln_w.dtype, Wcat.dtype, bcat.dtype, Wo.dtype, bo.dtype)
-        return out
+            ctx.set_materialize_grads(False)
+        return out, e                   # (result, alias of the input for the caller's residual add: see LNLinearFn)
 
     @staticmethod
-    def backward(ctx, dout):
+    def backward(ctx, dout, dalias=None):
         x2, m3, g, bt, Wc, bc, Woc, mean, rstd, stats, va = ctx.saved_tensors
+        if dout is None:
+            return (dalias,) + (None,) * 9
         cd, desc = ctx.cdtype, ctx.desc
         B, N, W = desc.B, desc.N, x2.shape[1]
         with torch.autocast("cuda", enabled=False):
@@ -208,8 +236,8 @@ class TripletAttentionFn(Function):
             dbo = do.sum(0, dtype=torch.float32)
             dva = torch.mm(do, Woc)
             del do
-            y, _, _ = layernorm_fwd(x2, g, bt, cd)
-            proj = torch.addmm(bc, y, Wc.t())
+            y, _, _ = layernorm_fwd(x2, g, bt, cd, aug=True)
+            proj = torch.addmm(bc, y[:, :W], Wc.t())
             dproj = torch.empty_like(proj)
             ws, wsb = _workspace(_C.lib().tgt_triplet_attn_workspace_bytes(desc, 1), x2.device)
             with timed("triplet_attn_bwd"):
@@ -218,12 +246,12 @@ class TripletAttentionFn(Function):
                                                        _C.stream_ptr()), "triplet_attn_bwd")
             del ws
             del proj, dva
-            dWc = torch.mm(dproj.t(), y)
-            dbc = dproj.sum(0, dtype=torch.float32)
+            dWa = torch.mm(dproj.t(), y)                  # [C, W+8]: weight gradient | bias gradient (column W)
+            dWc, dbc = dWa[:, :W], dWa[:, W]
             del y
             dy = torch.mm(dproj, Wc)
             del dproj
-            dx, dg, dbt = layernorm_bwd(dy, x2, g, mean, rstd)
+            dx, dg, dbt = layernorm_bwd(dy, x2, g, mean, rstd, _dres_for(dalias, x2))
         p = ctx.pdt
         return (dx.view(B, N, N, W).to(ctx.in_dtype), None, dg.to(p[0]), dbt.to(p[0]), dWc.to(p[1]), dbc.to(p[2]),
                 dWo.to(p[3]), dbo.to(p[4]), None, None)
@@ -262,11 +290,14 @@ class TripletAggregateFn(Function):
             ctx.cdtype = cdtype
             ctx.in_dtype = e.dtype
             ctx.pdt = (ln_w.dtype, Wcat.dtype, bcat.dtype, Wo.dtype, bo.dtype)
-        return out
+            ctx.set_materialize_grads(False)
+        return out, e                   # (result, alias of the input for the caller's residual add: see LNLinearFn)
 
     @staticmethod
-    def backward(ctx, dout):
+    def backward(ctx, dout, dalias=None):
         x2, m3, g, bt, Wc, bc, Woc, mean, rstd, aw, va = ctx.saved_tensors
+        if dout is None:
+            return (dalias,) + (None,) * 9
         cd, desc = ctx.cdtype, ctx.desc
         B, N, W = desc.B, desc.N, x2.shape[1]
         with torch.autocast("cuda", enabled=False):
@@ -275,8 +306,8 @@ class TripletAggregateFn(Function):
             dbo = do.sum(0, dtype=torch.float32)
             dva = torch.mm(do, Woc)
             del do
-            y, _, _ = layernorm_fwd(x2, g, bt, cd)
-            proj = torch.addmm(bc, y, Wc.t())
+            y, _, _ = layernorm_fwd(x2, g, bt, cd, aug=True)
+            proj = torch.addmm(bc, y[:, :W], Wc.t())
             dproj = torch.empty_like(proj)
             daw = torch.empty_like(aw)
             with timed("triplet_aggr_bwd"):
@@ -284,12 +315,12 @@ class TripletAggregateFn(Function):
                                                        _C.ptr(daw), _C.ptr(dproj), _C.stream_ptr()),
                          "triplet_aggr_bwd")
             del proj, dva, daw
-            dWc = torch.mm(dproj.t(), y)
-            dbc = dproj.sum(0, dtype=torch.float32)
+            dWa = torch.mm(dproj.t(), y)                  # [C, W+8]: weight gradient | bias gradient (column W)
+            dWc, dbc = dWa[:, :W], dWa[:, W]
             del y
             dy = torch.mm(dproj, Wc)
             del dproj
-            dx, dg, dbt = layernorm_bwd(dy, x2, g, mean, rstd)
+            dx, dg, dbt = layernorm_bwd(dy, x2, g, mean, rstd, _dres_for(dalias, x2))
         p = ctx.pdt
         return (dx.view(B, N, N, W).to(ctx.in_dtype), None, dg.to(p[0]), dbt.to(p[0]), dWc.to(p[1]), dbc.to(p[2]),
                 dWo.to(p[3]), dbo.to(p[4]), None, None)
@@ -373,12 +404,15 @@ class FFNGeluFn(Function):
             ctx.save_for_backward(x2, g, bt, W1c, W2c, mean, rstd, u)
             ctx.meta = (float(p_drop), int(seed), cdtype, x.dtype,
                         (ln_w.dtype, W1.dtype, b1.dtype, W2.dtype, b2.dtype))
-        return out
+            ctx.set_materialize_grads(False)
+        return out, x                   # (result, alias of the input for the caller's residual add: see LNLinearFn)
 
     @staticmethod
-    def backward(ctx, dout):
+    def backward(ctx, dout, dalias=None):
         x2, g, bt, W1c, W2c, mean, rstd, u = ctx.saved_tensors
         p_drop, seed, cd, in_dtype, p = ctx.meta
+        if dout is None:
+            return (dalias,) + (None,) * 9
         with torch.autocast("cuda", enabled=False):
             do = dout.reshape(-1, dout.shape[-1]).to(cd).contiguous()
             a = torch.empty_like(u)
@@ -391,12 +425,12 @@ class FFNGeluFn(Function):
             _C.check(_C.lib().tgt_gelu_dropout_bwd(_C.ptr(u), _C.ptr(da), _C.ptr(du), u.numel(), p_drop, seed,
                                                    _C.dtype_code(cd), _C.stream_ptr()), "gelu_dropout_bwd")
             del da
-            y, _, _ = layernorm_fwd(x2, g, bt, cd)
-            dW1 = torch.mm(du.t(), y)
-            db1 = du.sum(0, dtype=torch.float32)
+            y, _, _ = layernorm_fwd(x2, g, bt, cd, aug=True)
+            dWa = torch.mm(du.t(), y)
+            dW1, db1 = dWa[:, :x2.shape[1]], dWa[:, x2.shape[1]]
             del y
             dy = torch.mm(du, W1c)
-            dx, dg, dbt = layernorm_bwd(dy, x2, g, mean, rstd)
+            dx, dg, dbt = layernorm_bwd(dy, x2, g, mean, rstd, _dres_for(dalias, x2))
         return (dx.view(*dout.shape[:-1], x2.shape[-1]).to(in_dtype), dg.to(p[0]), dbt.to(p[0]), dW1.to(p[1]),
                 db1.to(p[2]), dW2.to(p[3]), db2.to(p[4]), None, None, None)
 
@@ -425,8 +459,13 @@ class ScaledResidualFn(Function):
         dres = dout if dout.dtype == ctx.res_dtype else dout.to(ctx.res_dtype)
         if ctx.scale is None:
             return dout, dres, None
-        sc = ctx.scale.view(-1, *([1] * (dout.dim() - 1)))
-        return (dout * sc).to(dout.dtype), dres, None
+        dc = dout.contiguous()
+        dx = torch.empty_like(dc)
+        B = dc.shape[0]
+        _C.check(_C.lib().tgt_scaled_residual(_C.ptr(dc), None, _C.ptr(ctx.scale), _C.ptr(dx), B, dc.numel() // B,
+                                              _C.dtype_code(dc.dtype), _C.dtype_code(dc.dtype), _C.stream_ptr()),
+                 "scaled_residual(bwd)")
+        return dx, dres, None
 
 
 def scaled_residual(x: Tensor, res: Tensor, scale: Optional[Tensor]) -> Tensor:

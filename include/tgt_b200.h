@@ -137,6 +137,47 @@ int tgt_egt_attn_bwd(const tgt_egt_desc *desc, const void *qkv, const void *eg, 
                      const void *dvatt, void *dqkv, void *deg, void *workspace, size_t workspace_bytes,
                      void *stream);
 
+/* ---- tcgen05 / TMA projection GEMM with fused epilogues ----------------------------------------
+ * D[M,N] = epilogue(A[M,K] * B[N,K]^T); A (pitch lda), B (pitch ldb, the nn.Linear weight layout)
+ * and D (pitch ldd) are 16-bit (dtype = TGT_BF16 / TGT_F16), accumulation is fp32 in tensor memory.
+ * K <= 512 and K, N, pitches multiples of 8; all base pointers 16-byte aligned.
+ * replaces the nn.Linear calls on edge rows: lib/tgt/layers/triplet.py:210-211,229-230,249 (and
+ * 50-51,72), layers.py:52,82,113,126,157,159 -- and, through the epilogue flags, the ops around them:
+ *   TGT_EPI_LN    nn.LayerNorm in front of the Linear (triplet.py:207, layers.py:49,112,156): the GEMM
+ *                 runs on the raw rows with B = W*gamma; out = rstd_r*(acc - mean_r*col_sum_c) (+ bias')
+ *                 where col_sum_c = sum_k B[c,k] and bias' = bias + W beta are prepared by the caller
+ *   TGT_EPI_BIAS  + bias_c (fp32 vector)
+ *   TGT_EPI_GELU  exact GELU then dropout(p_drop, seed) with the same counter hash as
+ *                 tgt_gelu_dropout_fwd (layers.py:157-158); requires TGT_EPI_STORE_U: the 16-bit
+ *                 pre-activation is also written to U (pitch ldu, must be N for the hash to match)
+ *   TGT_EPI_RES   D = res + row_scale[row / rows_per_scale] * value  (DropPath + residual add,
+ *                 layers.py:163-177, 269-290); res is 16-bit (dtype) or fp32 (res_dtype), row_scale
+ *                 may be NULL (= 1)                                                                  */
+#define TGT_EPI_LN      1
+#define TGT_EPI_BIAS    2
+#define TGT_EPI_GELU    4
+#define TGT_EPI_RES     8
+#define TGT_EPI_STORE_U 16
+typedef struct {
+  int64_t M;
+  int32_t N, K;
+  int64_t lda, ldb, ldd;
+  int32_t dtype, flags;
+  const float *row_mean, *row_rstd, *col_sum, *bias, *row_scale;
+  const void *res;
+  int64_t ldres;
+  int32_t res_dtype, rows_per_scale;
+  void *U;
+  int64_t ldu;
+  float p_drop;
+  uint64_t seed;
+} tgt_gemm_desc;
+int tgt_gemm_tc(const tgt_gemm_desc *desc, const void *A, const void *B, void *D, void *stream);
+
+/* per-row LayerNorm statistics of x:[rows,W] (16-bit, pitch ldx): mean, rstd = 1/sqrt(var + eps)   */
+int tgt_row_stats(const void *x, float *mean, float *rstd, int64_t rows, int W, int64_t ldx, float eps,
+                  int dtype, void *stream);
+
 /* ---- FFN activation: y = dropout(gelu(u)) (exact erf GELU) -----------------------------------
  * replaces F.gelu + nn.Dropout at lib/tgt/layers/layers.py:157-158.  The keep mask is a
  * counter-based hash of (seed, element index): nothing is stored, backward regenerates it. */

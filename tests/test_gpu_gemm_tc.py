@@ -1,0 +1,96 @@
+"""tcgen05 / TMA GEMM (tgt_gemm_tc) and row statistics against plain PyTorch fp32 references of the same ops.
+Tolerances: the kernel accumulates bf16 products in fp32 and rounds once to bf16, so outputs must agree with the
+fp32 reference rounded to bf16 within 2 bf16 ulps of the row scale (rel 1e-2 element-wise on O(1) data)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from tgt_b200 import ops
+    return ops
+
+
+def _rand(shape, dtype, seed, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(shape, generator=g, device="cuda") * scale).to(dtype)
+
+
+def _close(got, ref, tol):
+    err = (got.float() - ref.float()).abs().max().item()
+    scale = ref.float().abs().max().item() + 1e-6
+    assert err <= tol * scale, f"max err {err:.3e} vs scale {scale:.3e}"
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 256), (4096, 1600, 256), (1000, 128, 256), (5000, 256, 64),
+                                   (777, 256, 512), (300, 64, 256), (130, 16, 16), (257, 1000, 136),
+                                   (70000, 256, 256)])
+def test_gemm_plain_and_bias(M, N, K, dtype):
+    ops = _ops()
+    a, w = _rand((M, K), dtype, 1), _rand((N, K), dtype, 2, K ** -0.5)
+    bias = _rand((N,), torch.float32, 3)
+    ref = a.float() @ w.float().t()
+    _close(ops.gemm_tc(a, w), ref, 6e-3)
+    _close(ops.gemm_tc(a, w, bias=bias), ref + bias, 6e-3)
+
+
+def test_gemm_strided_operands():
+    ops = _ops()
+    big = _rand((3000, 304), torch.bfloat16, 4)
+    a = big[:, 8:264]                                   # pitch 304 elements = 608 B, 16-byte aligned rows
+    w = _rand((256, 256), torch.bfloat16, 5, 1 / 16)
+    out = torch.zeros((3000, 512), dtype=torch.bfloat16, device="cuda")
+    ops.gemm_tc(a, w, out=out[:, 256:])
+    _close(out[:, 256:], a.float() @ w.float().t(), 6e-3)
+    assert out[:, :256].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("W,N", [(256, 1600), (256, 128), (64, 256)])
+def test_gemm_layernorm_fold(W, N):
+    ops = _ops()
+    M = 5000
+    x = (_rand((M, W), torch.float32, 6) * 1.7 + 0.4).to(torch.bfloat16)
+    gamma, beta = 1 + 0.1 * _rand((W,), torch.float32, 7), 0.1 * _rand((W,), torch.float32, 8)
+    Wt, b = _rand((N, W), torch.float32, 9, W ** -0.5), _rand((N,), torch.float32, 10)
+    ref = torch.nn.functional.layer_norm(x.float(), (W,), gamma, beta) @ Wt.t() + b
+    mean, rstd = ops.row_stats(x)
+    xf = x.float()
+    assert torch.allclose(mean, xf.mean(1), atol=1e-5)
+    assert torch.allclose(rstd, (xf.var(1, unbiased=False) + 1e-5).rsqrt(), rtol=1e-4)
+    wg = (Wt * gamma).to(torch.bfloat16)
+    out = ops.gemm_tc(x, wg, bias=b + Wt @ beta, ln=(mean, rstd, wg.float().sum(1)))
+    _close(out, ref, 1e-2)
+
+
+@pytest.mark.parametrize("res_dtype", [torch.bfloat16, torch.float32])
+def test_gemm_residual_droppath(res_dtype):
+    ops = _ops()
+    Bb, rows_per = 5, 900
+    M, N, K = Bb * rows_per, 256, 512
+    a, w = _rand((M, K), torch.bfloat16, 11), _rand((N, K), torch.bfloat16, 12, K ** -0.5)
+    bias = _rand((N,), torch.float32, 13)
+    res = _rand((M, N), res_dtype, 14)
+    scale = torch.tensor([1.25, 0.0, 1.25, 1.25, 0.0], device="cuda")
+    lin = (a.float() @ w.float().t() + bias).to(torch.bfloat16).float()
+    ref = res.float() + scale.repeat_interleave(rows_per)[:, None] * lin
+    _close(ops.gemm_tc(a, w, bias=bias, res=res, row_scale=scale, rows_per_scale=rows_per), ref, 8e-3)
+    _close(ops.gemm_tc(a, w, bias=bias, res=res), res.float() + lin, 8e-3)
+
+
+@pytest.mark.parametrize("p_drop", [0.0, 0.1])
+def test_gemm_gelu_dropout_matches_elementwise_kernel(p_drop):
+    """the fused epilogue must reproduce tgt_gelu_dropout_fwd (same hash, same element index) on its own U."""
+    from tgt_b200 import _C
+    ops = _ops()
+    M, N, K = 3000, 256, 256
+    a, w = _rand((M, K), torch.bfloat16, 15), _rand((N, K), torch.bfloat16, 16, K ** -0.5)
+    bias = _rand((N,), torch.float32, 17)
+    out, u = ops.gemm_tc(a, w, bias=bias, gelu=(p_drop, 1234567))
+    _close(u, a.float() @ w.float().t() + bias, 6e-3)
+    want = torch.empty_like(u)
+    _C.check(_C.lib().tgt_gelu_dropout_fwd(_C.ptr(u), _C.ptr(want), u.numel(), p_drop, 1234567,
+                                           _C.dtype_code(u.dtype), _C.stream_ptr()), "gelu_dropout_fwd")
+    assert (out.float() - want.float()).abs().max().item() <= 1e-2 * want.float().abs().max().item()
+    assert ((out == 0) == (want == 0)).float().mean().item() > 0.9999

@@ -47,6 +47,20 @@ class EgtDesc(C.Structure):
                 ("dtype", C.c_int32)]
 
 
+class GemmDesc(C.Structure):
+    _fields_ = [("M", C.c_int64), ("N", C.c_int32), ("K", C.c_int32),
+                ("lda", C.c_int64), ("ldb", C.c_int64), ("ldd", C.c_int64),
+                ("dtype", C.c_int32), ("flags", C.c_int32),
+                ("row_mean", C.c_void_p), ("row_rstd", C.c_void_p), ("col_sum", C.c_void_p),
+                ("bias", C.c_void_p), ("row_scale", C.c_void_p),
+                ("res", C.c_void_p), ("ldres", C.c_int64), ("res_dtype", C.c_int32),
+                ("rows_per_scale", C.c_int32),
+                ("U", C.c_void_p), ("ldu", C.c_int64),
+                ("p_drop", C.c_float), ("seed", C.c_uint64)]
+
+
+EPI_LN, EPI_BIAS, EPI_GELU, EPI_RES, EPI_STORE_U = 1, 2, 4, 8, 16
+
 _P = C.c_void_p
 _SIGNATURES = {
     "tgt_version": (C.c_int, []),
@@ -65,6 +79,8 @@ _SIGNATURES = {
     "tgt_egt_attn_bwd": (C.c_int, [C.POINTER(EgtDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "tgt_gelu_dropout_fwd": (C.c_int, [_P, _P, C.c_int64, C.c_float, C.c_uint64, C.c_int, _P]),
     "tgt_gelu_dropout_bwd": (C.c_int, [_P, _P, _P, C.c_int64, C.c_float, C.c_uint64, C.c_int, _P]),
+    "tgt_gemm_tc": (C.c_int, [C.POINTER(GemmDesc), _P, _P, _P, _P]),
+    "tgt_row_stats": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, C.c_int64, C.c_float, C.c_int, _P]),
     "tgt_scaled_residual": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int, C.c_int, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

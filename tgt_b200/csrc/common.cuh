@@ -67,6 +67,42 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// ---------------------------------------------------------------- counter-based dropout (shared by the elementwise
+// gelu_dropout kernels and the fused GEMM epilogue: nothing is stored, backward regenerates the mask)
+// One 32-bit hash serves TWO neighbouring elements (16 bits each): element idx is dropped iff its 16-bit lane of
+// hash(idx >> 1) is below round(p * 65536); the survivors are scaled by 65536 / (65536 - threshold).
+struct DropCfg {
+  uint32_t seed_mix, thresh16;
+  float keep_scale;
+};
+__host__ __device__ inline DropCfg make_drop_cfg(float p_drop, unsigned long long seed) {
+  DropCfg c;
+  c.seed_mix = (uint32_t)seed * 0x9E3779B9u + (uint32_t)(seed >> 32) * 0x85EBCA6Bu + 0x27D4EB2Fu;
+  float t = p_drop * 65536.f + 0.5f;
+  c.thresh16 = p_drop > 0.f ? (uint32_t)(t < 1.f ? 1.f : (t > 65535.f ? 65535.f : t)) : 0u;
+  c.keep_scale = 65536.f / (float)(65536u - c.thresh16);
+  return c;
+}
+__device__ __forceinline__ uint32_t drop_hash_pair(const DropCfg &c, uint64_t pair_idx) {
+  uint32_t x = ((uint32_t)pair_idx ^ c.seed_mix) + (uint32_t)(pair_idx >> 32) * 0xC2B2AE35u;
+  x ^= x >> 16;
+  x *= 0x7FEB352Du;
+  x ^= x >> 15;
+  x *= 0x846CA68Bu;
+  x ^= x >> 16;
+  return x;
+}
+// multipliers (0 or keep_scale) of elements 2*pair_idx and 2*pair_idx + 1
+__device__ __forceinline__ void drop_mask_pair(const DropCfg &c, uint64_t pair_idx, float &m0, float &m1) {
+  const uint32_t h = drop_hash_pair(c, pair_idx);
+  m0 = (h & 0xFFFFu) < c.thresh16 ? 0.f : c.keep_scale;
+  m1 = (h >> 16) < c.thresh16 ? 0.f : c.keep_scale;
+}
+__device__ __forceinline__ float drop_mask_one(const DropCfg &c, uint64_t idx) {
+  const uint32_t h = drop_hash_pair(c, idx >> 1);
+  return ((idx & 1) ? (h >> 16) : (h & 0xFFFFu)) < c.thresh16 ? 0.f : c.keep_scale;
+}
+
 // 16-byte vector of T
 template <typename T> struct Vec16 { static constexpr int n = 16 / sizeof(T); };
 

@@ -1,0 +1,691 @@
+// Persistent, warp-specialised tcgen05 GEMM for the edge-channel projections of the TGT hot path:
+//
+//     D[M, N] = epilogue( A[M, K] * B[N, K]^T )          A, B, D 16-bit (bf16 / fp16), fp32 accumulation in TMEM
+//
+// M = B*N*N edge rows (~1e6), K <= 512, N <= a few thousand: the weight matrix is tiny and the activation matrix is
+// huge, so the kernel is WEIGHT-STATIONARY: N is cut into column slices of width bn <= 256; one CTA owns a slice,
+// loads its [bn, K] weight panel into shared memory ONCE (TMA, 128B swizzle) and then streams 128-row activation
+// tiles through a TMA ring.  One elected thread issues tcgen05.mma (M=128, N=bn, K=16) into one of two TMEM
+// accumulators while four epilogue warps drain the other one (tcgen05.ld 32x32b), apply the fused epilogue and store
+// with 16-byte vectors.  L2->SMEM traffic is 64 KB per 128x256x256 tile (32 B/clk/SM at full tensor rate), which is
+// what lets small-K GEMMs run at tensor-core speed without 2-CTA multicast.
+//
+// Fused epilogues (flags):
+//   LN    : the GEMM runs on the RAW rows x and  LN(x) W^T  is recovered as  rstd_r * (acc - mean_r * colsum_c) + b'_c
+//           with B = W o gamma, colsum_c = sum_k B[c,k], b' = b + W beta   (replaces nn.LayerNorm -> nn.Linear,
+//           lib/tgt/layers/triplet.py:207-211, layers.py:49-52,112-113,156-157)
+//   BIAS  : + bias_c
+//   GELU  : exact-erf GELU followed by counter-hash dropout (layers.py:157-158); optionally also stores the
+//           pre-activation U (saved for backward)
+//   RES   : D = res + scale[row / rows_per_scale] * v   (DropPath + residual add, layers.py:163-177, 269-290)
+#include "common.cuh"
+#include <cuda.h>
+#include <mutex>
+
+namespace tgt {
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint32_t bar, uint32_t dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, M = 128, N from idesc, K = 16 (16-bit operands)
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns: thread t of the warp gets lane (quadrant*32 + t)
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile with 128-byte rows, 128B swizzle: 8-row groups are 1024 B apart (SBO), LBO unused.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: fp32 accumulate, A/B K-major, M = 128
+template <typename T> __device__ __forceinline__ uint32_t umma_idesc(int n) {
+  const uint32_t fmt = (sizeof(T) == 2 && DT<T>::code == TGT_BF16) ? 1u : 0u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------- kernel
+enum : int { EPI_LN = 1, EPI_BIAS = 2, EPI_GELU = 4, EPI_RES = 8, EPI_STORE_U = 16, EPI_RES_F32 = 32 };
+
+struct GemmParams {
+  int64_t M;
+  int N, K, bn, n_slices, ctas_per_slice, kblocks, stages, tmem_cols;
+  void *D;
+  int64_t ldd;
+  void *U;
+  int64_t ldu;
+  const float *row_mean, *row_rstd, *col_sum, *bias, *row_scale;
+  const void *res;
+  int64_t ldres;
+  int rows_per_scale;
+  float p_drop;
+  unsigned long long seed;
+  int flags;
+};
+
+constexpr int GEMM_THREADS = 320;      // warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: epilogue
+constexpr int EPI_WARPS = 8;           // two per TMEM lane quadrant (they interleave 32-column groups)
+constexpr int A_STAGE_BYTES = 128 * 128;
+__host__ __device__ constexpr int epi_stage_bytes(int flags) { return EPI_WARPS * ((flags & 16) ? 4096 : 2048); }
+
+// GELU(u) = u * Phi(u) with Phi from the Abramowitz-Stegun 7.1.26 erfc approximation (|error| < 2e-7 in Phi): two MUFU
+// ops and ~10 FMA-pipe instructions per element -- the epilogue is issue-bound, CUDA's erff costs 3x as much.
+__device__ __forceinline__ float gelu_fast(float u) {
+  const float ax = fabsf(u) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.f)));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * ax * ax));
+  const float h = 0.5f * poly * t * e;          // 0.5 * erfc(|u| / sqrt 2)
+  return u * (u < 0.f ? h : 1.f - h);
+}
+
+template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t *>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t *>(&h);
+}
+template <typename T> __device__ __forceinline__ void unpack2(uint32_t w, float &a, float &b);
+template <> __device__ __forceinline__ void unpack2<__nv_bfloat16>(uint32_t w, float &a, float &b) {
+  a = __uint_as_float(w << 16);
+  b = __uint_as_float(w & 0xFFFF0000u);
+}
+template <> __device__ __forceinline__ void unpack2<__half>(uint32_t w, float &a, float &b) {
+  float2 f = __half22float2(*reinterpret_cast<__half2 *>(&w));
+  a = f.x;
+  b = f.y;
+}
+
+// 32 lanes x 32 consecutive fp32 columns
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 w;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "r"(addr) : "memory");
+  return w;
+}
+// staging tile of one epilogue warp: 32 rows x 4 pieces of 16 B (32 output columns), xor-swizzled so that both the
+// row-per-lane writes and the 8-rows-x-64-B coalesced reads are bank-conflict free
+__device__ __forceinline__ uint32_t stage_addr(uint32_t base, int row, int piece) {
+  return base + row * 64 + ((piece ^ ((row >> 1) & 3)) << 4);
+}
+
+template <typename T, int FLAGS>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int slice = blockIdx.x % p.n_slices;
+  const int q = blockIdx.x / p.n_slices;
+  const int64_t num_m_tiles = (p.M + 127) / 128;
+  const int bn = p.bn;
+
+  // shared memory carve-up (all operand regions 1024-byte aligned)
+  const uint32_t sB = smem_base;                                           // kblocks x [bn rows x 128 B]
+  const uint32_t sA = sB + (uint32_t)p.kblocks * bn * 128;                 // stages x 16 KB
+  const uint32_t sStage = sA + (uint32_t)p.stages * A_STAGE_BYTES;         // 8 warps x (D 2 KB [+ U 2 KB])
+  const uint32_t sVec = sStage + epi_stage_bytes(FLAGS);                         // colsum[256], bias[256] fp32
+  const uint32_t sBar = sVec + 2048;                                       // mbarriers
+  float *vec_colsum = reinterpret_cast<float *>(smem_gen + (sVec - smem_base));
+  float *vec_bias = vec_colsum + 256;
+  const uint32_t bar_full = sBar, bar_empty = sBar + 8 * 8, bar_bfull = sBar + 16 * 8;
+  const uint32_t bar_tfull = sBar + 17 * 8, bar_tempty = sBar + 19 * 8;
+  const uint32_t tmem_slot = sBar + 21 * 8;
+  volatile uint32_t *tmem_slot_gen = reinterpret_cast<volatile uint32_t *>(smem_gen + (tmem_slot - smem_base));
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(bar_full + i * 8, 1);
+      mbar_init(bar_empty + i * 8, 1);
+    }
+    mbar_init(bar_bfull, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_tfull + i * 8, 1);
+      mbar_init(bar_tempty + i * 8, EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tc_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (q < p.ctas_per_slice) {
+    if (warp == 0) {
+      // ------------------------------------------------------------------ TMA producer
+      if (lane == 0) {
+        mbar_expect_tx(bar_bfull, (uint32_t)p.kblocks * bn * 128);
+        for (int kb = 0; kb < p.kblocks; ++kb) tma_load_2d(&tmB, bar_bfull, sB + kb * bn * 128, kb * 64, slice * bn);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int64_t mt = q; mt < num_m_tiles; mt += p.ctas_per_slice) {
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait(bar_empty + stage * 8, phase ^ 1);
+            mbar_expect_tx(bar_full + stage * 8, A_STAGE_BYTES);
+            tma_load_2d(&tmA, bar_full + stage * 8, sA + stage * A_STAGE_BYTES, kb * 64, (int)(mt * 128));
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ------------------------------------------------------------------ MMA issuer (one thread)
+      if (lane == 0) {
+        const uint32_t idesc = umma_idesc<T>(bn);
+        mbar_wait(bar_bfull, 0);
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        for (int64_t mt = q; mt < num_m_tiles; mt += p.ctas_per_slice) {
+          mbar_wait(bar_tempty + acc * 8, acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + (uint32_t)(acc * bn);
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait(bar_full + stage * 8, phase);
+            tc_fence_after();
+            const int ksteps = min(4, (p.K - kb * 64 + 15) / 16);
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t ad = umma_desc_sw128(sA + stage * A_STAGE_BYTES + k * 32);
+              const uint64_t bd = umma_desc_sw128(sB + kb * bn * 128 + k * 32);
+              tc_mma(tmem_d, ad, bd, idesc, (uint32_t)((kb | k) != 0));
+            }
+            tc_commit(bar_empty + stage * 8);
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          tc_commit(bar_tfull + acc * 8);
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+        }
+      }
+    } else {
+      // ------------------------------------------------------------------ epilogue warps (TMEM lane quadrant = warp % 4)
+      const int quad = warp & 3;
+      const int half = (warp - 2) >> 2;  // which 32-column groups this warp drains: half, half + 2, ...
+      const int et = threadIdx.x - 64;   // 0..255
+      const int col0 = slice * bn;
+      {
+        const int gc = col0 + et;
+        vec_colsum[et] = ((FLAGS & EPI_LN) && et < bn && gc < p.N) ? p.col_sum[gc] : 0.f;
+        vec_bias[et] = ((FLAGS & EPI_BIAS) && et < bn && gc < p.N) ? p.bias[gc] : 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const DropCfg dc = make_drop_cfg(p.p_drop, p.seed);
+      constexpr uint32_t STAGE_PER_WARP = (FLAGS & EPI_STORE_U) ? 4096u : 2048u;
+      const uint32_t stD = sStage + (uint32_t)(warp - 2) * STAGE_PER_WARP, stU = stD + 2048;
+      const int crow = lane >> 2, cpiece = lane & 3;     // coalesced phase: 8 rows x 4 pieces per instruction
+      constexpr int RW = (FLAGS & EPI_RES_F32) ? 2 : 1;
+      T *Dp = reinterpret_cast<T *>(p.D);
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int64_t mt = q; mt < num_m_tiles; mt += p.ctas_per_slice) {
+        const int64_t row0 = mt * 128 + quad * 32;
+        const int64_t row = row0 + lane;
+        float rstd = 1.f, nmr = 0.f;
+        if ((FLAGS & EPI_LN) && row < p.M) {
+          rstd = p.row_rstd[row];
+          nmr = -p.row_mean[row] * rstd;
+        }
+        float rscale[4] = {1.f, 1.f, 1.f, 1.f};
+        if ((FLAGS & EPI_RES) && p.row_scale) {
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int64_t r = row0 + it * 8 + crow;
+            if (r < p.M) rscale[it] = p.row_scale[r / p.rows_per_scale];
+          }
+        }
+        // residual values of the coalesced phase are fetched one 32-column group ahead
+        uint4 rcur[4][RW], rnext[4][RW];
+        auto res_load = [&](int c, uint4(&rb)[4][RW]) {
+          const int gc = col0 + c + cpiece * 8;
+          if (c + cpiece * 8 < bn && gc < p.N) {
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int64_t grow = row0 + it * 8 + crow;
+              if (grow < p.M) {
+                if (FLAGS & EPI_RES_F32) {
+                  const float *rp = reinterpret_cast<const float *>(p.res) + grow * p.ldres + gc;
+                  rb[it][0] = *reinterpret_cast<const uint4 *>(rp);
+                  rb[it][RW - 1] = *reinterpret_cast<const uint4 *>(rp + 4);
+                } else {
+                  rb[it][0] = *reinterpret_cast<const uint4 *>(reinterpret_cast<const T *>(p.res) + grow * p.ldres + gc);
+                }
+              }
+            }
+          }
+        };
+        if (FLAGS & EPI_RES) res_load(half * 32, rcur);
+        mbar_wait(bar_tfull + acc * 8, acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * bn);
+        for (int c = half * 32; c < bn; c += 64) {
+          uint32_t v[32];
+          tc_ld32(taddr + c, v);
+          if ((FLAGS & EPI_RES) && c + 64 < bn) res_load(c + 64, rnext);
+          tc_ld_wait();
+          // ---- TMEM domain (lane = row): LN fold, bias, activation; 16-bit results go to the staging tile
+#pragma unroll
+          for (int pc = 0; pc < 4; ++pc) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[pc * 8 + i]);
+            if (FLAGS & EPI_LN) {
+              const float4 c0 = *reinterpret_cast<const float4 *>(vec_colsum + c + pc * 8);
+              const float4 c1 = *reinterpret_cast<const float4 *>(vec_colsum + c + pc * 8 + 4);
+              const float cs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], rstd, nmr * cs[i]);
+            }
+            if (FLAGS & EPI_BIAS) {
+              const float4 b0 = *reinterpret_cast<const float4 *>(vec_bias + c + pc * 8);
+              const float4 b1 = *reinterpret_cast<const float4 *>(vec_bias + c + pc * 8 + 4);
+              const float bs[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] += bs[i];
+            }
+            if (FLAGS & EPI_GELU) {
+              uint4 wu;
+              wu.x = pack2<T>(f[0], f[1]);
+              wu.y = pack2<T>(f[2], f[3]);
+              wu.z = pack2<T>(f[4], f[5]);
+              wu.w = pack2<T>(f[6], f[7]);
+              st_shared_v4(stage_addr(stU, lane, pc), wu);
+              const uint32_t wr[4] = {wu.x, wu.y, wu.z, wu.w};
+              const uint64_t pair0 = (uint64_t)(row * p.ldu + col0 + c + pc * 8) >> 1;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                // the activation is computed from the ROUNDED pre-activation: backward recomputes from the stored U
+                float u0, u1, m0 = 1.f, m1 = 1.f;
+                unpack2<T>(wr[j], u0, u1);
+                if (p.p_drop > 0.f) drop_mask_pair(dc, pair0 + j, m0, m1);
+                f[2 * j] = gelu_fast(u0) * m0;
+                f[2 * j + 1] = gelu_fast(u1) * m1;
+              }
+            }
+            uint4 w;
+            w.x = pack2<T>(f[0], f[1]);
+            w.y = pack2<T>(f[2], f[3]);
+            w.z = pack2<T>(f[4], f[5]);
+            w.w = pack2<T>(f[6], f[7]);
+            st_shared_v4(stage_addr(stD, lane, pc), w);
+          }
+          __syncwarp();
+          // ---- coalesced domain: each instruction moves 8 rows x 64 contiguous bytes
+          const int gc = col0 + c + cpiece * 8;
+          if (c + cpiece * 8 < bn && gc < p.N) {
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int r = it * 8 + crow;
+              const int64_t grow = row0 + r;
+              if (grow < p.M) {
+                uint4 w = ld_shared_v4(stage_addr(stD, r, cpiece));
+                if (FLAGS & EPI_RES) {
+                  const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+                  float f[8];
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) unpack2<T>(ww[j], f[2 * j], f[2 * j + 1]);
+                  if (FLAGS & EPI_RES_F32) {
+                    const uint4 q0 = rcur[it][0], q1 = rcur[it][RW - 1];
+                    const uint32_t rr[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], rscale[it], __uint_as_float(rr[i]));
+                  } else {
+                    const uint32_t rw[4] = {rcur[it][0].x, rcur[it][0].y, rcur[it][0].z, rcur[it][0].w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      float a, b;
+                      unpack2<T>(rw[j], a, b);
+                      f[2 * j] = fmaf(f[2 * j], rscale[it], a);
+                      f[2 * j + 1] = fmaf(f[2 * j + 1], rscale[it], b);
+                    }
+                  }
+                  w.x = pack2<T>(f[0], f[1]);
+                  w.y = pack2<T>(f[2], f[3]);
+                  w.z = pack2<T>(f[4], f[5]);
+                  w.w = pack2<T>(f[6], f[7]);
+                }
+                *reinterpret_cast<uint4 *>(Dp + grow * p.ldd + gc) = w;
+                if (FLAGS & EPI_STORE_U)
+                  *reinterpret_cast<uint4 *>(reinterpret_cast<T *>(p.U) + grow * p.ldu + gc) =
+                      ld_shared_v4(stage_addr(stU, r, cpiece));
+              }
+            }
+          }
+          __syncwarp();
+          if (FLAGS & EPI_RES) {
+#pragma unroll
+            for (int it = 0; it < 4; ++it)
+#pragma unroll
+              for (int k = 0; k < RW; ++k) rcur[it][k] = rnext[it][k];
+          }
+        }
+        tc_fence_before();
+        if (lane == 0) mbar_arrive(bar_tempty + acc * 8);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tc_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// per-row mean / rstd of x:[rows, W]: one warp per ROWS consecutive rows, ITS 16-byte vectors per lane and row
+// (all loads of an iteration are issued before the first reduction, so each warp keeps ROWS*ITS*512 B in flight)
+template <typename T, int ROWS, int ITS>
+__global__ void __launch_bounds__(256) row_stats_kernel(const T *__restrict__ x, float *__restrict__ mean,
+                                                        float *__restrict__ rstd, int64_t rows, int W, int64_t ldx,
+                                                        float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  constexpr int NV = 16 / sizeof(T);
+  for (int64_t r0 = warp0 * ROWS; r0 < rows; r0 += nwarps * ROWS) {
+    float v[ROWS][ITS][NV];
+#pragma unroll
+    for (int rr = 0; rr < ROWS; ++rr) {
+#pragma unroll
+      for (int it = 0; it < ITS; ++it) {
+        const int c = (it * 32 + lane) * NV;
+        if (r0 + rr < rows && c < W) {
+          load_vec<T, NV>(x + (r0 + rr) * ldx + c, v[rr][it]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < NV; ++i) v[rr][it][i] = 0.f;
+        }
+      }
+    }
+#pragma unroll
+    for (int rr = 0; rr < ROWS; ++rr) {
+      float s = 0.f;
+#pragma unroll
+      for (int it = 0; it < ITS; ++it)
+#pragma unroll
+        for (int i = 0; i < NV; ++i) s += v[rr][it][i];
+      s = warp_sum(s);
+      const float mu = s / (float)W;
+      float qd = 0.f;
+#pragma unroll
+      for (int it = 0; it < ITS; ++it) {
+        const int c = (it * 32 + lane) * NV;
+        if (c < W) {
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            const float d = v[rr][it][i] - mu;
+            qd += d * d;
+          }
+        }
+      }
+      qd = warp_sum(qd);
+      if (lane == 0 && r0 + rr < rows) {
+        mean[r0 + rr] = mu;
+        rstd[r0 + rr] = rsqrtf(qd / (float)W + eps);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+// 2-D K-major operand map: rows x K elements of 2 bytes, row pitch ld elements; box = 64 columns x box_rows, 128B swizzle
+static int make_operand_map(CUtensorMap *map, const void *base, int64_t rows, int K, int64_t ld, int box_rows,
+                            int dtype) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return fail("gemm_tc: cuTensorMapEncodeTiled is not available from the driver");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 2) % 16)
+    return fail("gemm_tc: operand base / pitch must be 16-byte aligned");
+  const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUtensorMapDataType dt = dtype == TGT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = enc(map, dt, 2, const_cast<void *>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("gemm_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+template <typename T, int FLAGS>
+static int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const GemmParams &p, size_t smem, cudaStream_t st) {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    cudaFuncSetAttribute(gemm_tc_kernel<T, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  });
+  gemm_tc_kernel<T, FLAGS><<<p.n_slices * p.ctas_per_slice, GEMM_THREADS, smem, st>>>(ma, mb, p);
+  return check_launch("gemm_tc");
+}
+
+template <typename T>
+static int dispatch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const GemmParams &p, size_t smem,
+                         cudaStream_t st) {
+  switch (p.flags) {
+#define TGT_GEMM_CASE(F) \
+  case (F): return launch_gemm<T, (F)>(ma, mb, p, smem, st);
+    TGT_GEMM_CASE(0)
+    TGT_GEMM_CASE(EPI_BIAS)
+    TGT_GEMM_CASE(EPI_LN | EPI_BIAS)
+    TGT_GEMM_CASE(EPI_LN | EPI_BIAS | EPI_GELU | EPI_STORE_U)
+    TGT_GEMM_CASE(EPI_BIAS | EPI_GELU | EPI_STORE_U)
+    TGT_GEMM_CASE(EPI_BIAS | EPI_RES)
+    TGT_GEMM_CASE(EPI_BIAS | EPI_RES | EPI_RES_F32)
+    TGT_GEMM_CASE(EPI_RES)
+#undef TGT_GEMM_CASE
+    default: return fail("gemm_tc: unsupported epilogue flag combination %d", p.flags);
+  }
+}
+
+}  // namespace tgt
+
+using namespace tgt;
+
+extern "C" int tgt_gemm_tc(const tgt_gemm_desc *g, const void *A, const void *B, void *D, void *stream) {
+  if (!g || !A || !B || !D) return fail("gemm_tc: null argument");
+  if (g->dtype != TGT_BF16 && g->dtype != TGT_F16) return fail("gemm_tc: operands must be bf16 or fp16");
+  if (g->M <= 0 || g->N <= 0 || g->K <= 0) return fail("gemm_tc: bad shape M=%lld N=%d K=%d", (long long)g->M, g->N, g->K);
+  if (g->M >= (1ll << 31) - 128) return fail("gemm_tc: M too large for a 32-bit TMA coordinate");
+  if (g->K % 8 || g->N % 8 || g->ldd % 8) return fail("gemm_tc: K, N and ldd must be multiples of 8");
+  if (g->K > 512) return fail("gemm_tc: K=%d > 512 unsupported (weight panel must fit in shared memory)", g->K);
+  if ((reinterpret_cast<uintptr_t>(D) & 15)) return fail("gemm_tc: D must be 16-byte aligned");
+  int flags = g->flags;
+  if ((flags & EPI_LN) && (!g->row_mean || !g->row_rstd || !g->col_sum)) return fail("gemm_tc: LN epilogue needs row stats and column sums");
+  if ((flags & EPI_BIAS) && !g->bias) return fail("gemm_tc: BIAS epilogue without bias");
+  if ((flags & EPI_RES) && (!g->res || g->ldres % 8 || (reinterpret_cast<uintptr_t>(g->res) & 15)))
+    return fail("gemm_tc: RES epilogue needs a 16-byte aligned residual with ldres %% 8 == 0");
+  if ((flags & EPI_RES) && g->row_scale && g->rows_per_scale <= 0) return fail("gemm_tc: rows_per_scale must be > 0");
+  if (flags & EPI_STORE_U) {
+    if (!(flags & EPI_GELU) || !g->U || g->ldu % 8 || (reinterpret_cast<uintptr_t>(g->U) & 15))
+      return fail("gemm_tc: STORE_U needs GELU and a 16-byte aligned U with ldu %% 8 == 0");
+  }
+  if ((flags & EPI_GELU) && !(flags & EPI_STORE_U)) return fail("gemm_tc: GELU epilogue is only built with STORE_U");
+  if ((flags & EPI_GELU) && (g->p_drop < 0.f || g->p_drop >= 1.f)) return fail("gemm_tc: p_drop=%f out of range", g->p_drop);
+
+  GemmParams p{};
+  p.M = g->M;
+  p.N = g->N;
+  p.K = g->K;
+  p.kblocks = (g->K + 63) / 64;
+  // widest slice whose weight panel leaves room for >= 3 activation stages
+  const int smem_budget = 232448 - 1024 - 2048 - 256 - epi_stage_bytes(flags);
+  int bn_max = 256;
+  while (bn_max > 16 && p.kblocks * bn_max * 128 + 3 * A_STAGE_BYTES > smem_budget) bn_max -= 16;
+  p.n_slices = (g->N + bn_max - 1) / bn_max;
+  p.bn = (((g->N + p.n_slices - 1) / p.n_slices) + 15) / 16 * 16;
+  const int64_t m_tiles = (g->M + 127) / 128;
+  const int sms = num_sms();
+  if (p.n_slices > sms) return fail("gemm_tc: N=%d needs more column slices than SMs", g->N);
+  p.ctas_per_slice = (int)std::min<int64_t>(sms / p.n_slices, m_tiles);
+  p.stages = std::min(8, (smem_budget - p.kblocks * p.bn * 128) / A_STAGE_BYTES);
+  p.tmem_cols = 32;
+  while (p.tmem_cols < 2 * p.bn + (p.bn % 32)) p.tmem_cols *= 2;     // the epilogue reads 32-column groups
+  p.D = D;
+  p.ldd = g->ldd;
+  p.U = g->U;
+  p.ldu = g->ldu;
+  p.row_mean = g->row_mean;
+  p.row_rstd = g->row_rstd;
+  p.col_sum = g->col_sum;
+  p.bias = g->bias;
+  p.row_scale = g->row_scale;
+  p.res = g->res;
+  p.ldres = g->ldres;
+  p.rows_per_scale = g->rows_per_scale;
+  p.p_drop = g->p_drop;
+  p.seed = g->seed;
+  if ((flags & EPI_RES) && g->res_dtype == TGT_F32) flags |= EPI_RES_F32;
+  else if ((flags & EPI_RES) && g->res_dtype != g->dtype) return fail("gemm_tc: residual dtype must be fp32 or the operand dtype");
+  p.flags = flags;
+
+  CUtensorMap ma, mb;
+  if (int e = make_operand_map(&ma, A, g->M, g->K, g->lda, 128, g->dtype)) return e;
+  if (int e = make_operand_map(&mb, B, g->N, g->K, g->ldb, p.bn, g->dtype)) return e;
+  const size_t smem = (size_t)p.kblocks * p.bn * 128 + (size_t)p.stages * A_STAGE_BYTES + epi_stage_bytes(flags) + 2048 + 256 + 1024;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (g->dtype == TGT_BF16) return dispatch_gemm<__nv_bfloat16>(ma, mb, p, smem, st);
+  return dispatch_gemm<__half>(ma, mb, p, smem, st);
+}
+
+extern "C" int tgt_row_stats(const void *x, float *mean, float *rstd, int64_t rows, int W, int64_t ldx, float eps,
+                             int dtype, void *stream) {
+  if (rows <= 0) return 0;
+  if (W % 8 || W > 1024 || W <= 0) return fail("row_stats: W=%d must be a multiple of 8 and <= 1024", W);
+  if (dtype != TGT_BF16 && dtype != TGT_F16) return fail("row_stats: 16-bit input only");
+  if (ldx % 8 || (reinterpret_cast<uintptr_t>(x) & 15)) return fail("row_stats: x must be 16-byte aligned rows");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rows_per_warp = W <= 256 ? 4 : 1;
+  const int64_t blocks = std::min<int64_t>((rows + 8 * rows_per_warp - 1) / (8 * rows_per_warp), (int64_t)num_sms() * 8);
+  TGT_DISPATCH_DTYPE(dtype, T, {
+    if constexpr (sizeof(T) == 2) {
+      const T *xp = reinterpret_cast<const T *>(x);
+      if (W <= 256)
+        row_stats_kernel<T, 4, 1><<<(unsigned)blocks, 256, 0, st>>>(xp, mean, rstd, rows, W, ldx, eps);
+      else
+        row_stats_kernel<T, 1, 4><<<(unsigned)blocks, 256, 0, st>>>(xp, mean, rstd, rows, W, ldx, eps);
+    }
+  });
+  return check_launch("row_stats");
+}

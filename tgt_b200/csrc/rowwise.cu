@@ -346,14 +346,6 @@ ln_bwd_w256(const T *__restrict__ dy, const T *__restrict__ x, const float *__re
 }
 
 // ------------------------------------------------------------------ gelu + dropout
-__device__ __forceinline__ uint32_t mix_hash(uint64_t seed, uint64_t idx) {
-  // splitmix64 finaliser over (seed + idx * golden); good avalanche, stateless
-  uint64_t z = seed + idx * 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  return (uint32_t)(z >> 32);
-}
 __device__ __forceinline__ float gelu_f(float u) { return 0.5f * u * (1.f + erff(u * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_grad(float u) {
   const float cdf = 0.5f * (1.f + erff(u * 0.70710678118654752f));
@@ -366,8 +358,7 @@ __global__ void __launch_bounds__(256)
 gelu_dropout_kernel(const T *__restrict__ u, const T *__restrict__ dy, T *__restrict__ out, int64_t n,
                     float p_drop, uint64_t seed) {
   constexpr int NV = 16 / sizeof(T);
-  const uint32_t thresh = p_drop > 0.f ? (uint32_t)fminf(p_drop * 4294967296.f, 4294967295.f) : 0u;
-  const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  const DropCfg dc = make_drop_cfg(p_drop, seed);
   const int64_t nvec = n / NV;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
@@ -376,19 +367,23 @@ gelu_dropout_kernel(const T *__restrict__ u, const T *__restrict__ dy, T *__rest
     float g[NV];
     if constexpr (BWD) load_vec<T, NV>(dy + i * NV, g);
 #pragma unroll
-    for (int q = 0; q < NV; ++q) {
-      float m = keep_scale;
-      if (p_drop > 0.f && mix_hash(seed, (uint64_t)(i * NV + q)) < thresh) m = 0.f;
-      if constexpr (BWD) o[q] = g[q] * m * gelu_grad(a[q]);
-      else o[q] = gelu_f(a[q]) * m;
+    for (int q = 0; q < NV; q += 2) {
+      float m0 = 1.f, m1 = 1.f;
+      if (p_drop > 0.f) drop_mask_pair(dc, (uint64_t)(i * NV + q) >> 1, m0, m1);
+      if constexpr (BWD) {
+        o[q] = g[q] * m0 * gelu_grad(a[q]);
+        o[q + 1] = g[q + 1] * m1 * gelu_grad(a[q + 1]);
+      } else {
+        o[q] = gelu_f(a[q]) * m0;
+        o[q + 1] = gelu_f(a[q + 1]) * m1;
+      }
     }
     store_vec<T, NV>(out + i * NV, o);
   }
   // tail
   if (blockIdx.x == 0) {
     for (int64_t e = nvec * NV + threadIdx.x; e < n; e += blockDim.x) {
-      float m = keep_scale;
-      if (p_drop > 0.f && mix_hash(seed, (uint64_t)e) < thresh) m = 0.f;
+      const float m = p_drop > 0.f ? drop_mask_one(dc, (uint64_t)e) : 1.f;
       const float a = to_f(u[e]);
       out[e] = from_f<T>(BWD ? to_f(dy[e]) * m * gelu_grad(a) : gelu_f(a) * m);
     }

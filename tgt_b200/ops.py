@@ -470,3 +470,61 @@ class ScaledResidualFn(Function):
 
 def scaled_residual(x: Tensor, res: Tensor, scale: Optional[Tensor]) -> Tensor:
     return ScaledResidualFn.apply(x, res, scale)
+
+
+# ------------------------------------------------------------------------------------------
+# tcgen05 / TMA projection GEMM with fused epilogues (csrc/gemm_tc.cu)
+# ------------------------------------------------------------------------------------------
+def row_stats(x2: Tensor, eps: float = 1e-5):
+    """per-row LayerNorm statistics (mean, rstd) of a 16-bit [rows, W] matrix."""
+    rows, W = x2.shape
+    mean = torch.empty(rows, dtype=torch.float32, device=x2.device)
+    rstd = torch.empty(rows, dtype=torch.float32, device=x2.device)
+    with timed(f"row_stats_W{W}"):
+        _C.check(_C.lib().tgt_row_stats(_C.ptr(x2), _C.ptr(mean), _C.ptr(rstd), rows, W, x2.stride(0), eps,
+                                        _C.dtype_code(x2.dtype), _C.stream_ptr()), "row_stats")
+    return mean, rstd
+
+
+def gemm_tc(a: Tensor, w: Tensor, *, bias: Optional[Tensor] = None, ln: Optional[tuple] = None,
+            gelu: Optional[tuple] = None, res: Optional[Tensor] = None, row_scale: Optional[Tensor] = None,
+            rows_per_scale: int = 0, out: Optional[Tensor] = None, name: str = "gemm_tc"):
+    """out[M,N] = epilogue(a[M,K] @ w[N,K]^T) on the tcgen05 kernel.
+
+    ln   = (row_mean, row_rstd, col_sum): LayerNorm folded into the epilogue (`w` must already be W*gamma and
+           `bias` = b + W beta);
+    gelu = (p_drop, seed): exact GELU + dropout; returns (out, u) with u the 16-bit pre-activation;
+    res / row_scale / rows_per_scale: out = res + row_scale[row // rows_per_scale] * value."""
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and a.stride(1) == 1 and w.stride(1) == 1
+    if out is None:
+        out = torch.empty((M, N), dtype=a.dtype, device=a.device)
+    g = _C.GemmDesc()
+    g.M, g.N, g.K = M, N, K
+    g.lda, g.ldb, g.ldd = a.stride(0), w.stride(0), out.stride(0)
+    g.dtype = _C.dtype_code(a.dtype)
+    flags = 0
+    keep = [a, w, out]
+    if ln is not None:
+        flags |= _C.EPI_LN
+        g.row_mean, g.row_rstd, g.col_sum = ln[0].data_ptr(), ln[1].data_ptr(), ln[2].data_ptr()
+    if bias is not None:
+        flags |= _C.EPI_BIAS
+        g.bias = bias.data_ptr()
+    u = None
+    if gelu is not None:
+        flags |= _C.EPI_GELU | _C.EPI_STORE_U
+        u = torch.empty((M, N), dtype=a.dtype, device=a.device)
+        g.U, g.ldu = u.data_ptr(), u.stride(0)
+        g.p_drop, g.seed = float(gelu[0]), int(gelu[1])
+    if res is not None:
+        flags |= _C.EPI_RES
+        g.res, g.ldres, g.res_dtype = res.data_ptr(), res.stride(0), _C.dtype_code(res.dtype)
+        if row_scale is not None:
+            g.row_scale, g.rows_per_scale = row_scale.data_ptr(), int(rows_per_scale)
+    g.flags = flags
+    with timed(name):
+        _C.check(_C.lib().tgt_gemm_tc(g, _C.ptr(a), _C.ptr(w), _C.ptr(out), _C.stream_ptr()), "gemm_tc")
+    del keep
+    return (out, u) if gelu is not None else out

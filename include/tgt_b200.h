@@ -158,6 +158,8 @@ int tgt_egt_attn_bwd(const tgt_egt_desc *desc, const void *qkv, const void *eg, 
 #define TGT_EPI_GELU    4
 #define TGT_EPI_RES     8
 #define TGT_EPI_STORE_U 16
+#define TGT_EPI_ROWSCALE 64   /* value *= row_scale[row / rows_per_scale] (DropPath in backward), no residual      */
+#define TGT_EPI_GELU_BWD 128  /* D = value * GELU'(u) * dropout mask(p_drop, seed); u = `res` (16-bit, pitch ldres) */
 typedef struct {
   int64_t M;
   int32_t N, K;

@@ -94,3 +94,42 @@ def test_gemm_gelu_dropout_matches_elementwise_kernel(p_drop):
                                            _C.dtype_code(u.dtype), _C.stream_ptr()), "gelu_dropout_fwd")
     assert (out.float() - want.float()).abs().max().item() <= 1e-2 * want.float().abs().max().item()
     assert ((out == 0) == (want == 0)).float().mean().item() > 0.9999
+
+
+@pytest.mark.parametrize("p_drop", [0.0, 0.1])
+def test_gemm_gelu_backward_epilogue(p_drop):
+    """value * GELU'(u) * mask with a DropPath row scale == tgt_gelu_dropout_bwd on the scaled GEMM result."""
+    from tgt_b200 import _C
+    ops = _ops()
+    Bb, rows_per = 6, 500
+    M, N, K = Bb * rows_per, 256, 256
+    do, w = _rand((M, K), torch.bfloat16, 21), _rand((N, K), torch.bfloat16, 22, K ** -0.5)
+    u = _rand((M, N), torch.bfloat16, 23)
+    scale = torch.tensor([1.25, 0.0, 1.25, 1.25, 0.0, 1.25], device="cuda")
+    got = ops.gemm_tc(do, w, row_scale=scale, rows_per_scale=rows_per, gelu_bwd=(u, p_drop, 777))
+    da = ((do.float() @ w.float().t()) * scale.repeat_interleave(rows_per)[:, None]).to(torch.bfloat16)
+    want = torch.empty_like(da)
+    _C.check(_C.lib().tgt_gelu_dropout_bwd(_C.ptr(u), _C.ptr(da), _C.ptr(want), u.numel(), p_drop, 777,
+                                           _C.dtype_code(u.dtype), _C.stream_ptr()), "gelu_dropout_bwd")
+    _close(got, want, 1.2e-2)
+    assert ((got == 0) == (want == 0)).float().mean().item() > 0.999
+    plain = ops.gemm_tc(do, w, row_scale=scale, rows_per_scale=rows_per)
+    _close(plain, da, 8e-3)
+
+
+def test_linear_residual_bwd_matches_autograd():
+    """DropPath-scaled linear backward (row-scale epilogue + per-graph batched weight gradient) vs autograd."""
+    ops = _ops()
+    Bb, rows_per, N, K = 4, 256, 64, 128
+    M = Bb * rows_per
+    a = _rand((M, K), torch.bfloat16, 31).float().requires_grad_(True)
+    W = _rand((N, K), torch.bfloat16, 32, K ** -0.5).float().requires_grad_(True)
+    b = torch.zeros(N, device="cuda", requires_grad=True)
+    scale = torch.tensor([1.25, 0.0, 1.25, 1.25], device="cuda")
+    do = _rand((M, N), torch.bfloat16, 33)
+    out = (a @ W.t() + b) * scale.repeat_interleave(rows_per)[:, None]
+    out.backward(do.float())
+    da, dW, db = ops.linear_residual_bwd(do, a.detach().bfloat16(), W.detach().bfloat16(), scale)
+    _close(da, a.grad, 8e-3)
+    _close(dW, W.grad, 8e-3)
+    _close(db, b.grad, 8e-3)

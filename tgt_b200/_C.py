@@ -59,7 +59,7 @@ class GemmDesc(C.Structure):
                 ("p_drop", C.c_float), ("seed", C.c_uint64)]
 
 
-EPI_LN, EPI_BIAS, EPI_GELU, EPI_RES, EPI_STORE_U = 1, 2, 4, 8, 16
+EPI_LN, EPI_BIAS, EPI_GELU, EPI_RES, EPI_STORE_U, EPI_ROWSCALE, EPI_GELU_BWD = 1, 2, 4, 8, 16, 64, 128
 
 _P = C.c_void_p
 _SIGNATURES = {

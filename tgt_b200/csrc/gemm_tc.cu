@@ -108,7 +108,8 @@ template <typename T> __device__ __forceinline__ uint32_t umma_idesc(int n) {
 }
 
 // ---------------------------------------------------------------------------------------------- kernel
-enum : int { EPI_LN = 1, EPI_BIAS = 2, EPI_GELU = 4, EPI_RES = 8, EPI_STORE_U = 16, EPI_RES_F32 = 32 };
+enum : int { EPI_LN = 1, EPI_BIAS = 2, EPI_GELU = 4, EPI_RES = 8, EPI_STORE_U = 16, EPI_RES_F32 = 32, EPI_ROWSCALE = 64,
+              EPI_GELU_BWD = 128 };
 
 struct GemmParams {
   int64_t M;
@@ -145,6 +146,20 @@ __device__ __forceinline__ float gelu_fast(float u) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * ax * ax));
   const float h = 0.5f * poly * t * e;          // 0.5 * erfc(|u| / sqrt 2)
   return u * (u < 0.f ? h : 1.f - h);
+}
+// d/du GELU(u) = Phi(u) + u * phi(u); the Gaussian exp(-u^2/2) is the one the erfc approximation already needs
+__device__ __forceinline__ float gelu_grad_fast(float u) {
+  const float ax = fabsf(u) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.f)));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * ax * ax));
+  const float h = 0.5f * poly * t * e;
+  return fmaf(u * 0.39894228040143268f, e, u < 0.f ? h : 1.f - h);
 }
 
 template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
@@ -321,14 +336,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           rstd = p.row_rstd[row];
           nmr = -p.row_mean[row] * rstd;
         }
-        float rscale[4] = {1.f, 1.f, 1.f, 1.f};
-        if ((FLAGS & EPI_RES) && p.row_scale) {
-#pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int64_t r = row0 + it * 8 + crow;
-            if (r < p.M) rscale[it] = p.row_scale[r / p.rows_per_scale];
-          }
-        }
+        float rs_lane = 1.f;                 // DropPath scale of this lane's row (TMEM domain)
+        if ((FLAGS & (EPI_RES | EPI_ROWSCALE)) && p.row_scale && row < p.M) rs_lane = p.row_scale[row / p.rows_per_scale];
         // residual values of the coalesced phase are fetched one 32-column group ahead
         uint4 rcur[4][RW], rnext[4][RW];
         auto res_load = [&](int c, uint4(&rb)[4][RW]) {
@@ -349,14 +358,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         };
-        if (FLAGS & EPI_RES) res_load(half * 32, rcur);
+        if (FLAGS & (EPI_RES | EPI_GELU_BWD)) res_load(half * 32, rcur);
         mbar_wait(bar_tfull + acc * 8, acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * bn);
         for (int c = half * 32; c < bn; c += 64) {
           uint32_t v[32];
           tc_ld32(taddr + c, v);
-          if ((FLAGS & EPI_RES) && c + 64 < bn) res_load(c + 64, rnext);
+          if ((FLAGS & (EPI_RES | EPI_GELU_BWD)) && c + 64 < bn) res_load(c + 64, rnext);
           tc_ld_wait();
           // ---- TMEM domain (lane = row): LN fold, bias, activation; 16-bit results go to the staging tile
 #pragma unroll
@@ -377,6 +386,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const float bs[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
               for (int i = 0; i < 8; ++i) f[i] += bs[i];
+            }
+            if (FLAGS & (EPI_RES | EPI_ROWSCALE)) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] *= rs_lane;
             }
             if (FLAGS & EPI_GELU) {
               uint4 wu;
@@ -414,6 +427,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const int64_t grow = row0 + r;
               if (grow < p.M) {
                 uint4 w = ld_shared_v4(stage_addr(stD, r, cpiece));
+                if (FLAGS & EPI_GELU_BWD) {
+                  // D = value * GELU'(u) * dropout mask, u = the saved pre-activation (p.res), same hash as forward
+                  const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+                  const uint32_t uw[4] = {rcur[it][0].x, rcur[it][0].y, rcur[it][0].z, rcur[it][0].w};
+                  const uint64_t pair0 = (uint64_t)(grow * p.ldres + gc) >> 1;
+                  float f[8];
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    float u0, u1, m0 = 1.f, m1 = 1.f;
+                    unpack2<T>(ww[j], f[2 * j], f[2 * j + 1]);
+                    unpack2<T>(uw[j], u0, u1);
+                    if (p.p_drop > 0.f) drop_mask_pair(dc, pair0 + j, m0, m1);
+                    f[2 * j] *= gelu_grad_fast(u0) * m0;
+                    f[2 * j + 1] *= gelu_grad_fast(u1) * m1;
+                  }
+                  w.x = pack2<T>(f[0], f[1]);
+                  w.y = pack2<T>(f[2], f[3]);
+                  w.z = pack2<T>(f[4], f[5]);
+                  w.w = pack2<T>(f[6], f[7]);
+                }
                 if (FLAGS & EPI_RES) {
                   const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
                   float f[8];
@@ -423,15 +456,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint4 q0 = rcur[it][0], q1 = rcur[it][RW - 1];
                     const uint32_t rr[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], rscale[it], __uint_as_float(rr[i]));
+                    for (int i = 0; i < 8; ++i) f[i] += __uint_as_float(rr[i]);
                   } else {
                     const uint32_t rw[4] = {rcur[it][0].x, rcur[it][0].y, rcur[it][0].z, rcur[it][0].w};
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                       float a, b;
                       unpack2<T>(rw[j], a, b);
-                      f[2 * j] = fmaf(f[2 * j], rscale[it], a);
-                      f[2 * j + 1] = fmaf(f[2 * j + 1], rscale[it], b);
+                      f[2 * j] += a;
+                      f[2 * j + 1] += b;
                     }
                   }
                   w.x = pack2<T>(f[0], f[1]);
@@ -447,7 +480,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           __syncwarp();
-          if (FLAGS & EPI_RES) {
+          if (FLAGS & (EPI_RES | EPI_GELU_BWD)) {
 #pragma unroll
             for (int it = 0; it < 4; ++it)
 #pragma unroll
@@ -594,6 +627,9 @@ static int dispatch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const Gem
     TGT_GEMM_CASE(EPI_BIAS | EPI_RES)
     TGT_GEMM_CASE(EPI_BIAS | EPI_RES | EPI_RES_F32)
     TGT_GEMM_CASE(EPI_RES)
+    TGT_GEMM_CASE(EPI_ROWSCALE)
+    TGT_GEMM_CASE(EPI_GELU_BWD)
+    TGT_GEMM_CASE(EPI_GELU_BWD | EPI_ROWSCALE)
 #undef TGT_GEMM_CASE
     default: return fail("gemm_tc: unsupported epilogue flag combination %d", p.flags);
   }
@@ -616,13 +652,17 @@ extern "C" int tgt_gemm_tc(const tgt_gemm_desc *g, const void *A, const void *B,
   if ((flags & EPI_BIAS) && !g->bias) return fail("gemm_tc: BIAS epilogue without bias");
   if ((flags & EPI_RES) && (!g->res || g->ldres % 8 || (reinterpret_cast<uintptr_t>(g->res) & 15)))
     return fail("gemm_tc: RES epilogue needs a 16-byte aligned residual with ldres %% 8 == 0");
-  if ((flags & EPI_RES) && g->row_scale && g->rows_per_scale <= 0) return fail("gemm_tc: rows_per_scale must be > 0");
+  if ((flags & EPI_GELU_BWD) && ((flags & EPI_RES) || !g->res || g->ldres % 8 || (reinterpret_cast<uintptr_t>(g->res) & 15) ||
+                                 g->res_dtype != g->dtype))
+    return fail("gemm_tc: GELU_BWD epilogue needs the 16-bit pre-activation in `res` (ldres %% 8 == 0) and excludes RES");
+  if ((flags & EPI_ROWSCALE) && !g->row_scale) return fail("gemm_tc: ROWSCALE epilogue without row_scale");
+  if ((flags & (EPI_RES | EPI_ROWSCALE)) && g->row_scale && g->rows_per_scale <= 0) return fail("gemm_tc: rows_per_scale must be > 0");
   if (flags & EPI_STORE_U) {
     if (!(flags & EPI_GELU) || !g->U || g->ldu % 8 || (reinterpret_cast<uintptr_t>(g->U) & 15))
       return fail("gemm_tc: STORE_U needs GELU and a 16-byte aligned U with ldu %% 8 == 0");
   }
   if ((flags & EPI_GELU) && !(flags & EPI_STORE_U)) return fail("gemm_tc: GELU epilogue is only built with STORE_U");
-  if ((flags & EPI_GELU) && (g->p_drop < 0.f || g->p_drop >= 1.f)) return fail("gemm_tc: p_drop=%f out of range", g->p_drop);
+  if ((flags & (EPI_GELU | EPI_GELU_BWD)) && (g->p_drop < 0.f || g->p_drop >= 1.f)) return fail("gemm_tc: p_drop=%f out of range", g->p_drop);
 
   GemmParams p{};
   p.M = g->M;

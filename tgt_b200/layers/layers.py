@@ -46,6 +46,19 @@ class EGT_Attention(nn.Module):
     def forward_alias(self, h, e, mask):
         """forward() plus an alias of the input `e` to be used for the caller's residual add (its gradient is
         then folded into the LayerNorm-backward kernel, see ops.LNLinearFn)."""
+        h, hhat, e_alias = self.forward_parts(h, e, mask)
+        if self.edge_update:
+            e = self.lin_O_e(hhat)
+        return h, e, e_alias
+
+    def edge_residual(self, hhat, e_alias, scale):
+        """e + scale[b] * lin_O_e(H_hat): the edge output projection (layers.py:81-82) with the caller's DropPath +
+        residual add (layers.py:278-279) as the epilogue of one GEMM."""
+        return ops.LinearResidualFn.apply(hhat, self.lin_O_e.weight, self.lin_O_e.bias, e_alias, scale,
+                                          ops.compute_dtype(e_alias))
+
+    def forward_parts(self, h, e, mask):
+        """(h_out, H_hat, alias of e): everything except the edge output projection."""
         cd = ops.compute_dtype(e)
         # node side: small [B*N, Wn] GEMMs -- plain library calls
         qkv = self.lin_QKV(self.mha_ln_h(h))
@@ -58,9 +71,7 @@ class EGT_Attention(nn.Module):
                        .bernoulli_(self.source_dropout) * torch.finfo(torch.float32).min
         hhat, vatt = ops.EGTCoreFn.apply(qkv, eg, mask, src, self.num_heads, True, self.scale_degree, cd)
         h = self.lin_O_h(vatt)
-        if self.edge_update:
-            e = self.lin_O_e(hhat)
-        return h, e, e_alias
+        return h, hhat, e_alias
 
 
 class EdgeUpdate(nn.Module):
@@ -87,13 +98,18 @@ class EdgeUpdate(nn.Module):
         return h, e
 
     def forward_alias(self, h, e, mask):
+        h, hhat, e_alias = self.forward_parts(h, e, mask)
+        return h, self.lin_O_e(hhat), e_alias
+
+    edge_residual = EGT_Attention.edge_residual
+
+    def forward_parts(self, h, e, mask):
         cd = ops.compute_dtype(e)
         qk = self.lin_QK(self.mha_ln_h(h))
         eb, e_alias = ops.LNLinearFn.apply(e, self.mha_ln_e.weight, self.mha_ln_e.bias, self.lin_E.weight,
                                            self.lin_E.bias, cd)
         hhat = ops.EGTCoreFn.apply(qk, eb, mask, None, self.num_heads, False, False, cd)
-        e = self.lin_O_e(hhat)
-        return h, e, e_alias
+        return h, hhat, e_alias
 
 
 class FFN(nn.Module):
@@ -119,18 +135,27 @@ class FFN(nn.Module):
 
     def forward_alias(self, x):
         """(FFN(x), alias of x for the caller's residual add -- see ops.LNLinearFn)."""
+        return self._run(x, None, False)
+
+    def forward_residual(self, x, scale):
+        """x + scale[b] * FFN(x): DropPath + residual add (reference layers.py:272-273, 289-290) fused in."""
+        return self._run(x, scale, True)
+
+    def _run(self, x, scale, fuse_res):
         if self.activation == 'gelu':
             p = self.act_dropout if self.training else 0.
             seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0 else 0      # CPU generator: no sync
             return ops.FFNGeluFn.apply(x, self.ffn_ln.weight, self.ffn_ln.bias, self.lin_W1.weight,
                                        self.lin_W1.bias, self.lin_W2.weight, self.lin_W2.bias, p, seed,
-                                       ops.compute_dtype(x))
+                                       ops.compute_dtype(x), scale, fuse_res)
         # gated activations (geglu/glu/swiglu) are not used by any shipped config: plain library ops on the
         # LayerNorm / GEMMs (still CUDA-only: the residual kernels around this module refuse CPU tensors)
         ops._require_cuda(x)
         x_ln = self.ffn_ln(x)
         y = self.ffn_fn(self.lin_W1(x_ln))
         y = self.dropout(y)
+        if fuse_res:
+            return ops.scaled_residual(self.lin_W2(y), x, scale)
         return self.lin_W2(y), x
 
 
@@ -220,20 +245,18 @@ class TGT_Layer(nn.Module):
         # residual gradient into the sub-module's LayerNorm-backward kernel (ops.LNLinearFn) -- same values as the
         # reference's `x.add_(x_r)` (layers.py:269-290)
         h_r1 = h
-        h, e_new, e_r1 = self.update.forward_alias(h, e, mask)
+        h, hhat, e_r1 = self.update.forward_parts(h, e, mask)
 
         if self.node_update:
             h = self._residual(h, h_r1)
-            d, h_r2 = self.node_ffn.forward_alias(h)
-            h = self._residual(d, h_r2)
+            h = self.node_ffn.forward_residual(h, self.drop_path.sample_scale(h))
 
         if self.edge_update:
-            e = self._residual(e_new, e_r1)
+            # each edge branch is ONE fused pass: x + drop_path(f(x)) comes out of the last GEMM's epilogue
+            e = self.update.edge_residual(hhat, e_r1, self.drop_path.sample_scale(e))
             if self._triplet_update:
-                d, e_rt = self.tria.forward_alias(e, mask)
-                e = self._residual(d, e_rt)
-            d, e_r2 = self.edge_ffn.forward_alias(e)
-            e = self._residual(d, e_r2)
+                e = self.tria.forward_residual(e, mask, self.drop_path.sample_scale(e))
+            e = self.edge_ffn.forward_residual(e, self.drop_path.sample_scale(e))
 
         g = g.copy()
         g.h, g.e = h, e

@@ -80,6 +80,13 @@ class _AttentionFamily(_TripletBase):
 
     def forward_alias(self, e, mask):
         """(module(e), alias of e for the caller's residual add -- see ops.LNLinearFn)."""
+        return self._run(e, mask, None, False)
+
+    def forward_residual(self, e, mask, scale):
+        """e + scale[b] * module(e): DropPath + residual add (reference layers.py:284-285) fused into the kernels."""
+        return self._run(e, mask, scale, True)
+
+    def _run(self, e, mask, scale, fuse_res):
         self._common_checks(e, mask)
         W, H, d = self.edge_width, self.num_heads, self._dot_dim
         dev = e.device
@@ -109,7 +116,7 @@ class _AttentionFamily(_TripletBase):
         Wo = self.lin_O.weight.index_select(1, _out_perm(W, H, dev))
         layout = (H, d, off_q, off_k, off_v, tuple(off_e), tuple(off_g))
         return ops.TripletAttentionFn.apply(e, mask, self.tri_ln_e.weight, self.tri_ln_e.bias, Wcat, bcat, Wo,
-                                            self.lin_O.bias, layout, ops.compute_dtype(e))
+                                            self.lin_O.bias, layout, ops.compute_dtype(e), scale, fuse_res)
 
 
 class TripletAttention(_AttentionFamily):
@@ -174,6 +181,13 @@ class _AggregateFamily(_TripletBase):
         return self.forward_alias(e, mask)[0]
 
     def forward_alias(self, e, mask):
+        return self._run(e, mask, None, False)
+
+    def forward_residual(self, e, mask, scale):
+        """e + scale[b] * module(e) (see _AttentionFamily.forward_residual)."""
+        return self._run(e, mask, scale, True)
+
+    def _run(self, e, mask, scale, fuse_res):
         self._common_checks(e, mask)
         W, H, d = self.edge_width, self.num_heads, self._dot_dim
         dev = e.device
@@ -200,7 +214,7 @@ class _AggregateFamily(_TripletBase):
         Wo = self.lin_O.weight.index_select(1, _out_perm(W, H, dev))
         layout = (H, d, (0, W), off_e, off_g, mask_dir)
         return ops.TripletAggregateFn.apply(e, mask, self.tri_ln_e.weight, self.tri_ln_e.bias, Wcat, bcat, Wo,
-                                            self.lin_O.bias, layout, ops.compute_dtype(e))
+                                            self.lin_O.bias, layout, ops.compute_dtype(e), scale, fuse_res)
 
 
 class TripletAggregate(_AggregateFamily):
@@ -247,3 +261,6 @@ class TriangularUpdate(_TripletBase):
         raise NotImplementedError("tgt_b200: TriangularUpdate has no CUDA kernel yet (no fallback by design)")
 
     forward_alias = forward
+
+    def forward_residual(self, e, mask, scale):
+        return self.forward(e, mask)

@@ -138,6 +138,178 @@ def _x_for_ln(e: Tensor, cdtype: torch.dtype) -> Tensor:
 
 
 # ------------------------------------------------------------------------------------------
+# tcgen05 / TMA projection GEMM with fused epilogues (csrc/gemm_tc.cu)
+# ------------------------------------------------------------------------------------------
+def row_stats(x2: Tensor, eps: float = 1e-5):
+    """per-row LayerNorm statistics (mean, rstd) of a 16-bit [rows, W] matrix."""
+    rows, W = x2.shape
+    mean = torch.empty(rows, dtype=torch.float32, device=x2.device)
+    rstd = torch.empty(rows, dtype=torch.float32, device=x2.device)
+    with timed(f"row_stats_W{W}"):
+        _C.check(_C.lib().tgt_row_stats(_C.ptr(x2), _C.ptr(mean), _C.ptr(rstd), rows, W, x2.stride(0), eps,
+                                        _C.dtype_code(x2.dtype), _C.stream_ptr()), "row_stats")
+    return mean, rstd
+
+
+def gemm_tc(a: Tensor, w: Tensor, *, bias: Optional[Tensor] = None, ln: Optional[tuple] = None,
+            gelu: Optional[tuple] = None, res: Optional[Tensor] = None, row_scale: Optional[Tensor] = None,
+            rows_per_scale: int = 0, gelu_bwd: Optional[tuple] = None, out: Optional[Tensor] = None,
+            name: str = "gemm_tc"):
+    """out[M,N] = epilogue(a[M,K] @ w[N,K]^T) on the tcgen05 kernel.
+
+    ln   = (row_mean, row_rstd, col_sum): LayerNorm folded into the epilogue (`w` must already be W*gamma and
+           `bias` = b + W beta);
+    gelu = (p_drop, seed): exact GELU + dropout; returns (out, u) with u the 16-bit pre-activation;
+    row_scale / rows_per_scale: value *= row_scale[row // rows_per_scale] (DropPath);
+    res: out = res + value;
+    gelu_bwd = (u, p_drop, seed): out = value * GELU'(u) * dropout mask (backward of `gelu`)."""
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and a.stride(1) == 1 and w.stride(1) == 1
+    if out is None:
+        out = torch.empty((M, N), dtype=a.dtype, device=a.device)
+    g = _C.GemmDesc()
+    g.M, g.N, g.K = M, N, K
+    g.lda, g.ldb, g.ldd = a.stride(0), w.stride(0), out.stride(0)
+    g.dtype = _C.dtype_code(a.dtype)
+    flags = 0
+    if ln is not None:
+        flags |= _C.EPI_LN
+        g.row_mean, g.row_rstd, g.col_sum = ln[0].data_ptr(), ln[1].data_ptr(), ln[2].data_ptr()
+    if bias is not None:
+        flags |= _C.EPI_BIAS
+        g.bias = bias.data_ptr()
+    u = None
+    if gelu is not None:
+        flags |= _C.EPI_GELU | _C.EPI_STORE_U
+        u = torch.empty((M, N), dtype=a.dtype, device=a.device)
+        g.U, g.ldu = u.data_ptr(), u.stride(0)
+        g.p_drop, g.seed = float(gelu[0]), int(gelu[1])
+    if res is not None:
+        flags |= _C.EPI_RES
+        g.res, g.ldres, g.res_dtype = res.data_ptr(), res.stride(0), _C.dtype_code(res.dtype)
+    if gelu_bwd is not None:
+        flags |= _C.EPI_GELU_BWD
+        ub = gelu_bwd[0]
+        g.res, g.ldres, g.res_dtype = ub.data_ptr(), ub.stride(0), _C.dtype_code(ub.dtype)
+        g.p_drop, g.seed = float(gelu_bwd[1]), int(gelu_bwd[2])
+    if row_scale is not None:
+        if res is None:
+            flags |= _C.EPI_ROWSCALE
+        g.row_scale, g.rows_per_scale = row_scale.data_ptr(), int(rows_per_scale)
+    g.flags = flags
+    with timed(name):
+        _C.check(_C.lib().tgt_gemm_tc(g, _C.ptr(a), _C.ptr(w), _C.ptr(out), _C.stream_ptr()), "gemm_tc")
+    return (out, u) if gelu is not None else out
+
+
+def tc_gemm_ok(a: Tensor, N: int, K: int) -> bool:
+    """shapes / dtypes the tcgen05 GEMM accepts (everything else takes the cuBLAS + elementwise-kernel route)."""
+    return (a.is_cuda and a.dtype in (torch.bfloat16, torch.float16) and a.dim() == 2 and a.stride(1) == 1
+            and K % 8 == 0 and N % 8 == 0 and 8 <= K <= 512 and a.stride(0) % 8 == 0 and a.data_ptr() % 16 == 0
+            and N <= 148 * 16)
+
+
+def _ln_fold(W: Tensor, b: Tensor, gamma: Tensor, beta: Tensor, cd: torch.dtype):
+    """LayerNorm folded into the following Linear:  LN(x) W^T + b = rstd*(x Wg^T - mean*colsum) + b'  with
+    Wg = W*gamma (rounded to the GEMM dtype), colsum = rowsum(Wg), b' = b + W beta."""
+    Wf = W.detach().float()
+    Wg = (Wf * gamma).to(cd).contiguous()
+    return Wg, (b.detach().float() + Wf @ beta).contiguous(), Wg.float().sum(1).contiguous()
+
+
+def _scale_rows(x2: Tensor, scale: Optional[Tensor]) -> Tensor:
+    """x2 * scale[b] with x2 viewed [B, -1] (DropPath backward); identity when scale is None."""
+    if scale is None:
+        return x2
+    xc = x2.contiguous()
+    out = torch.empty_like(xc)
+    B = scale.numel()
+    _C.check(_C.lib().tgt_scaled_residual(_C.ptr(xc), None, _C.ptr(scale), _C.ptr(out), B, xc.numel() // B,
+                                          _C.dtype_code(xc.dtype), _C.dtype_code(xc.dtype), _C.stream_ptr()),
+             "scaled_residual(bwd)")
+    return out
+
+
+def linear_residual(a2: Tensor, Wc: Tensor, bias: Tensor, res2: Optional[Tensor], scale: Optional[Tensor],
+                    out2: Optional[Tensor] = None, name: str = "gemm_tc_out") -> Tensor:
+    """res2 + scale[b] * (a2 @ Wc^T + bias)   (res2 / scale optional; scale is per graph, rows are graph-major).
+    One tcgen05 GEMM with the DropPath + residual epilogue when the shape allows, else cuBLAS + our residual kernel.
+    `out2`: optional preallocated [M, N] result (a 2-D view of the tensor the caller returns)."""
+    M, K = a2.shape
+    N = Wc.shape[0]
+    if out2 is None:
+        out2 = torch.empty((M, N), dtype=a2.dtype, device=a2.device)
+    if tc_gemm_ok(a2, N, K) and Wc.dtype == a2.dtype and (res2 is None or (
+            res2.dtype in (a2.dtype, torch.float32) and res2.stride(1) == 1 and res2.stride(0) % 8 == 0)):
+        rps = M // scale.numel() if scale is not None else 0
+        return gemm_tc(a2, Wc, bias=bias.detach().float().contiguous(), res=res2,
+                       row_scale=scale if res2 is not None else None, rows_per_scale=rps, out=out2, name=name)
+    if res2 is None:
+        return torch.addmm(bias.detach().to(a2.dtype), a2, Wc.t(), out=out2)
+    y = torch.addmm(bias.detach().to(a2.dtype), a2, Wc.t())
+    B = scale.numel() if scale is not None else 1
+    rc = res2.contiguous()
+    _C.check(_C.lib().tgt_scaled_residual(_C.ptr(y), _C.ptr(rc), _C.ptr(scale), _C.ptr(out2), B, y.numel() // B,
+                                          _C.dtype_code(y.dtype), _C.dtype_code(rc.dtype), _C.stream_ptr()),
+             "scaled_residual")
+    return out2
+
+
+try:                                           # fp32 results from 16-bit batched GEMMs (PyTorch >= 2.8)
+    torch.bmm(torch.zeros(1, 1, 8), torch.zeros(1, 8, 1), out_dtype=torch.float32)
+    _BMM_OUT_F32 = True
+except (TypeError, RuntimeError):
+    _BMM_OUT_F32 = False
+
+
+def linear_residual_bwd(do2: Tensor, a2: Tensor, Wc: Tensor, scale: Optional[Tensor], gelu_bwd: Optional[tuple] = None,
+                        name: str = "gemm_tc_dx"):
+    """Gradients of  out = res + scale[b] * (a2 Wc^T + bias)  given do2 = d out: (da2, dW, dbias).
+    The DropPath scale never costs a pass over an edge-sized tensor: da2 = scale[b] * (do2 Wc) is the row-scale
+    epilogue of the GEMM, dW = sum_b scale[b] * do2_b^T a2_b is a per-graph batched GEMM followed by a weighted sum.
+    gelu_bwd = (u, p_drop, seed) additionally multiplies da2 by GELU'(u) * dropout mask in the same epilogue."""
+    M, N = do2.shape
+    K = a2.shape[1]
+    if tc_gemm_ok(do2, K, N) and Wc.dtype == do2.dtype and (scale is not None or gelu_bwd is not None):
+        rps = M // scale.numel() if scale is not None else 0
+        da = gemm_tc(do2, Wc.t().contiguous(), row_scale=scale, rows_per_scale=rps, gelu_bwd=gelu_bwd, name=name)
+    else:
+        da = _scale_rows(torch.mm(do2, Wc), scale)
+        if gelu_bwd is not None:
+            u, p_drop, seed = gelu_bwd
+            du = torch.empty_like(da)
+            _C.check(_C.lib().tgt_gelu_dropout_bwd(_C.ptr(u), _C.ptr(da), _C.ptr(du), u.numel(), p_drop, seed,
+                                                   _C.dtype_code(da.dtype), _C.stream_ptr()), "gelu_dropout_bwd")
+            da = du
+    if scale is None:
+        return da, torch.mm(do2.t(), a2), do2.sum(0, dtype=torch.float32)
+    B = scale.numel()
+    dob = do2.view(B, M // B, N)
+    if _BMM_OUT_F32 and do2.dtype != torch.float32:
+        dWb = torch.bmm(dob.transpose(1, 2), a2.view(B, M // B, K), out_dtype=torch.float32)
+    else:
+        dWb = torch.bmm(dob.transpose(1, 2), a2.view(B, M // B, K)).float()
+    dW = torch.mv(dWb.view(B, N * K).t(), scale).view(N, K)
+    db = torch.mv(dob.sum(1, dtype=torch.float32).t(), scale)
+    return da, dW, db
+
+
+def ln_linear(x2: Tensor, g: Tensor, bt: Tensor, W: Tensor, b: Tensor, Wc: Tensor, cd: torch.dtype,
+              name: str = "gemm_tc_ln"):
+    """(LN(x2) W^T + b, mean, rstd, fold).  16-bit x2: row statistics + ONE tcgen05 GEMM on the raw rows with the
+    LayerNorm folded into its epilogue (the normalised tensor never exists), fold = (Wg, b', colsum) for an identical
+    recompute in backward; otherwise LN kernel + cuBLAS and fold = (None, None, None)."""
+    N, K = W.shape
+    if x2.dtype == cd and tc_gemm_ok(x2, N, K):
+        mean, rstd = row_stats(x2)
+        Wg, bp, cs = _ln_fold(W, b, g, bt, cd)
+        return gemm_tc(x2, Wg, bias=bp, ln=(mean, rstd, cs), name=name), mean, rstd, (Wg, bp, cs)
+    y, mean, rstd = layernorm_fwd(x2, g, bt, cd)
+    return torch.addmm(b.detach().to(cd), y, Wc.t()), mean, rstd, (None, None, None)
+
+
+# ------------------------------------------------------------------------------------------
 # LayerNorm -> Linear with LN recompute in backward  (EGT lin_EG / lin_E)
 # ------------------------------------------------------------------------------------------
 class LNLinearFn(Function):
@@ -148,10 +320,9 @@ class LNLinearFn(Function):
             shape = x.shape
             x2 = _x_for_ln(x, cdtype).view(-1, shape[-1])
             g, bt = _f32c(ln_w), _f32c(ln_b)
-            y, mean, rstd = layernorm_fwd(x2, g, bt, cdtype)
             Wc = W.detach().to(cdtype)
-            out = torch.empty((*shape[:-1], W.shape[0]), dtype=cdtype, device=x.device)
-            torch.addmm(b.detach().to(cdtype), y, Wc.t(), out=out.view(-1, W.shape[0]))
+            out2, mean, rstd, _ = ln_linear(x2, g, bt, W, b, Wc, cdtype, name="gemm_tc_ln_eg")
+            out = out2.view(*shape[:-1], W.shape[0])      # not modified in place by any caller (feeds the EGT core)
             ctx.save_for_backward(x2, g, bt, Wc, mean, rstd)
             ctx.cdtype = cdtype
             ctx.in_dtype = x.dtype
@@ -186,10 +357,13 @@ class LNLinearFn(Function):
 # ------------------------------------------------------------------------------------------
 class TripletAttentionFn(Function):
     """e:[B,N,N,W]; Wcat:[C,W] rows in kernel order (head-major q/k/v blocks, then bias/gate blocks);
-    Wo:[W,2W] with columns in kernel order (dir, h, dd).  `layout` = (H, d, off_q, off_k, off_v, off_e, off_g)."""
+    Wo:[W,2W] with columns in kernel order (dir, h, dd).  `layout` = (H, d, off_q, off_k, off_v, off_e, off_g).
+
+    fuse_res=False: returns (module(e), alias of e)  -- the caller adds the residual (reference layers.py:285).
+    fuse_res=True : returns e + res_scale[b] * module(e) (DropPath + residual fused into the lin_O GEMM epilogue)."""
 
     @staticmethod
-    def forward(ctx, e, mask, ln_w, ln_b, Wcat, bcat, Wo, bo, layout, cdtype):
+    def forward(ctx, e, mask, ln_w, ln_b, Wcat, bcat, Wo, bo, layout, cdtype, res_scale=None, fuse_res=False):
         _require_cuda(e, mask, Wcat)
         H, d, off_q, off_k, off_v, off_e, off_g = layout
         B, N, _, W = e.shape
@@ -198,11 +372,9 @@ class TripletAttentionFn(Function):
             x2 = _x_for_ln(e, cdtype).view(R, W)
             g, bt = _f32c(ln_w), _f32c(ln_b)
             Wc, bc = Wcat.detach().to(cdtype).contiguous(), bcat.detach().to(cdtype).contiguous()
-            Woc, boc = Wo.detach().to(cdtype).contiguous(), bo.detach().to(cdtype).contiguous()
+            Woc = Wo.detach().to(cdtype).contiguous()
             m3 = _f32c(mask).view(B, N, N)
-            y, mean, rstd = layernorm_fwd(x2, g, bt, cdtype)
-            proj = torch.addmm(bc, y, Wc.t())
-            del y
+            proj, mean, rstd, fold = ln_linear(x2, g, bt, Wcat, bcat, Wc, cdtype, name="gemm_tc_ln_proj")
             desc = _C.TripletAttnDesc(B, N, H, d, proj.shape[1], off_q, off_k, off_v, off_e, off_g,
                                       float(d) ** -0.5, _C.dtype_code(cdtype))
             va = torch.empty((R, 2 * H * d), dtype=cdtype, device=e.device)
@@ -213,31 +385,38 @@ class TripletAttentionFn(Function):
                                                        _C.ptr(ws), wsb, _C.stream_ptr()), "triplet_attn_fwd")
             del ws
             del proj
+            sc = _f32c(res_scale).view(B) if (fuse_res and res_scale is not None) else None
             out = torch.empty((B, N, N, W), dtype=cdtype, device=e.device)
-            torch.addmm(boc, va, Woc.t(), out=out.view(R, W))
-            ctx.save_for_backward(x2, m3, g, bt, Wc, bc, Woc, mean, rstd, stats, va)
+            linear_residual(va, Woc, bo, x2 if fuse_res else None, sc, out2=out.view(R, W), name="gemm_tc_lin_o")
+            ctx.save_for_backward(x2, m3, g, bt, Wc, bc, Woc, mean, rstd, stats, va, sc, *fold)
             ctx.desc = desc
             ctx.cdtype = cdtype
             ctx.in_dtype = e.dtype
+            ctx.fuse_res = fuse_res
             ctx.pdt = (ln_w.dtype, Wcat.dtype, bcat.dtype, Wo.dtype, bo.dtype)
             ctx.set_materialize_grads(False)
+        if fuse_res:
+            return out
         return out, e                   # (result, alias of the input for the caller's residual add: see LNLinearFn)
 
     @staticmethod
     def backward(ctx, dout, dalias=None):
-        x2, m3, g, bt, Wc, bc, Woc, mean, rstd, stats, va = ctx.saved_tensors
+        x2, m3, g, bt, Wc, bc, Woc, mean, rstd, stats, va, sc, Wg, bp, cs = ctx.saved_tensors
         if dout is None:
-            return (dalias,) + (None,) * 9
+            return (dalias,) + (None,) * 11
         cd, desc = ctx.cdtype, ctx.desc
         B, N, W = desc.B, desc.N, x2.shape[1]
         with torch.autocast("cuda", enabled=False):
             do = dout.reshape(-1, W).to(cd).contiguous()
-            dWo = torch.mm(do.t(), va)
-            dbo = do.sum(0, dtype=torch.float32)
-            dva = torch.mm(do, Woc)
+            if ctx.fuse_res:
+                dalias = dout                               # residual branch: d(e) += dout, folded into the LN backward
+            dva, dWo, dbo = linear_residual_bwd(do, va, Woc, sc, name="gemm_tc_dva")
             del do
             y, _, _ = layernorm_fwd(x2, g, bt, cd, aug=True)
-            proj = torch.addmm(bc, y[:, :W], Wc.t())
+            if Wg is not None:          # bit-identical recompute of the forward projection (same kernel, same inputs)
+                proj = gemm_tc(x2, Wg, bias=bp, ln=(mean, rstd, cs), name="gemm_tc_ln_proj")
+            else:
+                proj = torch.addmm(bc, y[:, :W], Wc.t())
             dproj = torch.empty_like(proj)
             ws, wsb = _workspace(_C.lib().tgt_triplet_attn_workspace_bytes(desc, 1), x2.device)
             with timed("triplet_attn_bwd"):
@@ -254,14 +433,14 @@ class TripletAttentionFn(Function):
             dx, dg, dbt = layernorm_bwd(dy, x2, g, mean, rstd, _dres_for(dalias, x2))
         p = ctx.pdt
         return (dx.view(B, N, N, W).to(ctx.in_dtype), None, dg.to(p[0]), dbt.to(p[0]), dWc.to(p[1]), dbc.to(p[2]),
-                dWo.to(p[3]), dbo.to(p[4]), None, None)
+                dWo.to(p[3]), dbo.to(p[4]), None, None, None, None)
 
 
 class TripletAggregateFn(Function):
     """`layout` = (H, d, off_v, off_e, off_g, mask_dir)."""
 
     @staticmethod
-    def forward(ctx, e, mask, ln_w, ln_b, Wcat, bcat, Wo, bo, layout, cdtype):
+    def forward(ctx, e, mask, ln_w, ln_b, Wcat, bcat, Wo, bo, layout, cdtype, res_scale=None, fuse_res=False):
         _require_cuda(e, mask, Wcat)
         H, d, off_v, off_e, off_g, mask_dir = layout
         B, N, _, W = e.shape
@@ -270,11 +449,9 @@ class TripletAggregateFn(Function):
             x2 = _x_for_ln(e, cdtype).view(R, W)
             g, bt = _f32c(ln_w), _f32c(ln_b)
             Wc, bc = Wcat.detach().to(cdtype).contiguous(), bcat.detach().to(cdtype).contiguous()
-            Woc, boc = Wo.detach().to(cdtype).contiguous(), bo.detach().to(cdtype).contiguous()
+            Woc = Wo.detach().to(cdtype).contiguous()
             m3 = _f32c(mask).view(B, N, N)
-            y, mean, rstd = layernorm_fwd(x2, g, bt, cdtype)
-            proj = torch.addmm(bc, y, Wc.t())
-            del y
+            proj, mean, rstd, fold = ln_linear(x2, g, bt, Wcat, bcat, Wc, cdtype, name="gemm_tc_ln_proj")
             desc = _C.TripletAggrDesc(B, N, H, d, proj.shape[1], off_v, off_e, off_g, mask_dir,
                                       _C.dtype_code(cdtype))
             va = torch.empty((R, 2 * H * d), dtype=cdtype, device=e.device)
@@ -283,31 +460,38 @@ class TripletAggregateFn(Function):
                 _C.check(_C.lib().tgt_triplet_aggr_fwd(desc, _C.ptr(proj), _C.ptr(m3), _C.ptr(va), _C.ptr(aw),
                                                        _C.stream_ptr()), "triplet_aggr_fwd")
             del proj
+            sc = _f32c(res_scale).view(B) if (fuse_res and res_scale is not None) else None
             out = torch.empty((B, N, N, W), dtype=cdtype, device=e.device)
-            torch.addmm(boc, va, Woc.t(), out=out.view(R, W))
-            ctx.save_for_backward(x2, m3, g, bt, Wc, bc, Woc, mean, rstd, aw, va)
+            linear_residual(va, Woc, bo, x2 if fuse_res else None, sc, out2=out.view(R, W), name="gemm_tc_lin_o")
+            ctx.save_for_backward(x2, m3, g, bt, Wc, bc, Woc, mean, rstd, aw, va, sc, *fold)
+            ctx.fuse_res = fuse_res
             ctx.desc = desc
             ctx.cdtype = cdtype
             ctx.in_dtype = e.dtype
             ctx.pdt = (ln_w.dtype, Wcat.dtype, bcat.dtype, Wo.dtype, bo.dtype)
             ctx.set_materialize_grads(False)
+        if fuse_res:
+            return out
         return out, e                   # (result, alias of the input for the caller's residual add: see LNLinearFn)
 
     @staticmethod
     def backward(ctx, dout, dalias=None):
-        x2, m3, g, bt, Wc, bc, Woc, mean, rstd, aw, va = ctx.saved_tensors
+        x2, m3, g, bt, Wc, bc, Woc, mean, rstd, aw, va, sc, Wg, bp, cs = ctx.saved_tensors
         if dout is None:
-            return (dalias,) + (None,) * 9
+            return (dalias,) + (None,) * 11
         cd, desc = ctx.cdtype, ctx.desc
         B, N, W = desc.B, desc.N, x2.shape[1]
         with torch.autocast("cuda", enabled=False):
             do = dout.reshape(-1, W).to(cd).contiguous()
-            dWo = torch.mm(do.t(), va)
-            dbo = do.sum(0, dtype=torch.float32)
-            dva = torch.mm(do, Woc)
+            if ctx.fuse_res:
+                dalias = dout                               # residual branch: d(e) += dout, folded into the LN backward
+            dva, dWo, dbo = linear_residual_bwd(do, va, Woc, sc, name="gemm_tc_dva")
             del do
             y, _, _ = layernorm_fwd(x2, g, bt, cd, aug=True)
-            proj = torch.addmm(bc, y[:, :W], Wc.t())
+            if Wg is not None:          # bit-identical recompute of the forward projection (same kernel, same inputs)
+                proj = gemm_tc(x2, Wg, bias=bp, ln=(mean, rstd, cs), name="gemm_tc_ln_proj")
+            else:
+                proj = torch.addmm(bc, y[:, :W], Wc.t())
             dproj = torch.empty_like(proj)
             daw = torch.empty_like(aw)
             with timed("triplet_aggr_bwd"):
@@ -323,7 +507,7 @@ class TripletAggregateFn(Function):
             dx, dg, dbt = layernorm_bwd(dy, x2, g, mean, rstd, _dres_for(dalias, x2))
         p = ctx.pdt
         return (dx.view(B, N, N, W).to(ctx.in_dtype), None, dg.to(p[0]), dbt.to(p[0]), dWc.to(p[1]), dbc.to(p[2]),
-                dWo.to(p[3]), dbo.to(p[4]), None, None)
+                dWo.to(p[3]), dbo.to(p[4]), None, None, None, None)
 
 
 # ------------------------------------------------------------------------------------------
@@ -385,46 +569,55 @@ class EGTCoreFn(Function):
 # FFN: LN -> W1 -> gelu -> dropout -> W2   (saves the input, LN stats and the pre-activation only)
 # ------------------------------------------------------------------------------------------
 class FFNGeluFn(Function):
+    """fuse_res=False: (FFN(x), alias of x); fuse_res=True: x + res_scale[b] * FFN(x) in one pass (the DropPath +
+    residual add is the epilogue of the W2 GEMM; LN, bias, GELU and dropout are the epilogue of the W1 GEMM)."""
+
     @staticmethod
-    def forward(ctx, x, ln_w, ln_b, W1, b1, W2, b2, p_drop, seed, cdtype):
+    def forward(ctx, x, ln_w, ln_b, W1, b1, W2, b2, p_drop, seed, cdtype, res_scale=None, fuse_res=False):
         _require_cuda(x, W1)
         with torch.autocast("cuda", enabled=False):
             shape = x.shape
             x2 = _x_for_ln(x, cdtype).view(-1, shape[-1])
             g, bt = _f32c(ln_w), _f32c(ln_b)
             W1c, W2c = W1.detach().to(cdtype).contiguous(), W2.detach().to(cdtype).contiguous()
-            y, mean, rstd = layernorm_fwd(x2, g, bt, cdtype)
-            u = torch.addmm(b1.detach().to(cdtype), y, W1c.t())
-            del y
-            a = torch.empty_like(u)
-            _C.check(_C.lib().tgt_gelu_dropout_fwd(_C.ptr(u), _C.ptr(a), u.numel(), float(p_drop), int(seed),
-                                                   _C.dtype_code(cdtype), _C.stream_ptr()), "gelu_dropout_fwd")
+            inner, K = W1.shape
+            if x2.dtype == cdtype and tc_gemm_ok(x2, inner, K):
+                mean, rstd = row_stats(x2)
+                W1g, b1p, cs = _ln_fold(W1, b1, g, bt, cdtype)
+                a, u = gemm_tc(x2, W1g, bias=b1p, ln=(mean, rstd, cs), gelu=(float(p_drop), int(seed)),
+                               name="gemm_tc_ln_gelu")
+            else:
+                y, mean, rstd = layernorm_fwd(x2, g, bt, cdtype)
+                u = torch.addmm(b1.detach().to(cdtype), y, W1c.t())
+                del y
+                a = torch.empty_like(u)
+                _C.check(_C.lib().tgt_gelu_dropout_fwd(_C.ptr(u), _C.ptr(a), u.numel(), float(p_drop), int(seed),
+                                                       _C.dtype_code(cdtype), _C.stream_ptr()), "gelu_dropout_fwd")
+            sc = None
+            if fuse_res and res_scale is not None:
+                sc = _f32c(res_scale).view(-1)
             out = torch.empty((*shape[:-1], W2.shape[0]), dtype=cdtype, device=x.device)
-            torch.addmm(b2.detach().to(cdtype), a, W2c.t(), out=out.view(-1, W2.shape[0]))
-            ctx.save_for_backward(x2, g, bt, W1c, W2c, mean, rstd, u)
+            linear_residual(a, W2c, b2, x2 if fuse_res else None, sc, out2=out.view(-1, W2.shape[0]), name="gemm_tc_w2")
+            ctx.save_for_backward(x2, g, bt, W1c, W2c, mean, rstd, u, a, sc)
             ctx.meta = (float(p_drop), int(seed), cdtype, x.dtype,
-                        (ln_w.dtype, W1.dtype, b1.dtype, W2.dtype, b2.dtype))
+                        (ln_w.dtype, W1.dtype, b1.dtype, W2.dtype, b2.dtype), fuse_res)
             ctx.set_materialize_grads(False)
+        if fuse_res:
+            return out
         return out, x                   # (result, alias of the input for the caller's residual add: see LNLinearFn)
 
     @staticmethod
     def backward(ctx, dout, dalias=None):
-        x2, g, bt, W1c, W2c, mean, rstd, u = ctx.saved_tensors
-        p_drop, seed, cd, in_dtype, p = ctx.meta
+        x2, g, bt, W1c, W2c, mean, rstd, u, a, sc = ctx.saved_tensors
+        p_drop, seed, cd, in_dtype, p, fuse_res = ctx.meta
         if dout is None:
-            return (dalias,) + (None,) * 9
+            return (dalias,) + (None,) * 11
         with torch.autocast("cuda", enabled=False):
             do = dout.reshape(-1, dout.shape[-1]).to(cd).contiguous()
-            a = torch.empty_like(u)
-            _C.check(_C.lib().tgt_gelu_dropout_fwd(_C.ptr(u), _C.ptr(a), u.numel(), p_drop, seed,
-                                                   _C.dtype_code(cd), _C.stream_ptr()), "gelu_dropout_fwd")
-            dW2 = torch.mm(do.t(), a)
-            db2 = do.sum(0, dtype=torch.float32)
-            da = torch.mm(do, W2c)
-            du = a  # reuse the buffer
-            _C.check(_C.lib().tgt_gelu_dropout_bwd(_C.ptr(u), _C.ptr(da), _C.ptr(du), u.numel(), p_drop, seed,
-                                                   _C.dtype_code(cd), _C.stream_ptr()), "gelu_dropout_bwd")
-            del da
+            if fuse_res:
+                dalias = dout
+            # du = scale[b] * (do W2) * GELU'(u) * dropout mask in ONE GEMM; `a` was saved by the forward epilogue
+            du, dW2, db2 = linear_residual_bwd(do, a, W2c, sc, gelu_bwd=(u, p_drop, seed), name="gemm_tc_du")
             y, _, _ = layernorm_fwd(x2, g, bt, cd, aug=True)
             dWa = torch.mm(du.t(), y)
             dW1, db1 = dWa[:, :x2.shape[1]], dWa[:, x2.shape[1]]
@@ -432,7 +625,38 @@ class FFNGeluFn(Function):
             dy = torch.mm(du, W1c)
             dx, dg, dbt = layernorm_bwd(dy, x2, g, mean, rstd, _dres_for(dalias, x2))
         return (dx.view(*dout.shape[:-1], x2.shape[-1]).to(in_dtype), dg.to(p[0]), dbt.to(p[0]), dW1.to(p[1]),
-                db1.to(p[2]), dW2.to(p[3]), db2.to(p[4]), None, None, None)
+                db1.to(p[2]), dW2.to(p[3]), db2.to(p[4]), None, None, None, None, None)
+
+
+class LinearResidualFn(Function):
+    """res + scale[b] * (a W^T + bias): the edge-channel output projection of EGT_Attention / EdgeUpdate
+    (lin_O_e, reference layers.py:82,126) with the caller's DropPath + residual add (layers.py:278-279) fused in."""
+
+    @staticmethod
+    def forward(ctx, a, W, bias, res, scale, cdtype):
+        _require_cuda(a, W, res)
+        with torch.autocast("cuda", enabled=False):
+            shape = res.shape
+            a2 = a.detach().to(cdtype).reshape(-1, a.shape[-1]).contiguous()
+            Wc = W.detach().to(cdtype).contiguous()
+            r2 = res.detach().reshape(-1, shape[-1])
+            if r2.dtype not in (cdtype, torch.float32):
+                r2 = r2.to(cdtype)
+            sc = _f32c(scale).view(-1) if scale is not None else None
+            out = torch.empty(shape, dtype=cdtype, device=a.device)
+            linear_residual(a2, Wc, bias, r2.contiguous(), sc, out2=out.view(-1, shape[-1]), name="gemm_tc_lin_o_e")
+            ctx.save_for_backward(a2, Wc, sc)
+            ctx.dts = (a.dtype, W.dtype, bias.dtype, res.dtype, a.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        a2, Wc, sc = ctx.saved_tensors
+        with torch.autocast("cuda", enabled=False):
+            do = dout.reshape(-1, dout.shape[-1]).to(a2.dtype).contiguous()
+            da, dW, db = linear_residual_bwd(do, a2, Wc, sc, name="gemm_tc_dhhat")
+        d = ctx.dts
+        return (da.view(d[4]).to(d[0]), dW.to(d[1]), db.to(d[2]), dout.to(d[3]), None, None)
 
 
 # ------------------------------------------------------------------------------------------
@@ -471,60 +695,3 @@ class ScaledResidualFn(Function):
 def scaled_residual(x: Tensor, res: Tensor, scale: Optional[Tensor]) -> Tensor:
     return ScaledResidualFn.apply(x, res, scale)
 
-
-# ------------------------------------------------------------------------------------------
-# tcgen05 / TMA projection GEMM with fused epilogues (csrc/gemm_tc.cu)
-# ------------------------------------------------------------------------------------------
-def row_stats(x2: Tensor, eps: float = 1e-5):
-    """per-row LayerNorm statistics (mean, rstd) of a 16-bit [rows, W] matrix."""
-    rows, W = x2.shape
-    mean = torch.empty(rows, dtype=torch.float32, device=x2.device)
-    rstd = torch.empty(rows, dtype=torch.float32, device=x2.device)
-    with timed(f"row_stats_W{W}"):
-        _C.check(_C.lib().tgt_row_stats(_C.ptr(x2), _C.ptr(mean), _C.ptr(rstd), rows, W, x2.stride(0), eps,
-                                        _C.dtype_code(x2.dtype), _C.stream_ptr()), "row_stats")
-    return mean, rstd
-
-
-def gemm_tc(a: Tensor, w: Tensor, *, bias: Optional[Tensor] = None, ln: Optional[tuple] = None,
-            gelu: Optional[tuple] = None, res: Optional[Tensor] = None, row_scale: Optional[Tensor] = None,
-            rows_per_scale: int = 0, out: Optional[Tensor] = None, name: str = "gemm_tc"):
-    """out[M,N] = epilogue(a[M,K] @ w[N,K]^T) on the tcgen05 kernel.
-
-    ln   = (row_mean, row_rstd, col_sum): LayerNorm folded into the epilogue (`w` must already be W*gamma and
-           `bias` = b + W beta);
-    gelu = (p_drop, seed): exact GELU + dropout; returns (out, u) with u the 16-bit pre-activation;
-    res / row_scale / rows_per_scale: out = res + row_scale[row // rows_per_scale] * value."""
-    M, K = a.shape
-    N = w.shape[0]
-    assert w.shape[1] == K and a.stride(1) == 1 and w.stride(1) == 1
-    if out is None:
-        out = torch.empty((M, N), dtype=a.dtype, device=a.device)
-    g = _C.GemmDesc()
-    g.M, g.N, g.K = M, N, K
-    g.lda, g.ldb, g.ldd = a.stride(0), w.stride(0), out.stride(0)
-    g.dtype = _C.dtype_code(a.dtype)
-    flags = 0
-    keep = [a, w, out]
-    if ln is not None:
-        flags |= _C.EPI_LN
-        g.row_mean, g.row_rstd, g.col_sum = ln[0].data_ptr(), ln[1].data_ptr(), ln[2].data_ptr()
-    if bias is not None:
-        flags |= _C.EPI_BIAS
-        g.bias = bias.data_ptr()
-    u = None
-    if gelu is not None:
-        flags |= _C.EPI_GELU | _C.EPI_STORE_U
-        u = torch.empty((M, N), dtype=a.dtype, device=a.device)
-        g.U, g.ldu = u.data_ptr(), u.stride(0)
-        g.p_drop, g.seed = float(gelu[0]), int(gelu[1])
-    if res is not None:
-        flags |= _C.EPI_RES
-        g.res, g.ldres, g.res_dtype = res.data_ptr(), res.stride(0), _C.dtype_code(res.dtype)
-        if row_scale is not None:
-            g.row_scale, g.rows_per_scale = row_scale.data_ptr(), int(rows_per_scale)
-    g.flags = flags
-    with timed(name):
-        _C.check(_C.lib().tgt_gemm_tc(g, _C.ptr(a), _C.ptr(w), _C.ptr(out), _C.stream_ptr()), "gemm_tc")
-    del keep
-    return (out, u) if gelu is not None else out

@@ -159,6 +159,8 @@ int tgt_egt_attn_bwd(const tgt_egt_desc *desc, const void *qkv, const void *eg, 
 #define TGT_EPI_RES     8
 #define TGT_EPI_STORE_U 16
 #define TGT_EPI_ROWSCALE 64   /* value *= row_scale[row / rows_per_scale] (DropPath in backward), no residual      */
+#define TGT_EPI_STATS    256  /* also write LayerNorm statistics (mean, 1/sqrt(var + stat_eps)) of the OUTPUT rows, for the
+                               * next LayerNorm-folded GEMM; needs N <= 256                                            */
 #define TGT_EPI_GELU_BWD 128  /* D = value * GELU'(u) * dropout mask(p_drop, seed); u = `res` (16-bit, pitch ldres) */
 typedef struct {
   int64_t M;
@@ -173,6 +175,8 @@ typedef struct {
   int64_t ldu;
   float p_drop;
   uint64_t seed;
+  float *stat_mean, *stat_rstd;   /* [M] out, TGT_EPI_STATS only */
+  float stat_eps;
 } tgt_gemm_desc;
 int tgt_gemm_tc(const tgt_gemm_desc *desc, const void *A, const void *B, void *D, void *stream);
 

@@ -133,3 +133,37 @@ def test_linear_residual_bwd_matches_autograd():
     _close(da, a.grad, 8e-3)
     _close(dW, W.grad, 8e-3)
     _close(db, b.grad, 8e-3)
+
+
+@pytest.mark.parametrize("N,K", [(256, 256), (256, 64), (64, 128)])
+def test_gemm_output_row_stats(N, K):
+    """EPI_STATS: mean / rstd of the rows the residual GEMM writes == LayerNorm statistics of its (rounded) output."""
+    ops = _ops()
+    M = 5003
+    a, w = _rand((M, K), torch.bfloat16, 41), _rand((N, K), torch.bfloat16, 42, K ** -0.5)
+    bias, res = _rand((N,), torch.float32, 43), (_rand((M, N), torch.float32, 44) * 2 + 0.7).to(torch.bfloat16)
+    mean = torch.empty(M, device="cuda")
+    rstd = torch.empty(M, device="cuda")
+    out = ops.gemm_tc(a, w, bias=bias, res=res, stats_out=(mean, rstd))
+    of = out.float()
+    assert torch.allclose(mean, of.mean(1), atol=2e-5, rtol=1e-5)
+    assert torch.allclose(rstd, (of.var(1, unbiased=False) + 1e-5).rsqrt(), rtol=2e-4)
+    m2, r2 = ops.row_stats(out)
+    assert torch.allclose(mean, m2, atol=2e-5) and torch.allclose(rstd, r2, rtol=2e-4)
+
+
+def test_stats_handoff_between_modules():
+    """the statistics attached by one fused module are consumed by the next one and change nothing numerically."""
+    from tgt_b200 import layers as L
+    from tgt_b200.harness.synthetic import make_edge_inputs
+    torch.manual_seed(0)
+    ffn1, ffn2 = L.FFN(64).cuda().eval(), L.FFN(64).cuda().eval()
+    e, _ = make_edge_inputs(3, 12, 64, [12, 7, 5], seed=3)
+    e = e.cuda().bfloat16()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y1 = ffn1.forward_residual(e, None)
+        assert getattr(y1, "_tgt_ln_stats", None) is not None
+        y2 = ffn2.forward_residual(y1, None)
+        y1b = y1.clone()                                  # same values, no attached statistics
+        y2b = ffn2.forward_residual(y1b, None)
+    assert (y2.float() - y2b.float()).abs().max().item() <= 2e-2 * y2b.float().abs().max().item()

@@ -56,10 +56,11 @@ class GemmDesc(C.Structure):
                 ("res", C.c_void_p), ("ldres", C.c_int64), ("res_dtype", C.c_int32),
                 ("rows_per_scale", C.c_int32),
                 ("U", C.c_void_p), ("ldu", C.c_int64),
-                ("p_drop", C.c_float), ("seed", C.c_uint64)]
+                ("p_drop", C.c_float), ("seed", C.c_uint64),
+                ("stat_mean", C.c_void_p), ("stat_rstd", C.c_void_p), ("stat_eps", C.c_float)]
 
 
-EPI_LN, EPI_BIAS, EPI_GELU, EPI_RES, EPI_STORE_U, EPI_ROWSCALE, EPI_GELU_BWD = 1, 2, 4, 8, 16, 64, 128
+EPI_LN, EPI_BIAS, EPI_GELU, EPI_RES, EPI_STORE_U, EPI_ROWSCALE, EPI_GELU_BWD, EPI_STATS = 1, 2, 4, 8, 16, 64, 128, 256
 
 _P = C.c_void_p
 _SIGNATURES = {

@@ -109,7 +109,7 @@ template <typename T> __device__ __forceinline__ uint32_t umma_idesc(int n) {
 
 // ---------------------------------------------------------------------------------------------- kernel
 enum : int { EPI_LN = 1, EPI_BIAS = 2, EPI_GELU = 4, EPI_RES = 8, EPI_STORE_U = 16, EPI_RES_F32 = 32, EPI_ROWSCALE = 64,
-              EPI_GELU_BWD = 128 };
+              EPI_GELU_BWD = 128, EPI_STATS = 256 };
 
 struct GemmParams {
   int64_t M;
@@ -125,6 +125,8 @@ struct GemmParams {
   float p_drop;
   unsigned long long seed;
   int flags;
+  float *stat_mean, *stat_rstd;      // EPI_STATS: LayerNorm statistics of the OUTPUT rows (needs one column slice)
+  float stat_eps;
 };
 
 constexpr int GEMM_THREADS = 320;      // warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: epilogue
@@ -227,7 +229,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t sA = sB + (uint32_t)p.kblocks * bn * 128;                 // stages x 16 KB
   const uint32_t sStage = sA + (uint32_t)p.stages * A_STAGE_BYTES;         // 8 warps x (D 2 KB [+ U 2 KB])
   const uint32_t sVec = sStage + epi_stage_bytes(FLAGS);                         // colsum[256], bias[256] fp32
-  const uint32_t sBar = sVec + 2048;                                       // mbarriers
+  const uint32_t sPart = sVec + 2048;                                      // EPI_STATS: [2 buffers][8 warps][32 rows] float2
+  const uint32_t sBar = sPart + 4096;                                      // mbarriers
+  float2 *part = reinterpret_cast<float2 *>(smem_gen + (sPart - smem_base));
   float *vec_colsum = reinterpret_cast<float *>(smem_gen + (sVec - smem_base));
   float *vec_bias = vec_colsum + 256;
   const uint32_t bar_full = sBar, bar_empty = sBar + 8 * 8, bar_bfull = sBar + 16 * 8;
@@ -328,16 +332,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       T *Dp = reinterpret_cast<T *>(p.D);
       int acc = 0;
       uint32_t acc_phase = 0;
+      // per-row epilogue inputs (LN statistics, DropPath scale) are fetched one tile ahead
+      float nx_rstd = 1.f, nx_mean = 0.f, nx_rs = 1.f;
+      auto row_inputs = [&](int64_t mt_) {
+        const int64_t r_ = mt_ * 128 + quad * 32 + lane;
+        nx_rstd = 1.f, nx_mean = 0.f, nx_rs = 1.f;
+        if (mt_ < num_m_tiles && r_ < p.M) {
+          if (FLAGS & EPI_LN) {
+            nx_rstd = p.row_rstd[r_];
+            nx_mean = p.row_mean[r_];
+          }
+          if ((FLAGS & (EPI_RES | EPI_ROWSCALE)) && p.row_scale) nx_rs = p.row_scale[r_ / p.rows_per_scale];
+        }
+      };
+      row_inputs(q);
       for (int64_t mt = q; mt < num_m_tiles; mt += p.ctas_per_slice) {
         const int64_t row0 = mt * 128 + quad * 32;
         const int64_t row = row0 + lane;
-        float rstd = 1.f, nmr = 0.f;
-        if ((FLAGS & EPI_LN) && row < p.M) {
-          rstd = p.row_rstd[row];
-          nmr = -p.row_mean[row] * rstd;
-        }
-        float rs_lane = 1.f;                 // DropPath scale of this lane's row (TMEM domain)
-        if ((FLAGS & (EPI_RES | EPI_ROWSCALE)) && p.row_scale && row < p.M) rs_lane = p.row_scale[row / p.rows_per_scale];
+        const float rstd = nx_rstd, nmr = -nx_mean * nx_rstd;
+        const float rs_lane = nx_rs;         // DropPath scale of this lane's row (TMEM domain)
+        row_inputs(mt + p.ctas_per_slice);
         // residual values of the coalesced phase are fetched one 32-column group ahead
         uint4 rcur[4][RW], rnext[4][RW];
         auto res_load = [&](int c, uint4(&rb)[4][RW]) {
@@ -359,12 +373,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         };
         if (FLAGS & (EPI_RES | EPI_GELU_BWD)) res_load(half * 32, rcur);
+        float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};   // EPI_STATS: sum / sum of squares per row
         mbar_wait(bar_tfull + acc * 8, acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * bn);
+        uint32_t v[32];
+        if (half * 32 < bn) tc_ld32(taddr + half * 32, v);
         for (int c = half * 32; c < bn; c += 64) {
-          uint32_t v[32];
-          tc_ld32(taddr + c, v);
+          // per-column epilogue vectors of this group (shared-memory broadcasts), issued before the TMEM wait
+          float4 csv[8], bsv[8];
+          if (FLAGS & EPI_LN) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) csv[k] = *reinterpret_cast<const float4 *>(vec_colsum + c + k * 4);
+          }
+          if (FLAGS & EPI_BIAS) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) bsv[k] = *reinterpret_cast<const float4 *>(vec_bias + c + k * 4);
+          }
           if ((FLAGS & (EPI_RES | EPI_GELU_BWD)) && c + 64 < bn) res_load(c + 64, rnext);
           tc_ld_wait();
           // ---- TMEM domain (lane = row): LN fold, bias, activation; 16-bit results go to the staging tile
@@ -374,16 +399,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[pc * 8 + i]);
             if (FLAGS & EPI_LN) {
-              const float4 c0 = *reinterpret_cast<const float4 *>(vec_colsum + c + pc * 8);
-              const float4 c1 = *reinterpret_cast<const float4 *>(vec_colsum + c + pc * 8 + 4);
-              const float cs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+              const float cs[8] = {csv[2 * pc].x, csv[2 * pc].y, csv[2 * pc].z, csv[2 * pc].w,
+                                   csv[2 * pc + 1].x, csv[2 * pc + 1].y, csv[2 * pc + 1].z, csv[2 * pc + 1].w};
+              if (FLAGS & EPI_BIAS) {
+                const float bs[8] = {bsv[2 * pc].x, bsv[2 * pc].y, bsv[2 * pc].z, bsv[2 * pc].w,
+                                     bsv[2 * pc + 1].x, bsv[2 * pc + 1].y, bsv[2 * pc + 1].z, bsv[2 * pc + 1].w};
 #pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], rstd, nmr * cs[i]);
-            }
-            if (FLAGS & EPI_BIAS) {
-              const float4 b0 = *reinterpret_cast<const float4 *>(vec_bias + c + pc * 8);
-              const float4 b1 = *reinterpret_cast<const float4 *>(vec_bias + c + pc * 8 + 4);
-              const float bs[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], rstd, fmaf(nmr, cs[i], bs[i]));
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], rstd, nmr * cs[i]);
+              }
+            } else if (FLAGS & EPI_BIAS) {
+              const float bs[8] = {bsv[2 * pc].x, bsv[2 * pc].y, bsv[2 * pc].z, bsv[2 * pc].w,
+                                   bsv[2 * pc + 1].x, bsv[2 * pc + 1].y, bsv[2 * pc + 1].z, bsv[2 * pc + 1].w};
 #pragma unroll
               for (int i = 0; i < 8; ++i) f[i] += bs[i];
             }
@@ -417,16 +446,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             w.w = pack2<T>(f[6], f[7]);
             st_shared_v4(stage_addr(stD, lane, pc), w);
           }
+          if (c + 64 < bn) tc_ld32(taddr + c + 64, v);      // next group's accumulators fly during the store phase
           __syncwarp();
           // ---- coalesced domain: each instruction moves 8 rows x 64 contiguous bytes
           const int gc = col0 + c + cpiece * 8;
+          uint4 wst[4], ust[4];
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            wst[it] = ld_shared_v4(stage_addr(stD, it * 8 + crow, cpiece));
+            if (FLAGS & EPI_STORE_U) ust[it] = ld_shared_v4(stage_addr(stU, it * 8 + crow, cpiece));
+          }
           if (c + cpiece * 8 < bn && gc < p.N) {
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
               const int r = it * 8 + crow;
               const int64_t grow = row0 + r;
               if (grow < p.M) {
-                uint4 w = ld_shared_v4(stage_addr(stD, r, cpiece));
+                uint4 w = wst[it];
                 if (FLAGS & EPI_GELU_BWD) {
                   // D = value * GELU'(u) * dropout mask, u = the saved pre-activation (p.res), same hash as forward
                   const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
@@ -473,9 +509,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   w.w = pack2<T>(f[6], f[7]);
                 }
                 *reinterpret_cast<uint4 *>(Dp + grow * p.ldd + gc) = w;
-                if (FLAGS & EPI_STORE_U)
-                  *reinterpret_cast<uint4 *>(reinterpret_cast<T *>(p.U) + grow * p.ldu + gc) =
-                      ld_shared_v4(stage_addr(stU, r, cpiece));
+                if (FLAGS & EPI_STATS) {          // statistics of the values as stored (16-bit rounded)
+                  const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    float a, b;
+                    unpack2<T>(ww[j], a, b);
+                    st1[it] += a + b;
+                    st2[it] = fmaf(a, a, fmaf(b, b, st2[it]));
+                  }
+                }
+                if (FLAGS & EPI_STORE_U) *reinterpret_cast<uint4 *>(reinterpret_cast<T *>(p.U) + grow * p.ldu + gc) = ust[it];
               }
             }
           }
@@ -489,6 +533,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         tc_fence_before();
         if (lane == 0) mbar_arrive(bar_tempty + acc * 8);
+        if (FLAGS & EPI_STATS) {
+          // row sums: 4 lanes (pieces) per row, then the two warps of this TMEM quadrant (even / odd column groups)
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            st1[it] += __shfl_xor_sync(0xffffffffu, st1[it], 1);
+            st1[it] += __shfl_xor_sync(0xffffffffu, st1[it], 2);
+            st2[it] += __shfl_xor_sync(0xffffffffu, st2[it], 1);
+            st2[it] += __shfl_xor_sync(0xffffffffu, st2[it], 2);
+          }
+          float2 *mine = part + (acc * EPI_WARPS + (warp - 2)) * 32;
+          if (cpiece == 0) {
+#pragma unroll
+            for (int it = 0; it < 4; ++it) mine[it * 8 + crow] = make_float2(st1[it], st2[it]);
+          }
+          asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");
+          if (half == 0 && cpiece == 0) {
+            const float2 *other = part + (acc * EPI_WARPS + (warp - 2) + 4) * 32;
+            const float inv_n = 1.f / (float)p.N;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int64_t grow = row0 + it * 8 + crow;
+              if (grow < p.M) {
+                const float2 o = other[it * 8 + crow];
+                const float mu = (st1[it] + o.x) * inv_n;
+                const float var = fmaxf((st2[it] + o.y) * inv_n - mu * mu, 0.f);
+                p.stat_mean[grow] = mu;
+                p.stat_rstd[grow] = rsqrtf(var + p.stat_eps);
+              }
+            }
+          }
+        }
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -627,6 +702,8 @@ static int dispatch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const Gem
     TGT_GEMM_CASE(EPI_BIAS | EPI_RES)
     TGT_GEMM_CASE(EPI_BIAS | EPI_RES | EPI_RES_F32)
     TGT_GEMM_CASE(EPI_RES)
+    TGT_GEMM_CASE(EPI_BIAS | EPI_RES | EPI_STATS)
+    TGT_GEMM_CASE(EPI_BIAS | EPI_RES | EPI_RES_F32 | EPI_STATS)
     TGT_GEMM_CASE(EPI_ROWSCALE)
     TGT_GEMM_CASE(EPI_GELU_BWD)
     TGT_GEMM_CASE(EPI_GELU_BWD | EPI_ROWSCALE)
@@ -670,7 +747,7 @@ extern "C" int tgt_gemm_tc(const tgt_gemm_desc *g, const void *A, const void *B,
   p.K = g->K;
   p.kblocks = (g->K + 63) / 64;
   // widest slice whose weight panel leaves room for >= 3 activation stages
-  const int smem_budget = 232448 - 1024 - 2048 - 256 - epi_stage_bytes(flags);
+  const int smem_budget = 232448 - 1024 - 2048 - 4096 - 256 - epi_stage_bytes(flags);
   int bn_max = 256;
   while (bn_max > 16 && p.kblocks * bn_max * 128 + 3 * A_STAGE_BYTES > smem_budget) bn_max -= 16;
   p.n_slices = (g->N + bn_max - 1) / bn_max;
@@ -699,11 +776,18 @@ extern "C" int tgt_gemm_tc(const tgt_gemm_desc *g, const void *A, const void *B,
   if ((flags & EPI_RES) && g->res_dtype == TGT_F32) flags |= EPI_RES_F32;
   else if ((flags & EPI_RES) && g->res_dtype != g->dtype) return fail("gemm_tc: residual dtype must be fp32 or the operand dtype");
   p.flags = flags;
+  if (flags & EPI_STATS) {
+    if (p.n_slices != 1 || p.bn < g->N || !g->stat_mean || !g->stat_rstd)
+      return fail("gemm_tc: STATS epilogue needs N <= 256 (one column slice) and the two output vectors");
+    p.stat_mean = g->stat_mean;
+    p.stat_rstd = g->stat_rstd;
+    p.stat_eps = g->stat_eps;
+  }
 
   CUtensorMap ma, mb;
   if (int e = make_operand_map(&ma, A, g->M, g->K, g->lda, 128, g->dtype)) return e;
   if (int e = make_operand_map(&mb, B, g->N, g->K, g->ldb, p.bn, g->dtype)) return e;
-  const size_t smem = (size_t)p.kblocks * p.bn * 128 + (size_t)p.stages * A_STAGE_BYTES + epi_stage_bytes(flags) + 2048 + 256 + 1024;
+  const size_t smem = (size_t)p.kblocks * p.bn * 128 + (size_t)p.stages * A_STAGE_BYTES + epi_stage_bytes(flags) + 2048 + 4096 + 256 + 1024;
   cudaStream_t st = (cudaStream_t)stream;
   if (g->dtype == TGT_BF16) return dispatch_gemm<__nv_bfloat16>(ma, mb, p, smem, st);
   return dispatch_gemm<__half>(ma, mb, p, smem, st);

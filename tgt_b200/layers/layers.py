@@ -54,8 +54,8 @@ class EGT_Attention(nn.Module):
     def edge_residual(self, hhat, e_alias, scale):
         """e + scale[b] * lin_O_e(H_hat): the edge output projection (layers.py:81-82) with the caller's DropPath +
         residual add (layers.py:278-279) as the epilogue of one GEMM."""
-        return ops.LinearResidualFn.apply(hhat, self.lin_O_e.weight, self.lin_O_e.bias, e_alias, scale,
-                                          ops.compute_dtype(e_alias))
+        return ops.unpack_fused(ops.LinearResidualFn.apply(hhat, self.lin_O_e.weight, self.lin_O_e.bias, e_alias,
+                                                           scale, ops.compute_dtype(e_alias)))
 
     def forward_parts(self, h, e, mask):
         """(h_out, H_hat, alias of e): everything except the edge output projection."""
@@ -145,9 +145,10 @@ class FFN(nn.Module):
         if self.activation == 'gelu':
             p = self.act_dropout if self.training else 0.
             seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0 else 0      # CPU generator: no sync
-            return ops.FFNGeluFn.apply(x, self.ffn_ln.weight, self.ffn_ln.bias, self.lin_W1.weight,
-                                       self.lin_W1.bias, self.lin_W2.weight, self.lin_W2.bias, p, seed,
-                                       ops.compute_dtype(x), scale, fuse_res)
+            res = ops.FFNGeluFn.apply(x, self.ffn_ln.weight, self.ffn_ln.bias, self.lin_W1.weight,
+                                      self.lin_W1.bias, self.lin_W2.weight, self.lin_W2.bias, p, seed,
+                                      ops.compute_dtype(x), scale, fuse_res)
+            return ops.unpack_fused(res) if fuse_res else res
         # gated activations (geglu/glu/swiglu) are not used by any shipped config: plain library ops on the
         # LayerNorm / GEMMs (still CUDA-only: the residual kernels around this module refuse CPU tensors)
         ops._require_cuda(x)

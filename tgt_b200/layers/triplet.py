@@ -115,8 +115,9 @@ class _AttentionFamily(_TripletBase):
         bcat = torch.cat(b_parts, 0)
         Wo = self.lin_O.weight.index_select(1, _out_perm(W, H, dev))
         layout = (H, d, off_q, off_k, off_v, tuple(off_e), tuple(off_g))
-        return ops.TripletAttentionFn.apply(e, mask, self.tri_ln_e.weight, self.tri_ln_e.bias, Wcat, bcat, Wo,
-                                            self.lin_O.bias, layout, ops.compute_dtype(e), scale, fuse_res)
+        res = ops.TripletAttentionFn.apply(e, mask, self.tri_ln_e.weight, self.tri_ln_e.bias, Wcat, bcat, Wo,
+                                           self.lin_O.bias, layout, ops.compute_dtype(e), scale, fuse_res)
+        return ops.unpack_fused(res) if fuse_res else res
 
 
 class TripletAttention(_AttentionFamily):
@@ -213,8 +214,9 @@ class _AggregateFamily(_TripletBase):
         bcat = torch.cat(b_parts, 0)
         Wo = self.lin_O.weight.index_select(1, _out_perm(W, H, dev))
         layout = (H, d, (0, W), off_e, off_g, mask_dir)
-        return ops.TripletAggregateFn.apply(e, mask, self.tri_ln_e.weight, self.tri_ln_e.bias, Wcat, bcat, Wo,
-                                            self.lin_O.bias, layout, ops.compute_dtype(e), scale, fuse_res)
+        res = ops.TripletAggregateFn.apply(e, mask, self.tri_ln_e.weight, self.tri_ln_e.bias, Wcat, bcat, Wo,
+                                           self.lin_O.bias, layout, ops.compute_dtype(e), scale, fuse_res)
+        return ops.unpack_fused(res) if fuse_res else res
 
 
 class TripletAggregate(_AggregateFamily):

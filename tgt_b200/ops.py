@@ -154,7 +154,7 @@ def row_stats(x2: Tensor, eps: float = 1e-5):
 def gemm_tc(a: Tensor, w: Tensor, *, bias: Optional[Tensor] = None, ln: Optional[tuple] = None,
             gelu: Optional[tuple] = None, res: Optional[Tensor] = None, row_scale: Optional[Tensor] = None,
             rows_per_scale: int = 0, gelu_bwd: Optional[tuple] = None, out: Optional[Tensor] = None,
-            name: str = "gemm_tc"):
+            stats_out: Optional[tuple] = None, name: str = "gemm_tc"):
     """out[M,N] = epilogue(a[M,K] @ w[N,K]^T) on the tcgen05 kernel.
 
     ln   = (row_mean, row_rstd, col_sum): LayerNorm folded into the epilogue (`w` must already be W*gamma and
@@ -162,7 +162,8 @@ def gemm_tc(a: Tensor, w: Tensor, *, bias: Optional[Tensor] = None, ln: Optional
     gelu = (p_drop, seed): exact GELU + dropout; returns (out, u) with u the 16-bit pre-activation;
     row_scale / rows_per_scale: value *= row_scale[row // rows_per_scale] (DropPath);
     res: out = res + value;
-    gelu_bwd = (u, p_drop, seed): out = value * GELU'(u) * dropout mask (backward of `gelu`)."""
+    gelu_bwd = (u, p_drop, seed): out = value * GELU'(u) * dropout mask (backward of `gelu`);
+    stats_out = (mean, rstd): fp32 [M] vectors that receive the LayerNorm statistics of the output rows (N <= 256)."""
     M, K = a.shape
     N = w.shape[0]
     assert w.shape[1] == K and a.stride(1) == 1 and w.stride(1) == 1
@@ -197,10 +198,28 @@ def gemm_tc(a: Tensor, w: Tensor, *, bias: Optional[Tensor] = None, ln: Optional
         if res is None:
             flags |= _C.EPI_ROWSCALE
         g.row_scale, g.rows_per_scale = row_scale.data_ptr(), int(rows_per_scale)
+    if stats_out is not None:
+        flags |= _C.EPI_STATS
+        g.stat_mean, g.stat_rstd, g.stat_eps = stats_out[0].data_ptr(), stats_out[1].data_ptr(), 1e-5
     g.flags = flags
     with timed(name):
         _C.check(_C.lib().tgt_gemm_tc(g, _C.ptr(a), _C.ptr(w), _C.ptr(out), _C.stream_ptr()), "gemm_tc")
     return (out, u) if gelu is not None else out
+
+
+def take_stats(x: Tensor, x2: Tensor) -> Optional[tuple]:
+    """LayerNorm statistics attached to `x` by the kernel that produced it (see linear_residual), if they describe
+    exactly the rows of x2 (no dtype conversion / copy happened in between)."""
+    st = getattr(x, "_tgt_ln_stats", None)
+    if st is None or x2.data_ptr() != x.data_ptr() or x2.dtype != x.dtype or st[0].numel() != x2.shape[0]:
+        return None
+    return st
+
+
+def attach_stats(out: Tensor, mean: Optional[Tensor], rstd: Optional[Tensor]) -> Tensor:
+    if mean is not None:
+        out._tgt_ln_stats = (mean, rstd)
+    return out
 
 
 def tc_gemm_ok(a: Tensor, N: int, K: int) -> bool:
@@ -232,10 +251,12 @@ def _scale_rows(x2: Tensor, scale: Optional[Tensor]) -> Tensor:
 
 
 def linear_residual(a2: Tensor, Wc: Tensor, bias: Tensor, res2: Optional[Tensor], scale: Optional[Tensor],
-                    out2: Optional[Tensor] = None, name: str = "gemm_tc_out") -> Tensor:
+                    out2: Optional[Tensor] = None, want_stats: bool = False, name: str = "gemm_tc_out"):
     """res2 + scale[b] * (a2 @ Wc^T + bias)   (res2 / scale optional; scale is per graph, rows are graph-major).
     One tcgen05 GEMM with the DropPath + residual epilogue when the shape allows, else cuBLAS + our residual kernel.
-    `out2`: optional preallocated [M, N] result (a 2-D view of the tensor the caller returns)."""
+    `out2`: optional preallocated [M, N] result (a 2-D view of the tensor the caller returns).
+    Returns (out2, stats): with want_stats the same GEMM also emits the LayerNorm statistics (mean, rstd) of the rows
+    it writes, so the next LayerNorm-folded GEMM needs no pass of its own (stats is None when not available)."""
     M, K = a2.shape
     N = Wc.shape[0]
     if out2 is None:
@@ -243,17 +264,24 @@ def linear_residual(a2: Tensor, Wc: Tensor, bias: Tensor, res2: Optional[Tensor]
     if tc_gemm_ok(a2, N, K) and Wc.dtype == a2.dtype and (res2 is None or (
             res2.dtype in (a2.dtype, torch.float32) and res2.stride(1) == 1 and res2.stride(0) % 8 == 0)):
         rps = M // scale.numel() if scale is not None else 0
-        return gemm_tc(a2, Wc, bias=bias.detach().float().contiguous(), res=res2,
-                       row_scale=scale if res2 is not None else None, rows_per_scale=rps, out=out2, name=name)
+        stats = None
+        # the statistics epilogue needs the whole output row in one CTA: the [N, K] weight panel must fit in smem
+        if want_stats and res2 is not None and N <= 256 and ((K + 63) // 64) * ((N + 15) // 16 * 16) * 128 <= 159000:
+            stats = (torch.empty(M, dtype=torch.float32, device=a2.device),
+                     torch.empty(M, dtype=torch.float32, device=a2.device))
+        gemm_tc(a2, Wc, bias=bias.detach().float().contiguous(), res=res2,
+                row_scale=scale if res2 is not None else None, rows_per_scale=rps, out=out2, stats_out=stats,
+                name=name)
+        return out2, stats
     if res2 is None:
-        return torch.addmm(bias.detach().to(a2.dtype), a2, Wc.t(), out=out2)
+        return torch.addmm(bias.detach().to(a2.dtype), a2, Wc.t(), out=out2), None
     y = torch.addmm(bias.detach().to(a2.dtype), a2, Wc.t())
     B = scale.numel() if scale is not None else 1
     rc = res2.contiguous()
     _C.check(_C.lib().tgt_scaled_residual(_C.ptr(y), _C.ptr(rc), _C.ptr(scale), _C.ptr(out2), B, y.numel() // B,
                                           _C.dtype_code(y.dtype), _C.dtype_code(rc.dtype), _C.stream_ptr()),
              "scaled_residual")
-    return out2
+    return out2, None
 
 
 try:                                           # fp32 results from 16-bit batched GEMMs (PyTorch >= 2.8)
@@ -296,17 +324,43 @@ def linear_residual_bwd(do2: Tensor, a2: Tensor, Wc: Tensor, scale: Optional[Ten
 
 
 def ln_linear(x2: Tensor, g: Tensor, bt: Tensor, W: Tensor, b: Tensor, Wc: Tensor, cd: torch.dtype,
-              name: str = "gemm_tc_ln"):
+              stats: Optional[tuple] = None, name: str = "gemm_tc_ln"):
     """(LN(x2) W^T + b, mean, rstd, fold).  16-bit x2: row statistics + ONE tcgen05 GEMM on the raw rows with the
     LayerNorm folded into its epilogue (the normalised tensor never exists), fold = (Wg, b', colsum) for an identical
     recompute in backward; otherwise LN kernel + cuBLAS and fold = (None, None, None)."""
     N, K = W.shape
     if x2.dtype == cd and tc_gemm_ok(x2, N, K):
-        mean, rstd = row_stats(x2)
+        # statistics: handed over by the GEMM that produced x2 (EPI_STATS) or one read-only pass
+        mean, rstd = stats if stats is not None else row_stats(x2)
         Wg, bp, cs = _ln_fold(W, b, g, bt, cd)
         return gemm_tc(x2, Wg, bias=bp, ln=(mean, rstd, cs), name=name), mean, rstd, (Wg, bp, cs)
     y, mean, rstd = layernorm_fwd(x2, g, bt, cd)
     return torch.addmm(b.detach().to(cd), y, Wc.t()), mean, rstd, (None, None, None)
+
+
+def _with_stats(ctx, out: Tensor, stats: Optional[tuple]):
+    """Function.forward return value of the fused-residual modes: (out, mean, rstd); the statistics (or two empty
+    placeholders) are non-differentiable side outputs that the module layer attaches to `out` (attach_stats)."""
+    if stats is None:
+        mean = rstd = torch.empty(0, dtype=torch.float32, device=out.device)
+        rstd = torch.empty(0, dtype=torch.float32, device=out.device)
+    else:
+        mean, rstd = stats
+    ctx.mark_non_differentiable(mean, rstd)
+    return out, mean, rstd
+
+
+def ctx_fused(ctx) -> bool:
+    f = getattr(ctx, "fuse_res", None)
+    if f is None:
+        f = ctx.meta[5]
+    return bool(f)
+
+
+def unpack_fused(res):
+    """(out, mean, rstd) from a fused-residual Function -> out with the statistics attached (if any)."""
+    out, mean, rstd = res
+    return attach_stats(out, mean if mean.numel() else None, rstd)
 
 
 # ------------------------------------------------------------------------------------------
@@ -321,7 +375,7 @@ class LNLinearFn(Function):
             x2 = _x_for_ln(x, cdtype).view(-1, shape[-1])
             g, bt = _f32c(ln_w), _f32c(ln_b)
             Wc = W.detach().to(cdtype)
-            out2, mean, rstd, _ = ln_linear(x2, g, bt, W, b, Wc, cdtype, name="gemm_tc_ln_eg")
+            out2, mean, rstd, _ = ln_linear(x2, g, bt, W, b, Wc, cdtype, stats=take_stats(x, x2), name="gemm_tc_ln_eg")
             out = out2.view(*shape[:-1], W.shape[0])      # not modified in place by any caller (feeds the EGT core)
             ctx.save_for_backward(x2, g, bt, Wc, mean, rstd)
             ctx.cdtype = cdtype
@@ -374,7 +428,8 @@ class TripletAttentionFn(Function):
             Wc, bc = Wcat.detach().to(cdtype).contiguous(), bcat.detach().to(cdtype).contiguous()
             Woc = Wo.detach().to(cdtype).contiguous()
             m3 = _f32c(mask).view(B, N, N)
-            proj, mean, rstd, fold = ln_linear(x2, g, bt, Wcat, bcat, Wc, cdtype, name="gemm_tc_ln_proj")
+            proj, mean, rstd, fold = ln_linear(x2, g, bt, Wcat, bcat, Wc, cdtype, stats=take_stats(e, x2),
+                                               name="gemm_tc_ln_proj")
             desc = _C.TripletAttnDesc(B, N, H, d, proj.shape[1], off_q, off_k, off_v, off_e, off_g,
                                       float(d) ** -0.5, _C.dtype_code(cdtype))
             va = torch.empty((R, 2 * H * d), dtype=cdtype, device=e.device)
@@ -387,7 +442,8 @@ class TripletAttentionFn(Function):
             del proj
             sc = _f32c(res_scale).view(B) if (fuse_res and res_scale is not None) else None
             out = torch.empty((B, N, N, W), dtype=cdtype, device=e.device)
-            linear_residual(va, Woc, bo, x2 if fuse_res else None, sc, out2=out.view(R, W), name="gemm_tc_lin_o")
+            _, ostats = linear_residual(va, Woc, bo, x2 if fuse_res else None, sc, out2=out.view(R, W),
+                                        want_stats=fuse_res, name="gemm_tc_lin_o")
             ctx.save_for_backward(x2, m3, g, bt, Wc, bc, Woc, mean, rstd, stats, va, sc, *fold)
             ctx.desc = desc
             ctx.cdtype = cdtype
@@ -396,11 +452,13 @@ class TripletAttentionFn(Function):
             ctx.pdt = (ln_w.dtype, Wcat.dtype, bcat.dtype, Wo.dtype, bo.dtype)
             ctx.set_materialize_grads(False)
         if fuse_res:
-            return out
+            return _with_stats(ctx, out, ostats)
         return out, e                   # (result, alias of the input for the caller's residual add: see LNLinearFn)
 
     @staticmethod
-    def backward(ctx, dout, dalias=None):
+    def backward(ctx, dout, dalias=None, _unused=None):
+        if ctx_fused(ctx):
+            dalias = None               # slots 2 and 3 are the (non-differentiable) statistics
         x2, m3, g, bt, Wc, bc, Woc, mean, rstd, stats, va, sc, Wg, bp, cs = ctx.saved_tensors
         if dout is None:
             return (dalias,) + (None,) * 11
@@ -451,7 +509,8 @@ class TripletAggregateFn(Function):
             Wc, bc = Wcat.detach().to(cdtype).contiguous(), bcat.detach().to(cdtype).contiguous()
             Woc = Wo.detach().to(cdtype).contiguous()
             m3 = _f32c(mask).view(B, N, N)
-            proj, mean, rstd, fold = ln_linear(x2, g, bt, Wcat, bcat, Wc, cdtype, name="gemm_tc_ln_proj")
+            proj, mean, rstd, fold = ln_linear(x2, g, bt, Wcat, bcat, Wc, cdtype, stats=take_stats(e, x2),
+                                               name="gemm_tc_ln_proj")
             desc = _C.TripletAggrDesc(B, N, H, d, proj.shape[1], off_v, off_e, off_g, mask_dir,
                                       _C.dtype_code(cdtype))
             va = torch.empty((R, 2 * H * d), dtype=cdtype, device=e.device)
@@ -462,7 +521,8 @@ class TripletAggregateFn(Function):
             del proj
             sc = _f32c(res_scale).view(B) if (fuse_res and res_scale is not None) else None
             out = torch.empty((B, N, N, W), dtype=cdtype, device=e.device)
-            linear_residual(va, Woc, bo, x2 if fuse_res else None, sc, out2=out.view(R, W), name="gemm_tc_lin_o")
+            _, ostats = linear_residual(va, Woc, bo, x2 if fuse_res else None, sc, out2=out.view(R, W),
+                                        want_stats=fuse_res, name="gemm_tc_lin_o")
             ctx.save_for_backward(x2, m3, g, bt, Wc, bc, Woc, mean, rstd, aw, va, sc, *fold)
             ctx.fuse_res = fuse_res
             ctx.desc = desc
@@ -471,11 +531,13 @@ class TripletAggregateFn(Function):
             ctx.pdt = (ln_w.dtype, Wcat.dtype, bcat.dtype, Wo.dtype, bo.dtype)
             ctx.set_materialize_grads(False)
         if fuse_res:
-            return out
+            return _with_stats(ctx, out, ostats)
         return out, e                   # (result, alias of the input for the caller's residual add: see LNLinearFn)
 
     @staticmethod
-    def backward(ctx, dout, dalias=None):
+    def backward(ctx, dout, dalias=None, _unused=None):
+        if ctx_fused(ctx):
+            dalias = None               # slots 2 and 3 are the (non-differentiable) statistics
         x2, m3, g, bt, Wc, bc, Woc, mean, rstd, aw, va, sc, Wg, bp, cs = ctx.saved_tensors
         if dout is None:
             return (dalias,) + (None,) * 11
@@ -582,7 +644,8 @@ class FFNGeluFn(Function):
             W1c, W2c = W1.detach().to(cdtype).contiguous(), W2.detach().to(cdtype).contiguous()
             inner, K = W1.shape
             if x2.dtype == cdtype and tc_gemm_ok(x2, inner, K):
-                mean, rstd = row_stats(x2)
+                st = take_stats(x, x2)
+                mean, rstd = st if st is not None else row_stats(x2)
                 W1g, b1p, cs = _ln_fold(W1, b1, g, bt, cdtype)
                 a, u = gemm_tc(x2, W1g, bias=b1p, ln=(mean, rstd, cs), gelu=(float(p_drop), int(seed)),
                                name="gemm_tc_ln_gelu")
@@ -597,17 +660,20 @@ class FFNGeluFn(Function):
             if fuse_res and res_scale is not None:
                 sc = _f32c(res_scale).view(-1)
             out = torch.empty((*shape[:-1], W2.shape[0]), dtype=cdtype, device=x.device)
-            linear_residual(a, W2c, b2, x2 if fuse_res else None, sc, out2=out.view(-1, W2.shape[0]), name="gemm_tc_w2")
+            _, ostats = linear_residual(a, W2c, b2, x2 if fuse_res else None, sc, out2=out.view(-1, W2.shape[0]),
+                                        want_stats=fuse_res, name="gemm_tc_w2")
             ctx.save_for_backward(x2, g, bt, W1c, W2c, mean, rstd, u, a, sc)
             ctx.meta = (float(p_drop), int(seed), cdtype, x.dtype,
                         (ln_w.dtype, W1.dtype, b1.dtype, W2.dtype, b2.dtype), fuse_res)
             ctx.set_materialize_grads(False)
         if fuse_res:
-            return out
+            return _with_stats(ctx, out, ostats)
         return out, x                   # (result, alias of the input for the caller's residual add: see LNLinearFn)
 
     @staticmethod
-    def backward(ctx, dout, dalias=None):
+    def backward(ctx, dout, dalias=None, _unused=None):
+        if ctx_fused(ctx):
+            dalias = None               # slots 2 and 3 are the (non-differentiable) statistics
         x2, g, bt, W1c, W2c, mean, rstd, u, a, sc = ctx.saved_tensors
         p_drop, seed, cd, in_dtype, p, fuse_res = ctx.meta
         if dout is None:
@@ -644,13 +710,14 @@ class LinearResidualFn(Function):
                 r2 = r2.to(cdtype)
             sc = _f32c(scale).view(-1) if scale is not None else None
             out = torch.empty(shape, dtype=cdtype, device=a.device)
-            linear_residual(a2, Wc, bias, r2.contiguous(), sc, out2=out.view(-1, shape[-1]), name="gemm_tc_lin_o_e")
+            _, ostats = linear_residual(a2, Wc, bias, r2.contiguous(), sc, out2=out.view(-1, shape[-1]),
+                                        want_stats=True, name="gemm_tc_lin_o_e")
             ctx.save_for_backward(a2, Wc, sc)
             ctx.dts = (a.dtype, W.dtype, bias.dtype, res.dtype, a.shape)
-        return out
+        return _with_stats(ctx, out, ostats)
 
     @staticmethod
-    def backward(ctx, dout):
+    def backward(ctx, dout, _m=None, _r=None):
         a2, Wc, sc = ctx.saved_tensors
         with torch.autocast("cuda", enabled=False):
             do = dout.reshape(-1, dout.shape[-1]).to(a2.dtype).contiguous()

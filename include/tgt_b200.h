@@ -37,7 +37,8 @@ const char *tgt_last_error(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 uint64_t    tgt_launch_count(void);
 /* 0 = pick the fastest kernel that supports the shape (default); 1 = force the generic
- * SIMT kernels (used by the tests to cross-check the tensor-core kernels). */
+ * SIMT kernels; 2 = tensor-core triplet kernels with cp.async staging instead of TMA (the
+ * tests cross-check the three families). */
 void        tgt_set_kernel_policy(int policy);
 
 /* ---- LayerNorm over the channel dim of edge rows ---------------------------------------

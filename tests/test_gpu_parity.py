@@ -66,7 +66,7 @@ def _oracle_autocast_error(fx, dtype):
     return rel_err(out.float().cpu(), fx["out"]), rel_err(e.grad.cpu(), fx["de"])
 
 
-@pytest.mark.parametrize("policy", [0, 1])
+@pytest.mark.parametrize("policy", [0, 1, 2])     # 0 = TMA-staged tensor-core kernels, 1 = generic SIMT, 2 = cp.async-staged
 @pytest.mark.parametrize("name", TRIPLET_FIX)
 def test_triplet_bf16_vs_golden(name, policy):
     fx = load_golden(name)
@@ -187,7 +187,7 @@ def test_shipped_width_bf16_vs_oracle(kind, N, nn_):
     ref.backward(dout)
     mod = mod.to(DEV)
     res = {}
-    for policy in (0, 1):
+    for policy in (0, 1, 2):
         _C.set_kernel_policy(policy)
         try:
             mod.zero_grad(set_to_none=True)
@@ -202,6 +202,8 @@ def test_shipped_width_bf16_vs_oracle(kind, N, nn_):
         assert rel_err(res[policy][1], ed.grad) < 2 * BF16_TOL
         assert_grads_close(res[policy][2], {k: v.grad for k, v in p.items()}, 3 * BF16_TOL, "l2")
     assert rel_err(res[0][0], res[1][0]) < BF16_TOL
+    # the TMA-staged and the cp.async-staged kernels run the same arithmetic on the same fragments
+    assert rel_err(res[0][0], res[2][0]) < 1e-6 and rel_err(res[0][1], res[2][1]) < 1e-6
 
 
 def test_outputs_survive_inplace_residual_add():

@@ -46,7 +46,7 @@ static int attn_check(const tgt_triplet_attn_desc *D) {
 
 extern "C" size_t tgt_triplet_attn_workspace_bytes(const tgt_triplet_attn_desc *D, int backward) {
   if (!D || attn_check(D)) return 0;
-  if (g_policy.load() == 0 && triplet_attn_mma_supported(*D)) return triplet_attn_mma_workspace(*D, backward);
+  if (g_policy.load() != 1 && triplet_attn_mma_supported(*D)) return triplet_attn_mma_workspace(*D, backward);
   return 0;
 }
 
@@ -54,7 +54,7 @@ extern "C" int tgt_triplet_attn_fwd(const tgt_triplet_attn_desc *D, const void *
                                     float *stats, void *ws, size_t ws_bytes, void *stream) {
   if (int e = attn_check(D)) return e;
   cudaStream_t st = (cudaStream_t)stream;
-  if (g_policy.load() == 0 && triplet_attn_mma_supported(*D))
+  if (g_policy.load() != 1 && triplet_attn_mma_supported(*D))
     return triplet_attn_fwd_mma(*D, proj, mask, va, stats, ws, ws_bytes, st);
   return triplet_attn_fwd_simt(*D, proj, mask, va, stats, st);
 }
@@ -64,7 +64,7 @@ extern "C" int tgt_triplet_attn_bwd(const tgt_triplet_attn_desc *D, const void *
                                     size_t ws_bytes, void *stream) {
   if (int e = attn_check(D)) return e;
   cudaStream_t st = (cudaStream_t)stream;
-  if (g_policy.load() == 0 && triplet_attn_mma_supported(*D))
+  if (g_policy.load() != 1 && triplet_attn_mma_supported(*D))
     return triplet_attn_bwd_mma(*D, proj, mask, va, dva, stats, dproj, ws, ws_bytes, st);
   return triplet_attn_bwd_simt(*D, proj, mask, va, dva, stats, dproj, st);
 }

@@ -1,0 +1,484 @@
+// Triplet attention core with TMA staging (bf16 / fp16, head dim 16, N <= 64) for sm_100a.
+//
+// Same math, CTA decomposition (one CTA = (head, direction, graph), loop over the junction atom j, bias / gate /
+// dE / dG tiles resident in registers) and parity contract as triplet_mma.cu; what changes is how bytes move:
+//   * the Q / K / V / dO 64x16 tiles of junction j are fetched by ONE thread with cp.async.bulk.tensor (TMA) through
+//     4-D tensor maps over the [B, N, N, C] projection / gradient tensors -- box {16 ch, 1, 64, 1} is "column j"
+//     (queries, and keys/values of the outward direction), box {16 ch, 64, 1, 1} is "row j" (keys/values of the inward
+//     direction).  Rows >= N are out of bounds: zero-filled on load, dropped on store.  SWIZZLE_32B reproduces the
+//     ldmatrix-friendly tile layout of triplet_common.cuh (chunk ^= row bit 2), completion is tracked by mbarriers;
+//   * results (Va; dQ, dK, dV) go from mma accumulators to shared memory with stmatrix and leave with TMA tensor
+//     stores (full 32-byte rows instead of 4-byte scattered stores); the dS / A exchange tiles use stmatrix too.
+// Net effect: ~100 fewer issue slots per thread and iteration (no address arithmetic, no cp.async, no predicated
+// 4-byte stores) and sector-exact HBM writes.  The cp.async kernels remain available (kernel policy 2) and the tests
+// cross-check the two families.
+#include "triplet_common.cuh"
+
+namespace tgt {
+
+constexpr int TILE_BYTES = TN * HD * 2;                       // one 64 x 16 operand tile: 2 KB
+
+// ------------------------------------------------------------------------------------------------ forward
+constexpr int TF_STAGES = 4;
+constexpr int TF_STAGE_BYTES = 3 * TILE_BYTES;                // Q, K, V
+constexpr int TF_SMEM = TF_STAGES * TF_STAGE_BYTES + 2 * TILE_BYTES + 64 + 1024;   // + 2 output tiles + barriers + align
+
+template <typename T>
+__global__ void __launch_bounds__(128, 4)
+tri_attn_fwd_tma(const tgt_triplet_attn_desc D, const __grid_constant__ CUtensorMap mPcol,
+                 const __grid_constant__ CUtensorMap mProw, const __grid_constant__ CUtensorMap mVA,
+                 const float *__restrict__ ws_e, const __half *__restrict__ ws_g, float *__restrict__ stats) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int N = D.N, H = D.H;
+  const int h = blockIdx.x, dir = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const int m0 = warp * 16;
+  const uint32_t sOut = sbase + TF_STAGES * TF_STAGE_BYTES;
+  const uint32_t bar_full = sOut + 2 * TILE_BYTES;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&mPcol);
+    tma_prefetch_desc(&mProw);
+    tma_prefetch_desc(&mVA);
+    for (int s = 0; s < TF_STAGES; ++s) mbar_init(bar_full + s * 8, 1);
+    fence_barrier_init();
+  }
+
+  // bias (log2 domain) and gate fragments, constant over j
+  float eb[8][4];
+  uint32_t gt[8][2];
+  {
+    const int64_t tbase = ((int64_t)(b * 2 + dir) * H + h) * TN * TN;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int col = nt * 8 + 2 * q;
+      const float2 e0 = *reinterpret_cast<const float2 *>(ws_e + tbase + (m0 + g) * TN + col);
+      const float2 e1 = *reinterpret_cast<const float2 *>(ws_e + tbase + (m0 + g + 8) * TN + col);
+      eb[nt][0] = e0.x; eb[nt][1] = e0.y; eb[nt][2] = e1.x; eb[nt][3] = e1.y;
+      gt[nt][0] = *reinterpret_cast<const uint32_t *>(ws_g + tbase + (m0 + g) * TN + col);
+      gt[nt][1] = *reinterpret_cast<const uint32_t *>(ws_g + tbase + (m0 + g + 8) * TN + col);
+    }
+  }
+  float c1r0, c1r1;
+  fix_fully_masked_rows(eb, D.scale * LOG2E, c1r0, c1r1);
+
+  const int cq = D.off_q[dir] + h * HD, ck = D.off_k[dir] + h * HD, cv = D.off_v[dir] + h * HD;
+  const int co = dir * H * HD + h * HD;
+  auto issue = [&](int j) {                   // thread 0 only
+    if (j < N) {
+      const uint32_t st = sbase + (j % TF_STAGES) * TF_STAGE_BYTES, bar = bar_full + (j % TF_STAGES) * 8;
+      mbar_expect_tx(bar, TF_STAGE_BYTES);
+      tma_load_4d(&mPcol, bar, st, cq, j, 0, b);
+      if (dir == 0) {
+        tma_load_4d(&mProw, bar, st + TILE_BYTES, ck, 0, j, b);
+        tma_load_4d(&mProw, bar, st + 2 * TILE_BYTES, cv, 0, j, b);
+      } else {
+        tma_load_4d(&mPcol, bar, st + TILE_BYTES, ck, j, 0, b);
+        tma_load_4d(&mPcol, bar, st + 2 * TILE_BYTES, cv, j, 0, b);
+      }
+    }
+  };
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < TF_STAGES - 1; ++s) issue(s);
+  }
+
+  for (int j = 0; j < N; ++j) {
+    if (tid == 0) tma_store_wait_read();            // the output tile written two iterations ago has left smem
+    mbar_wait(bar_full + (j % TF_STAGES) * 8, (uint32_t)((j / TF_STAGES) & 1));
+    __syncthreads();                                // stage j landed; everyone is done with iteration j-1
+    if (tid == 0) {
+      issue(j + TF_STAGES - 1);
+      if (j > 0) {
+        tma_store_4d(&mVA, sOut + ((j - 1) & 1) * TILE_BYTES, co, j - 1, 0, b);
+        tma_store_commit();
+      }
+    }
+    const uint32_t st = sbase + (j % TF_STAGES) * TF_STAGE_BYTES;
+    const uint32_t sQ = st, sK = st + TILE_BYTES, sV = st + 2 * TILE_BYTES;
+
+    uint32_t qa[4];
+    load_a_rows(qa, sQ, m0, lane);
+    float s[8][4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      uint32_t kb[4];
+      load_b_nk(kb, sK, p * 16, lane);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        s[2 * p + u][0] = s[2 * p + u][1] = s[2 * p + u][2] = s[2 * p + u][3] = 0.f;
+        Mma<T>::run(s[2 * p + u], qa, kb[2 * u], kb[2 * u + 1]);
+      }
+    }
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = fmaf(s[nt][0], c1r0, eb[nt][0]);
+      s[nt][1] = fmaf(s[nt][1], c1r0, eb[nt][1]);
+      s[nt][2] = fmaf(s[nt][2], c1r1, eb[nt][2]);
+      s[nt][3] = fmaf(s[nt][3], c1r1, eb[nt][3]);
+      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float l0 = 0.f, l1 = 0.f;
+    uint32_t pa[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float p0 = fast_exp2(s[nt][0] - mx0), p1 = fast_exp2(s[nt][1] - mx0);
+      const float p2 = fast_exp2(s[nt][2] - mx1), p3 = fast_exp2(s[nt][3] - mx1);
+      l0 += p0 + p1;
+      l1 += p2 + p3;
+      const float2 g0 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][0]));
+      const float2 g1 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][1]));
+      pa[nt >> 1][(nt & 1) * 2 + 0] = Mma<T>::pack(p0 * g0.x, p1 * g0.y);
+      pa[nt >> 1][(nt & 1) * 2 + 1] = Mma<T>::pack(p2 * g1.x, p3 * g1.y);
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+
+    float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      uint32_t vb[4];
+      load_b_kn(vb, sV, t * 16, lane);
+      Mma<T>::run(o[0], pa[t], vb[0], vb[1]);
+      Mma<T>::run(o[1], pa[t], vb[2], vb[3]);
+    }
+    o[0][0] *= inv0; o[0][1] *= inv0; o[1][0] *= inv0; o[1][1] *= inv0;
+    o[0][2] *= inv1; o[0][3] *= inv1; o[1][2] *= inv1; o[1][3] *= inv1;
+    store_c_tile<T>(sOut + (j & 1) * TILE_BYTES, m0, lane, o, 1.f);
+    fence_proxy_async();
+    const int i0 = m0 + g, i1 = m0 + g + 8;
+    if (q == 0) {          // one float per row: log2-domain log-sum-exp  (P = exp2(x - lse2))
+      float *stp = stats + (((int64_t)(b * 2 + dir) * H + h) * N + j) * N;
+      if (i0 < N) stp[i0] = mx0 + __log2f(l0);
+      if (i1 < N) stp[i1] = mx1 + __log2f(l1);
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    tma_store_4d(&mVA, sOut + ((N - 1) & 1) * TILE_BYTES, co, N - 1, 0, b);
+    tma_store_commit();
+    tma_store_wait_all();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+constexpr int TB_STAGES = 3;
+constexpr int TB_STAGE_BYTES = 4 * TILE_BYTES;               // Q, K, V, dO
+constexpr int TB_XCH_BYTES = TN * TN * 2;                    // one 64x64 16-bit exchange tile: 8 KB
+constexpr int TB_SMEM = TB_STAGES * TB_STAGE_BYTES + 4 * TB_XCH_BYTES + 3 * TILE_BYTES + 64 + 1024;
+
+template <typename T>
+__global__ void __launch_bounds__(128, 2)
+tri_attn_bwd_tma(const tgt_triplet_attn_desc D, const __grid_constant__ CUtensorMap mPcol,
+                 const __grid_constant__ CUtensorMap mProw, const __grid_constant__ CUtensorMap mDVA,
+                 const __grid_constant__ CUtensorMap mDPcol, const __grid_constant__ CUtensorMap mDProw,
+                 const float *__restrict__ ws_e, const __half *__restrict__ ws_g, const float *__restrict__ stats,
+                 float *__restrict__ ws_de, float *__restrict__ ws_dg) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int N = D.N, H = D.H;
+  const int h = blockIdx.x, dir = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const int m0 = warp * 16;
+  const uint32_t xbase = sbase + TB_STAGES * TB_STAGE_BYTES;
+  const uint32_t sOut = xbase + 4 * TB_XCH_BYTES;             // dQ, dK, dV staging tiles
+  const uint32_t bar_full = sOut + 3 * TILE_BYTES;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&mPcol);
+    tma_prefetch_desc(&mProw);
+    tma_prefetch_desc(&mDVA);
+    tma_prefetch_desc(&mDPcol);
+    tma_prefetch_desc(&mDProw);
+    for (int s = 0; s < TB_STAGES; ++s) mbar_init(bar_full + s * 8, 1);
+    fence_barrier_init();
+  }
+
+  float eb[8][4];
+  uint32_t gt[8][2];
+  const int64_t tbase = ((int64_t)(b * 2 + dir) * H + h) * TN * TN;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const int col = nt * 8 + 2 * q;
+    const float2 e0 = *reinterpret_cast<const float2 *>(ws_e + tbase + (m0 + g) * TN + col);
+    const float2 e1 = *reinterpret_cast<const float2 *>(ws_e + tbase + (m0 + g + 8) * TN + col);
+    eb[nt][0] = e0.x; eb[nt][1] = e0.y; eb[nt][2] = e1.x; eb[nt][3] = e1.y;
+    gt[nt][0] = *reinterpret_cast<const uint32_t *>(ws_g + tbase + (m0 + g) * TN + col);
+    gt[nt][1] = *reinterpret_cast<const uint32_t *>(ws_g + tbase + (m0 + g + 8) * TN + col);
+  }
+  float de[8][4], dg[8][4];          // sum_j dS   and   sum_j dA * P
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) de[nt][c] = dg[nt][c] = 0.f;
+
+  float c1r0, c1r1;
+  fix_fully_masked_rows(eb, D.scale * LOG2E, c1r0, c1r1);
+  const int cq = D.off_q[dir] + h * HD, ck = D.off_k[dir] + h * HD, cv = D.off_v[dir] + h * HD;
+  const int co = dir * H * HD + h * HD;
+  const int i0 = m0 + g, i1 = m0 + g + 8;
+  const float *stb = stats + (((int64_t)(b * 2 + dir) * H + h) * N) * N;
+
+  auto issue = [&](int j) {                   // thread 0 only
+    if (j < N) {
+      const uint32_t st = sbase + (j % TB_STAGES) * TB_STAGE_BYTES, bar = bar_full + (j % TB_STAGES) * 8;
+      mbar_expect_tx(bar, TB_STAGE_BYTES);
+      tma_load_4d(&mPcol, bar, st, cq, j, 0, b);
+      if (dir == 0) {
+        tma_load_4d(&mProw, bar, st + TILE_BYTES, ck, 0, j, b);
+        tma_load_4d(&mProw, bar, st + 2 * TILE_BYTES, cv, 0, j, b);
+      } else {
+        tma_load_4d(&mPcol, bar, st + TILE_BYTES, ck, j, 0, b);
+        tma_load_4d(&mPcol, bar, st + 2 * TILE_BYTES, cv, j, 0, b);
+      }
+      tma_load_4d(&mDVA, bar, st + 3 * TILE_BYTES, co, j, 0, b);
+    }
+  };
+  auto store_kv = [&](int j) {                // thread 0 only: dK / dV tiles of junction j
+    if (dir == 0) {
+      tma_store_4d(&mDProw, sOut + TILE_BYTES, ck, 0, j, b);
+      tma_store_4d(&mDProw, sOut + 2 * TILE_BYTES, cv, 0, j, b);
+    } else {
+      tma_store_4d(&mDPcol, sOut + TILE_BYTES, ck, j, 0, b);
+      tma_store_4d(&mDPcol, sOut + 2 * TILE_BYTES, cv, j, 0, b);
+    }
+    tma_store_commit();
+  };
+  // rows beyond N (tile padding) get lse2 = +inf  ->  P = exp2(-inf) = 0 for the whole row
+  auto load_stats = [&](int j, float &a, float &c) {
+    a = INFINITY;
+    c = INFINITY;
+    if (j < N) {
+      if (i0 < N) a = stb[(int64_t)j * N + i0];
+      if (i1 < N) c = stb[(int64_t)j * N + i1];
+    }
+  };
+
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < TB_STAGES - 1; ++s) issue(s);
+  }
+  float sa0, sa1, sb0, sb1;                  // lse of the next two junctions (fetched two iterations ahead)
+  load_stats(0, sa0, sa1);
+  load_stats(1, sb0, sb1);
+
+  for (int j = 0; j < N; ++j) {
+    if (tid == 0) tma_store_wait_read();             // dQ(j-1) has left its staging tile
+    mbar_wait(bar_full + (j % TB_STAGES) * 8, (uint32_t)((j / TB_STAGES) & 1));
+    __syncthreads();                                   // (A) stage j landed; everyone is done with iteration j-1
+    if (tid == 0) {
+      issue(j + TB_STAGES - 1);
+      if (j > 0) store_kv(j - 1);
+    }
+    const float lse0 = sa0, lse1 = sa1;
+    sa0 = sb0;
+    sa1 = sb1;
+    load_stats(j + 2, sb0, sb1);
+    const uint32_t st = sbase + (j % TB_STAGES) * TB_STAGE_BYTES;
+    const uint32_t sQ = st, sK = st + TILE_BYTES, sV = st + 2 * TILE_BYTES, sO = st + 3 * TILE_BYTES;
+    const uint32_t xS = xbase + (j & 1) * 2 * TB_XCH_BYTES, xA = xS + TB_XCH_BYTES;
+
+    uint32_t qa[4], oa[4];
+    load_a_rows(qa, sQ, m0, lane);
+    load_a_rows(oa, sO, m0, lane);
+    float s[8][4], da[8][4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      uint32_t kb[4], vb[4];
+      load_b_nk(kb, sK, p * 16, lane);
+      load_b_nk(vb, sV, p * 16, lane);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int nt = 2 * p + u;
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        da[nt][0] = da[nt][1] = da[nt][2] = da[nt][3] = 0.f;
+        Mma<T>::run(s[nt], qa, kb[2 * u], kb[2 * u + 1]);
+        Mma<T>::run(da[nt], oa, vb[2 * u], vb[2 * u + 1]);
+      }
+    }
+    // P (normalised), t = dA*g*P, delta = rowsum(t)
+    float dl0 = 0.f, dl1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float2 g0 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][0]));
+      const float2 g1 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][1]));
+      const float gg[4] = {g0.x, g0.y, g1.x, g1.y};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float p = fast_exp2(fmaf(s[nt][c], c < 2 ? c1r0 : c1r1, eb[nt][c]) - (c < 2 ? lse0 : lse1));
+        const float dap = da[nt][c] * p;
+        dg[nt][c] += dap;
+        s[nt][c] = p;                      // P
+        da[nt][c] = dap * gg[c];           // t = dA * g * P
+      }
+      dl0 += da[nt][0] + da[nt][1];
+      dl1 += da[nt][2] + da[nt][3];
+    }
+    dl0 += __shfl_xor_sync(0xffffffffu, dl0, 1);
+    dl0 += __shfl_xor_sync(0xffffffffu, dl0, 2);
+    dl1 += __shfl_xor_sync(0xffffffffu, dl1, 1);
+    dl1 += __shfl_xor_sync(0xffffffffu, dl1, 2);
+    // dS = t - P*delta ; A = P*g ; exchange through shared memory (stmatrix) ; dS also as A-fragments for dQ
+    uint32_t dsa[4][4];
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t aa[4];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int nt = 2 * np + u;
+        const float2 g0 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][0]));
+        const float2 g1 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][1]));
+        const float d0 = fmaf(-s[nt][0], dl0, da[nt][0]), d1 = fmaf(-s[nt][1], dl0, da[nt][1]);
+        const float d2 = fmaf(-s[nt][2], dl1, da[nt][2]), d3 = fmaf(-s[nt][3], dl1, da[nt][3]);
+        de[nt][0] += d0; de[nt][1] += d1; de[nt][2] += d2; de[nt][3] += d3;
+        dsa[np][u * 2 + 0] = Mma<T>::pack(d0, d1);
+        dsa[np][u * 2 + 1] = Mma<T>::pack(d2, d3);
+        aa[u * 2 + 0] = Mma<T>::pack(s[nt][0] * g0.x, s[nt][1] * g0.y);
+        aa[u * 2 + 1] = Mma<T>::pack(s[nt][2] * g1.x, s[nt][3] * g1.y);
+      }
+      store_xch_pair(xS, m0, lane, 2 * np, dsa[np][0], dsa[np][1], dsa[np][2], dsa[np][3]);
+      store_xch_pair(xA, m0, lane, 2 * np, aa[0], aa[1], aa[2], aa[3]);
+    }
+    // dQ = scale * dS K   (rows of this warp)
+    {
+      float dq[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        uint32_t kb[4];
+        load_b_kn(kb, sK, t * 16, lane);
+        Mma<T>::run(dq[0], dsa[t], kb[0], kb[1]);
+        Mma<T>::run(dq[1], dsa[t], kb[2], kb[3]);
+      }
+      store_c_tile<T>(sOut, m0, lane, dq, D.scale);
+    }
+    fence_proxy_async();
+    if (tid == 0) tma_store_wait_read();               // dK / dV (j-1) have left their staging tiles
+    __syncthreads();                                   // (B) dS / A / dQ tiles complete
+    if (tid == 0) {
+      tma_store_4d(&mDPcol, sOut, cq, j, 0, b);
+      tma_store_commit();
+    }
+    // dK = scale * dS^T Q ; dV = A^T dO   (this warp owns keys m0 .. m0+15)
+    {
+      float dk[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      float dv[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        uint32_t at[4], qb[4], ob[4];
+        load_a_xt(at, xS, m0, t * 16, lane);
+        load_b_kn(qb, sQ, t * 16, lane);
+        Mma<T>::run(dk[0], at, qb[0], qb[1]);
+        Mma<T>::run(dk[1], at, qb[2], qb[3]);
+        load_a_xt(at, xA, m0, t * 16, lane);
+        load_b_kn(ob, sO, t * 16, lane);
+        Mma<T>::run(dv[0], at, ob[0], ob[1]);
+        Mma<T>::run(dv[1], at, ob[2], ob[3]);
+      }
+      store_c_tile<T>(sOut + TILE_BYTES, m0, lane, dk, D.scale);
+      store_c_tile<T>(sOut + 2 * TILE_BYTES, m0, lane, dv, 1.f);
+    }
+    fence_proxy_async();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    store_kv(N - 1);
+    tma_store_wait_all();
+  }
+  // dE = sum_j dS ; dG = g (1 - g) sum_j dA P
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const int col = nt * 8 + 2 * q;
+    const float2 g0 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][0]));
+    const float2 g1 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][1]));
+    *reinterpret_cast<float2 *>(ws_de + tbase + (m0 + g) * TN + col) = make_float2(de[nt][0], de[nt][1]);
+    *reinterpret_cast<float2 *>(ws_de + tbase + (m0 + g + 8) * TN + col) = make_float2(de[nt][2], de[nt][3]);
+    *reinterpret_cast<float2 *>(ws_dg + tbase + (m0 + g) * TN + col) =
+        make_float2(dg[nt][0] * g0.x * (1.f - g0.x), dg[nt][1] * g0.y * (1.f - g0.y));
+    *reinterpret_cast<float2 *>(ws_dg + tbase + (m0 + g + 8) * TN + col) =
+        make_float2(dg[nt][2] * g1.x * (1.f - g1.x), dg[nt][3] * g1.y * (1.f - g1.y));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+// 4-D map over a [B, N, N, C] 16-bit tensor (row pitch ld elements): box = 64 rows of 16 channels taken along the
+// second-to-last index ("row" tiles, fixed first index) or along the first index ("column" tiles, fixed second index)
+static int make_tile_map(CUtensorMap *map, const void *base, int B, int N, int C, int64_t ld, bool column, int dtype) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return fail("triplet_attn: cuTensorMapEncodeTiled is not available from the driver");
+  const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)N, (cuuint64_t)N, (cuuint64_t)B};
+  const cuuint64_t gstride[3] = {(cuuint64_t)ld * 2, (cuuint64_t)N * ld * 2, (cuuint64_t)N * N * ld * 2};
+  const cuuint32_t box[4] = {(cuuint32_t)HD, column ? 1u : (cuuint32_t)TN, column ? (cuuint32_t)TN : 1u, 1u};
+  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  const CUtensorMapDataType dt = dtype == TGT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = enc(map, dt, 4, const_cast<void *>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("triplet_attn: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+bool triplet_attn_tma_available() { return encode_tiled_fn() != nullptr; }
+
+template <typename T>
+static int fwd_tma_impl(const tgt_triplet_attn_desc &D, const void *proj, void *va, float *stats, const float *ws_e,
+                        const __half *ws_g, cudaStream_t st) {
+  CUtensorMap mPcol, mProw, mVA;
+  const int C = (int)D.ld, Cv = 2 * D.H * HD;
+  if (int e = make_tile_map(&mPcol, proj, D.B, D.N, C, D.ld, true, D.dtype)) return e;
+  if (int e = make_tile_map(&mProw, proj, D.B, D.N, C, D.ld, false, D.dtype)) return e;
+  if (int e = make_tile_map(&mVA, va, D.B, D.N, Cv, Cv, true, D.dtype)) return e;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    cudaFuncSetAttribute(tri_attn_fwd_tma<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM);
+  });
+  tri_attn_fwd_tma<T><<<dim3(D.H, 2, D.B), 128, TF_SMEM, st>>>(D, mPcol, mProw, mVA, ws_e, ws_g, stats);
+  return check_launch("tri_attn_fwd_tma");
+}
+
+template <typename T>
+static int bwd_tma_impl(const tgt_triplet_attn_desc &D, const void *proj, const void *dva, const float *stats,
+                        void *dproj, const float *ws_e, const __half *ws_g, float *ws_de, float *ws_dg,
+                        cudaStream_t st) {
+  CUtensorMap mPcol, mProw, mDVA, mDPcol, mDProw;
+  const int C = (int)D.ld, Cv = 2 * D.H * HD;
+  if (int e = make_tile_map(&mPcol, proj, D.B, D.N, C, D.ld, true, D.dtype)) return e;
+  if (int e = make_tile_map(&mProw, proj, D.B, D.N, C, D.ld, false, D.dtype)) return e;
+  if (int e = make_tile_map(&mDVA, dva, D.B, D.N, Cv, Cv, true, D.dtype)) return e;
+  if (int e = make_tile_map(&mDPcol, dproj, D.B, D.N, C, D.ld, true, D.dtype)) return e;
+  if (int e = make_tile_map(&mDProw, dproj, D.B, D.N, C, D.ld, false, D.dtype)) return e;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    cudaFuncSetAttribute(tri_attn_bwd_tma<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM);
+  });
+  tri_attn_bwd_tma<T><<<dim3(D.H, 2, D.B), 128, TB_SMEM, st>>>(D, mPcol, mProw, mDVA, mDPcol, mDProw, ws_e, ws_g, stats,
+                                                              ws_de, ws_dg);
+  return check_launch("tri_attn_bwd_tma");
+}
+
+int triplet_attn_fwd_tma_launch(const tgt_triplet_attn_desc &D, const void *proj, void *va, float *stats,
+                                const float *ws_e, const __half *ws_g, cudaStream_t st) {
+  if (D.dtype == TGT_BF16) return fwd_tma_impl<__nv_bfloat16>(D, proj, va, stats, ws_e, ws_g, st);
+  return fwd_tma_impl<__half>(D, proj, va, stats, ws_e, ws_g, st);
+}
+
+int triplet_attn_bwd_tma_launch(const tgt_triplet_attn_desc &D, const void *proj, const void *dva, const float *stats,
+                                void *dproj, const float *ws_e, const __half *ws_g, float *ws_de, float *ws_dg,
+                                cudaStream_t st) {
+  if (D.dtype == TGT_BF16) return bwd_tma_impl<__nv_bfloat16>(D, proj, dva, stats, dproj, ws_e, ws_g, ws_de, ws_dg, st);
+  return bwd_tma_impl<__half>(D, proj, dva, stats, dproj, ws_e, ws_g, ws_de, ws_dg, st);
+}
+
+}  // namespace tgt

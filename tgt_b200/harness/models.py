@@ -59,6 +59,34 @@ class _Gaussian3D(nn.Module):
         return self.gbf_proj(self.gbf(dist, types.long()))
 
 
+class _EdgeEmbedFn(torch.autograd.Function):
+    """dist_embed(hops) + featm_embed(feature_matrix).sum(-2)  (reference models/pcqm/layers.py:69-72) as ONE
+    multi-hot GEMM.  Same values as the gather+sum; the point is the backward: the stock embedding backward sorts the
+    3*B*N^2 indices (~8 ms per step at B=256, N=64), here it is a [V, R] x [R, W] GEMM."""
+
+    @staticmethod
+    def forward(ctx, hops, fm, w_dist, w_featm):
+        shape = hops.shape
+        R = hops.numel()
+        Vd, Vf = w_dist.shape[0], w_featm.shape[0]
+        idx = torch.cat([hops.reshape(R, 1), fm.reshape(R, -1) + Vd], 1)
+        M = torch.zeros((R, Vd + Vf), dtype=w_dist.dtype, device=hops.device)
+        M.scatter_add_(1, idx, torch.ones_like(idx, dtype=M.dtype))
+        ctx.save_for_backward(M)
+        ctx.Vd = Vd
+        with torch.autocast(hops.device.type, enabled=False):          # embeddings stay fp32 under autocast
+            return (M @ torch.cat([w_dist, w_featm], 0)).view(*shape, -1)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (M,) = ctx.saved_tensors
+        with torch.autocast(dout.device.type, enabled=False):
+            dW = M.t() @ dout.reshape(M.shape[0], -1).to(M.dtype)
+        dwf = dW[ctx.Vd:].clone()
+        dwf[0].zero_()                                   # padding_idx = 0 of featm_embed
+        return None, None, dW[:ctx.Vd], dwf
+
+
 class EmbedInput(nn.Module):
     def __init__(self, node_width, edge_width, upto_hop=32, embed_3d_type='gaussian', num_3d_kernels=128):
         super().__init__()
@@ -77,7 +105,7 @@ class EmbedInput(nn.Module):
         nf = g.node_features.long()
         h = self.nodef_embed(nf).sum(dim=2)
         hops = g.distance_matrix.long().clamp(max=self.upto_hop + 1)
-        e = self.dist_embed(hops) + self.featm_embed(g.feature_matrix.long()).sum(dim=-2)
+        e = _EdgeEmbedFn.apply(hops, g.feature_matrix.long(), self.dist_embed.weight, self.featm_embed.weight)
         if self.uses_3d:
             n = nf.size(1)
             a = nf[:, :, 0]

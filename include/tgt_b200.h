@@ -89,6 +89,25 @@ int tgt_triplet_attn_bwd(const tgt_triplet_attn_desc *desc, const void *proj, co
                          const void *va, const void *dva, const float *stats, void *dproj,
                          void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- fused triplet attention forward: LayerNorm + lin_QKV_in/out + attention in one kernel ----------
+ * replaces lib/tgt/layers/triplet.py:207-246 for head dim 16, edge width We <= 256 (TGT-At): the
+ * [R, 6*We] q/k/v projection is produced on tcgen05 tensor cores tile by tile in tensor memory and
+ * consumed in place -- it never reaches HBM.  Returns 1 from ..._supported when desc / We qualify.
+ * x      : [B,N,N,We] raw edge rows (16-bit, row pitch ldx) -- NOT layer-normed
+ * row_mean,row_rstd : [R] LayerNorm statistics of x (tgt_row_stats or TGT_EPI_STATS)
+ * wf     : [(H/2)*192, We] LN-folded weights W*gamma, 16-bit, rows grouped per pair of heads (h0,h1) as
+ *          Qin h0,h1 | Qout h0,h1 | Kout h0,h1 | Vout h0,h1 | Kin h0,h1 | Vin h0,h1 (16 rows each)
+ * wcolsum, wbias : [(H/2)*192] f32, per wf row: sum_k wf[r,k] and b + W beta
+ * proj_eg: [R, desc->ld] the E|G columns (desc->off_e / off_g index THIS matrix; off_q/k/v are ignored)
+ * va, stats, workspace: as tgt_triplet_attn_fwd (the backward is tgt_triplet_attn_bwd on a recomputed
+ * projection; stats are interchangeable with the TMA / cp.async tensor-core kernels).                  */
+int tgt_triplet_attn_fused_supported(const tgt_triplet_attn_desc *desc, int We);
+int tgt_triplet_attn_fused_fwd(const tgt_triplet_attn_desc *desc, const void *x, int64_t ldx, int We,
+                               const float *row_mean, const float *row_rstd, const void *wf,
+                               const float *wcolsum, const float *wbias, const void *proj_eg,
+                               const float *mask, void *va, float *stats, void *workspace,
+                               size_t workspace_bytes, void *stream);
+
 /* ---- triplet aggregate core ---------------------------------------------------------------
  * replaces lib/tgt/layers/triplet.py:56-68 (TripletAggregate) and 106-120 (…Ungated).
  * proj column blocks: off_v[dir] (H*d, head-major), off_e[dir], off_g[dir] (H; off_g = -1 ->

@@ -333,3 +333,43 @@ def test_encoder_fp32_train_vs_oracle_grads():
     assert max_rel(g.h.cpu(), ho) < 5 * FP32_TOL and max_rel(g.e.cpu(), eo) < 5 * FP32_TOL
     assert_grads_close({k: v.grad for k, v in enc.named_parameters()}, {k: v.grad for k, v in p.items()},
                        1e-4, "max")
+
+
+@pytest.mark.parametrize("kind", ["attention", "attention_ungated", "axial_attention"])
+@pytest.mark.parametrize("N,nn_", [(64, [64, 37, 50]), (33, [33, 20, 9]), (8, [8, 5, 1])])
+def test_fused_forward_matches_unfused(kind, N, nn_):
+    """bf16 edge input at the shipped geometry: the fused projection+attention kernel (policy 0) must reproduce the
+    un-fused tensor-core path (policy 2: LN-folded GEMM -> [R, 6We] projection -> attention kernel) and both must sit
+    within bf16 tolerance of the fp64 oracle; gradients flow through the shared backward."""
+    from tgt_b200 import ops
+    torch.manual_seed(11)
+    mod = L.get_triplet_layer(kind)(256, 16)
+    e, mask = make_edge_inputs(3, N, 256, nn_, seed=7)
+    e16 = e.bfloat16()
+    p = {k: v.double().requires_grad_(True) for k, v in mod.state_dict().items()}
+    ed = e16.double().requires_grad_(True)
+    ref = O.TRIPLET_FNS[kind](p, ed, mask.double(), 16)
+    dout = torch.randn(ref.shape, generator=torch.Generator().manual_seed(2), dtype=torch.float64)
+    ref.backward(dout)
+    mod = mod.to(DEV)
+    res = {}
+    for policy in (0, 2):
+        _C.set_kernel_policy(policy)
+        ops.KernelTimer.reset(True)
+        try:
+            mod.zero_grad(set_to_none=True)
+            eg = e16.to(DEV).requires_grad_(True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out = mod(eg, mask.to(DEV))
+            out.backward(dout.to(DEV).to(out.dtype))
+            torch.cuda.synchronize()
+            names = set(ops.KernelTimer.summary())
+            res[policy] = (out.float().cpu(), eg.grad.float().cpu())
+        finally:
+            _C.set_kernel_policy(0)
+            ops.KernelTimer.reset(False)
+        assert ("triplet_fused_fwd" in names) == (policy == 0), names
+        assert rel_err(res[policy][0], ref) < BF16_TOL
+        assert rel_err(res[policy][1], ed.grad) < 2 * BF16_TOL
+    assert rel_err(res[0][0], res[2][0]) < 2e-3, rel_err(res[0][0], res[2][0])
+    assert rel_err(res[0][1], res[2][1]) < 2e-2

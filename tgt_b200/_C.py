@@ -73,6 +73,9 @@ _SIGNATURES = {
     "tgt_triplet_attn_workspace_bytes": (C.c_size_t, [C.POINTER(TripletAttnDesc), C.c_int]),
     "tgt_triplet_attn_fwd": (C.c_int, [C.POINTER(TripletAttnDesc), _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "tgt_triplet_attn_bwd": (C.c_int, [C.POINTER(TripletAttnDesc), _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "tgt_triplet_attn_fused_supported": (C.c_int, [C.POINTER(TripletAttnDesc), C.c_int]),
+    "tgt_triplet_attn_fused_fwd": (C.c_int, [C.POINTER(TripletAttnDesc), _P, C.c_int64, C.c_int, _P, _P, _P, _P, _P, _P, _P,
+                                             _P, _P, _P, C.c_size_t, _P]),
     "tgt_triplet_aggr_fwd": (C.c_int, [C.POINTER(TripletAggrDesc), _P, _P, _P, _P, _P]),
     "tgt_triplet_aggr_bwd": (C.c_int, [C.POINTER(TripletAggrDesc), _P, _P, _P, _P, _P, _P, _P]),
     "tgt_egt_attn_fwd": (C.c_int, [C.POINTER(EgtDesc), _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -20,6 +20,11 @@ int triplet_attn_fwd_mma(const tgt_triplet_attn_desc &, const void *, const floa
                          cudaStream_t);
 int triplet_attn_bwd_mma(const tgt_triplet_attn_desc &, const void *, const float *, const void *, const void *,
                          const float *, void *, void *, size_t, cudaStream_t);
+bool triplet_attn_fused_supported(const tgt_triplet_attn_desc &D, int We);
+int triplet_attn_fused_fwd(const tgt_triplet_attn_desc &D, int We, const void *x, int64_t ldx, const float *mean,
+                           const float *rstd, const void *wf, const float *wcolsum, const float *wbias,
+                           const void *proj_eg, const float *mask, void *va, float *stats, void *ws, size_t ws_bytes,
+                           cudaStream_t st);
 }  // namespace tgt
 
 using namespace tgt;
@@ -67,6 +72,23 @@ extern "C" int tgt_triplet_attn_bwd(const tgt_triplet_attn_desc *D, const void *
   if (g_policy.load() != 1 && triplet_attn_mma_supported(*D))
     return triplet_attn_bwd_mma(*D, proj, mask, va, dva, stats, dproj, ws, ws_bytes, st);
   return triplet_attn_bwd_simt(*D, proj, mask, va, dva, stats, dproj, st);
+}
+
+extern "C" int tgt_triplet_attn_fused_supported(const tgt_triplet_attn_desc *D, int We) {
+  if (!D || D->B <= 0 || D->N <= 0 || D->H <= 0) return 0;
+  return (g_policy.load() == 0 && triplet_attn_fused_supported(*D, We)) ? 1 : 0;
+}
+
+extern "C" int tgt_triplet_attn_fused_fwd(const tgt_triplet_attn_desc *D, const void *x, int64_t ldx, int We,
+                                          const float *row_mean, const float *row_rstd, const void *wf,
+                                          const float *wcolsum, const float *wbias, const void *proj_eg,
+                                          const float *mask, void *va, float *stats, void *ws, size_t ws_bytes,
+                                          void *stream) {
+  if (int e = attn_check(D)) return e;
+  if (!x || !row_mean || !row_rstd || !wf || !wcolsum || !wbias || !proj_eg || !mask || !va || !stats)
+    return fail("triplet_attn_fused_fwd: null argument");
+  return triplet_attn_fused_fwd(*D, We, x, ldx, row_mean, row_rstd, wf, wcolsum, wbias, proj_eg, mask, va, stats, ws,
+                                ws_bytes, (cudaStream_t)stream);
 }
 
 static int aggr_check(const tgt_triplet_aggr_desc *D) {

@@ -477,6 +477,11 @@ int triplet_attn_fwd_tma_launch(const tgt_triplet_attn_desc &D, const void *proj
 int triplet_attn_bwd_tma_launch(const tgt_triplet_attn_desc &D, const void *proj, const void *dva, const float *stats,
                                 void *dproj, const float *ws_e, const __half *ws_g, float *ws_de, float *ws_dg,
                                 cudaStream_t st);
+// triplet_fused.cu
+bool triplet_attn_fused_supported(const tgt_triplet_attn_desc &D, int We);
+int triplet_attn_fused_launch(const tgt_triplet_attn_desc &D, int We, const void *x, int64_t ldx, const float *mean,
+                              const float *rstd, const void *wf, const float *wcolsum, const float *wbias, void *va,
+                              float *stats, const float *ws_e, const __half *ws_g, cudaStream_t st);
 // kernel policy 0 (default): TMA-staged kernels; policy 2: the cp.async-staged kernels of this file
 static bool use_tma() { return g_policy.load() == 0 && triplet_attn_tma_available(); }
 
@@ -539,6 +544,28 @@ static int bwd_impl(const tgt_triplet_attn_desc &D, const void *proj, const floa
   if (int e = check_launch("tri_attn_bwd_mma")) return e;
   tri_post_bias_gate<T><<<dim3(D.N, 2, D.B), 256, psm, st>>>(D, w.de, w.dg, (T *)dproj);
   return check_launch("tri_post_bias_gate");
+}
+
+// fused forward: bias / gate tiles from the [R, D.ld] E|G projection `proj_eg` (columns D.off_e / D.off_g), then the
+// projection + attention kernel of triplet_fused.cu on the raw edge rows x
+int triplet_attn_fused_fwd(const tgt_triplet_attn_desc &D, int We, const void *x, int64_t ldx, const float *mean,
+                           const float *rstd, const void *wf, const float *wcolsum, const float *wbias,
+                           const void *proj_eg, const float *mask, void *va, float *stats, void *ws, size_t ws_bytes,
+                           cudaStream_t st) {
+  if (!triplet_attn_fused_supported(D, We)) return fail("triplet_attn_fused_fwd: unsupported shape / dtype");
+  if (!ws || ws_bytes < triplet_attn_mma_workspace(D, 0))
+    return fail("triplet_attn_fused_fwd: workspace too small (%zu < %zu bytes)", ws_bytes, triplet_attn_mma_workspace(D, 0));
+  if (((uintptr_t)x | (uintptr_t)va | (uintptr_t)wf) & 15) return fail("triplet_attn_fused_fwd: x / wf / va must be 16-byte aligned");
+  if (ldx % 8) return fail("triplet_attn_fused_fwd: ldx must be a multiple of 8");
+  if (D.B > 65535) return fail("triplet_attn_fused_fwd: B > 65535 unsupported");
+  const Ws w = carve_fwd(D, ws);
+  const size_t psm = 2 * (size_t)D.H * 65 * sizeof(float);
+  if (D.dtype == TGT_BF16)
+    tri_prep_bias_gate<__nv_bfloat16><<<dim3(TN, 2, D.B), 256, psm, st>>>(D, (const __nv_bfloat16 *)proj_eg, mask, w.e, w.g);
+  else
+    tri_prep_bias_gate<__half><<<dim3(TN, 2, D.B), 256, psm, st>>>(D, (const __half *)proj_eg, mask, w.e, w.g);
+  if (int e = check_launch("tri_prep_bias_gate")) return e;
+  return triplet_attn_fused_launch(D, We, x, ldx, mean, rstd, wf, wcolsum, wbias, va, stats, w.e, w.g, st);
 }
 
 int triplet_attn_fwd_mma(const tgt_triplet_attn_desc &D, const void *proj, const float *mask, void *va, float *stats,

@@ -409,6 +409,47 @@ class LNLinearFn(Function):
 # ------------------------------------------------------------------------------------------
 # triplet attention module: LN -> [QKV_in|QKV_out|EG_in|EG_out] GEMM -> core -> lin_O
 # ------------------------------------------------------------------------------------------
+_PANEL_IDX = {}
+
+
+def _panel_rows(H: int, d: int, W: int, device) -> Tensor:
+    """Row gather that regroups the kernel-order projection weights ([Q_in|K_in|V_in|Q_out|K_out|V_out], head-major)
+    per PAIR of heads in the order the fused kernel's accumulator columns use:
+    Qin h0,h1 | Qout h0,h1 | Kout h0,h1 | Vout h0,h1 | Kin h0,h1 | Vin h0,h1   (d rows each)."""
+    key = (H, d, W, str(device))
+    if key not in _PANEL_IDX:
+        dd = torch.arange(d)
+        rows = []
+        for hp in range(H // 2):
+            for base in (0, 3 * W, 4 * W, 5 * W, W, 2 * W):          # Qin, Qout, Kout, Vout, Kin, Vin
+                for h in (2 * hp, 2 * hp + 1):
+                    rows.append(base + h * d + dd)
+        _PANEL_IDX[key] = torch.cat(rows).to(device)
+    return _PANEL_IDX[key]
+
+
+def _fused_triplet_fwd(x2, mean, rstd, fold, m3, va, stats, B, N, H, d, W, off_e, off_g, cdtype):
+    Wg, bp, cs = fold
+    idx = _panel_rows(H, d, W, x2.device)
+    wf = Wg.index_select(0, idx).contiguous()
+    wcs, wbs = cs.index_select(0, idx).contiguous(), bp.index_select(0, idx).contiguous()
+    neg = Wg.shape[0] - 6 * W                      # E|G columns (padded to a multiple of 8); 0 for AxialAttention
+    if neg > 0:
+        proj_eg = gemm_tc(x2, Wg[6 * W:], bias=bp[6 * W:].contiguous(), ln=(mean, rstd, cs[6 * W:].contiguous()),
+                          name="gemm_tc_ln_eg_tri")
+    else:
+        proj_eg = x2
+    rel = lambda o: tuple(v - 6 * W if v >= 0 else -1 for v in o)
+    desc = _C.TripletAttnDesc(B, N, H, d, max(neg, 8), (0, 0), (0, 0), (0, 0), rel(off_e), rel(off_g),
+                              float(d) ** -0.5, _C.dtype_code(cdtype))
+    ws, wsb = _workspace(_C.lib().tgt_triplet_attn_workspace_bytes(desc, 0), x2.device)
+    with timed("triplet_fused_fwd"):
+        _C.check(_C.lib().tgt_triplet_attn_fused_fwd(desc, _C.ptr(x2), x2.stride(0), W, _C.ptr(mean), _C.ptr(rstd),
+                                                     _C.ptr(wf), _C.ptr(wcs), _C.ptr(wbs), _C.ptr(proj_eg), _C.ptr(m3),
+                                                     _C.ptr(va), _C.ptr(stats), _C.ptr(ws), wsb, _C.stream_ptr()),
+                 "triplet_attn_fused_fwd")
+
+
 class TripletAttentionFn(Function):
     """e:[B,N,N,W]; Wcat:[C,W] rows in kernel order (head-major q/k/v blocks, then bias/gate blocks);
     Wo:[W,2W] with columns in kernel order (dir, h, dd).  `layout` = (H, d, off_q, off_k, off_v, off_e, off_g).
@@ -428,18 +469,27 @@ class TripletAttentionFn(Function):
             Wc, bc = Wcat.detach().to(cdtype).contiguous(), bcat.detach().to(cdtype).contiguous()
             Woc = Wo.detach().to(cdtype).contiguous()
             m3 = _f32c(mask).view(B, N, N)
-            proj, mean, rstd, fold = ln_linear(x2, g, bt, Wcat, bcat, Wc, cdtype, stats=take_stats(e, x2),
-                                               name="gemm_tc_ln_proj")
-            desc = _C.TripletAttnDesc(B, N, H, d, proj.shape[1], off_q, off_k, off_v, off_e, off_g,
+            desc = _C.TripletAttnDesc(B, N, H, d, Wcat.shape[0], off_q, off_k, off_v, off_e, off_g,
                                       float(d) ** -0.5, _C.dtype_code(cdtype))
             va = torch.empty((R, 2 * H * d), dtype=cdtype, device=e.device)
             stats = torch.empty((B, 2, H, N, N, 2), dtype=torch.float32, device=e.device)
-            ws, wsb = _workspace(_C.lib().tgt_triplet_attn_workspace_bytes(desc, 0), e.device)
-            with timed("triplet_attn_fwd"):
-                _C.check(_C.lib().tgt_triplet_attn_fwd(desc, _C.ptr(proj), _C.ptr(m3), _C.ptr(va), _C.ptr(stats),
-                                                       _C.ptr(ws), wsb, _C.stream_ptr()), "triplet_attn_fwd")
-            del ws
-            del proj
+            if (x2.dtype == cdtype and tc_gemm_ok(x2, Wcat.shape[0], W) and tuple(off_q) == (0, 3 * W)
+                    and tuple(off_k) == (W, 4 * W) and tuple(off_v) == (2 * W, 5 * W)
+                    and _C.lib().tgt_triplet_attn_fused_supported(desc, W)):
+                # fused forward: the q/k/v projection is produced and consumed on chip (csrc/triplet_fused.cu)
+                st_in = take_stats(e, x2)
+                mean, rstd = st_in if st_in is not None else row_stats(x2)
+                fold = _ln_fold(Wcat, bcat, g, bt, cdtype)
+                _fused_triplet_fwd(x2, mean, rstd, fold, m3, va, stats, B, N, H, d, W, off_e, off_g, cdtype)
+            else:
+                proj, mean, rstd, fold = ln_linear(x2, g, bt, Wcat, bcat, Wc, cdtype, stats=take_stats(e, x2),
+                                                   name="gemm_tc_ln_proj")
+                ws, wsb = _workspace(_C.lib().tgt_triplet_attn_workspace_bytes(desc, 0), e.device)
+                with timed("triplet_attn_fwd"):
+                    _C.check(_C.lib().tgt_triplet_attn_fwd(desc, _C.ptr(proj), _C.ptr(m3), _C.ptr(va), _C.ptr(stats),
+                                                           _C.ptr(ws), wsb, _C.stream_ptr()), "triplet_attn_fwd")
+                del ws
+                del proj
             sc = _f32c(res_scale).view(B) if (fuse_res and res_scale is not None) else None
             out = torch.empty((B, N, N, W), dtype=cdtype, device=e.device)
             _, ostats = linear_residual(va, Woc, bo, x2 if fuse_res else None, sc, out2=out.view(R, W),

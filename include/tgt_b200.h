@@ -37,8 +37,9 @@ const char *tgt_last_error(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 uint64_t    tgt_launch_count(void);
 /* 0 = pick the fastest kernel that supports the shape (default); 1 = force the generic
- * SIMT kernels; 2 = tensor-core triplet kernels with cp.async staging instead of TMA (the
- * tests cross-check the three families). */
+ * SIMT kernels; 2 = tensor-core triplet kernels with cp.async staging instead of TMA; 3 = like 0
+ * but the triplet-attention forward runs the fused projection + attention kernel
+ * (tgt_triplet_attn_fused_fwd).  The tests cross-check the families. */
 void        tgt_set_kernel_policy(int policy);
 
 /* ---- LayerNorm over the channel dim of edge rows ---------------------------------------

@@ -338,9 +338,9 @@ def test_encoder_fp32_train_vs_oracle_grads():
 @pytest.mark.parametrize("kind", ["attention", "attention_ungated", "axial_attention"])
 @pytest.mark.parametrize("N,nn_", [(64, [64, 37, 50]), (33, [33, 20, 9]), (8, [8, 5, 1])])
 def test_fused_forward_matches_unfused(kind, N, nn_):
-    """bf16 edge input at the shipped geometry: the fused projection+attention kernel (policy 0) must reproduce the
-    un-fused tensor-core path (policy 2: LN-folded GEMM -> [R, 6We] projection -> attention kernel) and both must sit
-    within bf16 tolerance of the fp64 oracle; gradients flow through the shared backward."""
+    """bf16 edge input at the shipped geometry: the fused projection+attention kernel (policy 3) must reproduce the
+    un-fused tensor-core path (policy 0: LN-folded GEMM -> [R, 6We] projection -> TMA attention kernel) and both must
+    sit within bf16 tolerance of the fp64 oracle; gradients flow through the shared backward."""
     from tgt_b200 import ops
     torch.manual_seed(11)
     mod = L.get_triplet_layer(kind)(256, 16)
@@ -353,7 +353,7 @@ def test_fused_forward_matches_unfused(kind, N, nn_):
     ref.backward(dout)
     mod = mod.to(DEV)
     res = {}
-    for policy in (0, 2):
+    for policy in (3, 0):
         _C.set_kernel_policy(policy)
         ops.KernelTimer.reset(True)
         try:
@@ -368,8 +368,8 @@ def test_fused_forward_matches_unfused(kind, N, nn_):
         finally:
             _C.set_kernel_policy(0)
             ops.KernelTimer.reset(False)
-        assert ("triplet_fused_fwd" in names) == (policy == 0), names
+        assert ("triplet_fused_fwd" in names) == (policy == 3), names
         assert rel_err(res[policy][0], ref) < BF16_TOL
         assert rel_err(res[policy][1], ed.grad) < 2 * BF16_TOL
-    assert rel_err(res[0][0], res[2][0]) < 2e-3, rel_err(res[0][0], res[2][0])
-    assert rel_err(res[0][1], res[2][1]) < 2e-2
+    assert rel_err(res[3][0], res[0][0]) < 2e-3, rel_err(res[3][0], res[0][0])
+    assert rel_err(res[3][1], res[0][1]) < 2e-2

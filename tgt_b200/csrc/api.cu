@@ -76,7 +76,9 @@ extern "C" int tgt_triplet_attn_bwd(const tgt_triplet_attn_desc *D, const void *
 
 extern "C" int tgt_triplet_attn_fused_supported(const tgt_triplet_attn_desc *D, int We) {
   if (!D || D->B <= 0 || D->N <= 0 || D->H <= 0) return 0;
-  return (g_policy.load() == 0 && triplet_attn_fused_supported(*D, We)) ? 1 : 0;
+  // opt-in (policy 3): measured on B200 the fused kernel is bound by L2->SM operand traffic (8 CTAs per graph each
+  // stream the graph's edge rows twice) and does not yet beat the un-fused TMA path -- see DESIGN.md section 4.3
+  return (g_policy.load() == 3 && triplet_attn_fused_supported(*D, We)) ? 1 : 0;
 }
 
 extern "C" int tgt_triplet_attn_fused_fwd(const tgt_triplet_attn_desc *D, const void *x, int64_t ldx, int We,

@@ -264,13 +264,13 @@ static int egt_check(const tgt_egt_desc *D) {
 
 extern "C" size_t tgt_egt_attn_workspace_bytes(const tgt_egt_desc *D) {
   if (!D || egt_check(D)) return 0;
-  return (g_policy.load() == 0 && egt_fast_supported(*D)) ? egt_fast_workspace(*D) : 0;
+  return (g_policy.load() != 1 && egt_fast_supported(*D)) ? egt_fast_workspace(*D) : 0;
 }
 
 extern "C" int tgt_egt_attn_fwd(const tgt_egt_desc *D, const void *qkv, const void *eg, const float *mask,
                                 const float *src_mask, void *hhat, void *vatt, float *stats, void *stream) {
   if (int e = egt_check(D)) return e;
-  if (g_policy.load() == 0 && egt_fast_supported(*D))
+  if (g_policy.load() != 1 && egt_fast_supported(*D))
     return egt_fwd_fast_launch(*D, qkv, eg, mask, src_mask, hhat, vatt, stats, (cudaStream_t)stream);
   TGT_DISPATCH_DTYPE(D->dtype, T, return egt_fwd_t<T>(*D, qkv, eg, mask, src_mask, hhat, vatt, stats, (cudaStream_t)stream));
   return 0;
@@ -280,7 +280,7 @@ extern "C" int tgt_egt_attn_bwd(const tgt_egt_desc *D, const void *qkv, const vo
                                 const float *src_mask, const float *stats, const void *vatt, const void *dhhat,
                                 const void *dvatt, void *dqkv, void *deg, void *ws, size_t ws_bytes, void *stream) {
   if (int e = egt_check(D)) return e;
-  if (g_policy.load() == 0 && egt_fast_supported(*D))
+  if (g_policy.load() != 1 && egt_fast_supported(*D))
     return egt_bwd_fast_launch(*D, qkv, eg, mask, src_mask, stats, vatt, dhhat, dvatt, dqkv, deg, ws, ws_bytes,
                                (cudaStream_t)stream);
   TGT_DISPATCH_DTYPE(D->dtype, T, return egt_bwd_t<T>(*D, qkv, eg, mask, src_mask, stats, dhhat, dvatt, dqkv, deg, (cudaStream_t)stream));

@@ -6,12 +6,12 @@
 // in ONE kernel, so that the [R, 6*We] projection tensor (3.2 GB at B=256, N=64 -- 75% of the bytes the un-fused
 // forward moves) never exists in HBM.  One CTA = (graph b, pair of heads); it loops over pairs of junction atoms j:
 //
-//   warp 0    TMA producer: the LN-folded weight rows of its two heads (192 x We, once) and, per junction pair, the raw
+//   warp 0    lane 0 = TMA producer: the LN-folded weight rows of its two heads (192 x We, once) and, per junction pair, the raw
 //             edge rows as 128-row tiles: "column" tile rows (i, j0..j0+1) and "row" tile rows (j0..j0+1, k), 64-channel
 //             K-blocks, 128B swizzle, 4-stage mbarrier ring, 4-D tensor maps (rows >= N zero-filled)
-//   warp 1    tcgen05.mma issuer (one thread): D_col[128 x 128] = Xcol * [Q_in|Q_out|K_out|V_out]^T and
+//   warp 0    lane 1 = tcgen05.mma issuer: D_col[128 x 128] = Xcol * [Q_in|Q_out|K_out|V_out]^T and
 //             D_row[128 x 64] = Xrow * [K_in|V_in]^T into one of two TMEM accumulator sets
-//   warps 2-17  four attention warpgroups, one per (head, direction): tcgen05.ld their 3 x 16 accumulator columns, apply
+//   warps 4-19  four attention warpgroups (setmaxnreg moves the control warpgroup's registers to them), one per (head, direction): tcgen05.ld their 3 x 16 accumulator columns, apply
 //             the LayerNorm fold (rstd_r * (acc - mean_r * colsum_c) + bias'_c, the epilogue of gemm_tc.cu), round to
 //             16 bit into ldmatrix-ready 64 x 16 tiles, then run the same register-resident mma.sync attention as
 //             triplet_tma.cu (bias / gate tiles of the (head, direction) pinned in registers for all N junctions) and
@@ -20,6 +20,8 @@
 // The tensor pipe works on junction pair t+1 while the attention warpgroups are busy with pair t.
 // Bias / gate tiles come from a small LN-folded GEMM (E|G columns only) + tri_prep_bias_gate, as in the un-fused path.
 #include "triplet_common.cuh"
+#include <stdlib.h>
+#include <algorithm>
 
 namespace tgt {
 
@@ -32,7 +34,9 @@ constexpr int STAGES = 4;
 constexpr int STAGE_BYTES = 128 * 128;          // one 128-row x 64-channel K-block
 constexpr int KB_MAX = 4;                       // edge width <= 256
 constexpr int WG = 4;                           // attention warpgroups
-constexpr int THREADS = 64 + WG * 128;          // 576
+constexpr int THREADS = 128 + WG * 128;         // 640: control warpgroup (warp 0: lane 0 = TMA producer, lane 1 = MMA issuer;
+                                                //      warps 1-3 idle) + 4 attention warpgroups
+constexpr int REGS_CTRL = 24, REGS_ATTN = 112;  // setmaxnreg: 128*24 + 512*112 = 60416 <= 65536
 constexpr int TILE_B = TN * HD * 2;             // 2 KB operand tile
 constexpr int TILES_PER_WG = 2 * 3;             // (jj, {Q,K,V})
 constexpr int SMEM_W = KB_MAX * NW * 128;       // 96 KB
@@ -59,14 +63,14 @@ __device__ __forceinline__ void fused_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "memory");
 }
 
-template <typename T>
+template <typename T, int CL>
 __global__ void __launch_bounds__(fused::THREADS, 1)
 tri_fused_fwd(const tgt_triplet_attn_desc D, const int We, const __grid_constant__ CUtensorMap mXcol,
               const __grid_constant__ CUtensorMap mXrow, const __grid_constant__ CUtensorMap mWc,
               const __grid_constant__ CUtensorMap mWr, const __grid_constant__ CUtensorMap mVA,
               const float *__restrict__ row_mean, const float *__restrict__ row_rstd,
               const float *__restrict__ wcolsum, const float *__restrict__ wbias, const float *__restrict__ ws_e,
-              const __half *__restrict__ ws_g, float *__restrict__ stats) {
+              const __half *__restrict__ ws_g, float *__restrict__ stats, const int dbg) {
   using namespace fused;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -97,7 +101,7 @@ tri_fused_fwd(const tgt_triplet_attn_desc D, const int We, const __grid_constant
     tma_prefetch_desc(&mVA);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + s * 8, 1);
-      mbar_init(bar_empty + s * 8, 1);
+      mbar_init(bar_empty + s * 8, CL);               // every CTA of the cluster must have drained the stage
     }
     mbar_init(bar_w, 1);
     for (int i = 0; i < 2; ++i) {
@@ -106,7 +110,7 @@ tri_fused_fwd(const tgt_triplet_attn_desc D, const int We, const __grid_constant
     }
     fence_barrier_init();
   }
-  if (warp == 1) tc_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 0) tc_alloc(tmem_slot, TMEM_COLS);
   // LN-fold vectors of this head pair (weight rows are already in panel order)
   for (int c = tid; c < NW; c += THREADS) {
     vec_cs[c] = wcolsum[hp * NW + c];
@@ -114,11 +118,21 @@ tri_fused_fwd(const tgt_triplet_attn_desc D, const int We, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();                    // barriers of every CTA exist before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+  constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
+  constexpr int SLICE_ROWS = 128 / CL;               // each CTA fetches 1/CL of every activation tile and multicasts it
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------------------------------ TMA producer
+  if (warp < 4) {
+    // the control warpgroup hands its registers to the attention warpgroups
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CTRL));
+  }
+  if (warp >= 1 && warp < 4) {
+    // idle warps of the control warpgroup
+  } else if (warp == 0) {
+    // ------------------------------------------------------------------------------------------ TMA producer (lane 0)
     if (lane == 0) {
       mbar_expect_tx(bar_w, (uint32_t)kblocks * NW * 128);
       for (int kb = 0; kb < kblocks; ++kb) {
@@ -132,8 +146,15 @@ tri_fused_fwd(const tgt_triplet_attn_desc D, const int We, const __grid_constant
           for (int kb = 0; kb < kblocks; ++kb) {
             mbar_wait(bar_empty + stage * 8, phase ^ 1);
             mbar_expect_tx(bar_full + stage * 8, STAGE_BYTES);
-            if (half == 0) tma_load_4d(&mXcol, bar_full + stage * 8, sA + stage * STAGE_BYTES, kb * 64, 2 * t, 0, b);
-            else tma_load_4d(&mXrow, bar_full + stage * 8, sA + stage * STAGE_BYTES, kb * 64, 0, 2 * t, b);
+            const CUtensorMap *mp = half == 0 ? &mXcol : &mXrow;
+            if (CL == 1) {
+              tma_load_4d(mp, bar_full + stage * 8, sA + stage * STAGE_BYTES, kb * 64, 0, 2 * t, b);
+            } else {
+              // tile rows are (jj, row): slice `crank` = rows [crank*SLICE_ROWS, +SLICE_ROWS) of the 128
+              const int r0 = (int)crank * SLICE_ROWS;
+              tma_load_4d_mc(mp, bar_full + stage * 8, sA + stage * STAGE_BYTES + r0 * 128, kb * 64, r0 & 63,
+                             2 * t + (r0 >> 6), b, CMASK);
+            }
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
@@ -141,10 +162,8 @@ tri_fused_fwd(const tgt_triplet_attn_desc D, const int We, const __grid_constant
           }
         }
       }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    } else if (lane == 1) {
+      // ---------------------------------------------------------------------------------------- MMA issuer (lane 1)
       const uint32_t idesc_c = fused_idesc<T>(NCOL), idesc_r = fused_idesc<T>(NROW);
       mbar_wait(bar_w, 0);
       int stage = 0;
@@ -162,9 +181,10 @@ tri_fused_fwd(const tgt_triplet_attn_desc D, const int We, const __grid_constant
             for (int k = 0; k < ksteps; ++k) {
               const uint64_t ad = fused_desc_sw128(sA + stage * STAGE_BYTES + k * 32);
               const uint64_t bd = fused_desc_sw128((half ? sWr + kb * NROW * 128 : sWc + kb * NCOL * 128) + k * 32);
-              tc_mma(tmem_d, ad, bd, half ? idesc_r : idesc_c, (uint32_t)((kb | k) != 0));
+              if (!(dbg & 2)) tc_mma(tmem_d, ad, bd, half ? idesc_r : idesc_c, (uint32_t)((kb | k) != 0));
             }
-            tc_commit(bar_empty + stage * 8);
+            if (CL == 1) tc_commit(bar_empty + stage * 8);
+            else tc_commit_mc(bar_empty + stage * 8, CMASK);
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
@@ -174,11 +194,13 @@ tri_fused_fwd(const tgt_triplet_attn_desc D, const int We, const __grid_constant
         tc_commit(bar_tfull + buf * 8);
       }
     }
+    __syncwarp();
   } else {
     // ------------------------------------------------------------------------------------------ attention warpgroups
-    const int wg = (warp - 2) >> 2;              // 0..3
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_ATTN));
+    const int wg = (warp - 4) >> 2;              // 0..3
     const int wq = warp & 3;                     // TMEM lane quadrant of this warp
-    const int wl = (warp - 2) & 3;               // warp index inside the warpgroup -> 16 query rows
+    const int wl = warp & 3;                     // warp index inside the warpgroup -> 16 query rows
     const int hl = wg & 1, dir = wg >> 1;
     const int h = hp * HPC + hl;
     const int g = lane >> 2, q = lane & 3;
@@ -210,10 +232,10 @@ tri_fused_fwd(const tgt_triplet_attn_desc D, const int We, const __grid_constant
     const int cK = dir ? (2 * HPC * HD + hl * HD) : (NCOL + hl * HD);
     const int cV = dir ? (3 * HPC * HD + hl * HD) : (NCOL + HPC * HD + hl * HD);
     const int co = dir * H * HD + h * HD;
-    // the TMEM lane of this thread: r = wq*32 + lane.  column tile rows are (i, jj) = (r >> 1, r & 1); row tile rows are
-    // (jj, k) = (r >> 6, r & 63)
+    // the TMEM lane of this thread: r = wq*32 + lane.  Both tiles are ordered (jj, row): column tile rows are
+    // (jj, i) = (r >> 6, r & 63), row tile rows are (jj, k) = (r >> 6, r & 63)
     const int r = wq * 32 + lane;
-    const int ci = r >> 1, cjj = r & 1, rjj = r >> 6, rk = r & 63;
+    const int ci = r & 63, cjj = r >> 6, rjj = r >> 6, rk = r & 63;
 
     for (int t = 0; t < npairs; ++t) {
       const int buf = t & 1;
@@ -235,6 +257,12 @@ tri_fused_fwd(const tgt_triplet_attn_desc D, const int We, const __grid_constant
       mbar_wait(bar_tfull + buf * 8, (uint32_t)((t >> 1) & 1));
       tc_fence_after();
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      if (dbg & 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + buf * 8);
+        continue;
+      }
       // ---- TMEM -> LN fold -> 16-bit operand tiles
       const uint32_t tbase = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * NW);
 #pragma unroll
@@ -275,7 +303,7 @@ tri_fused_fwd(const tgt_triplet_attn_desc D, const int We, const __grid_constant
 #pragma unroll 1
       for (int jj = 0; jj < 2; ++jj) {
         const int j = j0 + jj;
-        if (j >= N) break;
+        if (j >= N || (dbg & 4)) break;
         const uint32_t sQ = myT + (uint32_t)(jj * 3) * TILE_B, sK = sQ + TILE_B, sV = sK + TILE_B;
         uint32_t qa[4];
         load_a_rows(qa, sQ, m0, lane);
@@ -355,7 +383,8 @@ tri_fused_fwd(const tgt_triplet_attn_desc D, const int We, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (CL > 1) cluster_sync_all();                    // nobody leaves while a peer may still multicast into it
+  if (warp == 0) {
     tc_fence_after();
     tc_dealloc(tmem_base, fused::TMEM_COLS);
   }
@@ -381,18 +410,22 @@ bool triplet_attn_fused_supported(const tgt_triplet_attn_desc &D, int We) {
   return encode_tiled_fn() != nullptr;
 }
 
-template <typename T>
+template <typename T, int CL>
 static int fused_impl(const tgt_triplet_attn_desc &D, int We, const void *x, int64_t ldx, const float *mean,
                       const float *rstd, const void *wf, const float *wcolsum, const float *wbias, void *va,
                       float *stats, const float *ws_e, const __half *ws_g, cudaStream_t st) {
   using namespace fused;
   CUtensorMap mXcol, mXrow, mWc, mWr, mVA;
   {
+    // x[b, i, j, :]: the row tile walks the last edge index (stride ldx), the column tile the first one (stride N*ldx);
+    // both maps list the walked index first so that either tile lands as [2 junctions][64 rows][64 channels]
     const cuuint64_t gdim[4] = {(cuuint64_t)We, (cuuint64_t)D.N, (cuuint64_t)D.N, (cuuint64_t)D.B};
-    const cuuint64_t gstr[3] = {(cuuint64_t)ldx * 2, (cuuint64_t)D.N * ldx * 2, (cuuint64_t)D.N * D.N * ldx * 2};
-    const cuuint32_t bc[4] = {64u, 2u, 64u, 1u}, br[4] = {64u, 64u, 2u, 1u};
-    if (int e = fused_map(&mXcol, x, 4, gdim, gstr, bc, CU_TENSOR_MAP_SWIZZLE_128B, D.dtype)) return e;
-    if (int e = fused_map(&mXrow, x, 4, gdim, gstr, br, CU_TENSOR_MAP_SWIZZLE_128B, D.dtype)) return e;
+    const cuuint64_t gstr_r[3] = {(cuuint64_t)ldx * 2, (cuuint64_t)D.N * ldx * 2, (cuuint64_t)D.N * D.N * ldx * 2};
+    const cuuint64_t gstr_c[3] = {(cuuint64_t)D.N * ldx * 2, (cuuint64_t)ldx * 2, (cuuint64_t)D.N * D.N * ldx * 2};
+    // CL == 1: one box = the whole tile [2][64 rows]; CL > 1: one box = this CTA's slice of 128 / CL rows
+    const cuuint32_t bx[4] = {64u, CL == 1 ? 64u : (cuuint32_t)std::min(64, 128 / CL), CL == 1 ? 2u : (CL == 2 ? 1u : 1u), 1u};
+    if (int e = fused_map(&mXcol, x, 4, gdim, gstr_c, bx, CU_TENSOR_MAP_SWIZZLE_128B, D.dtype)) return e;
+    if (int e = fused_map(&mXrow, x, 4, gdim, gstr_r, bx, CU_TENSOR_MAP_SWIZZLE_128B, D.dtype)) return e;
   }
   {
     const cuuint64_t gdim[2] = {(cuuint64_t)We, (cuuint64_t)(D.H / HPC) * NW};
@@ -410,19 +443,54 @@ static int fused_impl(const tgt_triplet_attn_desc &D, int We, const void *x, int
   }
   static std::once_flag once;
   std::call_once(once, [] {
-    cudaFuncSetAttribute(tri_fused_fwd<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+    cudaFuncSetAttribute(tri_fused_fwd<T, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
   });
-  tri_fused_fwd<T><<<dim3(D.H / HPC, D.B), THREADS, SMEM_TOTAL, st>>>(D, We, mXcol, mXrow, mWc, mWr, mVA, mean, rstd,
-                                                                     wcolsum, wbias, ws_e, ws_g, stats);
+  static const int dbg = [] { const char *v = getenv("TGT_FUSED_DEBUG"); return v ? atoi(v) : 0; }();   // ablations
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(D.H / HPC, D.B);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = SMEM_TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t err = cudaLaunchKernelEx(&cfg, tri_fused_fwd<T, CL>, D, We, mXcol, mXrow, mWc, mWr, mVA, mean, rstd, wcolsum,
+                                       wbias, ws_e, ws_g, stats, dbg);
+  if (err != cudaSuccess) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return fail("tri_fused_fwd: %s", cudaGetErrorString(err));
+  }
   return check_launch("tri_fused_fwd");
+}
+
+// cluster size: the 8 head-pair CTAs of a graph share their activation tiles by TMA multicast (TGT_FUSED_CLUSTER=1/2/4/8)
+static int fused_cluster(int ctas_per_graph) {
+  static const int want = [] { const char *v = getenv("TGT_FUSED_CLUSTER"); return v ? atoi(v) : 1; }();
+  int cl = want;
+  while (cl > 1 && (ctas_per_graph % cl)) cl >>= 1;
+  return cl < 1 ? 1 : cl;
 }
 
 int triplet_attn_fused_launch(const tgt_triplet_attn_desc &D, int We, const void *x, int64_t ldx, const float *mean,
                               const float *rstd, const void *wf, const float *wcolsum, const float *wbias, void *va,
                               float *stats, const float *ws_e, const __half *ws_g, cudaStream_t st) {
-  if (D.dtype == TGT_BF16)
-    return fused_impl<__nv_bfloat16>(D, We, x, ldx, mean, rstd, wf, wcolsum, wbias, va, stats, ws_e, ws_g, st);
-  return fused_impl<__half>(D, We, x, ldx, mean, rstd, wf, wcolsum, wbias, va, stats, ws_e, ws_g, st);
+#define TGT_FUSED_GO(TT, C) return fused_impl<TT, C>(D, We, x, ldx, mean, rstd, wf, wcolsum, wbias, va, stats, ws_e, ws_g, st)
+  const int cl = fused_cluster(D.H / fused::HPC);
+  if (D.dtype == TGT_BF16) {
+    if (cl == 8) TGT_FUSED_GO(__nv_bfloat16, 8);
+    if (cl == 4) TGT_FUSED_GO(__nv_bfloat16, 4);
+    if (cl == 2) TGT_FUSED_GO(__nv_bfloat16, 2);
+    TGT_FUSED_GO(__nv_bfloat16, 1);
+  }
+  if (cl == 8) TGT_FUSED_GO(__half, 8);
+  if (cl == 4) TGT_FUSED_GO(__half, 4);
+  if (cl == 2) TGT_FUSED_GO(__half, 2);
+  TGT_FUSED_GO(__half, 1);
+#undef TGT_FUSED_GO
 }
 
 }  // namespace tgt

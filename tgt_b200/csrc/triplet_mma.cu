@@ -483,7 +483,7 @@ int triplet_attn_fused_launch(const tgt_triplet_attn_desc &D, int We, const void
                               const float *rstd, const void *wf, const float *wcolsum, const float *wbias, void *va,
                               float *stats, const float *ws_e, const __half *ws_g, cudaStream_t st);
 // kernel policy 0 (default): TMA-staged kernels; policy 2: the cp.async-staged kernels of this file
-static bool use_tma() { return g_policy.load() == 0 && triplet_attn_tma_available(); }
+static bool use_tma() { return (g_policy.load() == 0 || g_policy.load() == 3) && triplet_attn_tma_available(); }
 
 struct Ws {
   float *e; __half *g; float *de; float *dg;

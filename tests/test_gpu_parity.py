@@ -202,8 +202,9 @@ def test_shipped_width_bf16_vs_oracle(kind, N, nn_):
         assert rel_err(res[policy][1], ed.grad) < 2 * BF16_TOL
         assert_grads_close(res[policy][2], {k: v.grad for k, v in p.items()}, 3 * BF16_TOL, "l2")
     assert rel_err(res[0][0], res[1][0]) < BF16_TOL
-    # the TMA-staged and the cp.async-staged kernels run the same arithmetic on the same fragments
-    assert rel_err(res[0][0], res[2][0]) < 1e-6 and rel_err(res[0][1], res[2][1]) < 1e-6
+    # the TMA-staged and the cp.async-staged kernels run the same arithmetic on the same fragments; only the order of
+    # the fp32 row sums differs (packed f32x2 partial sums), i.e. a few 16-bit roundings flip
+    assert rel_err(res[0][0], res[2][0]) < 1e-3 and rel_err(res[0][1], res[2][1]) < 1e-3
 
 
 def test_outputs_survive_inplace_residual_add():

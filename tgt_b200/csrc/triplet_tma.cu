@@ -113,33 +113,38 @@ tri_attn_fwd_tma(const tgt_triplet_attn_desc D, const __grid_constant__ CUtensor
         Mma<T>::run(s[2 * p + u], qa, kb[2 * u], kb[2 * u + 1]);
       }
     }
+    // logits, row max, exp, gate: packed f32x2 arithmetic (two accumulator columns of a row per instruction)
+    const float2 c1p0 = make_float2(c1r0, c1r0), c1p1 = make_float2(c1r1, c1r1);
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      s[nt][0] = fmaf(s[nt][0], c1r0, eb[nt][0]);
-      s[nt][1] = fmaf(s[nt][1], c1r0, eb[nt][1]);
-      s[nt][2] = fmaf(s[nt][2], c1r1, eb[nt][2]);
-      s[nt][3] = fmaf(s[nt][3], c1r1, eb[nt][3]);
-      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
-      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+      float2 &s01 = *reinterpret_cast<float2 *>(&s[nt][0]), &s23 = *reinterpret_cast<float2 *>(&s[nt][2]);
+      s01 = __ffma2_rn(s01, c1p0, *reinterpret_cast<const float2 *>(&eb[nt][0]));
+      s23 = __ffma2_rn(s23, c1p1, *reinterpret_cast<const float2 *>(&eb[nt][2]));
+      mx0 = fmaxf(mx0, fmaxf(s01.x, s01.y));
+      mx1 = fmaxf(mx1, fmaxf(s23.x, s23.y));
     }
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    float l0 = 0.f, l1 = 0.f;
+    const float2 nm0 = make_float2(-mx0, -mx0), nm1 = make_float2(-mx1, -mx1);
+    float2 lp0 = make_float2(0.f, 0.f), lp1 = make_float2(0.f, 0.f);
     uint32_t pa[4][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      const float p0 = fast_exp2(s[nt][0] - mx0), p1 = fast_exp2(s[nt][1] - mx0);
-      const float p2 = fast_exp2(s[nt][2] - mx1), p3 = fast_exp2(s[nt][3] - mx1);
-      l0 += p0 + p1;
-      l1 += p2 + p3;
-      const float2 g0 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][0]));
-      const float2 g1 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][1]));
-      pa[nt >> 1][(nt & 1) * 2 + 0] = Mma<T>::pack(p0 * g0.x, p1 * g0.y);
-      pa[nt >> 1][(nt & 1) * 2 + 1] = Mma<T>::pack(p2 * g1.x, p3 * g1.y);
+      const float2 x01 = __fadd2_rn(*reinterpret_cast<float2 *>(&s[nt][0]), nm0);
+      const float2 x23 = __fadd2_rn(*reinterpret_cast<float2 *>(&s[nt][2]), nm1);
+      const float2 p01 = make_float2(fast_exp2(x01.x), fast_exp2(x01.y));
+      const float2 p23 = make_float2(fast_exp2(x23.x), fast_exp2(x23.y));
+      lp0 = __fadd2_rn(lp0, p01);
+      lp1 = __fadd2_rn(lp1, p23);
+      const float2 w01 = __fmul2_rn(p01, __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][0])));
+      const float2 w23 = __fmul2_rn(p23, __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][1])));
+      pa[nt >> 1][(nt & 1) * 2 + 0] = Mma<T>::pack(w01.x, w01.y);
+      pa[nt >> 1][(nt & 1) * 2 + 1] = Mma<T>::pack(w23.x, w23.y);
     }
+    float l0 = lp0.x + lp0.y, l1 = lp1.x + lp1.y;
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
     l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
@@ -310,29 +315,40 @@ tri_attn_bwd_tma(const tgt_triplet_attn_desc D, const __grid_constant__ CUtensor
         Mma<T>::run(da[nt], oa, vb[2 * u], vb[2 * u + 1]);
       }
     }
-    // P (normalised), t = dA*g*P, delta = rowsum(t)
-    float dl0 = 0.f, dl1 = 0.f;
+    // P (normalised), t = dA*g*P, delta = rowsum(t).  The element-wise math runs on packed f32x2 instructions
+    // (fma/add/mul.rn.f32x2: two accumulator columns of one row per issue slot); results are identical to scalar fp32.
+    const float2 c1p0 = make_float2(c1r0, c1r0), c1p1 = make_float2(c1r1, c1r1);
+    const float2 nl0 = make_float2(-lse0, -lse0), nl1 = make_float2(-lse1, -lse1);
+    float2 dlp0 = make_float2(0.f, 0.f), dlp1 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       const float2 g0 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][0]));
       const float2 g1 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][1]));
-      const float gg[4] = {g0.x, g0.y, g1.x, g1.y};
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float p = fast_exp2(fmaf(s[nt][c], c < 2 ? c1r0 : c1r1, eb[nt][c]) - (c < 2 ? lse0 : lse1));
-        const float dap = da[nt][c] * p;
-        dg[nt][c] += dap;
-        s[nt][c] = p;                      // P
-        da[nt][c] = dap * gg[c];           // t = dA * g * P
-      }
-      dl0 += da[nt][0] + da[nt][1];
-      dl1 += da[nt][2] + da[nt][3];
+      float2 &s01 = *reinterpret_cast<float2 *>(&s[nt][0]), &s23 = *reinterpret_cast<float2 *>(&s[nt][2]);
+      float2 &a01 = *reinterpret_cast<float2 *>(&da[nt][0]), &a23 = *reinterpret_cast<float2 *>(&da[nt][2]);
+      float2 &e01 = *reinterpret_cast<float2 *>(&eb[nt][0]), &e23 = *reinterpret_cast<float2 *>(&eb[nt][2]);
+      float2 &q01 = *reinterpret_cast<float2 *>(&dg[nt][0]), &q23 = *reinterpret_cast<float2 *>(&dg[nt][2]);
+      const float2 x01 = __ffma2_rn(s01, c1p0, __fadd2_rn(e01, nl0));
+      const float2 x23 = __ffma2_rn(s23, c1p1, __fadd2_rn(e23, nl1));
+      const float2 p01 = make_float2(fast_exp2(x01.x), fast_exp2(x01.y));
+      const float2 p23 = make_float2(fast_exp2(x23.x), fast_exp2(x23.y));
+      const float2 dap01 = __fmul2_rn(a01, p01), dap23 = __fmul2_rn(a23, p23);
+      q01 = __fadd2_rn(q01, dap01);
+      q23 = __fadd2_rn(q23, dap23);
+      s01 = p01;                             // P
+      s23 = p23;
+      a01 = __fmul2_rn(dap01, g0);           // t = dA * g * P
+      a23 = __fmul2_rn(dap23, g1);
+      dlp0 = __fadd2_rn(dlp0, a01);
+      dlp1 = __fadd2_rn(dlp1, a23);
     }
+    float dl0 = dlp0.x + dlp0.y, dl1 = dlp1.x + dlp1.y;
     dl0 += __shfl_xor_sync(0xffffffffu, dl0, 1);
     dl0 += __shfl_xor_sync(0xffffffffu, dl0, 2);
     dl1 += __shfl_xor_sync(0xffffffffu, dl1, 1);
     dl1 += __shfl_xor_sync(0xffffffffu, dl1, 2);
     // dS = t - P*delta ; A = P*g ; exchange through shared memory (stmatrix) ; dS also as A-fragments for dQ
+    const float2 nd0 = make_float2(-dl0, -dl0), nd1 = make_float2(-dl1, -dl1);
     uint32_t dsa[4][4];
 #pragma unroll
     for (int np = 0; np < 4; ++np) {
@@ -342,13 +358,17 @@ tri_attn_bwd_tma(const tgt_triplet_attn_desc D, const __grid_constant__ CUtensor
         const int nt = 2 * np + u;
         const float2 g0 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][0]));
         const float2 g1 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][1]));
-        const float d0 = fmaf(-s[nt][0], dl0, da[nt][0]), d1 = fmaf(-s[nt][1], dl0, da[nt][1]);
-        const float d2 = fmaf(-s[nt][2], dl1, da[nt][2]), d3 = fmaf(-s[nt][3], dl1, da[nt][3]);
-        de[nt][0] += d0; de[nt][1] += d1; de[nt][2] += d2; de[nt][3] += d3;
-        dsa[np][u * 2 + 0] = Mma<T>::pack(d0, d1);
-        dsa[np][u * 2 + 1] = Mma<T>::pack(d2, d3);
-        aa[u * 2 + 0] = Mma<T>::pack(s[nt][0] * g0.x, s[nt][1] * g0.y);
-        aa[u * 2 + 1] = Mma<T>::pack(s[nt][2] * g1.x, s[nt][3] * g1.y);
+        const float2 p01 = *reinterpret_cast<float2 *>(&s[nt][0]), p23 = *reinterpret_cast<float2 *>(&s[nt][2]);
+        const float2 d01 = __ffma2_rn(p01, nd0, *reinterpret_cast<float2 *>(&da[nt][0]));
+        const float2 d23 = __ffma2_rn(p23, nd1, *reinterpret_cast<float2 *>(&da[nt][2]));
+        float2 &f01 = *reinterpret_cast<float2 *>(&de[nt][0]), &f23 = *reinterpret_cast<float2 *>(&de[nt][2]);
+        f01 = __fadd2_rn(f01, d01);
+        f23 = __fadd2_rn(f23, d23);
+        dsa[np][u * 2 + 0] = Mma<T>::pack(d01.x, d01.y);
+        dsa[np][u * 2 + 1] = Mma<T>::pack(d23.x, d23.y);
+        const float2 w01 = __fmul2_rn(p01, g0), w23 = __fmul2_rn(p23, g1);
+        aa[u * 2 + 0] = Mma<T>::pack(w01.x, w01.y);
+        aa[u * 2 + 1] = Mma<T>::pack(w23.x, w23.y);
       }
       store_xch_pair(xS, m0, lane, 2 * np, dsa[np][0], dsa[np][1], dsa[np][2], dsa[np][3]);
       store_xch_pair(xA, m0, lane, 2 * np, aa[0], aa[1], aa[2], aa[3]);

@@ -42,6 +42,12 @@ uint64_t    tgt_launch_count(void);
  * (tgt_triplet_attn_fused_fwd).  The tests cross-check the families. */
 void        tgt_set_kernel_policy(int policy);
 
+/* optional device-side timing of the MAIN kernel of each call (prep / post helpers excluded): enable,
+ * run, then read "name launches total_ms" lines (the read synchronises on the recorded CUDA events;
+ * disabling frees them).  Diagnostics only -- this is the one place the library creates CUDA objects. */
+void        tgt_kernel_timer_enable(int on);
+int         tgt_kernel_timer_read(char *buf, size_t n);
+
 /* ---- LayerNorm over the channel dim of edge rows ---------------------------------------
  * replaces nn.LayerNorm calls at lib/tgt/layers/triplet.py:47,207; layers.py:49,112,156.
  * x:[rows,W] (x_dtype)  y:[rows,ldy] (y_dtype)  gamma,beta:[W] f32  mean,rstd:[rows] f32.

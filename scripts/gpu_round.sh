@@ -9,7 +9,7 @@ python - <<PY
 import json
 try:
     d = json.load(open("gpurun_out/bench_$TAG.json"))
-    print({k: d[k] for k in ("value", "ms_per_step", "gpu_launches", "peak_mem_gib", "clocks")}, d["e2e"], d["cpu_baseline"])
+    print({k: d[k] for k in ("value", "ms_per_step", "gpu_launches", "peak_mem_gib", "clocks")}, d["e2e"], d["cpu_baseline"]); print("roofline", d["roofline"]); print("module", d.get("triplet_module_fwd")); print("device", d.get("device_kernels"))
     for k, v in sorted(d["kernels"].items(), key=lambda kv: -kv[1]["share_of_step"]):
         print(f"  {k:24s} n/step={v['launches_per_step']:5.0f} ms={v['ms_per_launch']:8.3f} share={v['share_of_step']:.3f} "
               f"hbm={v.get('hbm_frac', 0):.3f} tc={v.get('tc_frac', 0):.4f}")

@@ -68,6 +68,8 @@ _SIGNATURES = {
     "tgt_last_error": (C.c_char_p, []),
     "tgt_launch_count": (C.c_uint64, []),
     "tgt_set_kernel_policy": (None, [C.c_int]),
+    "tgt_kernel_timer_enable": (None, [C.c_int]),
+    "tgt_kernel_timer_read": (C.c_int, [C.c_char_p, C.c_size_t]),
     "tgt_layernorm_fwd": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int64, C.c_float, C.c_int, C.c_int, _P]),
     "tgt_layernorm_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, _P]),
     "tgt_triplet_attn_workspace_bytes": (C.c_size_t, [C.POINTER(TripletAttnDesc), C.c_int]),
@@ -130,6 +132,21 @@ def stream_ptr() -> C.c_void_p:
 
 def launch_count() -> int:
     return int(lib().tgt_launch_count())
+
+
+def kernel_timer(enable: bool) -> None:
+    lib().tgt_kernel_timer_enable(1 if enable else 0)
+
+
+def kernel_timer_read() -> dict:
+    """{kernel name: (launches, total_ms)} measured on the device around each main kernel since kernel_timer(True)."""
+    buf = C.create_string_buffer(1 << 16)
+    lib().tgt_kernel_timer_read(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, n, ms = line.split()
+        out[name] = (int(n), float(ms))
+    return out
 
 
 def set_kernel_policy(policy: int) -> None:

@@ -1,10 +1,41 @@
 // C-ABI entry points that dispatch between the tensor-core and the generic kernels, plus library state.
 #include "common.cuh"
+#include <mutex>
+#include <vector>
+#include <string>
+#include <map>
+#include <algorithm>
+#include <string.h>
 
 namespace tgt {
 thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
 std::atomic<int> g_policy{0};
+
+// ---- optional device-side kernel timer (see common.cuh)
+static std::atomic<int> g_timer_on{0};
+struct TimerRec {
+  const char *name;
+  cudaEvent_t a, b;
+};
+static std::mutex g_timer_mu;
+static std::vector<TimerRec> g_timer_recs;
+static thread_local cudaEvent_t g_timer_open_b = nullptr;
+
+void kernel_timer_begin(const char *name, cudaStream_t st) {
+  g_timer_open_b = nullptr;
+  if (!g_timer_on.load(std::memory_order_relaxed)) return;
+  TimerRec r{name, nullptr, nullptr};
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+  cudaEventRecord(r.a, st);
+  g_timer_open_b = r.b;
+  std::lock_guard<std::mutex> lk(g_timer_mu);
+  g_timer_recs.push_back(r);
+}
+void kernel_timer_end(cudaStream_t st) {
+  if (g_timer_open_b) cudaEventRecord(g_timer_open_b, st);
+  g_timer_open_b = nullptr;
+}
 
 // triplet_simt.cu
 int triplet_attn_fwd_simt(const tgt_triplet_attn_desc &, const void *, const float *, void *, float *, cudaStream_t);
@@ -33,6 +64,41 @@ extern "C" int tgt_version(void) { return 100; }
 extern "C" const char *tgt_last_error(void) { return g_err; }
 extern "C" uint64_t tgt_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" void tgt_set_kernel_policy(int policy) { g_policy.store(policy); }
+
+extern "C" void tgt_kernel_timer_enable(int on) {
+  g_timer_on.store(on ? 1 : 0);
+  if (on) return;
+  std::lock_guard<std::mutex> lk(g_timer_mu);
+  for (auto &r : g_timer_recs) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_timer_recs.clear();
+}
+
+// writes "name launches total_ms\n" lines into buf (NUL-terminated, truncated to n); returns the number of lines
+extern "C" int tgt_kernel_timer_read(char *buf, size_t n) {
+  std::map<std::string, std::pair<int, double>> agg;
+  {
+    std::lock_guard<std::mutex> lk(g_timer_mu);
+    for (auto &r : g_timer_recs) {
+      float ms = 0.f;
+      if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+        auto &e = agg[r.name];
+        e.first += 1;
+        e.second += ms;
+      }
+    }
+  }
+  std::string out;
+  for (auto &kv : agg) out += kv.first + " " + std::to_string(kv.second.first) + " " + std::to_string(kv.second.second) + "\n";
+  if (buf && n) {
+    const size_t m = std::min(n - 1, out.size());
+    memcpy(buf, out.data(), m);
+    buf[m] = 0;
+  }
+  return (int)agg.size();
+}
 
 static int attn_check(const tgt_triplet_attn_desc *D) {
   if (!D) return fail("triplet_attn: null descriptor");

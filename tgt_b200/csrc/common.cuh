@@ -31,6 +31,18 @@ inline int check_launch(const char *what) {
   return 0;
 }
 
+// ---------------------------------------------------------------- optional per-kernel device timing (bench / profiling)
+// Off by default.  When enabled through tgt_kernel_timer_enable(1) the launchers bracket their MAIN kernel with CUDA
+// events on the launching stream (prep / post helper kernels excluded); tgt_kernel_timer_read() synchronises on the
+// recorded events and reports launches + total milliseconds per kernel name.
+void kernel_timer_begin(const char *name, cudaStream_t st);
+void kernel_timer_end(cudaStream_t st);
+struct KernelTimerScope {
+  cudaStream_t st;
+  KernelTimerScope(const char *name, cudaStream_t s) : st(s) { kernel_timer_begin(name, s); }
+  ~KernelTimerScope() { kernel_timer_end(st); }
+};
+
 #define TGT_CUDA_OK(expr)                                                        \
   do {                                                                           \
     cudaError_t _e = (expr);                                                     \

@@ -67,11 +67,13 @@ __device__ __forceinline__ void stage_rows(unsigned char *sm, const T *src, int6
 }
 
 // ------------------------------------------------------------------------------------------------ forward
+constexpr int EF_FCHUNK = 4;     // keys per shared-memory stage of the forward (double buffered)
+
 template <typename T, int HC, int DC, int ATT>
 __global__ void __launch_bounds__(EF_ROWS * 32, 2)
 egt_fwd_fast(const tgt_egt_desc D, const T *__restrict__ qkv, const T *__restrict__ eg, const float *__restrict__ mask,
              const float *__restrict__ src, T *__restrict__ hhat, T *__restrict__ vatt, float *__restrict__ stats) {
-  extern __shared__ __align__(16) unsigned char sm[];           // [EF_CHUNK][2*Wn] K|V   (or [EF_CHUNK][Wn] K only)
+  extern __shared__ __align__(16) unsigned char sm[];           // 2 x [EF_FCHUNK][2*Wn] K|V   (or K only)
   const int N = D.N, H = HC ? HC : D.H, d = DC ? DC : D.d, Wn = H * d;   // HC/DC: compile-time shape (0 = runtime)
   constexpr int DL = DC ? DC : EF_DMAX;
   const int b = blockIdx.y, l = blockIdx.x * EF_ROWS + (threadIdx.x >> 5), hp = threadIdx.x & 31;
@@ -79,59 +81,72 @@ egt_fwd_fast(const tgt_egt_desc D, const T *__restrict__ qkv, const T *__restric
   const int la = l < N ? l : N - 1;
   const bool attend = ATT < 0 ? D.attend != 0 : ATT != 0;     // ATT: compile-time attend flag (-1 = runtime)
   const int kvw = attend ? 2 * Wn : Wn;
-  const T *smT = reinterpret_cast<const T *>(sm);
+  const int stage_bytes = EF_FCHUNK * kvw * 2;
 
-  float q0[DL], q1[DL], o0[DL], o1[DL];
+  // one thread = one query row x one PAIR of heads: the pair rides in packed f32x2 registers (fma.rn.f32x2)
+  float2 qv[DL], ov[DL];
 #pragma unroll
   for (int dd = 0; dd < DL; ++dd) {
-    q0[dd] = q1[dd] = o0[dd] = o1[dd] = 0.f;
+    qv[dd] = ov[dd] = make_float2(0.f, 0.f);
     if (dd < d && active) {
       const float2 v = Pair<T>::unpack(ldg32(qkv + (int64_t)(b * N + la) * D.ld_qkv + dd * H + 2 * hp));
-      q0[dd] = v.x * D.scale;
-      q1[dd] = v.y * D.scale;
+      qv[dd] = make_float2(v.x * D.scale, v.y * D.scale);
     }
   }
   float mx0 = -INFINITY, mx1 = -INFINITY, ls0 = 0.f, ls1 = 0.f, dg0 = 0.f, dg1 = 0.f;
   const int64_t erow0 = (int64_t)(b * N + la) * N;
 
-  for (int mc = 0; mc < N; mc += EF_CHUNK) {
-    __syncthreads();
-    stage_rows<T>(sm, qkv, (int64_t)b * N, mc, N, D.ld_qkv, Wn, kvw, 0, kvw);
-    // prefetch this chunk's bias / gate pairs and masks while the copy is in flight
-    uint32_t ep[EF_CHUNK], gp[EF_CHUNK];
-    float mk[EF_CHUNK];
+  // stage `mc` : K|V rows of keys mc .. mc+EF_FCHUNK-1 into buffer `buf` (cp.async) + this thread's bias / gate / mask
+  auto stage_kv = [&](int mc, int buf) {
+    const int vec_per_row = kvw / 8;
+    for (int idx = threadIdx.x; idx < EF_FCHUNK * vec_per_row; idx += blockDim.x) {
+      const int r = idx / vec_per_row, v = idx - r * vec_per_row;
+      const bool ok = (mc + r) < N;
+      const T *g = qkv + ((int64_t)b * N + (ok ? mc + r : 0)) * D.ld_qkv + Wn + v * 8;
+      ef_cp16((uint32_t)__cvta_generic_to_shared(sm) + (uint32_t)(buf * stage_bytes + (r * kvw + v * 8) * 2), g, ok);
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+  uint32_t ep[EF_FCHUNK], gp[EF_FCHUNK], epn[EF_FCHUNK], gpn[EF_FCHUNK];
+  float mk[EF_FCHUNK], mkn[EF_FCHUNK];
+  auto fetch_eg = [&](int mc, uint32_t(&e_)[EF_FCHUNK], uint32_t(&g_)[EF_FCHUNK], float(&m_)[EF_FCHUNK]) {
 #pragma unroll
-    for (int mm = 0; mm < EF_CHUNK; ++mm) {
+    for (int mm = 0; mm < EF_FCHUNK; ++mm) {
       const int m = mc + mm;
-      ep[mm] = gp[mm] = 0u;
-      mk[mm] = 0.f;
+      e_[mm] = g_[mm] = 0u;
+      m_[mm] = 0.f;
       if (active && m < N) {
-        ep[mm] = ldg32(eg + (erow0 + m) * D.ld_eg + 2 * hp);
+        e_[mm] = ldg32(eg + (erow0 + m) * D.ld_eg + 2 * hp);
         if (attend) {
-          gp[mm] = ldg32(eg + (erow0 + m) * D.ld_eg + H + 2 * hp);
-          mk[mm] = mask[erow0 + m] + (src ? src[b * N + m] : 0.f);
+          g_[mm] = ldg32(eg + (erow0 + m) * D.ld_eg + H + 2 * hp);
+          m_[mm] = mask[erow0 + m] + (src ? src[b * N + m] : 0.f);
         }
       }
     }
-    ef_commit_wait();
-    __syncthreads();
+  };
+  stage_kv(0, 0);
+  fetch_eg(0, ep, gp, mk);
+
+  for (int mc = 0, it = 0; mc < N; mc += EF_FCHUNK, ++it) {
+    asm volatile("cp.async.wait_group 0;\n" ::);
+    __syncthreads();                 // stage `it` landed; everyone is done with stage it-1 (the buffer refilled next)
+    if (mc + EF_FCHUNK < N) {
+      stage_kv(mc + EF_FCHUNK, (it + 1) & 1);
+      fetch_eg(mc + EF_FCHUNK, epn, gpn, mkn);
+    }
+    const T *smT = reinterpret_cast<const T *>(sm + (it & 1) * stage_bytes);
     if (active) {
 #pragma unroll
-      for (int mm = 0; mm < EF_CHUNK; ++mm) {
+      for (int mm = 0; mm < EF_FCHUNK; ++mm) {
         const int m = mc + mm;
         if (m >= N) continue;
         const T *kp = smT + mm * kvw + 2 * hp;
-        float s0 = 0.f, s1 = 0.f;
+        float2 sv = make_float2(0.f, 0.f);
 #pragma unroll
         for (int dd = 0; dd < DL; ++dd)
-          if (dd < d) {
-            const float2 kv = Pair<T>::unpack(*reinterpret_cast<const uint32_t *>(kp + dd * H));
-            s0 = fmaf(q0[dd], kv.x, s0);
-            s1 = fmaf(q1[dd], kv.y, s1);
-          }
+          if (dd < d) sv = __ffma2_rn(qv[dd], Pair<T>::unpack(*reinterpret_cast<const uint32_t *>(kp + dd * H)), sv);
         const float2 ev = Pair<T>::unpack(ep[mm]);
-        s0 += ev.x;
-        s1 += ev.y;
+        float s0 = sv.x + ev.x, s1 = sv.y + ev.y;
         stg32(hhat + (erow0 + m) * H + 2 * hp, Pair<T>::pack(s0, s1));
         if (attend) {
           const float2 gv = Pair<T>::unpack(gp[mm]);
@@ -144,21 +159,24 @@ egt_fwd_fast(const tgt_egt_desc D, const T *__restrict__ qkv, const T *__restric
           const float p0 = s0 == -INFINITY ? 0.f : __expf(s0 - n0), p1 = s1 == -INFINITY ? 0.f : __expf(s1 - n1);
           ls0 = ls0 * c0 + p0;
           ls1 = ls1 * c1 + p1;
-          const float a0 = p0 * g0, a1 = p1 * g1;
+          const float2 cc = make_float2(c0, c1), aa = make_float2(p0 * g0, p1 * g1);
           const T *vp = kp + Wn;
 #pragma unroll
           for (int dd = 0; dd < DL; ++dd)
-            if (dd < d) {
-              const float2 vv = Pair<T>::unpack(*reinterpret_cast<const uint32_t *>(vp + dd * H));
-              o0[dd] = fmaf(o0[dd], c0, a0 * vv.x);
-              o1[dd] = fmaf(o1[dd], c1, a1 * vv.y);
-            }
+            if (dd < d)
+              ov[dd] = __ffma2_rn(ov[dd], cc, __fmul2_rn(aa, Pair<T>::unpack(*reinterpret_cast<const uint32_t *>(vp + dd * H))));
           dg0 += g0;
           dg1 += g1;
           mx0 = n0;
           mx1 = n1;
         }
       }
+    }
+#pragma unroll
+    for (int mm = 0; mm < EF_FCHUNK; ++mm) {
+      ep[mm] = epn[mm];
+      gp[mm] = gpn[mm];
+      mk[mm] = mkn[mm];
     }
   }
   if (active && attend) {
@@ -167,7 +185,7 @@ egt_fwd_fast(const tgt_egt_desc D, const T *__restrict__ qkv, const T *__restric
     T *op = vatt + (int64_t)(b * N + l) * Wn + 2 * hp;
 #pragma unroll
     for (int dd = 0; dd < DL; ++dd)
-      if (dd < d) stg32(op + dd * H, Pair<T>::pack(o0[dd] * i0 * sc0, o1[dd] * i1 * sc1));
+      if (dd < d) stg32(op + dd * H, Pair<T>::pack(ov[dd].x * i0 * sc0, ov[dd].y * i1 * sc1));
     float *st = stats + ((int64_t)(b * N + l) * H + 2 * hp) * 3;
     st[0] = mx0; st[1] = i0; st[2] = dg0;
     st[3] = mx1; st[4] = i1; st[5] = dg1;
@@ -388,7 +406,7 @@ size_t egt_fast_workspace(const tgt_egt_desc &D) {
 template <typename T>
 static int fwd_t(const tgt_egt_desc &D, const void *qkv, const void *eg, const float *mask, const float *src, void *hhat,
                  void *vatt, float *stats, cudaStream_t st) {
-  const size_t smem = (size_t)EF_CHUNK * (D.attend ? 2 : 1) * D.H * D.d * 2;
+  const size_t smem = 2 * (size_t)EF_FCHUNK * (D.attend ? 2 : 1) * D.H * D.d * 2;
   dim3 grid((D.N + EF_ROWS - 1) / EF_ROWS, D.B);
 #define L(HC, DC, AT)                                                                                                     \
   do {                                                                                                                \

@@ -458,6 +458,7 @@ static int fused_impl(const tgt_triplet_attn_desc &D, int We, const void *x, int
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  KernelTimerScope ts("tri_fused_fwd", st);
   cudaError_t err = cudaLaunchKernelEx(&cfg, tri_fused_fwd<T, CL>, D, We, mXcol, mXrow, mWc, mWr, mVA, mean, rstd, wcolsum,
                                        wbias, ws_e, ws_g, stats, dbg);
   if (err != cudaSuccess) {

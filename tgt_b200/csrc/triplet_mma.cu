@@ -516,6 +516,7 @@ static int fwd_impl(const tgt_triplet_attn_desc &D, const void *proj, const floa
   tri_prep_bias_gate<T><<<dim3(TN, 2, D.B), 256, psm, st>>>(D, (const T *)proj, mask, w.e, w.g);
   if (int e = check_launch("tri_prep_bias_gate")) return e;
   if (use_tma()) return triplet_attn_fwd_tma_launch(D, proj, va, stats, w.e, w.g, st);
+  KernelTimerScope ts("tri_attn_fwd_mma", st);
   tri_attn_fwd_mma<T><<<dim3(D.H, 2, D.B), 128, 0, st>>>(D, (const T *)proj, w.e, w.g, (T *)va, stats);
   return check_launch("tri_attn_fwd_mma");
 }
@@ -539,7 +540,10 @@ static int bwd_impl(const tgt_triplet_attn_desc &D, const void *proj, const floa
     tri_attn_bwd_mma<T, MB><<<dim3(D.H, 2, D.B), 128, BWD_SMEM, st>>>(D, (const T *)proj, w.e, w.g, (const T *)dva,    \
                                                                       stats, (T *)dproj, w.de, w.dg);                 \
   } while (0)
-  if (minb == 3) L(3); else L(2);
+  {
+    KernelTimerScope ts("tri_attn_bwd_mma", st);
+    if (minb == 3) L(3); else L(2);
+  }
 #undef L
   if (int e = check_launch("tri_attn_bwd_mma")) return e;
   tri_post_bias_gate<T><<<dim3(D.N, 2, D.B), 256, psm, st>>>(D, w.de, w.dg, (T *)dproj);

@@ -464,6 +464,7 @@ static int fwd_tma_impl(const tgt_triplet_attn_desc &D, const void *proj, void *
   std::call_once(once, [] {
     cudaFuncSetAttribute(tri_attn_fwd_tma<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM);
   });
+  KernelTimerScope ts("tri_attn_fwd_tma", st);
   tri_attn_fwd_tma<T><<<dim3(D.H, 2, D.B), 128, TF_SMEM, st>>>(D, mPcol, mProw, mVA, ws_e, ws_g, stats);
   return check_launch("tri_attn_fwd_tma");
 }
@@ -483,6 +484,7 @@ static int bwd_tma_impl(const tgt_triplet_attn_desc &D, const void *proj, const 
   std::call_once(once, [] {
     cudaFuncSetAttribute(tri_attn_bwd_tma<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM);
   });
+  KernelTimerScope ts("tri_attn_bwd_tma", st);
   tri_attn_bwd_tma<T><<<dim3(D.H, 2, D.B), 128, TB_SMEM, st>>>(D, mPcol, mProw, mDVA, mDPcol, mDProw, ws_e, ws_g, stats,
                                                               ws_de, ws_dg);
   return check_launch("tri_attn_bwd_tma");

@@ -109,7 +109,7 @@ def run_reference(args):
                cpu_baseline=base,
                e2e=dict(value=base["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                gpu_launches=0)
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -356,12 +356,32 @@ def run_ours(args):
                             d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps),
                    gpu_launches=int(launches), clocks=clk, roofline=roofline, device_kernels=dev_kernels,
                    triplet_module_fwd=module, kernels=kernels, cpu_baseline=base, peak_mem_gib=peak_mem)
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _reserve_stdout():
+    """stdout must carry exactly ONE JSON line: libraries (NCCL prints its version banner to fd 1) and stray prints are
+    sent to stderr for the whole run, the result goes to the saved descriptor."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(os.dup(2), "w", buffering=1)
+    return os.fdopen(saved, "w", buffering=1)
+
+
+RESULT_OUT = None
+
+
+def emit(obj):
+    (RESULT_OUT or sys.__stdout__).write(json.dumps(obj) + "\n")
+    (RESULT_OUT or sys.__stdout__).flush()
+
+
 def main():
+    global RESULT_OUT
+    RESULT_OUT = _reserve_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

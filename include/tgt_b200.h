@@ -225,6 +225,15 @@ int tgt_gelu_dropout_bwd(const void *u, const void *dy, void *du, int64_t n, flo
 int tgt_scaled_residual(const void *x, const void *res, const float *scale, void *out,
                         int64_t B, int64_t inner, int dtype, int res_dtype, void *stream);
 
+/* ---- Gaussian basis of the 3-D distance embedding ("next" row 8f-3) ---------------------------
+ * replaces the element-wise chain of lib/models/pcqm/layers.py:25-48 (GaussianLayer):
+ * out[r,k] = exp(-0.5 ((x_r - mu_k)/sd_k)^2) / (sqrt(2*3.14159) sd_k),  x:[rows] f32, mu,sd:[K] f32,
+ * K <= 128, K % 4 == 0.  Backward recomputes the basis from x; dmu, dsd:[K] must be ZERO on entry. */
+int tgt_gaussian_basis_fwd(const float *x, const float *mu, const float *sd, void *out, int64_t rows,
+                           int K, int out_dtype, void *stream);
+int tgt_gaussian_basis_bwd(const float *x, const float *mu, const float *sd, const void *dout, float *dx,
+                           float *dmu, float *dsd, int64_t rows, int K, int dout_dtype, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

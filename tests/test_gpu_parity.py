@@ -374,3 +374,24 @@ def test_fused_forward_matches_unfused(kind, N, nn_):
         assert rel_err(res[policy][1], ed.grad) < 2 * BF16_TOL
     assert rel_err(res[3][0], res[0][0]) < 2e-3, rel_err(res[3][0], res[0][0])
     assert rel_err(res[3][1], res[0][1]) < 2e-2
+
+
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+def test_gaussian_basis_kernel_vs_torch(out_dtype):
+    """tgt_gaussian_basis_fwd/bwd against the reference's element-wise formula (models/pcqm/layers.py:25-48)."""
+    from tgt_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    x = (torch.rand(3, 17, 17, generator=g) * 6).to(DEV).requires_grad_(True)
+    mu = (torch.rand(128, generator=g) * 3).to(DEV).requires_grad_(True)
+    sd = (torch.rand(128, generator=g) * 3 + 0.01).to(DEV).requires_grad_(True)
+    ref = torch.exp(-0.5 * ((x.unsqueeze(-1) - mu) / sd) ** 2) / ((2 * 3.14159) ** 0.5 * sd)
+    dout = torch.randn(ref.shape, generator=g).to(DEV)
+    ref.backward(dout)
+    want = (x.grad.clone(), mu.grad.clone(), sd.grad.clone())
+    x.grad = mu.grad = sd.grad = None
+    out = ops.GaussianBasisFn.apply(x, mu, sd, out_dtype)
+    out.backward(dout.to(out_dtype))
+    tol = 1e-5 if out_dtype == torch.float32 else 1e-2
+    assert rel_err(out.float().cpu(), ref.detach().cpu()) < tol
+    for got, w in zip((x.grad, mu.grad, sd.grad), want):
+        assert rel_err(got.cpu(), w.cpu()) < (1e-4 if out_dtype == torch.float32 else 1e-2)

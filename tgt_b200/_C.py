@@ -87,6 +87,8 @@ _SIGNATURES = {
     "tgt_gelu_dropout_bwd": (C.c_int, [_P, _P, _P, C.c_int64, C.c_float, C.c_uint64, C.c_int, _P]),
     "tgt_gemm_tc": (C.c_int, [C.POINTER(GemmDesc), _P, _P, _P, _P]),
     "tgt_row_stats": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, C.c_int64, C.c_float, C.c_int, _P]),
+    "tgt_gaussian_basis_fwd": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, _P]),
+    "tgt_gaussian_basis_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, _P]),
     "tgt_scaled_residual": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int, C.c_int, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

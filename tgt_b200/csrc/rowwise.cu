@@ -214,6 +214,9 @@ ln_bwd_kernel(const YT *__restrict__ dy, const XT *__restrict__ x, const float *
 // One warp per row, one 16-byte vector per lane, RU rows in flight per warp so that enough bytes are
 // outstanding per SM to cover the HBM latency (Little: ~45 KB/SM at 6.5 TB/s).
 template <typename T> struct V8 {
+  typedef uint4 Raw;
+  static __device__ __forceinline__ Raw load(const T *p) { return *reinterpret_cast<const uint4 *>(p); }
+  static __device__ __forceinline__ void store(T *p, const float (&o)[8]) { *reinterpret_cast<uint4 *>(p) = pack(o); }
   static __device__ __forceinline__ void unpack(const uint4 &raw, float (&o)[8]) {
     const T *e = reinterpret_cast<const T *>(&raw);
 #pragma unroll
@@ -228,9 +231,27 @@ template <typename T> struct V8 {
   }
 };
 
-template <typename T, int RU>
+// fp32 rows (the embedding output that enters the first layer): 8 elements = two 16-byte vectors
+template <> struct V8<float> {
+  struct Raw { float4 a, b; };
+  static __device__ __forceinline__ Raw load(const float *p) {
+    Raw r;
+    r.a = *reinterpret_cast<const float4 *>(p);
+    r.b = *reinterpret_cast<const float4 *>(p + 4);
+    return r;
+  }
+  static __device__ __forceinline__ void unpack(const Raw &r, float (&o)[8]) {
+    o[0] = r.a.x; o[1] = r.a.y; o[2] = r.a.z; o[3] = r.a.w; o[4] = r.b.x; o[5] = r.b.y; o[6] = r.b.z; o[7] = r.b.w;
+  }
+  static __device__ __forceinline__ void store(float *p, const float (&o)[8]) {
+    *reinterpret_cast<float4 *>(p) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4 *>(p + 4) = make_float4(o[4], o[5], o[6], o[7]);
+  }
+};
+
+template <typename XT, typename T, int RU>
 __global__ void __launch_bounds__(256)
-ln_fwd_w256(const T *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ beta,
+ln_fwd_w256(const XT *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ beta,
             T *__restrict__ y, float *__restrict__ mean, float *__restrict__ rstd, int64_t rows, float eps, int64_t ldy) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -243,15 +264,15 @@ ln_fwd_w256(const T *__restrict__ x, const float *__restrict__ gamma, const floa
     bt[0] = b0.x; bt[1] = b0.y; bt[2] = b0.z; bt[3] = b0.w; bt[4] = b1.x; bt[5] = b1.y; bt[6] = b1.z; bt[7] = b1.w;
   }
   for (int64_t r0 = warp0 * RU; r0 < rows; r0 += nwarps * RU) {
-    uint4 raw[RU];
+    typename V8<XT>::Raw raw[RU];
 #pragma unroll
     for (int u = 0; u < RU; ++u)
-      if (r0 + u < rows) raw[u] = *reinterpret_cast<const uint4 *>(x + (r0 + u) * 256 + lane * 8);
+      if (r0 + u < rows) raw[u] = V8<XT>::load(x + (r0 + u) * 256 + lane * 8);
 #pragma unroll
     for (int u = 0; u < RU; ++u) {
       if (r0 + u >= rows) continue;
       float v[8];
-      V8<T>::unpack(raw[u], v);
+      V8<XT>::unpack(raw[u], v);
       float s = 0.f;
 #pragma unroll
       for (int q = 0; q < 8; ++q) s += v[q];
@@ -272,11 +293,11 @@ ln_fwd_w256(const T *__restrict__ x, const float *__restrict__ gamma, const floa
   }
 }
 
-template <typename T, int RU>
+template <typename XT, typename T, int RU>
 __global__ void __launch_bounds__(256)
-ln_bwd_w256(const T *__restrict__ dy, const T *__restrict__ x, const float *__restrict__ gamma,
-            const float *__restrict__ mean, const float *__restrict__ rstd, const T *__restrict__ dres,
-            T *__restrict__ dx, float *__restrict__ dgamma, float *__restrict__ dbeta, int64_t rows) {
+ln_bwd_w256(const T *__restrict__ dy, const XT *__restrict__ x, const float *__restrict__ gamma,
+            const float *__restrict__ mean, const float *__restrict__ rstd, const XT *__restrict__ dres,
+            XT *__restrict__ dx, float *__restrict__ dgamma, float *__restrict__ dbeta, int64_t rows) {
   __shared__ float sm[2 * 256];
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -291,14 +312,15 @@ ln_bwd_w256(const T *__restrict__ dy, const T *__restrict__ x, const float *__re
 #pragma unroll
   for (int q = 0; q < 8; ++q) ag[q] = ab[q] = 0.f;
   for (int64_t r0 = warp0 * RU; r0 < rows; r0 += nwarps * RU) {
-    uint4 rx[RU], rd[RU], rr[RU];
+    typename V8<XT>::Raw rx[RU], rr[RU];
+    uint4 rd[RU];
     float mu[RU], rs[RU];
 #pragma unroll
     for (int u = 0; u < RU; ++u) {
       if (r0 + u < rows) {
-        rx[u] = *reinterpret_cast<const uint4 *>(x + (r0 + u) * 256 + lane * 8);
+        rx[u] = V8<XT>::load(x + (r0 + u) * 256 + lane * 8);
         rd[u] = *reinterpret_cast<const uint4 *>(dy + (r0 + u) * 256 + lane * 8);
-        if (dres) rr[u] = *reinterpret_cast<const uint4 *>(dres + (r0 + u) * 256 + lane * 8);
+        if (dres) rr[u] = V8<XT>::load(dres + (r0 + u) * 256 + lane * 8);
         mu[u] = mean[r0 + u];
         rs[u] = rstd[r0 + u];
       }
@@ -307,7 +329,7 @@ ln_bwd_w256(const T *__restrict__ dy, const T *__restrict__ x, const float *__re
     for (int u = 0; u < RU; ++u) {
       if (r0 + u >= rows) continue;
       float xv[8], dv[8];
-      V8<T>::unpack(rx[u], xv);
+      V8<XT>::unpack(rx[u], xv);
       V8<T>::unpack(rd[u], dv);
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -326,11 +348,11 @@ ln_bwd_w256(const T *__restrict__ dy, const T *__restrict__ x, const float *__re
       for (int q = 0; q < 8; ++q) o[q] = rs[u] * (dv[q] - s1 - xv[q] * s2);
       if (dres) {
         float rv[8];
-        V8<T>::unpack(rr[u], rv);
+        V8<XT>::unpack(rr[u], rv);
 #pragma unroll
         for (int q = 0; q < 8; ++q) o[q] += rv[q];
       }
-      *reinterpret_cast<uint4 *>(dx + (r0 + u) * 256 + lane * 8) = V8<T>::pack(o);
+      V8<XT>::store(dx + (r0 + u) * 256 + lane * 8, o);
     }
   }
 #pragma unroll
@@ -439,6 +461,115 @@ scaled_residual_kernel(const T *__restrict__ x, const RT *__restrict__ res, cons
   }
 }
 
+// ------------------------------------------------------------------ Gaussian basis of the 3-D distance embedding
+// out[r,k] = exp(-0.5 ((x_r - mu_k) / sd_k)^2) / (sqrt(2*3.14159) sd_k)      (reference models/pcqm/layers.py:25-48)
+// One warp per row, K <= 128 kernels (4 per lane).  Backward recomputes the basis from x (nothing O(R*K) is saved) and
+// reduces d mu / d sd over the rows in registers -> shared memory -> one atomic per kernel and CTA.
+constexpr float GB_NORM = 2.5066272622f;      // (2 * 3.14159) ** 0.5, the reference's constant
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+gaussian_basis_fwd_kernel(const float *__restrict__ x, const float *__restrict__ mu, const float *__restrict__ sd,
+                          T *__restrict__ out, int64_t rows, int K) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  float m[4], is[4], nrm[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int k = lane * 4 + q;
+    m[q] = k < K ? mu[k] : 0.f;
+    const float s_ = k < K ? sd[k] : 1.f;
+    is[q] = 1.f / s_;
+    nrm[q] = 1.f / (GB_NORM * s_);
+  }
+  for (int64_t r = warp0; r < rows; r += nwarps) {
+    const float xr = x[r];
+    float o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float z = (xr - m[q]) * is[q];
+      o[q] = __expf(-0.5f * z * z) * nrm[q];
+    }
+    if (lane * 4 + 3 < K) {
+      if constexpr (sizeof(T) == 4) {
+        *reinterpret_cast<float4 *>(out + r * K + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);
+      } else {
+        T v[4] = {from_f<T>(o[0]), from_f<T>(o[1]), from_f<T>(o[2]), from_f<T>(o[3])};
+        *reinterpret_cast<uint2 *>(out + r * K + lane * 4) = *reinterpret_cast<uint2 *>(v);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (lane * 4 + q < K) out[r * K + lane * 4 + q] = from_f<T>(o[q]);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+gaussian_basis_bwd_kernel(const float *__restrict__ x, const float *__restrict__ mu, const float *__restrict__ sd,
+                          const T *__restrict__ dout, float *__restrict__ dx, float *__restrict__ dmu,
+                          float *__restrict__ dsd, int64_t rows, int K) {
+  __shared__ float sm[2 * 128];
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int c = threadIdx.x; c < 256; c += blockDim.x) sm[c] = 0.f;
+  __syncthreads();
+  float m[4], is[4], nrm[4], am[4], as[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int k = lane * 4 + q;
+    m[q] = k < K ? mu[k] : 0.f;
+    const float s_ = k < K ? sd[k] : 1.f;
+    is[q] = 1.f / s_;
+    nrm[q] = k < K ? 1.f / (GB_NORM * s_) : 0.f;
+    am[q] = as[q] = 0.f;
+  }
+  for (int64_t r = warp0; r < rows; r += nwarps) {
+    const float xr = x[r];
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
+    if (lane * 4 + 3 < K) {
+      if constexpr (sizeof(T) == 4) {
+        const float4 v = *reinterpret_cast<const float4 *>(dout + r * K + lane * 4);
+        g[0] = v.x; g[1] = v.y; g[2] = v.z; g[3] = v.w;
+      } else {
+        const uint2 raw = *reinterpret_cast<const uint2 *>(dout + r * K + lane * 4);
+        const T *e = reinterpret_cast<const T *>(&raw);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) g[q] = to_f(e[q]);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (lane * 4 + q < K) g[q] = to_f(dout[r * K + lane * 4 + q]);
+    }
+    float dxr = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float z = (xr - m[q]) * is[q];
+      const float go = g[q] * __expf(-0.5f * z * z) * nrm[q];      // dout * out
+      const float t = go * z * is[q];                               // dout * out * z / sd
+      dxr -= t;
+      am[q] += t;
+      as[q] += go * (z * z - 1.f) * is[q];
+    }
+    dxr = warp_sum(dxr);
+    if (lane == 0) dx[r] = dxr;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    atomicAdd(&sm[lane * 4 + q], am[q]);
+    atomicAdd(&sm[128 + lane * 4 + q], as[q]);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < K; c += blockDim.x) {
+    atomicAdd(&dmu[c], sm[c]);
+    atomicAdd(&dsd[c], sm[128 + c]);
+  }
+}
+
 static int grid_for(int64_t work_items, int per_block) {
   int64_t g = (work_items + per_block - 1) / per_block;
   const int64_t cap = 148 * 16;       // a few resident CTAs per SM, multiple of the SM count
@@ -450,9 +581,9 @@ static int grid_for(int64_t work_items, int per_block) {
 template <typename XT, typename YT>
 static int ln_fwd_launch(const void *x, const float *gamma, const float *beta, void *y, float *mean,
                          float *rstd, int64_t rows, int W, float eps, int64_t ldy, cudaStream_t st) {
-  if constexpr (sizeof(XT) == 2 && std::is_same<XT, YT>::value) {
+  if constexpr (sizeof(YT) == 2 && (std::is_same<XT, YT>::value || std::is_same<XT, float>::value)) {
     if (W == 256 && (ldy == 256 || ldy == 264) && (((uintptr_t)x | (uintptr_t)y) & 15) == 0) {
-      ln_fwd_w256<XT, 4><<<grid_for(rows, 8 * 4), 256, 0, st>>>((const XT *)x, gamma, beta, (YT *)y, mean, rstd, rows, eps,
+      ln_fwd_w256<XT, YT, 4><<<grid_for(rows, 8 * 4), 256, 0, st>>>((const XT *)x, gamma, beta, (YT *)y, mean, rstd, rows, eps,
                                                                  ldy);
       return check_launch("ln_fwd_w256");
     }
@@ -465,11 +596,11 @@ template <typename XT, typename YT>
 static int ln_bwd_launch(const void *dy, const void *x, const float *gamma, const float *mean,
                          const float *rstd, const void *dres, void *dx, float *dgamma, float *dbeta,
                          int64_t rows, int W, cudaStream_t st) {
-  if constexpr (sizeof(XT) == 2 && std::is_same<XT, YT>::value) {
+  if constexpr (sizeof(YT) == 2 && (std::is_same<XT, YT>::value || std::is_same<XT, float>::value)) {
     if (W == 256 && (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx | (uintptr_t)dres) & 15) == 0) {
       int g = grid_for(rows, 8 * 2 * 8);
       if (g > 148 * 8) g = 148 * 8;
-      ln_bwd_w256<XT, 2><<<g, 256, 0, st>>>((const YT *)dy, (const XT *)x, gamma, mean, rstd, (const XT *)dres, (XT *)dx,
+      ln_bwd_w256<XT, YT, 2><<<g, 256, 0, st>>>((const YT *)dy, (const XT *)x, gamma, mean, rstd, (const XT *)dres, (XT *)dx,
                                             dgamma, dbeta, rows);
       return check_launch("ln_bwd_w256");
     }
@@ -560,4 +691,25 @@ extern "C" int tgt_scaled_residual(const void *x, const void *res, const float *
     return fail("scaled_residual: unsupported dtype combination %d/%d", dtype, res_dtype);
   }
   return check_launch("scaled_residual");
+}
+
+extern "C" int tgt_gaussian_basis_fwd(const float *x, const float *mu, const float *sd, void *out, int64_t rows, int K,
+                                      int out_dtype, void *stream) {
+  if (rows <= 0) return 0;
+  if (K <= 0 || K > 128 || K % 4) return fail("gaussian_basis: K=%d must be a multiple of 4 and <= 128", K);
+  cudaStream_t st = (cudaStream_t)stream;
+  TGT_DISPATCH_DTYPE(out_dtype, T,
+                     (gaussian_basis_fwd_kernel<T><<<grid_for(rows, 8 * 8), 256, 0, st>>>(x, mu, sd, (T *)out, rows, K)));
+  return check_launch("gaussian_basis_fwd");
+}
+
+extern "C" int tgt_gaussian_basis_bwd(const float *x, const float *mu, const float *sd, const void *dout, float *dx,
+                                      float *dmu, float *dsd, int64_t rows, int K, int dout_dtype, void *stream) {
+  if (rows <= 0) return 0;
+  if (K <= 0 || K > 128 || K % 4) return fail("gaussian_basis: K=%d must be a multiple of 4 and <= 128", K);
+  cudaStream_t st = (cudaStream_t)stream;
+  TGT_DISPATCH_DTYPE(dout_dtype, T,
+                     (gaussian_basis_bwd_kernel<T><<<grid_for(rows, 8 * 8), 256, 0, st>>>(x, mu, sd, (const T *)dout, dx,
+                                                                                      dmu, dsd, rows, K)));
+  return check_launch("gaussian_basis_bwd");
 }

@@ -10,7 +10,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .. import TGT_Encoder, Graph
+from .. import TGT_Encoder, Graph, ops
 from .synthetic import (NODE_FEATURES_OFFSET, NUM_NODE_FEATURES, EDGE_FEATURES_OFFSET, NUM_EDGE_FEATURES)
 
 HL_MEAN = 5.6894608
@@ -32,9 +32,15 @@ class _GaussianBasis(nn.Module):
     def forward(self, dist, types):
         scale = self.mul(types).sum(dim=-2)
         shift = self.bias(types).sum(dim=-2)
-        x = (scale * dist.unsqueeze(-1) + shift).expand(-1, -1, -1, self.K).float()
         mu = self.means.weight.float().view(-1)
         sd = self.stds.weight.float().view(-1).abs() + 1e-2
+        if dist.is_cuda and self.K % 4 == 0 and self.K <= 128:
+            # one kernel each way instead of ~6 element-wise passes over [B,N,N,K]; under autocast the basis is written
+            # directly in the dtype the following Linear would cast it to
+            x = (scale * dist.unsqueeze(-1) + shift).squeeze(-1).float()
+            odt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else self.means.weight.dtype
+            return ops.GaussianBasisFn.apply(x, mu, sd, odt)
+        x = (scale * dist.unsqueeze(-1) + shift).expand(-1, -1, -1, self.K).float()
         norm = (2 * 3.14159) ** 0.5
         return (torch.exp(-0.5 * ((x - mu) / sd) ** 2) / (norm * sd)).type_as(self.means.weight)
 
@@ -142,6 +148,10 @@ class _TaskModel(nn.Module):
         return self.pred((h * m).sum(dim=1) / (m.sum(dim=1) + 1e-9)).squeeze(-1)
 
     def _bins(self, g):
+        if g.e.is_cuda:
+            # final LayerNorm folded into the distance-bin GEMM (statistics come with g.e from the last edge FFN)
+            return ops.LNLinearFn.apply(g.e, self.final_ln_edge.weight, self.final_ln_edge.bias, self.dist_pred.weight,
+                                        self.dist_pred.bias, ops.compute_dtype(g.e))[0]
         return self.dist_pred(self.final_ln_edge(g.e))
 
 

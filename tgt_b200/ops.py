@@ -812,3 +812,35 @@ class ScaledResidualFn(Function):
 def scaled_residual(x: Tensor, res: Tensor, scale: Optional[Tensor]) -> Tensor:
     return ScaledResidualFn.apply(x, res, scale)
 
+
+
+# ------------------------------------------------------------------------------------------
+# Gaussian basis of the 3-D distance embedding (models/pcqm/layers.py:25-48): one kernel each way
+# ------------------------------------------------------------------------------------------
+class GaussianBasisFn(Function):
+    """x:[...] f32 (scaled distances), mu, sd:[K] f32  ->  [..., K] in `out_dtype`; backward recomputes the basis."""
+
+    @staticmethod
+    def forward(ctx, x, mu, sd, out_dtype):
+        _require_cuda(x, mu, sd)
+        xc, muc, sdc = _f32c(x), _f32c(mu), _f32c(sd)
+        K = muc.numel()
+        out = torch.empty((*x.shape, K), dtype=out_dtype, device=x.device)
+        _C.check(_C.lib().tgt_gaussian_basis_fwd(_C.ptr(xc), _C.ptr(muc), _C.ptr(sdc), _C.ptr(out), xc.numel(), K,
+                                                 _C.dtype_code(out_dtype), _C.stream_ptr()), "gaussian_basis_fwd")
+        ctx.save_for_backward(xc, muc, sdc)
+        ctx.dts = (x.dtype, mu.dtype, sd.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        xc, muc, sdc = ctx.saved_tensors
+        K = muc.numel()
+        do = dout.contiguous()
+        dx = torch.empty_like(xc)
+        dms = torch.zeros((2, K), dtype=torch.float32, device=xc.device)
+        _C.check(_C.lib().tgt_gaussian_basis_bwd(_C.ptr(xc), _C.ptr(muc), _C.ptr(sdc), _C.ptr(do), _C.ptr(dx),
+                                                 _C.ptr(dms[0]), _C.ptr(dms[1]), xc.numel(), K, _C.dtype_code(do.dtype),
+                                                 _C.stream_ptr()), "gaussian_basis_bwd")
+        d = ctx.dts
+        return dx.to(d[0]), dms[0].to(d[1]), dms[1].to(d[2]), None

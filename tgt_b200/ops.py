@@ -284,11 +284,21 @@ def linear_residual(a2: Tensor, Wc: Tensor, bias: Tensor, res2: Optional[Tensor]
     return out2, None
 
 
-try:                                           # fp32 results from 16-bit batched GEMMs (PyTorch >= 2.8)
-    torch.bmm(torch.zeros(1, 1, 8), torch.zeros(1, 8, 1), out_dtype=torch.float32)
-    _BMM_OUT_F32 = True
-except (TypeError, RuntimeError):
-    _BMM_OUT_F32 = False
+_BMM_OUT_F32 = {}
+
+
+def _bmm_f32(a: Tensor, b: Tensor) -> Tensor:
+    """fp32 result of a 16-bit batched GEMM (PyTorch >= 2.8 on CUDA: `out_dtype`), else bmm + cast."""
+    key = (a.device.type, a.dtype)
+    if key not in _BMM_OUT_F32:
+        try:
+            torch.bmm(a[:1, :8, :8].contiguous(), b[:1, :8, :8].contiguous(), out_dtype=torch.float32)
+            _BMM_OUT_F32[key] = True
+        except (TypeError, RuntimeError):
+            _BMM_OUT_F32[key] = False
+    if _BMM_OUT_F32[key] and a.dtype != torch.float32:
+        return torch.bmm(a, b, out_dtype=torch.float32)
+    return torch.bmm(a, b).float()
 
 
 def linear_residual_bwd(do2: Tensor, a2: Tensor, Wc: Tensor, scale: Optional[Tensor], gelu_bwd: Optional[tuple] = None,
@@ -313,11 +323,13 @@ def linear_residual_bwd(do2: Tensor, a2: Tensor, Wc: Tensor, scale: Optional[Ten
     if scale is None:
         return da, torch.mm(do2.t(), a2), do2.sum(0, dtype=torch.float32)
     B = scale.numel()
+    if B * N * K * 4 > M * (N + K):
+        # few rows per graph (node-side tensors): the per-graph [B, N, K] intermediate would dwarf the operands --
+        # scale the (small) gradient explicitly instead
+        dos = _scale_rows(do2, scale)
+        return da, torch.mm(dos.t(), a2), dos.sum(0, dtype=torch.float32)
     dob = do2.view(B, M // B, N)
-    if _BMM_OUT_F32 and do2.dtype != torch.float32:
-        dWb = torch.bmm(dob.transpose(1, 2), a2.view(B, M // B, K), out_dtype=torch.float32)
-    else:
-        dWb = torch.bmm(dob.transpose(1, 2), a2.view(B, M // B, K)).float()
+    dWb = _bmm_f32(dob.transpose(1, 2), a2.view(B, M // B, K))
     dW = torch.mv(dWb.view(B, N * K).t(), scale).view(N, K)
     db = torch.mv(dob.sum(1, dtype=torch.float32).t(), scale)
     return da, dW, db

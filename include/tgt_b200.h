@@ -96,6 +96,14 @@ int tgt_triplet_attn_bwd(const tgt_triplet_attn_desc *desc, const void *proj, co
                          const void *va, const void *dva, const float *stats, void *dproj,
                          void *workspace, size_t workspace_bytes, void *stream);
 
+/* Same, reusing the bias / gate tiles of the forward: `fwd_workspace` is the workspace buffer the forward
+ * call (tgt_triplet_attn_fwd or tgt_triplet_attn_fused_fwd, same desc geometry, same kernel policy) was
+ * given, kept alive and unmodified by the caller; NULL recomputes the tiles from proj.                 */
+int tgt_triplet_attn_bwd_tiles(const tgt_triplet_attn_desc *desc, const void *proj, const float *mask,
+                               const void *va, const void *dva, const float *stats, void *dproj,
+                               void *workspace, size_t workspace_bytes, const void *fwd_workspace,
+                               void *stream);
+
 /* ---- fused triplet attention forward: LayerNorm + lin_QKV_in/out + attention in one kernel ----------
  * replaces lib/tgt/layers/triplet.py:207-246 for head dim 16, edge width We <= 256 (TGT-At): the
  * [R, 6*We] q/k/v projection is produced on tcgen05 tensor cores tile by tile in tensor memory and
@@ -188,6 +196,10 @@ int tgt_egt_attn_bwd(const tgt_egt_desc *desc, const void *qkv, const void *eg, 
 #define TGT_EPI_ROWSCALE 64   /* value *= row_scale[row / rows_per_scale] (DropPath in backward), no residual      */
 #define TGT_EPI_STATS    256  /* also write LayerNorm statistics (mean, 1/sqrt(var + stat_eps)) of the OUTPUT rows, for the
                                * next LayerNorm-folded GEMM; needs N <= 256                                            */
+#define TGT_EPI_LN_BWD   512  /* LayerNorm backward as the epilogue of the data-gradient GEMM dy = A B^T (N = LN width <= 256,
+                               * N % 64 == 0): D = rstd*(g - mean(g) - xhat*mean(g*xhat)) [+ res2], g = dy*gamma;
+                               * x = `res` (16-bit), gamma = col_sum, row_mean / row_rstd = forward statistics;
+                               * with TGT_EPI_RES the residual gradient res2 (16-bit, pitch ldres2) is added          */
 #define TGT_EPI_GELU_BWD 128  /* D = value * GELU'(u) * dropout mask(p_drop, seed); u = `res` (16-bit, pitch ldres) */
 typedef struct {
   int64_t M;
@@ -204,6 +216,8 @@ typedef struct {
   uint64_t seed;
   float *stat_mean, *stat_rstd;   /* [M] out, TGT_EPI_STATS only */
   float stat_eps;
+  const void *res2;               /* TGT_EPI_LN_BWD | TGT_EPI_RES */
+  int64_t ldres2;
 } tgt_gemm_desc;
 int tgt_gemm_tc(const tgt_gemm_desc *desc, const void *A, const void *B, void *D, void *stream);
 

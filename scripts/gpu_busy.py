@@ -34,7 +34,7 @@ for e in evs: agg[e.name[:70]] += e.device_time / 1e3
 for k, v in agg.most_common(12): print(f"{v:8.2f} {k}")
 
 print("-- copy-like ops by input shape")
-rows = [a for a in prof.key_averages(group_by_input_shape=True) if a.key in ("aten::copy_", "aten::_to_copy", "aten::contiguous", "aten::clone", "aten::cat", "aten::index_select", "aten::sum", "aten::mul", "aten::add", "aten::add_", "aten::bmm", "aten::mv", "aten::mm", "aten::addmm")]
-rows.sort(key=lambda a: -a.device_time_total)
-for a in rows[:40]:
-    print(f"{a.device_time_total / 1e3:8.2f} ms  n={a.count:4d}  {a.key:18s} {str(a.input_shapes)[:110]}")
+rows = [a for a in prof.key_averages(group_by_input_shape=True) if a.self_device_time_total > 0]
+rows.sort(key=lambda a: -a.self_device_time_total)
+for a in rows[:60]:
+    print(f"{a.self_device_time_total / 1e3:8.2f} ms  n={a.count:4d}  {a.key[:28]:28s} {str(a.input_shapes)[:100]}")

@@ -167,3 +167,30 @@ def test_stats_handoff_between_modules():
         y1b = y1.clone()                                  # same values, no attached statistics
         y2b = ffn2.forward_residual(y1b, None)
     assert (y2.float() - y2b.float()).abs().max().item() <= 2e-2 * y2b.float().abs().max().item()
+
+
+@pytest.mark.parametrize("W,C,with_res", [(256, 256, True), (256, 128, False), (64, 256, True), (128, 64, True)])
+def test_gemm_layernorm_backward_epilogue(W, C, with_res):
+    """dx of LayerNorm->Linear from ONE GEMM (LN backward in the epilogue) and the parameter gradients from the
+    affine-free weight-gradient GEMM, against autograd on the same bf16-rounded operands."""
+    ops = _ops()
+    M = 4099
+    x = (_rand((M, W), torch.float32, 51) * 1.3 + 0.2).to(torch.bfloat16)
+    gamma = (1 + 0.2 * _rand((W,), torch.float32, 52)).requires_grad_(True)
+    beta = (0.1 * _rand((W,), torch.float32, 53)).requires_grad_(True)
+    Wt = _rand((C, W), torch.bfloat16, 54, W ** -0.5).float().requires_grad_(True)
+    b = torch.zeros(C, device="cuda", requires_grad=True)
+    dout = _rand((M, C), torch.bfloat16, 55)
+    dres = _rand((M, W), torch.bfloat16, 56) if with_res else None
+    xf = x.float().requires_grad_(True)
+    out = torch.nn.functional.layer_norm(xf, (W,), gamma, beta) @ Wt.t() + b
+    out.backward(dout.float())
+    want_dx = xf.grad + (dres.float() if with_res else 0)
+    mean, rstd = ops.row_stats(x)
+    dx, dg, dbt, dW, db = ops.ln_linear_bwd(dout, x, gamma.detach(), beta.detach(), Wt.detach().bfloat16(), mean, rstd,
+                                            dres, torch.bfloat16, fused=True)
+    _close(dx, want_dx, 1.5e-2)
+    _close(dg, gamma.grad, 1e-2)
+    _close(dbt, beta.grad, 1e-2)
+    _close(dW, Wt.grad, 1e-2)
+    _close(db, b.grad, 1e-2)

@@ -57,10 +57,11 @@ class GemmDesc(C.Structure):
                 ("rows_per_scale", C.c_int32),
                 ("U", C.c_void_p), ("ldu", C.c_int64),
                 ("p_drop", C.c_float), ("seed", C.c_uint64),
-                ("stat_mean", C.c_void_p), ("stat_rstd", C.c_void_p), ("stat_eps", C.c_float)]
+                ("stat_mean", C.c_void_p), ("stat_rstd", C.c_void_p), ("stat_eps", C.c_float),
+                ("res2", C.c_void_p), ("ldres2", C.c_int64)]
 
 
-EPI_LN, EPI_BIAS, EPI_GELU, EPI_RES, EPI_STORE_U, EPI_ROWSCALE, EPI_GELU_BWD, EPI_STATS = 1, 2, 4, 8, 16, 64, 128, 256
+EPI_LN, EPI_BIAS, EPI_GELU, EPI_RES, EPI_STORE_U, EPI_ROWSCALE, EPI_GELU_BWD, EPI_STATS, EPI_LN_BWD = 1, 2, 4, 8, 16, 64, 128, 256, 512
 
 _P = C.c_void_p
 _SIGNATURES = {
@@ -75,6 +76,7 @@ _SIGNATURES = {
     "tgt_triplet_attn_workspace_bytes": (C.c_size_t, [C.POINTER(TripletAttnDesc), C.c_int]),
     "tgt_triplet_attn_fwd": (C.c_int, [C.POINTER(TripletAttnDesc), _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "tgt_triplet_attn_bwd": (C.c_int, [C.POINTER(TripletAttnDesc), _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "tgt_triplet_attn_bwd_tiles": (C.c_int, [C.POINTER(TripletAttnDesc), _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P, _P]),
     "tgt_triplet_attn_fused_supported": (C.c_int, [C.POINTER(TripletAttnDesc), C.c_int]),
     "tgt_triplet_attn_fused_fwd": (C.c_int, [C.POINTER(TripletAttnDesc), _P, C.c_int64, C.c_int, _P, _P, _P, _P, _P, _P, _P,
                                              _P, _P, _P, C.c_size_t, _P]),
@@ -151,6 +153,16 @@ def kernel_timer_read() -> dict:
     return out
 
 
+_policy = 0
+
+
 def set_kernel_policy(policy: int) -> None:
-    """0 = fastest supported kernel (default), 1 = force the generic SIMT kernels."""
+    """0 = fastest supported kernel (default), 1 = generic SIMT kernels, 2 = cp.async-staged tensor-core triplet kernels,
+    3 = fused projection + attention forward (see include/tgt_b200.h)."""
+    global _policy
+    _policy = int(policy)
     lib().tgt_set_kernel_policy(int(policy))
+
+
+def kernel_policy() -> int:
+    return _policy

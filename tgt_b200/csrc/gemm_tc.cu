@@ -34,7 +34,7 @@ template <typename T> __device__ __forceinline__ uint32_t umma_idesc(int n) {
 
 // ---------------------------------------------------------------------------------------------- kernel
 enum : int { EPI_LN = 1, EPI_BIAS = 2, EPI_GELU = 4, EPI_RES = 8, EPI_STORE_U = 16, EPI_RES_F32 = 32, EPI_ROWSCALE = 64,
-              EPI_GELU_BWD = 128, EPI_STATS = 256 };
+              EPI_GELU_BWD = 128, EPI_STATS = 256, EPI_LN_BWD = 512 };
 
 struct GemmParams {
   int64_t M;
@@ -52,6 +52,8 @@ struct GemmParams {
   int flags;
   float *stat_mean, *stat_rstd;      // EPI_STATS: LayerNorm statistics of the OUTPUT rows (needs one column slice)
   float stat_eps;
+  const void *res2;                  // EPI_LN_BWD: residual gradient added to dx (16-bit, pitch ldres2); `res` is x
+  int64_t ldres2;
 };
 
 constexpr int GEMM_THREADS = 320;      // warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: epilogue
@@ -245,7 +247,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int col0 = slice * bn;
       {
         const int gc = col0 + et;
-        vec_colsum[et] = ((FLAGS & EPI_LN) && et < bn && gc < p.N) ? p.col_sum[gc] : 0.f;
+        vec_colsum[et] = ((FLAGS & (EPI_LN | EPI_LN_BWD)) && et < bn && gc < p.N) ? p.col_sum[gc] : 0.f;
         vec_bias[et] = ((FLAGS & EPI_BIAS) && et < bn && gc < p.N) ? p.bias[gc] : 0.f;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -254,6 +256,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t stD = sStage + (uint32_t)(warp - 2) * STAGE_PER_WARP, stU = stD + 2048;
       const int crow = lane >> 2, cpiece = lane & 3;     // coalesced phase: 8 rows x 4 pieces per instruction
       constexpr int RW = (FLAGS & EPI_RES_F32) ? 2 : 1;
+      constexpr bool LNB = (FLAGS & EPI_LN_BWD) != 0;
       T *Dp = reinterpret_cast<T *>(p.D);
       int acc = 0;
       uint32_t acc_phase = 0;
@@ -263,7 +266,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int64_t r_ = mt_ * 128 + quad * 32 + lane;
         nx_rstd = 1.f, nx_mean = 0.f, nx_rs = 1.f;
         if (mt_ < num_m_tiles && r_ < p.M) {
-          if (FLAGS & EPI_LN) {
+          if (FLAGS & (EPI_LN | EPI_LN_BWD)) {
             nx_rstd = p.row_rstd[r_];
             nx_mean = p.row_mean[r_];
           }
@@ -279,6 +282,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         row_inputs(mt + p.ctas_per_slice);
         // residual values of the coalesced phase are fetched one 32-column group ahead
         uint4 rcur[4][RW], rnext[4][RW];
+        // second operand of the coalesced phase: the residual (RES), the pre-activation (GELU_BWD) or, with LN_BWD, the
+        // residual gradient res2 (there `res` is x and is consumed in the TMEM domain)
+        const void *cres = LNB ? p.res2 : p.res;
+        const int64_t ldc = LNB ? p.ldres2 : p.ldres;
         auto res_load = [&](int c, uint4(&rb)[4][RW]) {
           const int gc = col0 + c + cpiece * 8;
           if (c + cpiece * 8 < bn && gc < p.N) {
@@ -287,11 +294,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const int64_t grow = row0 + it * 8 + crow;
               if (grow < p.M) {
                 if (FLAGS & EPI_RES_F32) {
-                  const float *rp = reinterpret_cast<const float *>(p.res) + grow * p.ldres + gc;
+                  const float *rp = reinterpret_cast<const float *>(cres) + grow * ldc + gc;
                   rb[it][0] = *reinterpret_cast<const uint4 *>(rp);
                   rb[it][RW - 1] = *reinterpret_cast<const uint4 *>(rp + 4);
                 } else {
-                  rb[it][0] = *reinterpret_cast<const uint4 *>(reinterpret_cast<const T *>(p.res) + grow * p.ldres + gc);
+                  rb[it][0] = *reinterpret_cast<const uint4 *>(reinterpret_cast<const T *>(cres) + grow * ldc + gc);
                 }
               }
             }
@@ -299,12 +306,61 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         };
         if (FLAGS & (EPI_RES | EPI_GELU_BWD)) res_load(half * 32, rcur);
         float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};   // EPI_STATS: sum / sum of squares per row
+        // LN_BWD: this lane's row of x for the (up to 4) column groups of this warp, fetched before the accumulator wait
+        uint32_t xh[LNB ? 4 : 1][16];
+        if (LNB) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int c = half * 32 + k * 64;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) xh[LNB ? k : 0][j] = 0u;
+            if (c < bn && row < p.M) {
+              const uint4 *xp = reinterpret_cast<const uint4 *>(reinterpret_cast<const T *>(p.res) + row * p.ldres + col0 + c);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 t = xp[j];
+                xh[LNB ? k : 0][4 * j + 0] = t.x; xh[LNB ? k : 0][4 * j + 1] = t.y;
+                xh[LNB ? k : 0][4 * j + 2] = t.z; xh[LNB ? k : 0][4 * j + 3] = t.w;
+              }
+            }
+          }
+        }
         mbar_wait(bar_tfull + acc * 8, acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * bn);
         uint32_t v[32];
+        float lnb_s1 = 0.f, lnb_s2 = 0.f;     // LN_BWD: mean_c(g), mean_c(g * xhat) of this lane's row, g = dy * gamma
+        if (LNB) {
+          // pass 1 over the accumulators: row sums; pass 2 (the main loop below) re-reads them from tensor memory
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int c = half * 32 + k * 64;
+            if (c < bn) {
+              tc_ld32(taddr + c, v);
+              tc_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                float x0, x1;
+                unpack2<T>(xh[LNB ? k : 0][i], x0, x1);
+                const float g0 = __uint_as_float(v[2 * i]) * vec_colsum[c + 2 * i];
+                const float g1 = __uint_as_float(v[2 * i + 1]) * vec_colsum[c + 2 * i + 1];
+                lnb_s1 += g0 + g1;
+                lnb_s2 = fmaf(g0, fmaf(x0, rstd, nmr), fmaf(g1, fmaf(x1, rstd, nmr), lnb_s2));
+              }
+            }
+          }
+          float2 *mine = part + (acc * EPI_WARPS + (warp - 2)) * 32;
+          mine[lane] = make_float2(lnb_s1, lnb_s2);
+          asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");
+          const float2 o = part[(acc * EPI_WARPS + ((warp - 2) ^ 4)) * 32 + lane];
+          const float inv_n = 1.f / (float)p.N;
+          lnb_s1 = (lnb_s1 + o.x) * inv_n;
+          lnb_s2 = (lnb_s2 + o.y) * inv_n;
+        }
         if (half * 32 < bn) tc_ld32(taddr + half * 32, v);
-        for (int c = half * 32; c < bn; c += 64) {
+#pragma unroll
+        for (int kq = 0; kq < (LNB ? 4 : 1); ++kq)
+        for (int c = half * 32 + kq * 64; c < bn; c += (LNB ? (1 << 20) : 64)) {
           // per-column epilogue vectors of this group (shared-memory broadcasts), issued before the TMEM wait
           float4 csv[8], bsv[8];
           if (FLAGS & EPI_LN) {
@@ -323,6 +379,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float f[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[pc * 8 + i]);
+            if (LNB) {
+              // dx = rstd * (g - mean(g) - xhat * mean(g xhat)),  g = dy * gamma,  xhat = (x - mean) * rstd
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float x0, x1;
+                unpack2<T>(xh[LNB ? kq : 0][pc * 4 + j], x0, x1);
+                const float g0 = f[2 * j] * vec_colsum[c + pc * 8 + 2 * j];
+                const float g1 = f[2 * j + 1] * vec_colsum[c + pc * 8 + 2 * j + 1];
+                f[2 * j] = rstd * (g0 - lnb_s1 - fmaf(x0, rstd, nmr) * lnb_s2);
+                f[2 * j + 1] = rstd * (g1 - lnb_s1 - fmaf(x1, rstd, nmr) * lnb_s2);
+              }
+            }
             if (FLAGS & EPI_LN) {
               const float cs[8] = {csv[2 * pc].x, csv[2 * pc].y, csv[2 * pc].z, csv[2 * pc].w,
                                    csv[2 * pc + 1].x, csv[2 * pc + 1].y, csv[2 * pc + 1].z, csv[2 * pc + 1].w};
@@ -615,6 +683,8 @@ static int dispatch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const Gem
     TGT_GEMM_CASE(EPI_ROWSCALE)
     TGT_GEMM_CASE(EPI_GELU_BWD)
     TGT_GEMM_CASE(EPI_GELU_BWD | EPI_ROWSCALE)
+    TGT_GEMM_CASE(EPI_LN_BWD)
+    TGT_GEMM_CASE(EPI_LN_BWD | EPI_RES)
 #undef TGT_GEMM_CASE
     default: return fail("gemm_tc: unsupported epilogue flag combination %d", p.flags);
   }
@@ -681,9 +751,18 @@ extern "C" int tgt_gemm_tc(const tgt_gemm_desc *g, const void *A, const void *B,
   p.rows_per_scale = g->rows_per_scale;
   p.p_drop = g->p_drop;
   p.seed = g->seed;
-  if ((flags & EPI_RES) && g->res_dtype == TGT_F32) flags |= EPI_RES_F32;
+  if ((flags & EPI_RES) && !(flags & EPI_LN_BWD) && g->res_dtype == TGT_F32) flags |= EPI_RES_F32;
   else if ((flags & EPI_RES) && g->res_dtype != g->dtype) return fail("gemm_tc: residual dtype must be fp32 or the operand dtype");
   p.flags = flags;
+  if (flags & EPI_LN_BWD) {
+    if (p.n_slices != 1 || p.bn != g->N || g->N % 64 || !g->res || g->res_dtype != g->dtype || !g->row_mean ||
+        !g->row_rstd || !g->col_sum || g->ldres % 8 || (reinterpret_cast<uintptr_t>(g->res) & 15))
+      return fail("gemm_tc: LN_BWD epilogue needs N %% 64 == 0, N <= 256, x (16-bit) in `res`, row stats and gamma in col_sum");
+    if ((flags & EPI_RES) && (!g->res2 || g->ldres2 % 8 || (reinterpret_cast<uintptr_t>(g->res2) & 15)))
+      return fail("gemm_tc: LN_BWD + RES needs the residual gradient in res2");
+    p.res2 = g->res2;
+    p.ldres2 = g->ldres2;
+  }
   if (flags & EPI_STATS) {
     if (p.n_slices != 1 || p.bn < g->N || !g->stat_mean || !g->stat_rstd)
       return fail("gemm_tc: STATS epilogue needs N <= 256 (one column slice) and the two output vectors");

@@ -523,11 +523,18 @@ static int fwd_impl(const tgt_triplet_attn_desc &D, const void *proj, const floa
 
 template <typename T>
 static int bwd_impl(const tgt_triplet_attn_desc &D, const void *proj, const float *mask, const void *dva,
-                    const float *stats, void *dproj, void *ws, cudaStream_t st) {
-  const Ws w = carve(D, ws);
+                    const float *stats, void *dproj, void *ws, const void *fwd_ws, cudaStream_t st) {
+  Ws w = carve(D, ws);
   const size_t psm = 2 * (size_t)D.H * 65 * sizeof(float);
-  tri_prep_bias_gate<T><<<dim3(TN, 2, D.B), 256, psm, st>>>(D, (const T *)proj, mask, w.e, w.g);
-  if (int e = check_launch("tri_prep_bias_gate")) return e;
+  if (fwd_ws) {
+    // bias / gate tiles of the forward call, kept alive by the caller: identical to what prep would recompute
+    const Ws wf = carve_fwd(D, const_cast<void *>(fwd_ws));
+    w.e = wf.e;
+    w.g = wf.g;
+  } else {
+    tri_prep_bias_gate<T><<<dim3(TN, 2, D.B), 256, psm, st>>>(D, (const T *)proj, mask, w.e, w.g);
+    if (int e = check_launch("tri_prep_bias_gate")) return e;
+  }
   if (use_tma()) {
     if (int e = triplet_attn_bwd_tma_launch(D, proj, dva, stats, dproj, w.e, w.g, w.de, w.dg, st)) return e;
     tri_post_bias_gate<T><<<dim3(D.N, 2, D.B), 256, psm, st>>>(D, w.de, w.dg, (T *)dproj);
@@ -584,15 +591,15 @@ int triplet_attn_fwd_mma(const tgt_triplet_attn_desc &D, const void *proj, const
 
 int triplet_attn_bwd_mma(const tgt_triplet_attn_desc &D, const void *proj, const float *mask, const void *va,
                          const void *dva, const float *stats, void *dproj, void *ws, size_t ws_bytes,
-                         cudaStream_t st) {
+                         const void *fwd_ws, cudaStream_t st) {
   (void)va;      // delta = rowsum(dP o P) is recomputed in registers; the forward output is not needed
   if (!ws || ws_bytes < triplet_attn_mma_workspace(D, 1))
     return fail("triplet_attn_bwd: workspace too small (%zu < %zu bytes)", ws_bytes, triplet_attn_mma_workspace(D, 1));
   if (((uintptr_t)proj | (uintptr_t)dva | (uintptr_t)dproj) & 15)
     return fail("triplet_attn_bwd: proj / dva / dproj must be 16-byte aligned");
   if (D.B > 65535) return fail("triplet_attn_bwd: B > 65535 unsupported");
-  if (D.dtype == TGT_BF16) return bwd_impl<__nv_bfloat16>(D, proj, mask, dva, stats, dproj, ws, st);
-  return bwd_impl<__half>(D, proj, mask, dva, stats, dproj, ws, st);
+  if (D.dtype == TGT_BF16) return bwd_impl<__nv_bfloat16>(D, proj, mask, dva, stats, dproj, ws, fwd_ws, st);
+  return bwd_impl<__half>(D, proj, mask, dva, stats, dproj, ws, fwd_ws, st);
 }
 
 }  // namespace tgt

@@ -154,7 +154,7 @@ def row_stats(x2: Tensor, eps: float = 1e-5):
 def gemm_tc(a: Tensor, w: Tensor, *, bias: Optional[Tensor] = None, ln: Optional[tuple] = None,
             gelu: Optional[tuple] = None, res: Optional[Tensor] = None, row_scale: Optional[Tensor] = None,
             rows_per_scale: int = 0, gelu_bwd: Optional[tuple] = None, out: Optional[Tensor] = None,
-            stats_out: Optional[tuple] = None, name: str = "gemm_tc"):
+            stats_out: Optional[tuple] = None, ln_bwd: Optional[tuple] = None, name: str = "gemm_tc"):
     """out[M,N] = epilogue(a[M,K] @ w[N,K]^T) on the tcgen05 kernel.
 
     ln   = (row_mean, row_rstd, col_sum): LayerNorm folded into the epilogue (`w` must already be W*gamma and
@@ -163,7 +163,9 @@ def gemm_tc(a: Tensor, w: Tensor, *, bias: Optional[Tensor] = None, ln: Optional
     row_scale / rows_per_scale: value *= row_scale[row // rows_per_scale] (DropPath);
     res: out = res + value;
     gelu_bwd = (u, p_drop, seed): out = value * GELU'(u) * dropout mask (backward of `gelu`);
-    stats_out = (mean, rstd): fp32 [M] vectors that receive the LayerNorm statistics of the output rows (N <= 256)."""
+    stats_out = (mean, rstd): fp32 [M] vectors that receive the LayerNorm statistics of the output rows (N <= 256);
+    ln_bwd = (x, mean, rstd, gamma[, dres]): the GEMM result is dy of a LayerNorm over its N columns and `out` becomes
+           dx = LN'(dy) (+ dres): LayerNorm backward (data gradient) as the epilogue."""
     M, K = a.shape
     N = w.shape[0]
     assert w.shape[1] == K and a.stride(1) == 1 and w.stride(1) == 1
@@ -198,6 +200,14 @@ def gemm_tc(a: Tensor, w: Tensor, *, bias: Optional[Tensor] = None, ln: Optional
         if res is None:
             flags |= _C.EPI_ROWSCALE
         g.row_scale, g.rows_per_scale = row_scale.data_ptr(), int(rows_per_scale)
+    if ln_bwd is not None:
+        flags |= _C.EPI_LN_BWD
+        xb = ln_bwd[0]
+        g.res, g.ldres, g.res_dtype = xb.data_ptr(), xb.stride(0), _C.dtype_code(xb.dtype)
+        g.row_mean, g.row_rstd, g.col_sum = ln_bwd[1].data_ptr(), ln_bwd[2].data_ptr(), ln_bwd[3].data_ptr()
+        if len(ln_bwd) > 4 and ln_bwd[4] is not None:
+            flags |= _C.EPI_RES
+            g.res2, g.ldres2 = ln_bwd[4].data_ptr(), ln_bwd[4].stride(0)
     if stats_out is not None:
         flags |= _C.EPI_STATS
         g.stat_mean, g.stat_rstd, g.stat_eps = stats_out[0].data_ptr(), stats_out[1].data_ptr(), 1e-5
@@ -375,6 +385,49 @@ def unpack_fused(res):
     return attach_stats(out, mean if mean.numel() else None, rstd)
 
 
+import os as _os
+
+# Measured at config 3 (profiles/r1_16): the LayerNorm-backward GEMM epilogue takes 0.76 ms against 0.16 (cuBLAS dy GEMM)
+# + 0.43 ms (LayerNorm-backward kernel) -- its row-per-lane reads of x are the bottleneck -- so it is opt-in for now.
+_LN_BWD_FUSED = _os.environ.get("TGT_LN_BWD_FUSED", "0") == "1"
+
+
+def ln_linear_bwd(dout2: Tensor, x2: Tensor, g: Tensor, bt: Tensor, Wc: Tensor, mean: Tensor, rstd: Tensor,
+                  dres: Optional[Tensor], cd: torch.dtype, name: str = "gemm_tc_ln_bwd", fused: Optional[bool] = None):
+    """Backward of  out = LN(x2) Wc^T + b  given dout2 = d out [M, C]:  (dx, dgamma, dbeta, dW, db).
+
+    16-bit x2 of width <= 256: ONE tcgen05 GEMM computes dy = dout2 Wc and applies the LayerNorm backward in its
+    epilogue (dx = LN'(dy) + dres; dy never reaches HBM); the parameter gradients come from the weight-gradient GEMM
+    against the affine-free normalised rows:  G|db = dout2^T [xhat | 1],  dW = G*gamma + db (x) beta,
+    dgamma = colsum(Wc * G),  dbeta = db Wc  (tiny [C, W] operations, no pass over an edge-sized tensor).
+    Otherwise: LN recompute + cuBLAS + the LayerNorm-backward kernel."""
+    M, W = x2.shape
+    C = Wc.shape[0]
+    # (the epilogue needs whole rows in one CTA: the [W, C] weight panel must fit in shared memory next to the ring)
+    if fused is None:
+        fused = _LN_BWD_FUSED
+    if (fused and x2.dtype == cd and dout2.dtype == cd and tc_gemm_ok(dout2, W, C) and W % 64 == 0 and W <= 256
+            and ((C + 63) // 64) * W * 128 <= 159000 and (dres is None or dres.dtype == cd)):
+        ones = torch.ones(W, dtype=torch.float32, device=x2.device)
+        xh, _, _ = layernorm_fwd(x2, ones, torch.zeros_like(ones), cd, aug=True)          # [xhat | 1 | 0...]
+        Ga = torch.mm(dout2.t(), xh).float()                                              # [C, W+8]
+        G, db = Ga[:, :W], Ga[:, W]
+        del xh
+        Wf = Wc.float()
+        dW = G * g + db[:, None] * bt
+        dg = (Wf * G).sum(0)
+        dbt = db @ Wf
+        dx = gemm_tc(dout2, Wc.t().contiguous(), ln_bwd=(x2, mean, rstd, g, dres), name=name)
+        return dx, dg, dbt, dW, db
+    y, _, _ = layernorm_fwd(x2, g, bt, cd, aug=True)
+    dWa = torch.mm(dout2.t(), y)
+    dW, db = dWa[:, :W], dWa[:, W]
+    dy = torch.mm(dout2, Wc)
+    del y
+    dx, dg, dbt = layernorm_bwd(dy, x2, g, mean, rstd, dres)
+    return dx, dg, dbt, dW, db
+
+
 # ------------------------------------------------------------------------------------------
 # LayerNorm -> Linear with LN recompute in backward  (EGT lin_EG / lin_E)
 # ------------------------------------------------------------------------------------------
@@ -408,12 +461,8 @@ class LNLinearFn(Function):
             return (dalias, None, None, None, None, None)
         with torch.autocast("cuda", enabled=False):
             do = dout.reshape(-1, dout.shape[-1]).to(cd).contiguous()
-            y, _, _ = layernorm_fwd(x2, g, bt, cd, aug=True)
-            dWa = torch.mm(do.t(), y)                     # [out, W+8]: weight gradient | bias gradient
-            dW, db = dWa[:, :x2.shape[1]], dWa[:, x2.shape[1]]
-            dy = torch.mm(do, Wc)
-            del y
-            dx, dg, dbt = layernorm_bwd(dy, x2, g, mean, rstd, _dres_for(dalias, x2))
+            dx, dg, dbt, dW, db = ln_linear_bwd(do, x2, g, bt, Wc, mean, rstd, _dres_for(dalias, x2), cd,
+                                                name="gemm_tc_ln_bwd_eg")
         return (dx.view(*dout.shape[:-1], x2.shape[-1]).to(ctx.in_dtype), dg.to(ctx.pdt[0]), dbt.to(ctx.pdt[0]),
                 dW.to(ctx.pdt[1]), db.to(ctx.pdt[2]), None)
 
@@ -460,6 +509,7 @@ def _fused_triplet_fwd(x2, mean, rstd, fold, m3, va, stats, B, N, H, d, W, off_e
                                                      _C.ptr(wf), _C.ptr(wcs), _C.ptr(wbs), _C.ptr(proj_eg), _C.ptr(m3),
                                                      _C.ptr(va), _C.ptr(stats), _C.ptr(ws), wsb, _C.stream_ptr()),
                  "triplet_attn_fused_fwd")
+    return ws
 
 
 class TripletAttentionFn(Function):
@@ -492,7 +542,7 @@ class TripletAttentionFn(Function):
                 st_in = take_stats(e, x2)
                 mean, rstd = st_in if st_in is not None else row_stats(x2)
                 fold = _ln_fold(Wcat, bcat, g, bt, cdtype)
-                _fused_triplet_fwd(x2, mean, rstd, fold, m3, va, stats, B, N, H, d, W, off_e, off_g, cdtype)
+                ws = _fused_triplet_fwd(x2, mean, rstd, fold, m3, va, stats, B, N, H, d, W, off_e, off_g, cdtype)
             else:
                 proj, mean, rstd, fold = ln_linear(x2, g, bt, Wcat, bcat, Wc, cdtype, stats=take_stats(e, x2),
                                                    name="gemm_tc_ln_proj")
@@ -500,13 +550,16 @@ class TripletAttentionFn(Function):
                 with timed("triplet_attn_fwd"):
                     _C.check(_C.lib().tgt_triplet_attn_fwd(desc, _C.ptr(proj), _C.ptr(m3), _C.ptr(va), _C.ptr(stats),
                                                            _C.ptr(ws), wsb, _C.stream_ptr()), "triplet_attn_fwd")
-                del ws
                 del proj
+            # the [B,2,H,64,64] bias / gate tiles in `ws` (0.2 GB at config 3) are kept for the backward, which then
+            # skips its prep pass; only the tensor-core families write them (policy fixed between forward and backward)
+            tiles = ws if (ws is not None and _C.kernel_policy() != 1) else None
+            ctx.tile_policy = _C.kernel_policy()
             sc = _f32c(res_scale).view(B) if (fuse_res and res_scale is not None) else None
             out = torch.empty((B, N, N, W), dtype=cdtype, device=e.device)
             _, ostats = linear_residual(va, Woc, bo, x2 if fuse_res else None, sc, out2=out.view(R, W),
                                         want_stats=fuse_res, name="gemm_tc_lin_o")
-            ctx.save_for_backward(x2, m3, g, bt, Wc, bc, Woc, mean, rstd, stats, va, sc, *fold)
+            ctx.save_for_backward(x2, m3, g, bt, Wc, bc, Woc, mean, rstd, stats, va, sc, *fold, tiles)
             ctx.desc = desc
             ctx.cdtype = cdtype
             ctx.in_dtype = e.dtype
@@ -521,7 +574,7 @@ class TripletAttentionFn(Function):
     def backward(ctx, dout, dalias=None, _unused=None):
         if ctx_fused(ctx):
             dalias = None               # slots 2 and 3 are the (non-differentiable) statistics
-        x2, m3, g, bt, Wc, bc, Woc, mean, rstd, stats, va, sc, Wg, bp, cs = ctx.saved_tensors
+        x2, m3, g, bt, Wc, bc, Woc, mean, rstd, stats, va, sc, Wg, bp, cs, tiles = ctx.saved_tensors
         if dout is None:
             return (dalias,) + (None,) * 11
         cd, desc = ctx.cdtype, ctx.desc
@@ -539,10 +592,12 @@ class TripletAttentionFn(Function):
                 proj = torch.addmm(bc, y[:, :W], Wc.t())
             dproj = torch.empty_like(proj)
             ws, wsb = _workspace(_C.lib().tgt_triplet_attn_workspace_bytes(desc, 1), x2.device)
+            if tiles is not None and ctx.tile_policy != _C.kernel_policy():
+                tiles = None                                # kernel family changed since the forward: recompute
             with timed("triplet_attn_bwd"):
-                _C.check(_C.lib().tgt_triplet_attn_bwd(desc, _C.ptr(proj), _C.ptr(m3), _C.ptr(va), _C.ptr(dva),
-                                                       _C.ptr(stats), _C.ptr(dproj), _C.ptr(ws), wsb,
-                                                       _C.stream_ptr()), "triplet_attn_bwd")
+                _C.check(_C.lib().tgt_triplet_attn_bwd_tiles(desc, _C.ptr(proj), _C.ptr(m3), _C.ptr(va), _C.ptr(dva),
+                                                             _C.ptr(stats), _C.ptr(dproj), _C.ptr(ws), wsb,
+                                                             _C.ptr(tiles), _C.stream_ptr()), "triplet_attn_bwd")
             del ws
             del proj, dva
             dWa = torch.mm(dproj.t(), y)                  # [C, W+8]: weight gradient | bias gradient (column W)
@@ -746,12 +801,8 @@ class FFNGeluFn(Function):
                 dalias = dout
             # du = scale[b] * (do W2) * GELU'(u) * dropout mask in ONE GEMM; `a` was saved by the forward epilogue
             du, dW2, db2 = linear_residual_bwd(do, a, W2c, sc, gelu_bwd=(u, p_drop, seed), name="gemm_tc_du")
-            y, _, _ = layernorm_fwd(x2, g, bt, cd, aug=True)
-            dWa = torch.mm(du.t(), y)
-            dW1, db1 = dWa[:, :x2.shape[1]], dWa[:, x2.shape[1]]
-            del y
-            dy = torch.mm(du, W1c)
-            dx, dg, dbt = layernorm_bwd(dy, x2, g, mean, rstd, _dres_for(dalias, x2))
+            dx, dg, dbt, dW1, db1 = ln_linear_bwd(du, x2, g, bt, W1c, mean, rstd, _dres_for(dalias, x2), cd,
+                                                  name="gemm_tc_ln_bwd_ffn")
         return (dx.view(*dout.shape[:-1], x2.shape[-1]).to(in_dtype), dg.to(p[0]), dbt.to(p[0]), dW1.to(p[1]),
                 db1.to(p[2]), dW2.to(p[3]), db2.to(p[4]), None, None, None, None, None)
 

@@ -3,6 +3,7 @@ from __future__ import annotations
 
 from torch import nn
 
+from . import ops
 from .layers import TGT_Layer
 
 
@@ -65,8 +66,15 @@ class TGT_Encoder(nn.Module):
 
     def apply_layer(self, layer_idx, graph):
         layer = self.TGT_layers[layer_idx]
-        for _ in range(self.layer_multiplier):
-            graph = layer(graph)
+        total = self.model_height * self.layer_multiplier
+        for rep in range(self.layer_multiplier):
+            # position of this layer application in the stack: lets the triplet op decide how many of the LAST layers
+            # may keep their projection for backward instead of recomputing it (ops.keep_projection)
+            ops.set_layer_hint(layer_idx * self.layer_multiplier + rep, total)
+            try:
+                graph = layer(graph)
+            finally:
+                ops.set_layer_hint(None, None)
         return graph
 
     def forward(self, inputs):

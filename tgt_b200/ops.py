@@ -470,6 +470,45 @@ class LNLinearFn(Function):
 # ------------------------------------------------------------------------------------------
 # triplet attention module: LN -> [QKV_in|QKV_out|EG_in|EG_out] GEMM -> core -> lin_O
 # ------------------------------------------------------------------------------------------
+# ------------------------------------------------------------------------------------------
+# memory-for-time: keep the [R, 6We+4Ht] projection of the LAST k layers for backward when HBM allows
+# ------------------------------------------------------------------------------------------
+_LAYER_HINT = None          # (index, total) of the layer application being executed (set by TGT_Encoder)
+_KEEP_STATE = {}            # per device: live bytes after layers 0 / 1, decided k
+
+
+def set_layer_hint(index, total) -> None:
+    global _LAYER_HINT
+    _LAYER_HINT = None if index is None else (int(index), int(total))
+
+
+def keep_projection(nbytes: int, device, needs_grad: bool) -> bool:
+    """Should this triplet call keep its projection (nbytes) for backward instead of recomputing it (one GEMM, ~1.1 ms
+    at config 3)?  Decided per step from the allocator's live-byte counter: the growth between layer 0 and layer 1 is
+    extrapolated to the end of the forward; whatever stays below 88 % of the device memory after a 10 % reserve for the
+    heads, the loss and the backward transients is handed to the LAST k layers (their backward runs first, so the extra
+    buffers are the first to be freed).  TGT_KEEP_PROJ_LAYERS overrides k (0 disables).  Without a layer hint: never."""
+    if _LAYER_HINT is None or not needs_grad:
+        return False
+    i, L = _LAYER_HINT
+    st = _KEEP_STATE.setdefault(str(device), {})
+    live = torch.cuda.memory_allocated(device)
+    if i == 0:
+        st["live0"], st["k"] = live, 0
+        return False
+    if i == 1 and "live0" in st:
+        env = _os.environ.get("TGT_KEEP_PROJ_LAYERS")
+        if env is not None:
+            st["k"] = max(0, min(int(env), L - 2))
+        else:
+            total = torch.cuda.get_device_properties(device).total_memory
+            predicted_end = live + (live - st["live0"]) * (L - 1)
+            budget = 0.88 * total - predicted_end - 0.10 * total
+            st["k"] = max(0, min(int(budget // (nbytes + (64 << 20))), L - 2))
+        return False
+    return i >= L - st.get("k", 0)
+
+
 _PANEL_IDX = {}
 
 
@@ -535,6 +574,7 @@ class TripletAttentionFn(Function):
                                       float(d) ** -0.5, _C.dtype_code(cdtype))
             va = torch.empty((R, 2 * H * d), dtype=cdtype, device=e.device)
             stats = torch.empty((B, 2, H, N, N, 2), dtype=torch.float32, device=e.device)
+            kept_proj = None
             if (x2.dtype == cdtype and tc_gemm_ok(x2, Wcat.shape[0], W) and tuple(off_q) == (0, 3 * W)
                     and tuple(off_k) == (W, 4 * W) and tuple(off_v) == (2 * W, 5 * W)
                     and _C.lib().tgt_triplet_attn_fused_supported(desc, W)):
@@ -550,6 +590,9 @@ class TripletAttentionFn(Function):
                 with timed("triplet_attn_fwd"):
                     _C.check(_C.lib().tgt_triplet_attn_fwd(desc, _C.ptr(proj), _C.ptr(m3), _C.ptr(va), _C.ptr(stats),
                                                            _C.ptr(ws), wsb, _C.stream_ptr()), "triplet_attn_fwd")
+                if fold[0] is not None and keep_projection(proj.numel() * proj.element_size(), e.device,
+                                                           any(ctx.needs_input_grad)):
+                    kept_proj = proj
                 del proj
             # the [B,2,H,64,64] bias / gate tiles in `ws` (0.2 GB at config 3) are kept for the backward, which then
             # skips its prep pass; only the tensor-core families write them (policy fixed between forward and backward)
@@ -559,7 +602,7 @@ class TripletAttentionFn(Function):
             out = torch.empty((B, N, N, W), dtype=cdtype, device=e.device)
             _, ostats = linear_residual(va, Woc, bo, x2 if fuse_res else None, sc, out2=out.view(R, W),
                                         want_stats=fuse_res, name="gemm_tc_lin_o")
-            ctx.save_for_backward(x2, m3, g, bt, Wc, bc, Woc, mean, rstd, stats, va, sc, *fold, tiles)
+            ctx.save_for_backward(x2, m3, g, bt, Wc, bc, Woc, mean, rstd, stats, va, sc, *fold, tiles, kept_proj)
             ctx.desc = desc
             ctx.cdtype = cdtype
             ctx.in_dtype = e.dtype
@@ -574,7 +617,7 @@ class TripletAttentionFn(Function):
     def backward(ctx, dout, dalias=None, _unused=None):
         if ctx_fused(ctx):
             dalias = None               # slots 2 and 3 are the (non-differentiable) statistics
-        x2, m3, g, bt, Wc, bc, Woc, mean, rstd, stats, va, sc, Wg, bp, cs, tiles = ctx.saved_tensors
+        x2, m3, g, bt, Wc, bc, Woc, mean, rstd, stats, va, sc, Wg, bp, cs, tiles, kept_proj = ctx.saved_tensors
         if dout is None:
             return (dalias,) + (None,) * 11
         cd, desc = ctx.cdtype, ctx.desc
@@ -586,7 +629,9 @@ class TripletAttentionFn(Function):
             dva, dWo, dbo = linear_residual_bwd(do, va, Woc, sc, name="gemm_tc_dva")
             del do
             y, _, _ = layernorm_fwd(x2, g, bt, cd, aug=True)
-            if Wg is not None:          # bit-identical recompute of the forward projection (same kernel, same inputs)
+            if kept_proj is not None:   # one of the last layers: HBM had room to keep the projection (keep_projection)
+                proj = kept_proj
+            elif Wg is not None:        # bit-identical recompute of the forward projection (same kernel, same inputs)
                 proj = gemm_tc(x2, Wg, bias=bp, ln=(mean, rstd, cs), name="gemm_tc_ln_proj")
             else:
                 proj = torch.addmm(bc, y[:, :W], Wc.t())

@@ -210,25 +210,22 @@ egt_bwd_rows_fast(const tgt_egt_desc D, const T *__restrict__ qkv, const T *__re
   const int kvw = attend ? 2 * Wn : Wn;
   const T *smT = reinterpret_cast<const T *>(sm);
 
-  float q0[DL], q1[DL], go0[DL], go1[DL], dq0[DL], dq1[DL];
-  float dsc0 = 0.f, dsc1 = 0.f;
+  // one thread = one query row x one PAIR of heads, carried in packed f32x2 registers (fma.rn.f32x2)
+  float2 qv[DL], gov[DL], dqv[DL];
+  float2 dsc = make_float2(0.f, 0.f);
 #pragma unroll
   for (int dd = 0; dd < DL; ++dd) {
-    q0[dd] = q1[dd] = go0[dd] = go1[dd] = dq0[dd] = dq1[dd] = 0.f;
+    qv[dd] = gov[dd] = dqv[dd] = make_float2(0.f, 0.f);
     if (dd < d && active) {
       const float2 v = Pair<T>::unpack(ldg32(qkv + (int64_t)(b * N + la) * D.ld_qkv + dd * H + 2 * hp));
-      q0[dd] = v.x * D.scale;
-      q1[dd] = v.y * D.scale;
+      qv[dd] = make_float2(v.x * D.scale, v.y * D.scale);
       if (attend) {
-        const float2 gv = Pair<T>::unpack(ldg32(dvatt + (int64_t)(b * N + la) * Wn + dd * H + 2 * hp));
-        const float2 ov = Pair<T>::unpack(ldg32(vatt + (int64_t)(b * N + la) * Wn + dd * H + 2 * hp));
-        go0[dd] = gv.x;
-        go1[dd] = gv.y;
-        dsc0 = fmaf(gv.x, ov.x, dsc0);
-        dsc1 = fmaf(gv.y, ov.y, dsc1);
+        gov[dd] = Pair<T>::unpack(ldg32(dvatt + (int64_t)(b * N + la) * Wn + dd * H + 2 * hp));
+        dsc = __ffma2_rn(gov[dd], Pair<T>::unpack(ldg32(vatt + (int64_t)(b * N + la) * Wn + dd * H + 2 * hp)), dsc);
       }
     }
   }
+  const float dsc0 = dsc.x, dsc1 = dsc.y;
   float mx0 = 0.f, mx1 = 0.f, i0 = 0.f, i1 = 0.f, sc0 = 1.f, sc1 = 1.f, dd0 = 0.f, dd1 = 0.f;
   // dsc* currently hold dV_att . V_att = delta (dU . U);  ddeg = (dV_att . U) / (1 + deg) = delta / (sc (1 + deg))
   float delta0 = dsc0, delta1 = dsc1;
@@ -276,19 +273,15 @@ egt_bwd_rows_fast(const tgt_egt_desc D, const T *__restrict__ qkv, const T *__re
         float dH0 = dhv.x, dH1 = dhv.y;
         if (attend) {
           const T *vp = kp + Wn;
-          float s0 = 0.f, s1 = 0.f, dA0 = 0.f, dA1 = 0.f;
+          float2 sv = make_float2(0.f, 0.f), dAv = make_float2(0.f, 0.f);
 #pragma unroll
           for (int dd = 0; dd < DL; ++dd)
             if (dd < d) {
-              const float2 kv = Pair<T>::unpack(*reinterpret_cast<const uint32_t *>(kp + dd * H));
-              const float2 vv = Pair<T>::unpack(*reinterpret_cast<const uint32_t *>(vp + dd * H));
-              s0 = fmaf(q0[dd], kv.x, s0);
-              s1 = fmaf(q1[dd], kv.y, s1);
-              dA0 = fmaf(go0[dd], vv.x, dA0);
-              dA1 = fmaf(go1[dd], vv.y, dA1);
+              sv = __ffma2_rn(qv[dd], Pair<T>::unpack(*reinterpret_cast<const uint32_t *>(kp + dd * H)), sv);
+              dAv = __ffma2_rn(gov[dd], Pair<T>::unpack(*reinterpret_cast<const uint32_t *>(vp + dd * H)), dAv);
             }
-          dA0 *= sc0;
-          dA1 *= sc1;
+          float s0 = sv.x, s1 = sv.y;
+          const float dA0 = dAv.x * sc0, dA1 = dAv.y * sc1;
           const float2 ev = Pair<T>::unpack(ep[mm]);
           const float2 gv = Pair<T>::unpack(gp[mm]);
           s0 += ev.x + mk[mm];
@@ -302,13 +295,10 @@ egt_bwd_rows_fast(const tgt_egt_desc D, const T *__restrict__ qkv, const T *__re
           stg32(aw + (erow0 + m) * H + 2 * hp, Pair<T>::pack(p0 * g0 * sc0, p1 * g1 * sc1));
         }
         stg32(deg_out + (erow0 + m) * D.ld_eg + 2 * hp, Pair<T>::pack(dH0, dH1));
+        const float2 dHv = make_float2(dH0, dH1);
 #pragma unroll
         for (int dd = 0; dd < DL; ++dd)
-          if (dd < d) {
-            const float2 kv = Pair<T>::unpack(*reinterpret_cast<const uint32_t *>(kp + dd * H));
-            dq0[dd] = fmaf(dH0, kv.x, dq0[dd]);
-            dq1[dd] = fmaf(dH1, kv.y, dq1[dd]);
-          }
+          if (dd < d) dqv[dd] = __ffma2_rn(dHv, Pair<T>::unpack(*reinterpret_cast<const uint32_t *>(kp + dd * H)), dqv[dd]);
       }
     }
   }
@@ -316,7 +306,7 @@ egt_bwd_rows_fast(const tgt_egt_desc D, const T *__restrict__ qkv, const T *__re
     T *op = dqkv + (int64_t)(b * N + l) * D.ld_qkv + 2 * hp;
 #pragma unroll
     for (int dd = 0; dd < DL; ++dd)
-      if (dd < d) stg32(op + dd * H, Pair<T>::pack(dq0[dd] * D.scale, dq1[dd] * D.scale));
+      if (dd < d) stg32(op + dd * H, Pair<T>::pack(dqv[dd].x * D.scale, dqv[dd].y * D.scale));
   }
 }
 
@@ -336,9 +326,9 @@ egt_bwd_cols_fast(const tgt_egt_desc D, const T *__restrict__ qkv, const T *__re
   const int qw = attend ? 2 * Wn : Wn;
   const T *smT = reinterpret_cast<const T *>(sm);
 
-  float dk0[DL], dk1[DL], dv0[DL], dv1[DL];
+  float2 dkv[DL], dvv[DL];
 #pragma unroll
-  for (int dd = 0; dd < DL; ++dd) dk0[dd] = dk1[dd] = dv0[dd] = dv1[dd] = 0.f;
+  for (int dd = 0; dd < DL; ++dd) dkv[dd] = dvv[dd] = make_float2(0.f, 0.f);
 
   for (int lc = 0; lc < N; lc += EF_CHUNK) {
     __syncthreads();
@@ -367,14 +357,9 @@ egt_bwd_cols_fast(const tgt_egt_desc D, const T *__restrict__ qkv, const T *__re
 #pragma unroll
         for (int dd = 0; dd < DL; ++dd)
           if (dd < d) {
-            const float2 qv = Pair<T>::unpack(*reinterpret_cast<const uint32_t *>(qp + dd * H));
-            dk0[dd] = fmaf(dh.x, qv.x, dk0[dd]);
-            dk1[dd] = fmaf(dh.y, qv.y, dk1[dd]);
-            if (attend) {
-              const float2 gv = Pair<T>::unpack(*reinterpret_cast<const uint32_t *>(qp + Wn + dd * H));
-              dv0[dd] = fmaf(av.x, gv.x, dv0[dd]);
-              dv1[dd] = fmaf(av.y, gv.y, dv1[dd]);
-            }
+            dkv[dd] = __ffma2_rn(dh, Pair<T>::unpack(*reinterpret_cast<const uint32_t *>(qp + dd * H)), dkv[dd]);
+            if (attend)
+              dvv[dd] = __ffma2_rn(av, Pair<T>::unpack(*reinterpret_cast<const uint32_t *>(qp + Wn + dd * H)), dvv[dd]);
           }
       }
     }
@@ -384,8 +369,8 @@ egt_bwd_cols_fast(const tgt_egt_desc D, const T *__restrict__ qkv, const T *__re
 #pragma unroll
     for (int dd = 0; dd < DL; ++dd)
       if (dd < d) {
-        stg32(okp + dd * H, Pair<T>::pack(dk0[dd] * D.scale, dk1[dd] * D.scale));
-        if (attend) stg32(okp + Wn + dd * H, Pair<T>::pack(dv0[dd], dv1[dd]));
+        stg32(okp + dd * H, Pair<T>::pack(dkv[dd].x * D.scale, dkv[dd].y * D.scale));
+        if (attend) stg32(okp + Wn + dd * H, Pair<T>::pack(dvv[dd].x, dvv[dd].y));
       }
   }
 }

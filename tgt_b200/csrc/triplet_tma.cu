@@ -13,6 +13,7 @@
 // 4-byte stores) and sector-exact HBM writes.  The cp.async kernels remain available (kernel policy 2) and the tests
 // cross-check the two families.
 #include "triplet_common.cuh"
+#include <stdlib.h>
 
 namespace tgt {
 
@@ -433,6 +434,303 @@ tri_attn_bwd_tma(const tgt_triplet_attn_desc D, const __grid_constant__ CUtensor
   }
 }
 
+// ------------------------------------------------------------------------------------------------ backward, warp-specialised
+// Same arithmetic as tri_attn_bwd_tma, re-organised so that more warps hide the latency of the register-heavy part:
+// one CTA per SM (head, direction, graph) with three warpgroups
+//   WG0 / WG1  "score" warpgroups: junctions j = 0,2,4,.. / 1,3,5,..  (each holds the bias / gate tiles and its own partial
+//              dE / dG sums in registers): S, dA, P, dS, dQ; dS and A go to this warpgroup's exchange tiles
+//   WG2        "key" warpgroup: for every j, dK = dS^T Q and dV = A^T dO from the exchange tiles; its first thread is
+//              also the TMA producer (4-stage ring: a stage is re-filled as soon as the key pass of its junction is done)
+// setmaxnreg gives the score warpgroups 224 registers and leaves 56 to the key warpgroup.  Hand-over between warpgroups
+// uses mbarriers (xch_ready / xch_free), results leave with stmatrix + TMA tensor stores as in tri_attn_bwd_tma.
+constexpr int TW_STAGES = 4;
+constexpr int TW_SMEM = TW_STAGES * TB_STAGE_BYTES + 4 * TB_XCH_BYTES + 4 * TILE_BYTES + 128 + 1024;
+constexpr int TW_REGS_SCORE = 224, TW_REGS_KEY = 56;
+
+template <typename T>
+__global__ void __launch_bounds__(384, 1)
+tri_attn_bwd_ws(const tgt_triplet_attn_desc D, const __grid_constant__ CUtensorMap mPcol,
+                const __grid_constant__ CUtensorMap mProw, const __grid_constant__ CUtensorMap mDVA,
+                const __grid_constant__ CUtensorMap mDPcol, const __grid_constant__ CUtensorMap mDProw,
+                const float *__restrict__ ws_e, const __half *__restrict__ ws_g, const float *__restrict__ stats,
+                float *__restrict__ ws_de, float *__restrict__ ws_dg) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int N = D.N, H = D.H;
+  const int h = blockIdx.x, dir = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wgrp = warp >> 2;                      // 0, 1: score warpgroups; 2: key warpgroup
+  const int wl = warp & 3;
+  const int g = lane >> 2, q = lane & 3;
+  const int m0 = wl * 16;
+  const uint32_t xbase = sbase + TW_STAGES * TB_STAGE_BYTES;        // [wg][dS, A] exchange tiles
+  const uint32_t sOut = xbase + 4 * TB_XCH_BYTES;                   // dQ(wg0), dQ(wg1), dK, dV staging tiles
+  const uint32_t bar_full = sOut + 4 * TILE_BYTES;                  // 4 x full
+  const uint32_t bar_ready = bar_full + 8 * TW_STAGES;              // 2 x xch_ready
+  const uint32_t bar_free = bar_ready + 16;                         // 2 x xch_free
+
+  if (tid == 0) {
+    tma_prefetch_desc(&mPcol);
+    tma_prefetch_desc(&mProw);
+    tma_prefetch_desc(&mDVA);
+    tma_prefetch_desc(&mDPcol);
+    tma_prefetch_desc(&mDProw);
+    for (int s = 0; s < TW_STAGES; ++s) mbar_init(bar_full + s * 8, 1);
+    for (int w = 0; w < 2; ++w) {
+      mbar_init(bar_ready + w * 8, 128);
+      mbar_init(bar_free + w * 8, 128);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  const int cq = D.off_q[dir] + h * HD, ck = D.off_k[dir] + h * HD, cv = D.off_v[dir] + h * HD;
+  const int co = dir * H * HD + h * HD;
+  const int64_t tbase = ((int64_t)(b * 2 + dir) * H + h) * TN * TN;
+
+  if (wgrp == 2) {
+    // ====================================================================================== key warpgroup + TMA producer
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TW_REGS_KEY));
+    auto issue = [&](int j) {                   // first thread of the warpgroup only
+      if (j < N) {
+        const uint32_t st = sbase + (j % TW_STAGES) * TB_STAGE_BYTES, bar = bar_full + (j % TW_STAGES) * 8;
+        mbar_expect_tx(bar, TB_STAGE_BYTES);
+        tma_load_4d(&mPcol, bar, st, cq, j, 0, b);
+        if (dir == 0) {
+          tma_load_4d(&mProw, bar, st + TILE_BYTES, ck, 0, j, b);
+          tma_load_4d(&mProw, bar, st + 2 * TILE_BYTES, cv, 0, j, b);
+        } else {
+          tma_load_4d(&mPcol, bar, st + TILE_BYTES, ck, j, 0, b);
+          tma_load_4d(&mPcol, bar, st + 2 * TILE_BYTES, cv, j, 0, b);
+        }
+        tma_load_4d(&mDVA, bar, st + 3 * TILE_BYTES, co, j, 0, b);
+      }
+    };
+    const bool first = (wl == 0 && lane == 0);
+    if (first) {
+#pragma unroll
+      for (int s = 0; s < TW_STAGES; ++s) issue(s);
+    }
+    for (int j = 0; j < N; ++j) {
+      const int w = j & 1, k = j >> 1;
+      const uint32_t st = sbase + (j % TW_STAGES) * TB_STAGE_BYTES;
+      const uint32_t sQ = st, sO = st + 3 * TILE_BYTES;
+      const uint32_t xS = xbase + w * 2 * TB_XCH_BYTES, xA = xS + TB_XCH_BYTES;
+      mbar_wait(bar_ready + w * 8, (uint32_t)(k & 1));           // dS / A of junction j are in the exchange tiles
+      float dk[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      float dv[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        uint32_t at[4], qb[4], ob[4];
+        load_a_xt(at, xS, m0, t * 16, lane);
+        load_b_kn(qb, sQ, t * 16, lane);
+        Mma<T>::run(dk[0], at, qb[0], qb[1]);
+        Mma<T>::run(dk[1], at, qb[2], qb[3]);
+        load_a_xt(at, xA, m0, t * 16, lane);
+        load_b_kn(ob, sO, t * 16, lane);
+        Mma<T>::run(dv[0], at, ob[0], ob[1]);
+        Mma<T>::run(dv[1], at, ob[2], ob[3]);
+      }
+      mbar_arrive(bar_free + w * 8);                               // this thread no longer reads the exchange tiles
+      if (first) tma_store_wait_read();                           // dK / dV (j-1) have left their staging tiles
+      asm volatile("bar.sync 3, 128;" ::: "memory");
+      store_c_tile<T>(sOut + 2 * TILE_BYTES, m0, lane, dk, D.scale);
+      store_c_tile<T>(sOut + 3 * TILE_BYTES, m0, lane, dv, 1.f);
+      fence_proxy_async();
+      asm volatile("bar.sync 3, 128;" ::: "memory");
+      if (first) {
+        if (dir == 0) {
+          tma_store_4d(&mDProw, sOut + 2 * TILE_BYTES, ck, 0, j, b);
+          tma_store_4d(&mDProw, sOut + 3 * TILE_BYTES, cv, 0, j, b);
+        } else {
+          tma_store_4d(&mDPcol, sOut + 2 * TILE_BYTES, ck, j, 0, b);
+          tma_store_4d(&mDPcol, sOut + 3 * TILE_BYTES, cv, j, 0, b);
+        }
+        tma_store_commit();
+        issue(j + TW_STAGES);                                      // stage j is free: both warpgroups are done with it
+      }
+    }
+    if (first) tma_store_wait_all();
+  } else {
+    // ====================================================================================== score warpgroups
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TW_REGS_SCORE));
+    const int w = wgrp;
+    const int bar_id = 1 + w;
+    const bool first = (wl == 0 && lane == 0);
+    float eb[8][4];
+    uint32_t gt[8][2];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int col = nt * 8 + 2 * q;
+      const float2 e0 = *reinterpret_cast<const float2 *>(ws_e + tbase + (m0 + g) * TN + col);
+      const float2 e1 = *reinterpret_cast<const float2 *>(ws_e + tbase + (m0 + g + 8) * TN + col);
+      eb[nt][0] = e0.x; eb[nt][1] = e0.y; eb[nt][2] = e1.x; eb[nt][3] = e1.y;
+      gt[nt][0] = *reinterpret_cast<const uint32_t *>(ws_g + tbase + (m0 + g) * TN + col);
+      gt[nt][1] = *reinterpret_cast<const uint32_t *>(ws_g + tbase + (m0 + g + 8) * TN + col);
+    }
+    float de[8][4], dg[8][4];          // partial sums over this warpgroup's junctions
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) de[nt][c] = dg[nt][c] = 0.f;
+    float c1r0, c1r1;
+    fix_fully_masked_rows(eb, D.scale * LOG2E, c1r0, c1r1);
+    const int i0 = m0 + g, i1 = m0 + g + 8;
+    const float *stb = stats + (((int64_t)(b * 2 + dir) * H + h) * N) * N;
+    auto load_stats = [&](int j, float &a, float &c) {
+      a = INFINITY;
+      c = INFINITY;
+      if (j < N) {
+        if (i0 < N) a = stb[(int64_t)j * N + i0];
+        if (i1 < N) c = stb[(int64_t)j * N + i1];
+      }
+    };
+    float sa0, sa1, sb0, sb1;
+    load_stats(w, sa0, sa1);
+    load_stats(w + 2, sb0, sb1);
+    const uint32_t xS = xbase + w * 2 * TB_XCH_BYTES, xA = xS + TB_XCH_BYTES;
+    const uint32_t sDQ = sOut + w * TILE_BYTES;
+
+    for (int j = w, k = 0; j < N; j += 2, ++k) {
+      const float lse0 = sa0, lse1 = sa1;
+      sa0 = sb0;
+      sa1 = sb1;
+      load_stats(j + 4, sb0, sb1);
+      const uint32_t st = sbase + (j % TW_STAGES) * TB_STAGE_BYTES;
+      const uint32_t sQ = st, sK = st + TILE_BYTES, sV = st + 2 * TILE_BYTES, sO = st + 3 * TILE_BYTES;
+      mbar_wait(bar_full + (j % TW_STAGES) * 8, (uint32_t)((j / TW_STAGES) & 1));
+
+      uint32_t qa[4], oa[4];
+      load_a_rows(qa, sQ, m0, lane);
+      load_a_rows(oa, sO, m0, lane);
+      float s[8][4], da[8][4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        uint32_t kb[4], vb[4];
+        load_b_nk(kb, sK, p * 16, lane);
+        load_b_nk(vb, sV, p * 16, lane);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int nt = 2 * p + u;
+          s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+          da[nt][0] = da[nt][1] = da[nt][2] = da[nt][3] = 0.f;
+          Mma<T>::run(s[nt], qa, kb[2 * u], kb[2 * u + 1]);
+          Mma<T>::run(da[nt], oa, vb[2 * u], vb[2 * u + 1]);
+        }
+      }
+      const float2 c1p0 = make_float2(c1r0, c1r0), c1p1 = make_float2(c1r1, c1r1);
+      const float2 nl0 = make_float2(-lse0, -lse0), nl1 = make_float2(-lse1, -lse1);
+      float2 dlp0 = make_float2(0.f, 0.f), dlp1 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const float2 g0 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][0]));
+        const float2 g1 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][1]));
+        float2 &s01 = *reinterpret_cast<float2 *>(&s[nt][0]), &s23 = *reinterpret_cast<float2 *>(&s[nt][2]);
+        float2 &a01 = *reinterpret_cast<float2 *>(&da[nt][0]), &a23 = *reinterpret_cast<float2 *>(&da[nt][2]);
+        float2 &e01 = *reinterpret_cast<float2 *>(&eb[nt][0]), &e23 = *reinterpret_cast<float2 *>(&eb[nt][2]);
+        float2 &q01 = *reinterpret_cast<float2 *>(&dg[nt][0]), &q23 = *reinterpret_cast<float2 *>(&dg[nt][2]);
+        const float2 x01 = __ffma2_rn(s01, c1p0, __fadd2_rn(e01, nl0));
+        const float2 x23 = __ffma2_rn(s23, c1p1, __fadd2_rn(e23, nl1));
+        const float2 p01 = make_float2(fast_exp2(x01.x), fast_exp2(x01.y));
+        const float2 p23 = make_float2(fast_exp2(x23.x), fast_exp2(x23.y));
+        const float2 dap01 = __fmul2_rn(a01, p01), dap23 = __fmul2_rn(a23, p23);
+        q01 = __fadd2_rn(q01, dap01);
+        q23 = __fadd2_rn(q23, dap23);
+        s01 = p01;
+        s23 = p23;
+        a01 = __fmul2_rn(dap01, g0);
+        a23 = __fmul2_rn(dap23, g1);
+        dlp0 = __fadd2_rn(dlp0, a01);
+        dlp1 = __fadd2_rn(dlp1, a23);
+      }
+      float dl0 = dlp0.x + dlp0.y, dl1 = dlp1.x + dlp1.y;
+      dl0 += __shfl_xor_sync(0xffffffffu, dl0, 1);
+      dl0 += __shfl_xor_sync(0xffffffffu, dl0, 2);
+      dl1 += __shfl_xor_sync(0xffffffffu, dl1, 1);
+      dl1 += __shfl_xor_sync(0xffffffffu, dl1, 2);
+      // the key warpgroup must be done with this warpgroup's previous exchange tiles, the previous dQ store must have
+      // left its staging tile
+      if (k > 0) mbar_wait(bar_free + w * 8, (uint32_t)((k - 1) & 1));
+      if (first) tma_store_wait_read();
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      const float2 nd0 = make_float2(-dl0, -dl0), nd1 = make_float2(-dl1, -dl1);
+      uint32_t dsa[4][4];
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t aa[4];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int nt = 2 * np + u;
+          const float2 g0 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][0]));
+          const float2 g1 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][1]));
+          const float2 p01 = *reinterpret_cast<float2 *>(&s[nt][0]), p23 = *reinterpret_cast<float2 *>(&s[nt][2]);
+          const float2 d01 = __ffma2_rn(p01, nd0, *reinterpret_cast<float2 *>(&da[nt][0]));
+          const float2 d23 = __ffma2_rn(p23, nd1, *reinterpret_cast<float2 *>(&da[nt][2]));
+          float2 &f01 = *reinterpret_cast<float2 *>(&de[nt][0]), &f23 = *reinterpret_cast<float2 *>(&de[nt][2]);
+          f01 = __fadd2_rn(f01, d01);
+          f23 = __fadd2_rn(f23, d23);
+          dsa[np][u * 2 + 0] = Mma<T>::pack(d01.x, d01.y);
+          dsa[np][u * 2 + 1] = Mma<T>::pack(d23.x, d23.y);
+          const float2 w01 = __fmul2_rn(p01, g0), w23 = __fmul2_rn(p23, g1);
+          aa[u * 2 + 0] = Mma<T>::pack(w01.x, w01.y);
+          aa[u * 2 + 1] = Mma<T>::pack(w23.x, w23.y);
+        }
+        store_xch_pair(xS, m0, lane, 2 * np, dsa[np][0], dsa[np][1], dsa[np][2], dsa[np][3]);
+        store_xch_pair(xA, m0, lane, 2 * np, aa[0], aa[1], aa[2], aa[3]);
+      }
+      {
+        float dq[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          uint32_t kb[4];
+          load_b_kn(kb, sK, t * 16, lane);
+          Mma<T>::run(dq[0], dsa[t], kb[0], kb[1]);
+          Mma<T>::run(dq[1], dsa[t], kb[2], kb[3]);
+        }
+        store_c_tile<T>(sDQ, m0, lane, dq, D.scale);
+      }
+      fence_proxy_async();
+      mbar_arrive(bar_ready + w * 8);           // exchange tiles written and this thread is done with stage j
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      if (first) {
+        tma_store_4d(&mDPcol, sDQ, cq, j, 0, b);
+        tma_store_commit();
+      }
+    }
+    if (first) tma_store_wait_all();
+    // dE = sum_j dS ; dG = g (1 - g) sum_j dA P : warpgroup 0 stores its partial sums, warpgroup 1 adds its own
+    if (w == 0) {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int col = nt * 8 + 2 * q;
+        *reinterpret_cast<float2 *>(ws_de + tbase + (m0 + g) * TN + col) = make_float2(de[nt][0], de[nt][1]);
+        *reinterpret_cast<float2 *>(ws_de + tbase + (m0 + g + 8) * TN + col) = make_float2(de[nt][2], de[nt][3]);
+        *reinterpret_cast<float2 *>(ws_dg + tbase + (m0 + g) * TN + col) = make_float2(dg[nt][0], dg[nt][1]);
+        *reinterpret_cast<float2 *>(ws_dg + tbase + (m0 + g + 8) * TN + col) = make_float2(dg[nt][2], dg[nt][3]);
+      }
+      __threadfence_block();
+    }
+    asm volatile("bar.sync 4, 256;" ::: "memory");          // both score warpgroups
+    if (w == 1) {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int col = nt * 8 + 2 * q;
+        const float2 g0 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][0]));
+        const float2 g1 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][1]));
+        float2 *pe0 = reinterpret_cast<float2 *>(ws_de + tbase + (m0 + g) * TN + col);
+        float2 *pe1 = reinterpret_cast<float2 *>(ws_de + tbase + (m0 + g + 8) * TN + col);
+        float2 *pg0 = reinterpret_cast<float2 *>(ws_dg + tbase + (m0 + g) * TN + col);
+        float2 *pg1 = reinterpret_cast<float2 *>(ws_dg + tbase + (m0 + g + 8) * TN + col);
+        const float2 a0 = *pe0, a1 = *pe1, b0 = *pg0, b1 = *pg1;
+        *pe0 = make_float2(a0.x + de[nt][0], a0.y + de[nt][1]);
+        *pe1 = make_float2(a1.x + de[nt][2], a1.y + de[nt][3]);
+        *pg0 = make_float2((b0.x + dg[nt][0]) * g0.x * (1.f - g0.x), (b0.y + dg[nt][1]) * g0.y * (1.f - g0.y));
+        *pg1 = make_float2((b1.x + dg[nt][2]) * g1.x * (1.f - g1.x), (b1.y + dg[nt][3]) * g1.y * (1.f - g1.y));
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host
 // 4-D map over a [B, N, N, C] 16-bit tensor (row pitch ld elements): box = 64 rows of 16 channels taken along the
 // second-to-last index ("row" tiles, fixed first index) or along the first index ("column" tiles, fixed second index)
@@ -480,6 +778,19 @@ static int bwd_tma_impl(const tgt_triplet_attn_desc &D, const void *proj, const 
   if (int e = make_tile_map(&mDVA, dva, D.B, D.N, Cv, Cv, true, D.dtype)) return e;
   if (int e = make_tile_map(&mDPcol, dproj, D.B, D.N, C, D.ld, true, D.dtype)) return e;
   if (int e = make_tile_map(&mDProw, dproj, D.B, D.N, C, D.ld, false, D.dtype)) return e;
+  // warp-specialised variant (three warpgroups, one CTA per SM): correct (tests) but measured slower than two 4-warp CTAs
+  // per SM (3.1 vs 2.55 ms at config 3, profiles/r1_18_*), so it is opt-in: TGT_TRI_BWD_WS=1
+  static const int use_ws = [] { const char *v = getenv("TGT_TRI_BWD_WS"); return v ? atoi(v) : 0; }();
+  if (use_ws) {
+    static std::once_flag once_ws;
+    std::call_once(once_ws, [] {
+      cudaFuncSetAttribute(tri_attn_bwd_ws<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM);
+    });
+    KernelTimerScope ts("tri_attn_bwd_ws", st);
+    tri_attn_bwd_ws<T><<<dim3(D.H, 2, D.B), 384, TW_SMEM, st>>>(D, mPcol, mProw, mDVA, mDPcol, mDProw, ws_e, ws_g, stats,
+                                                              ws_de, ws_dg);
+    return check_launch("tri_attn_bwd_ws");
+  }
   static std::once_flag once;
   std::call_once(once, [] {
     cudaFuncSetAttribute(tri_attn_bwd_tma<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM);

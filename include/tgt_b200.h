@@ -143,6 +143,28 @@ int tgt_triplet_aggr_fwd(const tgt_triplet_aggr_desc *desc, const void *proj, co
 int tgt_triplet_aggr_bwd(const tgt_triplet_aggr_desc *desc, const void *proj, const float *mask,
                          const void *dva, const float *aw, float *daw, void *dproj, void *stream);
 
+/* ---- triangular update core ("next" row 8f-2) ----------------------------------------------
+ * replaces lib/tgt/layers/triplet.py:154-170 (TriangularUpdate: mask add, four siglin gates, two einsums).
+ * proj : [R, ld]; lin_V output (V_in_g | V_in_l | V_out_g | V_out_l, H columns each, triplet.py:154) at
+ *        column off_v, lin_E output (E_in_g | E_in_l | E_out_g | E_out_l, triplet.py:155) at column off_e.
+ * mask : [B,N,N] f32 additive, added to the four gates (triplet.py:157-160)
+ * va   : [R, 2H] out = [Va_in | Va_out] (triplet.py:166-169).  N <= 64.
+ * bwd  : dproj [R, ld] receives the gradient of all eight blocks (other columns are not touched). */
+typedef struct {
+  int32_t B, N, H;
+  int64_t ld;
+  int32_t off_v, off_e;
+  int32_t dtype;
+} tgt_triangular_desc;
+
+int tgt_triangular_fwd(const tgt_triangular_desc *desc, const void *proj, const float *mask, void *va,
+                       void *stream);
+int tgt_triangular_bwd(const tgt_triangular_desc *desc, const void *proj, const float *mask,
+                       const void *dva, void *dproj, void *stream);
+/* y[r,c] = sigmoid(x[r,c]) * x[r,W+c], x:[rows,2W], y:[rows,W] (triplet.py:129-131, 172-175); W % (16/sizeof) == 0 */
+int tgt_siglin_fwd(const void *x, void *y, int64_t rows, int W, int dtype, void *stream);
+int tgt_siglin_bwd(const void *x, const void *dy, void *dx, int64_t rows, int W, int dtype, void *stream);
+
 /* ---- EGT node/edge attention core ---------------------------------------------------------
  * replaces lib/tgt/layers/layers.py:62-78 (EGT_Attention) and 121-125 (EdgeUpdate).
  * Reference-native d-major channel layout: channel c = dd*H + h.

@@ -22,8 +22,7 @@ DEV = "cuda"
 FP32_TOL = 1e-5
 BF16_TOL = 1e-2
 
-TRIPLET_FIX = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "triplet_*.pt"))
-                     if "tiangular" not in p)
+TRIPLET_FIX = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "triplet_*.pt")))
 
 
 def _module_from_fixture(fx):
@@ -231,8 +230,8 @@ def test_unsupported_inputs_raise():
         mod2(e.to(DEV), mask.to(DEV))
     mod2.eval()
     mod2(e.to(DEV), mask.to(DEV))          # dropout inactive in eval: fine
-    with pytest.raises(NotImplementedError):
-        L.TriangularUpdate(32, 2).to(DEV)(e.to(DEV), mask.to(DEV))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        L.TriangularUpdate(32, 2)(e, mask)             # CPU tensors: refuse, never fall back
 
 
 def test_padding_leak_of_aggregate_is_reproduced():

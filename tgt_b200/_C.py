@@ -40,6 +40,11 @@ class TripletAggrDesc(C.Structure):
                 ("mask_dir", C.c_int32 * 2), ("dtype", C.c_int32)]
 
 
+class TriangularDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("N", C.c_int32), ("H", C.c_int32), ("ld", C.c_int64),
+                ("off_v", C.c_int32), ("off_e", C.c_int32), ("dtype", C.c_int32)]
+
+
 class EgtDesc(C.Structure):
     _fields_ = [("B", C.c_int32), ("N", C.c_int32), ("H", C.c_int32), ("d", C.c_int32),
                 ("ld_qkv", C.c_int64), ("ld_eg", C.c_int64),
@@ -82,6 +87,10 @@ _SIGNATURES = {
                                              _P, _P, _P, C.c_size_t, _P]),
     "tgt_triplet_aggr_fwd": (C.c_int, [C.POINTER(TripletAggrDesc), _P, _P, _P, _P, _P]),
     "tgt_triplet_aggr_bwd": (C.c_int, [C.POINTER(TripletAggrDesc), _P, _P, _P, _P, _P, _P, _P]),
+    "tgt_triangular_fwd": (C.c_int, [C.POINTER(TriangularDesc), _P, _P, _P, _P]),
+    "tgt_triangular_bwd": (C.c_int, [C.POINTER(TriangularDesc), _P, _P, _P, _P, _P]),
+    "tgt_siglin_fwd": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, _P]),
+    "tgt_siglin_bwd": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, C.c_int, _P]),
     "tgt_egt_attn_fwd": (C.c_int, [C.POINTER(EgtDesc), _P, _P, _P, _P, _P, _P, _P, _P]),
     "tgt_egt_attn_workspace_bytes": (C.c_size_t, [C.POINTER(EgtDesc)]),
     "tgt_egt_attn_bwd": (C.c_int, [C.POINTER(EgtDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),

@@ -248,8 +248,8 @@ class TripletAggregateUngated(_AggregateFamily):
 
 
 class TriangularUpdate(_TripletBase):
-    """Reference: triplet.py:134-176.  Parameters and state dict are kept; the kernel for this variant is
-    a 'next' row and until it lands forward refuses instead of falling back."""
+    """Reference: triplet.py:134-176.  LN -> [lin_V | lin_E] (one LayerNorm-folded GEMM) -> gated triangular
+    contraction kernel (ops.TriangularCoreFn) -> lin_O -> sigmoid(gate)*lin kernel (ops.SigLinFn)."""
 
     def __init__(self, edge_width, num_heads, attention_dropout=0):
         super().__init__(edge_width, num_heads, attention_dropout)
@@ -260,9 +260,20 @@ class TriangularUpdate(_TripletBase):
         self.lin_O = nn.Linear(H * 2, W * 2)
 
     def forward(self, e, mask):
-        raise NotImplementedError("tgt_b200: TriangularUpdate has no CUDA kernel yet (no fallback by design)")
+        return self.forward_alias(e, mask)[0]
 
-    forward_alias = forward
+    def forward_alias(self, e, mask):
+        """(module(e), alias of e for the caller's residual add -- see ops.LNLinearFn)."""
+        self._common_checks(e, mask)       # the reference never applies attention_dropout in this variant either
+        cd = ops.compute_dtype(e)
+        Wcat = torch.cat([self.lin_V.weight, self.lin_E.weight], 0)
+        bcat = torch.cat([self.lin_V.bias, self.lin_E.bias], 0)
+        proj, alias = ops.LNLinearFn.apply(e, self.tri_ln_e.weight, self.tri_ln_e.bias, Wcat, bcat, cd)
+        va = ops.TriangularCoreFn.apply(proj, mask, self.num_heads, cd)
+        lo = nn.functional.linear(va, self.lin_O.weight.to(cd), self.lin_O.bias.to(cd))     # K = 2H: plain library GEMM
+        return ops.SigLinFn.apply(lo), alias
 
     def forward_residual(self, e, mask, scale):
-        return self.forward(e, mask)
+        """e + scale[b] * module(e) (see _AttentionFamily.forward_residual)."""
+        out, alias = self.forward_alias(e, mask)
+        return ops.scaled_residual(out, alias, scale)

@@ -735,6 +735,68 @@ class TripletAggregateFn(Function):
 
 
 # ------------------------------------------------------------------------------------------
+# TriangularUpdate core (triplet.py:154-170) and sigmoid(gate)*lin (triplet.py:129-131)
+# ------------------------------------------------------------------------------------------
+class TriangularCoreFn(Function):
+    """proj [B,N,N,8H] = [lin_V | lin_E] outputs, mask -> Va [B,N,N,2H].  The gated O(N^2 H) operands live only in
+    shared memory; backward recomputes them from `proj` (saved: it is the module's smallest tensor)."""
+
+    @staticmethod
+    def forward(ctx, proj, mask, H, cdtype):
+        _require_cuda(proj, mask)
+        B, N = proj.shape[0], proj.shape[1]
+        with torch.autocast("cuda", enabled=False):
+            pc = proj.detach().to(cdtype).contiguous()
+            m3 = _f32c(mask).view(B, N, N)
+            desc = _C.TriangularDesc(B, N, H, pc.shape[-1], 0, 4 * H, _C.dtype_code(cdtype))
+            va = torch.empty((B, N, N, 2 * H), dtype=cdtype, device=proj.device)
+            with timed("triangular_fwd"):
+                _C.check(_C.lib().tgt_triangular_fwd(desc, _C.ptr(pc), _C.ptr(m3), _C.ptr(va), _C.stream_ptr()),
+                         "triangular_fwd")
+        ctx.save_for_backward(pc, m3)
+        ctx.desc = desc
+        ctx.in_dtype = proj.dtype
+        return va
+
+    @staticmethod
+    def backward(ctx, dva):
+        pc, m3 = ctx.saved_tensors
+        with torch.autocast("cuda", enabled=False):
+            dv = dva.to(pc.dtype).contiguous()
+            dproj = torch.empty_like(pc)
+            with timed("triangular_bwd"):
+                _C.check(_C.lib().tgt_triangular_bwd(ctx.desc, _C.ptr(pc), _C.ptr(m3), _C.ptr(dv), _C.ptr(dproj),
+                                                     _C.stream_ptr()), "triangular_bwd")
+        return dproj.to(ctx.in_dtype), None, None, None
+
+
+class SigLinFn(Function):
+    """x [..., 2W] = (gates | lins) -> sigmoid(gates) * lins [..., W]; backward recomputes the sigmoid from x."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _require_cuda(x)
+        xc = x.detach().contiguous()
+        W = xc.shape[-1] // 2
+        rows = xc.numel() // (2 * W)
+        y = torch.empty((*xc.shape[:-1], W), dtype=xc.dtype, device=xc.device)
+        _C.check(_C.lib().tgt_siglin_fwd(_C.ptr(xc), _C.ptr(y), rows, W, _C.dtype_code(xc.dtype), _C.stream_ptr()),
+                 "siglin_fwd")
+        ctx.save_for_backward(xc)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (xc,) = ctx.saved_tensors
+        W = xc.shape[-1] // 2
+        dc = dy.to(xc.dtype).contiguous()
+        dx = torch.empty_like(xc)
+        _C.check(_C.lib().tgt_siglin_bwd(_C.ptr(xc), _C.ptr(dc), _C.ptr(dx), xc.numel() // (2 * W), W,
+                                         _C.dtype_code(xc.dtype), _C.stream_ptr()), "siglin_bwd")
+        return dx
+
+
+# ------------------------------------------------------------------------------------------
 # EGT node/edge attention core
 # ------------------------------------------------------------------------------------------
 class EGTCoreFn(Function):

@@ -293,11 +293,14 @@ ln_fwd_w256(const XT *__restrict__ x, const float *__restrict__ gamma, const flo
   }
 }
 
-template <typename XT, typename T, int RU>
+// EMIT_Y: also write y = LN(x) (the normalised rows are in registers anyway) as [rows, ldy] with the augmentation columns
+// -- the weight-gradient GEMM of the Linear behind the LayerNorm then needs no separate LayerNorm recompute pass.
+template <typename XT, typename T, int RU, bool EMIT_Y = false>
 __global__ void __launch_bounds__(256)
 ln_bwd_w256(const T *__restrict__ dy, const XT *__restrict__ x, const float *__restrict__ gamma,
             const float *__restrict__ mean, const float *__restrict__ rstd, const XT *__restrict__ dres,
-            XT *__restrict__ dx, float *__restrict__ dgamma, float *__restrict__ dbeta, int64_t rows) {
+            XT *__restrict__ dx, float *__restrict__ dgamma, float *__restrict__ dbeta, int64_t rows,
+            const float *__restrict__ beta = nullptr, T *__restrict__ y = nullptr, int64_t ldy = 0) {
   __shared__ float sm[2 * 256];
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -311,6 +314,11 @@ ln_bwd_w256(const T *__restrict__ dy, const XT *__restrict__ x, const float *__r
   }
 #pragma unroll
   for (int q = 0; q < 8; ++q) ag[q] = ab[q] = 0.f;
+  float bt[8];
+  if constexpr (EMIT_Y) {
+    const float4 b0 = *reinterpret_cast<const float4 *>(beta + lane * 8), b1 = *reinterpret_cast<const float4 *>(beta + lane * 8 + 4);
+    bt[0] = b0.x; bt[1] = b0.y; bt[2] = b0.z; bt[3] = b0.w; bt[4] = b1.x; bt[5] = b1.y; bt[6] = b1.z; bt[7] = b1.w;
+  }
   for (int64_t r0 = warp0 * RU; r0 < rows; r0 += nwarps * RU) {
     typename V8<XT>::Raw rx[RU], rr[RU];
     uint4 rd[RU];
@@ -340,6 +348,16 @@ ln_bwd_w256(const T *__restrict__ dy, const XT *__restrict__ x, const float *__r
         dv[q] *= g[q];                            // g * dy
         s1 += dv[q];
         s2 += dv[q] * xv[q];
+      }
+      if constexpr (EMIT_Y) {                     // same expression as ln_fwd_w256: bit-identical to the recompute
+        float yv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) yv[q] = xv[q] * g[q] + bt[q];
+        *reinterpret_cast<uint4 *>(y + (r0 + u) * ldy + lane * 8) = V8<T>::pack(yv);
+        if (ldy > 256 && lane == 0) {
+          const float one[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          *reinterpret_cast<uint4 *>(y + (r0 + u) * ldy + 256) = V8<T>::pack(one);
+        }
       }
       s1 = warp_sum(s1) * (1.f / 256.f);
       s2 = warp_sum(s2) * (1.f / 256.f);
@@ -595,16 +613,24 @@ static int ln_fwd_launch(const void *x, const float *gamma, const float *beta, v
 template <typename XT, typename YT>
 static int ln_bwd_launch(const void *dy, const void *x, const float *gamma, const float *mean,
                          const float *rstd, const void *dres, void *dx, float *dgamma, float *dbeta,
-                         int64_t rows, int W, cudaStream_t st) {
+                         int64_t rows, int W, cudaStream_t st, const float *beta = nullptr, void *y = nullptr,
+                         int64_t ldy = 0) {
   if constexpr (sizeof(YT) == 2 && (std::is_same<XT, YT>::value || std::is_same<XT, float>::value)) {
-    if (W == 256 && (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx | (uintptr_t)dres) & 15) == 0) {
+    if (W == 256 && (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx | (uintptr_t)dres | (uintptr_t)y) & 15) == 0) {
       int g = grid_for(rows, 8 * 2 * 8);
       if (g > 148 * 8) g = 148 * 8;
+      if (y) {
+        if (!beta || (ldy != 256 && ldy != 264)) return fail("layernorm_bwd_y: beta is required and ldy must be 256 or 264");
+        ln_bwd_w256<XT, YT, 2, true><<<g, 256, 0, st>>>((const YT *)dy, (const XT *)x, gamma, mean, rstd, (const XT *)dres,
+                                                        (XT *)dx, dgamma, dbeta, rows, beta, (YT *)y, ldy);
+        return check_launch("ln_bwd_w256_y");
+      }
       ln_bwd_w256<XT, YT, 2><<<g, 256, 0, st>>>((const YT *)dy, (const XT *)x, gamma, mean, rstd, (const XT *)dres, (XT *)dx,
                                             dgamma, dbeta, rows);
       return check_launch("ln_bwd_w256");
     }
   }
+  if (y) return fail("layernorm_bwd_y: only the W = 256, 16-bit gradient fast path can emit y");
   int g = grid_for(rows, 8 * 16);
   if (g > 148 * 4) g = 148 * 4;
   ln_bwd_kernel<XT, YT><<<g, 256, 2 * W * sizeof(float), st>>>((const YT *)dy, (const XT *)x, gamma, mean, rstd,
@@ -648,6 +674,20 @@ extern "C" int tgt_layernorm_bwd(const void *dy, const void *x, const float *gam
   LN_COMBOS(X)
 #undef X
   return fail("layernorm_bwd: unsupported dtype combination x=%d y=%d", x_dtype, y_dtype);
+}
+
+extern "C" int tgt_layernorm_bwd_y(const void *dy, const void *x, const float *gamma, const float *beta, const float *mean,
+                                   const float *rstd, const void *dres, void *dx, float *dgamma, float *dbeta, void *y,
+                                   int64_t ldy, int64_t rows, int W, int x_dtype, int y_dtype, void *stream) {
+  if (!y || !beta) return fail("layernorm_bwd_y: y and beta are required");
+  if (rows <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+#define X(xc, yc, XT, YT)                   \
+  if (x_dtype == xc && y_dtype == yc)       \
+    return ln_bwd_launch<XT, YT>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, rows, W, st, beta, y, ldy);
+  LN_COMBOS(X)
+#undef X
+  return fail("layernorm_bwd_y: unsupported dtype combination x=%d y=%d", x_dtype, y_dtype);
 }
 
 extern "C" int tgt_gelu_dropout_fwd(const void *u, void *y, int64_t n, float p_drop, uint64_t seed, int dtype,

@@ -99,11 +99,28 @@ def layernorm_fwd(x2: Tensor, gamma: Tensor, beta: Tensor, out_dtype: torch.dtyp
     return y, mean, rstd
 
 
+def ln_bwd_emits_y(x2: Tensor, cd: torch.dtype) -> bool:
+    """The W = 256 LayerNorm-backward kernel can also write y = LN(x) (augmented) for the weight-gradient GEMM."""
+    return x2.shape[1] == 256 and cd in (torch.bfloat16, torch.float16) and x2.dtype in (cd, torch.float32)
+
+
 def layernorm_bwd(dy: Tensor, x2: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor,
-                  dres: Optional[Tensor] = None):
+                  dres: Optional[Tensor] = None, beta: Optional[Tensor] = None):
+    """(dx, dgamma, dbeta[, y]).  With `beta` given (see ln_bwd_emits_y) the kernel also emits the augmented
+    y = [LN(x) | 1 | 0...] in dy's dtype, so callers order their weight-gradient GEMM after this call instead of
+    running a LayerNorm recompute pass for it."""
     rows, W = x2.shape
     dx = torch.empty_like(x2)
     dgb = torch.zeros((2, W), dtype=torch.float32, device=x2.device)
+    if beta is not None:
+        y = torch.empty((rows, W + AUG), dtype=dy.dtype, device=x2.device)
+        with timed(f"layernorm_bwd_W{W}"):
+            _C.check(_C.lib().tgt_layernorm_bwd_y(_C.ptr(dy), _C.ptr(x2), _C.ptr(gamma), _C.ptr(beta), _C.ptr(mean),
+                                                  _C.ptr(rstd), _C.ptr(dres), _C.ptr(dx), _C.ptr(dgb[0]),
+                                                  _C.ptr(dgb[1]), _C.ptr(y), W + AUG, rows, W,
+                                                  _C.dtype_code(x2.dtype), _C.dtype_code(dy.dtype), _C.stream_ptr()),
+                     "layernorm_bwd_y")
+        return dx, dgb[0], dgb[1], y
     with timed(f"layernorm_bwd_W{W}"):
         _C.check(_C.lib().tgt_layernorm_bwd(_C.ptr(dy), _C.ptr(x2), _C.ptr(gamma), _C.ptr(mean), _C.ptr(rstd),
                                             _C.ptr(dres), _C.ptr(dx), _C.ptr(dgb[0]), _C.ptr(dgb[1]), rows, W,
@@ -419,6 +436,12 @@ def ln_linear_bwd(dout2: Tensor, x2: Tensor, g: Tensor, bt: Tensor, Wc: Tensor, 
         dbt = db @ Wf
         dx = gemm_tc(dout2, Wc.t().contiguous(), ln_bwd=(x2, mean, rstd, g, dres), name=name)
         return dx, dg, dbt, dW, db
+    if ln_bwd_emits_y(x2, cd) and dout2.dtype == cd:
+        dy = torch.mm(dout2, Wc)
+        dx, dg, dbt, y = layernorm_bwd(dy, x2, g, mean, rstd, dres, beta=bt)
+        del dy
+        dWa = torch.mm(dout2.t(), y)
+        return dx, dg, dbt, dWa[:, :W], dWa[:, W]
     y, _, _ = layernorm_fwd(x2, g, bt, cd, aug=True)
     dWa = torch.mm(dout2.t(), y)
     dW, db = dWa[:, :W], dWa[:, W]
@@ -628,7 +651,8 @@ class TripletAttentionFn(Function):
                 dalias = dout                               # residual branch: d(e) += dout, folded into the LN backward
             dva, dWo, dbo = linear_residual_bwd(do, va, Woc, sc, name="gemm_tc_dva")
             del do
-            y, _, _ = layernorm_fwd(x2, g, bt, cd, aug=True)
+            late_y = (kept_proj is not None or Wg is not None) and ln_bwd_emits_y(x2, cd)
+            y = None if late_y else layernorm_fwd(x2, g, bt, cd, aug=True)[0]
             if kept_proj is not None:   # one of the last layers: HBM had room to keep the projection (keep_projection)
                 proj = kept_proj
             elif Wg is not None:        # bit-identical recompute of the forward projection (same kernel, same inputs)
@@ -645,12 +669,20 @@ class TripletAttentionFn(Function):
                                                              _C.ptr(tiles), _C.stream_ptr()), "triplet_attn_bwd")
             del ws
             del proj, dva
-            dWa = torch.mm(dproj.t(), y)                  # [C, W+8]: weight gradient | bias gradient (column W)
-            dWc, dbc = dWa[:, :W], dWa[:, W]
-            del y
-            dy = torch.mm(dproj, Wc)
-            del dproj
-            dx, dg, dbt = layernorm_bwd(dy, x2, g, mean, rstd, _dres_for(dalias, x2))
+            if late_y:                  # LN(x) comes out of the LayerNorm-backward kernel: no recompute pass
+                dy = torch.mm(dproj, Wc)
+                dx, dg, dbt, y = layernorm_bwd(dy, x2, g, mean, rstd, _dres_for(dalias, x2), beta=bt)
+                del dy
+                dWa = torch.mm(dproj.t(), y)              # [C, W+8]: weight gradient | bias gradient (column W)
+                dWc, dbc = dWa[:, :W], dWa[:, W]
+                del y, dproj
+            else:
+                dWa = torch.mm(dproj.t(), y)
+                dWc, dbc = dWa[:, :W], dWa[:, W]
+                del y
+                dy = torch.mm(dproj, Wc)
+                del dproj
+                dx, dg, dbt = layernorm_bwd(dy, x2, g, mean, rstd, _dres_for(dalias, x2))
         p = ctx.pdt
         return (dx.view(B, N, N, W).to(ctx.in_dtype), None, dg.to(p[0]), dbt.to(p[0]), dWc.to(p[1]), dbc.to(p[2]),
                 dWo.to(p[3]), dbo.to(p[4]), None, None, None, None)
@@ -711,7 +743,8 @@ class TripletAggregateFn(Function):
                 dalias = dout                               # residual branch: d(e) += dout, folded into the LN backward
             dva, dWo, dbo = linear_residual_bwd(do, va, Woc, sc, name="gemm_tc_dva")
             del do
-            y, _, _ = layernorm_fwd(x2, g, bt, cd, aug=True)
+            late_y = Wg is not None and ln_bwd_emits_y(x2, cd)
+            y = None if late_y else layernorm_fwd(x2, g, bt, cd, aug=True)[0]
             if Wg is not None:          # bit-identical recompute of the forward projection (same kernel, same inputs)
                 proj = gemm_tc(x2, Wg, bias=bp, ln=(mean, rstd, cs), name="gemm_tc_ln_proj")
             else:
@@ -723,12 +756,20 @@ class TripletAggregateFn(Function):
                                                        _C.ptr(daw), _C.ptr(dproj), _C.stream_ptr()),
                          "triplet_aggr_bwd")
             del proj, dva, daw
-            dWa = torch.mm(dproj.t(), y)                  # [C, W+8]: weight gradient | bias gradient (column W)
-            dWc, dbc = dWa[:, :W], dWa[:, W]
-            del y
-            dy = torch.mm(dproj, Wc)
-            del dproj
-            dx, dg, dbt = layernorm_bwd(dy, x2, g, mean, rstd, _dres_for(dalias, x2))
+            if late_y:                  # LN(x) comes out of the LayerNorm-backward kernel: no recompute pass
+                dy = torch.mm(dproj, Wc)
+                dx, dg, dbt, y = layernorm_bwd(dy, x2, g, mean, rstd, _dres_for(dalias, x2), beta=bt)
+                del dy
+                dWa = torch.mm(dproj.t(), y)              # [C, W+8]: weight gradient | bias gradient (column W)
+                dWc, dbc = dWa[:, :W], dWa[:, W]
+                del y, dproj
+            else:
+                dWa = torch.mm(dproj.t(), y)
+                dWc, dbc = dWa[:, :W], dWa[:, W]
+                del y
+                dy = torch.mm(dproj, Wc)
+                del dproj
+                dx, dg, dbt = layernorm_bwd(dy, x2, g, mean, rstd, _dres_for(dalias, x2))
         p = ctx.pdt
         return (dx.view(B, N, N, W).to(ctx.in_dtype), None, dg.to(p[0]), dbt.to(p[0]), dWc.to(p[1]), dbc.to(p[2]),
                 dWo.to(p[3]), dbo.to(p[4]), None, None, None, None)

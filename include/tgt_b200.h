@@ -278,6 +278,14 @@ int tgt_gaussian_basis_fwd(const float *x, const float *mu, const float *sd, voi
 int tgt_gaussian_basis_bwd(const float *x, const float *mu, const float *sd, const void *dout, float *dx,
                            float *dmu, float *dsd, int64_t rows, int K, int dout_dtype, void *stream);
 
+/* ---- distance-bin decoding of the two-stage inference path ("next" row 8f-3) -------------------
+ * replaces lib/training_schemes/pcqm/dist_pred/scheme.py:186-194 (softmax over bins, p + p^T over the atom pair,
+ * argmax) and commons.py:72-82 (BinsProcessor.bins2dist: (bin + 0.5) * bin_size, d + d^T, zero diagonal) in one
+ * pass over the logits.  logits:[B,N,N,num_bins] (dtype) ; bins:[B,N,N] int16 out or NULL ; dist:[B,N,N] f32 out
+ * or NULL ; num_bins <= 512 ; ties go to the lowest bin (torch.argmax).                                          */
+int tgt_bins_decode(const void *logits, int16_t *bins, float *dist, int B, int N, int num_bins,
+                    float bin_size, int shift_half, int zero_diag, int dtype, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

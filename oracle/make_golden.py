@@ -142,5 +142,32 @@ def main():
         print(f"  {n:40s} {os.path.getsize(os.path.join(OUT, n)) / 1024:8.1f} KB")
 
 
+def bins_fixture():
+    """tests/golden/bins_decode.pt: the reference's own `predict_bins` (dist_pred/scheme.py:181-205, called unbound on a
+    stub that replays fixed logits) and `BinsProcessor.bins2dist` (commons.py:72-82) on random logits."""
+    import tempfile
+    from types import SimpleNamespace
+    from lib.training_schemes.pcqm.dist_pred.scheme import SCHEME as DistScheme
+    from lib.training_schemes.pcqm.commons import BinsProcessor
+
+    g = torch.Generator().manual_seed(11)
+    B, N, nb, S = 3, 10, 256, 2
+    logits = [torch.randn(B, N, N, nb, generator=g) * 3.0 for _ in range(S)]
+    it = iter(logits)
+    stub = SimpleNamespace(nb_draw_samples=S, model=lambda batch: next(it))
+    bins = DistScheme.predict_bins(stub, None)                      # [B, S, N, N] int64
+    with tempfile.TemporaryDirectory() as d:
+        with open(os.path.join(d, "meta.json"), "w") as f:
+            json.dump(dict(num_samples=S, num_bins=nb, range_bins=8), f)
+        dist = BinsProcessor(d).bins2dist(bins)
+    torch.save(dict(logits=torch.stack(logits, 1), bins=bins.to(torch.int16), dist=f32(dist), num_bins=nb, range_bins=8.0),
+               os.path.join(OUT, "bins_decode.pt"))
+    print("bins_decode.pt written", tuple(bins.shape), float(dist.max()))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "bins":
+        bins_fixture()
+    else:
+        main()
+        bins_fixture()

@@ -393,6 +393,30 @@ def pretrain_loss(gap: Tensor, logits: Tensor, batch: Dict[str, Tensor], num_bin
 
 
 # --------------------------------------------------------------------------
+# two-stage inference glue (BASELINE config 5)
+# --------------------------------------------------------------------------
+def bins_from_logits(logits: Tensor) -> Tensor:
+    """One sample of predict_bins -- lib/training_schemes/pcqm/dist_pred/scheme.py:190-193:
+    softmax over bins, symmetrise over the atom pair (p + p^T), argmax."""
+    p = torch.softmax(logits.float(), dim=-1)
+    p = p + p.transpose(-2, -3)
+    return p.argmax(dim=-1)
+
+
+def bins2dist(bins: Tensor, num_bins: int, range_bins: float = 8.0, shift_half: bool = True,
+              zero_diag: bool = True) -> Tensor:
+    """BinsProcessor.bins2dist -- lib/training_schemes/pcqm/commons.py:68-82 (bin_size = range / (num_bins - 1))."""
+    d = bins.float()
+    if shift_half:
+        d = d + 0.5
+    d = d * (range_bins / (num_bins - 1))
+    d = d + d.transpose(-2, -1)
+    if zero_diag:
+        d = d * (1 - torch.eye(d.size(-1), dtype=d.dtype, device=d.device))
+    return d
+
+
+# --------------------------------------------------------------------------
 # closed-form backward of the gated attention core (second oracle for the CUDA
 # backward; SURVEY.md Appendix A, verified against autograd in the tests)
 # --------------------------------------------------------------------------

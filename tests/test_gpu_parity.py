@@ -394,3 +394,70 @@ def test_gaussian_basis_kernel_vs_torch(out_dtype):
     assert rel_err(out.float().cpu(), ref.detach().cpu()) < tol
     for got, w in zip((x.grad, mu.grad, sd.grad), want):
         assert rel_err(got.cpu(), w.cpu()) < (1e-4 if out_dtype == torch.float32 else 1e-2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_bins_decode_kernel_vs_golden_and_oracle(dtype):
+    """tgt_bins_decode (softmax + p + p^T + argmax + bins2dist in one pass) vs the reference-made fixture (fp32 logits:
+    bit-exact bins and distances) and vs the oracle on the 16-bit-rounded logits.  A bin may only differ where the two
+    best symmetrised probabilities are closer than fp32 softmax rounding (1e-6 relative)."""
+    fx = load_golden("bins_decode.pt")
+    lg = fx["logits"].to(dtype)
+    B, S, N = lg.shape[:3]
+    for s in range(S):
+        bins, dist = ops.bins_decode(lg[:, s].to(DEV), range_bins=fx["range_bins"])
+        ref_bins = O.bins_from_logits(lg[:, s].float())
+        ref_dist = O.bins2dist(ref_bins, fx["num_bins"], fx["range_bins"])
+        if dtype == torch.float32:
+            assert torch.equal(ref_bins.to(torch.int16), fx["bins"][:, s])
+        p = torch.softmax(lg[:, s].float(), -1)
+        p = p + p.transpose(-2, -3)
+        top2 = p.topk(2, dim=-1).values
+        clear = (top2[..., 0] - top2[..., 1]) > 1e-6 * top2[..., 0]
+        same = bins.cpu().long() == ref_bins
+        assert bool((same | ~clear).all()) and float(same.float().mean()) > 0.999
+        assert torch.equal(dist.cpu()[same], ref_dist[same])
+        assert torch.equal(bins, bins.transpose(-1, -2)) and torch.equal(dist, dist.transpose(-1, -2))
+
+
+def test_bins_decode_edge_cases():
+    """ragged sizes, num_bins not a multiple of 32, exact ties (lowest bin wins like torch.argmax), limits."""
+    g = torch.Generator().manual_seed(5)
+    for B, N, nb in [(1, 1, 8), (2, 7, 100), (1, 64, 512), (3, 5, 33)]:
+        lg = torch.randn(B, N, N, nb, generator=g)
+        bins, dist = ops.bins_decode(lg.to(DEV), range_bins=8.0)
+        rb = O.bins_from_logits(lg)
+        assert float((bins.cpu().long() == rb).float().mean()) > 0.999
+    lg = torch.zeros(1, 4, 4, 64)                                  # all bins tie -> bin 0 everywhere
+    lg[0, 1, 2, 10] = lg[0, 1, 2, 20] = 5.0                       # two-way tie of the pair (1, 2)
+    lg[0, 2, 1, 10] = lg[0, 2, 1, 20] = 5.0
+    bins, dist = ops.bins_decode(lg.to(DEV), range_bins=8.0)
+    assert int(bins[0, 0, 3]) == 0 and int(bins[0, 1, 2]) == 10 and int(bins[0, 2, 1]) == 10
+    assert float(dist[0, 0, 0]) == 0.0 and abs(float(dist[0, 1, 2]) - 2 * 10.5 * 8.0 / 63) < 1e-6
+    with pytest.raises(RuntimeError, match="num_bins"):
+        ops.bins_decode(torch.zeros(1, 2, 2, 1024, device=DEV))
+
+
+def test_two_stage_inference_matches_oracle_pipeline():
+    """Config 5 glue: TGT_Distance -> bins -> distances -> TGT_Gap (harness.inference) vs the same pipeline with the oracle's
+    bins_from_logits / bins2dist on OUR logits (eval mode, fp32, one sample: deterministic)."""
+    from tgt_b200.harness import inference as INF
+    torch.manual_seed(0)
+    cfg = dict(node_width=64, edge_width=32, num_heads=4, triplet_heads=2, triplet_type="attention")
+    dm = HM.TGT_Distance(model_height=2, num_dist_bins=64, embed_3d_type="none", **cfg).to(DEV).eval()
+    gm = HM.TGT_Gap(model_height=2, **cfg).to(DEV).eval()
+    batch = {k: v.to(DEV) for k, v in make_batch(3, 9, seed=2).items()}
+    bins, d = INF.predict_dist_inputs(dm, batch, samples=1, amp_dtype=None, want_bins=True)
+    from tgt_b200.harness.synthetic import add_scheme_fields
+    with torch.no_grad():
+        logits = dm(add_scheme_fields(batch, with_3d=False))
+    rb = O.bins_from_logits(logits.cpu())
+    assert float((bins[:, 0].cpu().long() == rb).float().mean()) > 0.99
+    assert torch.allclose(d[:, 0].cpu(), O.bins2dist(bins[:, 0].cpu().long(), 64), atol=1e-6)
+    pred = INF.predict_gap(gm, batch, d, samples=1, amp_dtype=None)
+    b2 = dict(add_scheme_fields(batch, with_3d=False))
+    b2["dist_input"] = d[:, 0]
+    with torch.no_grad():
+        ref = gm(b2)
+    assert torch.allclose(pred, ref.float(), rtol=1e-5, atol=1e-5)
+    assert pred.shape == (3,) and bool(torch.isfinite(pred).all())

@@ -133,3 +133,14 @@ def test_config1_known_answer(reference_lib):
     out = O.triplet_attention(_dbl(mod.state_dict()), e.double(), mask.double(), 8)
     assert abs(float(out.sum()) - kat["sum"]) < 1e-8 * max(1.0, abs(kat["abs_sum"]))
     assert abs(float(out.abs().sum()) - kat["abs_sum"]) < 1e-8 * kat["abs_sum"]
+
+
+def test_bins_decode_oracle_vs_golden():
+    """bins_from_logits / bins2dist against the fixture made by the reference's own predict_bins + BinsProcessor."""
+    fx = load_golden("bins_decode.pt")
+    S = fx["logits"].shape[1]
+    bins = torch.stack([O.bins_from_logits(fx["logits"][:, s]) for s in range(S)], 1)
+    assert torch.equal(bins.to(torch.int16), fx["bins"])
+    d = O.bins2dist(bins, fx["num_bins"], fx["range_bins"])
+    assert torch.equal(d, fx["dist"])
+    assert torch.equal(d, d.transpose(-1, -2)) and float(d.diagonal(dim1=-2, dim2=-1).abs().max()) == 0.0

@@ -42,6 +42,13 @@ int triplet_attn_fwd_simt(const tgt_triplet_attn_desc &, const void *, const flo
 int triplet_attn_bwd_simt(const tgt_triplet_attn_desc &, const void *, const float *, const void *, const void *,
                           const float *, void *, cudaStream_t);
 int triplet_aggr_fwd_simt(const tgt_triplet_aggr_desc &, const void *, const float *, void *, float *, cudaStream_t);
+int triplet_aggr_weights_simt(const tgt_triplet_aggr_desc &, const void *, const float *, float *, cudaStream_t);
+int triplet_aggr_bwd_weights_simt(const tgt_triplet_aggr_desc &, const void *, const float *, const float *, void *,
+                                  cudaStream_t);
+bool triplet_aggr_tma_supported(const tgt_triplet_aggr_desc &);
+int triplet_aggr_fwd_tma_launch(const tgt_triplet_aggr_desc &, const void *, void *, const float *, cudaStream_t);
+int triplet_aggr_bwd_tma_launch(const tgt_triplet_aggr_desc &, const void *, const void *, const float *, float *, void *,
+                                cudaStream_t);
 int triplet_aggr_bwd_simt(const tgt_triplet_aggr_desc &, const void *, const float *, const void *, const float *,
                           float *, void *, cudaStream_t);
 // triplet_mma.cu
@@ -177,14 +184,26 @@ static int aggr_check(const tgt_triplet_aggr_desc *D) {
   return 0;
 }
 
+// 16-bit, head dim 16: softmax/gate weights (O(N^2 H), SIMT) + tensor-core / TMA apply kernels (O(N^3), triplet_tma.cu);
+// kernel policy 1 and every other shape: the generic SIMT kernels
 extern "C" int tgt_triplet_aggr_fwd(const tgt_triplet_aggr_desc *D, const void *proj, const float *mask, void *va,
                                     float *aw, void *stream) {
   if (int e = aggr_check(D)) return e;
-  return triplet_aggr_fwd_simt(*D, proj, mask, va, aw, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (g_policy.load() != 1 && triplet_aggr_tma_supported(*D)) {
+    if (int e = triplet_aggr_weights_simt(*D, proj, mask, aw, st)) return e;
+    return triplet_aggr_fwd_tma_launch(*D, proj, va, aw, st);
+  }
+  return triplet_aggr_fwd_simt(*D, proj, mask, va, aw, st);
 }
 
 extern "C" int tgt_triplet_aggr_bwd(const tgt_triplet_aggr_desc *D, const void *proj, const float *mask,
                                     const void *dva, const float *aw, float *daw, void *dproj, void *stream) {
   if (int e = aggr_check(D)) return e;
-  return triplet_aggr_bwd_simt(*D, proj, mask, dva, aw, daw, dproj, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (g_policy.load() != 1 && triplet_aggr_tma_supported(*D)) {
+    if (int e = triplet_aggr_bwd_tma_launch(*D, proj, dva, aw, daw, dproj, st)) return e;
+    return triplet_aggr_bwd_weights_simt(*D, proj, mask, daw, dproj, st);
+  }
+  return triplet_aggr_bwd_simt(*D, proj, mask, dva, aw, daw, dproj, st);
 }

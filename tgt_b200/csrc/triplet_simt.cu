@@ -453,6 +453,122 @@ static int aggr_bwd_simt(const tgt_triplet_aggr_desc &D, const void *proj, const
   return check_launch("tri_aggr_bwd_weights");
 }
 
+// ------------------------------------------------------------------------------------------
+// aggregate weights, row-per-CTA versions: block (i, dir, b) reads the E | G values of its N edge rows as contiguous
+// H-wide segments (one 32-byte sector per row and block instead of 2-byte gathers per thread), transposes through shared
+// memory, and one warp per head runs the softmax over k with warp reductions.  Same arithmetic as tri_aggr_weights /
+// tri_aggr_bwd_weights (which remain the generic path for H > 32).
+// ------------------------------------------------------------------------------------------
+constexpr int AGW_LD = SIMT_MAX_N + 1;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+tri_aggr_weights_rows(const tgt_triplet_aggr_desc D, const T *__restrict__ proj, const float *__restrict__ mask,
+                      float *__restrict__ aw) {
+  extern __shared__ float sm[];
+  const int N = D.N, H = D.H;
+  const int i = blockIdx.x, dir = blockIdx.y, b = blockIdx.z;
+  constexpr bool ACC = sizeof(T) == 4;
+  const int64_t ld = D.ld;
+  const bool use_m = D.mask_dir[dir] != 0, has_g = D.off_g[dir] >= 0;
+  float *se = sm, *sg = sm + H * AGW_LD;
+  for (int idx = threadIdx.x; idx < N * H; idx += blockDim.x) {
+    const int k = idx / H, h = idx - k * H;
+    const int64_t brow = dir == 0 ? ((int64_t)(b * N + i) * N + k) : ((int64_t)(b * N + k) * N + i);
+    const float mk = use_m ? mask[brow] : 0.f;
+    se[h * AGW_LD + k] = to_f(proj[brow * ld + D.off_e[dir] + h]) + mk;
+    sg[h * AGW_LD + k] = has_g ? sigm<ACC>(to_f(proj[brow * ld + D.off_g[dir] + h]) + mk) : 1.f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  for (int h = threadIdx.x >> 5; h < H; h += blockDim.x >> 5) {
+    const float s0 = lane < N ? se[h * AGW_LD + lane] : -INFINITY;
+    const float s1 = lane + 32 < N ? se[h * AGW_LD + lane + 32] : -INFINITY;
+    const float m = warp_max(fmaxf(s0, s1));
+    const float p0 = lane < N ? expf(s0 - m) : 0.f, p1 = lane + 32 < N ? expf(s1 - m) : 0.f;
+    const float inv = 1.f / warp_sum(p0 + p1);
+    float *out = aw + (((int64_t)(b * 2 + dir) * H + h) * N + i) * N;
+    if (lane < N) out[lane] = p0 * inv * sg[h * AGW_LD + lane];
+    if (lane + 32 < N) out[lane + 32] = p1 * inv * sg[h * AGW_LD + lane + 32];
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+tri_aggr_bwd_weights_rows(const tgt_triplet_aggr_desc D, const T *__restrict__ proj, const float *__restrict__ mask,
+                          const float *__restrict__ daw, T *__restrict__ dproj) {
+  extern __shared__ float sm[];
+  const int N = D.N, H = D.H;
+  const int i = blockIdx.x, dir = blockIdx.y, b = blockIdx.z;
+  constexpr bool ACC = sizeof(T) == 4;
+  const int64_t ld = D.ld;
+  const bool use_m = D.mask_dir[dir] != 0, has_g = D.off_g[dir] >= 0;
+  float *se = sm, *sg = sm + H * AGW_LD;           // logits -> dE ; gates -> dG
+  for (int idx = threadIdx.x; idx < N * H; idx += blockDim.x) {
+    const int k = idx / H, h = idx - k * H;
+    const int64_t brow = dir == 0 ? ((int64_t)(b * N + i) * N + k) : ((int64_t)(b * N + k) * N + i);
+    const float mk = use_m ? mask[brow] : 0.f;
+    se[h * AGW_LD + k] = to_f(proj[brow * ld + D.off_e[dir] + h]) + mk;
+    sg[h * AGW_LD + k] = has_g ? sigm<ACC>(to_f(proj[brow * ld + D.off_g[dir] + h]) + mk) : 1.f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  for (int h = threadIdx.x >> 5; h < H; h += blockDim.x >> 5) {
+    const float *da = daw + (((int64_t)(b * 2 + dir) * H + h) * N + i) * N;
+    const bool v0 = lane < N, v1 = lane + 32 < N;
+    const float s0 = v0 ? se[h * AGW_LD + lane] : -INFINITY, s1 = v1 ? se[h * AGW_LD + lane + 32] : -INFINITY;
+    const float m = warp_max(fmaxf(s0, s1));
+    float p0 = v0 ? expf(s0 - m) : 0.f, p1 = v1 ? expf(s1 - m) : 0.f;
+    const float inv = 1.f / warp_sum(p0 + p1);
+    p0 *= inv;
+    p1 *= inv;
+    const float g0 = v0 ? sg[h * AGW_LD + lane] : 0.f, g1 = v1 ? sg[h * AGW_LD + lane + 32] : 0.f;
+    const float d0 = v0 ? da[lane] : 0.f, d1 = v1 ? da[lane + 32] : 0.f;
+    const float delta = warp_sum(d0 * g0 * p0 + d1 * g1 * p1);
+    if (v0) {
+      se[h * AGW_LD + lane] = p0 * (d0 * g0 - delta);
+      sg[h * AGW_LD + lane] = d0 * p0 * g0 * (1.f - g0);
+    }
+    if (v1) {
+      se[h * AGW_LD + lane + 32] = p1 * (d1 * g1 - delta);
+      sg[h * AGW_LD + lane + 32] = d1 * p1 * g1 * (1.f - g1);
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < N * H; idx += blockDim.x) {
+    const int k = idx / H, h = idx - k * H;
+    const int64_t brow = dir == 0 ? ((int64_t)(b * N + i) * N + k) : ((int64_t)(b * N + k) * N + i);
+    dproj[brow * ld + D.off_e[dir] + h] = from_f<T>(se[h * AGW_LD + k]);
+    if (has_g) dproj[brow * ld + D.off_g[dir] + h] = from_f<T>(sg[h * AGW_LD + k]);
+  }
+}
+
+// the O(N^2 H) halves alone (softmax / gate weights and their backward): the tensor-core apply kernels of triplet_tma.cu
+// sit between them
+int triplet_aggr_weights_simt(const tgt_triplet_aggr_desc &D, const void *proj, const float *mask, float *aw,
+                              cudaStream_t st) {
+  if (D.H <= 32) {
+    const size_t smem = 2 * (size_t)D.H * AGW_LD * sizeof(float);
+    TGT_DISPATCH_DTYPE(D.dtype, T, tri_aggr_weights_rows<T><<<dim3(D.N, 2, D.B), 256, smem, st>>>(D, (const T *)proj, mask, aw));
+    return check_launch("tri_aggr_weights_rows");
+  }
+  TGT_DISPATCH_DTYPE(D.dtype, T,
+                     tri_aggr_weights<T><<<dim3(D.H, 2, D.B), SIMT_MAX_N, 0, st>>>(D, (const T *)proj, mask, aw));
+  return check_launch("tri_aggr_weights");
+}
+int triplet_aggr_bwd_weights_simt(const tgt_triplet_aggr_desc &D, const void *proj, const float *mask, const float *daw,
+                                  void *dproj, cudaStream_t st) {
+  if (D.H <= 32) {
+    const size_t smem = 2 * (size_t)D.H * AGW_LD * sizeof(float);
+    TGT_DISPATCH_DTYPE(D.dtype, T, tri_aggr_bwd_weights_rows<T><<<dim3(D.N, 2, D.B), 256, smem, st>>>(
+                                       D, (const T *)proj, mask, daw, (T *)dproj));
+    return check_launch("tri_aggr_bwd_weights_rows");
+  }
+  TGT_DISPATCH_DTYPE(D.dtype, T, tri_aggr_bwd_weights<T><<<dim3(D.H, 2, D.B), SIMT_MAX_N, 0, st>>>(
+                                     D, (const T *)proj, mask, daw, (T *)dproj));
+  return check_launch("tri_aggr_bwd_weights");
+}
+
 int triplet_aggr_fwd_simt(const tgt_triplet_aggr_desc &D, const void *proj, const float *mask, void *va,
                           float *aw, cudaStream_t st) {
   TGT_DISPATCH_DTYPE(D.dtype, T, return aggr_fwd_simt<T>(D, proj, mask, va, aw, st));

@@ -1462,6 +1462,251 @@ static int bwd_tma_impl(const tgt_triplet_attn_desc &D, const void *proj, const 
   return check_launch("tri_attn_bwd_tma");
 }
 
+// ------------------------------------------------------------------------------------------------ TripletAggregate (TGT-Agx2)
+// Va[b,i,j,dir,h,:] = sum_k A[i,k] V[keyrow(j,k)][h,:]  (triplet.py:61, 68) is the "P V" half of the attention kernel with
+// weights A that do not depend on the junction j: one CTA = (head, direction, graph) holds A (64 x 64, 16-bit) as mma
+// A-fragments in registers for all N junctions and streams the V tiles through the same TMA ring / stmatrix / TMA store
+// path as tri_attn_fwd_tma.  Per junction a CTA moves 2 KB in and 2 KB out and issues 32 mma: purely HBM-bound.
+// Backward: dV_j = A^T dO_j (A^T fragments resident) and dA += dO_j V_j^T accumulated over j in registers.
+template <typename T>
+__device__ __forceinline__ void load_aw_frags(uint32_t (&pa)[4][4], const float *__restrict__ a, int N, int m0, int g, int q,
+                                              bool transpose) {
+  // pa[t] = A-fragment of rows m0..m0+15, columns 16t..16t+15 of A (or of A^T), zero beyond N
+  auto at = [&](int r, int c) -> float {
+    if (r >= N || c >= N) return 0.f;
+    return transpose ? a[(int64_t)c * N + r] : a[(int64_t)r * N + c];
+  };
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int c0 = 16 * t + 2 * q;
+    pa[t][0] = Mma<T>::pack(at(m0 + g, c0), at(m0 + g, c0 + 1));
+    pa[t][1] = Mma<T>::pack(at(m0 + g + 8, c0), at(m0 + g + 8, c0 + 1));
+    pa[t][2] = Mma<T>::pack(at(m0 + g, c0 + 8), at(m0 + g, c0 + 9));
+    pa[t][3] = Mma<T>::pack(at(m0 + g + 8, c0 + 8), at(m0 + g + 8, c0 + 9));
+  }
+}
+
+constexpr int TA_STAGES = 4;
+constexpr int TA_SMEM = TA_STAGES * TILE_BYTES + 2 * TILE_BYTES + 64 + 1024;
+
+template <typename T>
+__global__ void __launch_bounds__(128, 6)
+tri_aggr_fwd_tma(const tgt_triplet_aggr_desc D, const __grid_constant__ CUtensorMap mPcol,
+                 const __grid_constant__ CUtensorMap mProw, const __grid_constant__ CUtensorMap mVA,
+                 const float *__restrict__ aw) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int N = D.N, H = D.H;
+  const int h = blockIdx.x, dir = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const int m0 = warp * 16;
+  const uint32_t sOut = sbase + TA_STAGES * TILE_BYTES;
+  const uint32_t bar_full = sOut + 2 * TILE_BYTES;
+  if (tid == 0) {
+    tma_prefetch_desc(&mPcol);
+    tma_prefetch_desc(&mProw);
+    tma_prefetch_desc(&mVA);
+    for (int s = 0; s < TA_STAGES; ++s) mbar_init(bar_full + s * 8, 1);
+    fence_barrier_init();
+  }
+  uint32_t pa[4][4];
+  load_aw_frags<T>(pa, aw + ((int64_t)(b * 2 + dir) * H + h) * N * N, N, m0, g, q, false);
+  const int cv = D.off_v[dir] + h * HD, co = dir * H * HD + h * HD;
+  auto issue = [&](int j) {                   // thread 0 only
+    if (j < N) {
+      const uint32_t st = sbase + (j % TA_STAGES) * TILE_BYTES, bar = bar_full + (j % TA_STAGES) * 8;
+      mbar_expect_tx(bar, TILE_BYTES);
+      if (dir == 0) tma_load_4d(&mProw, bar, st, cv, 0, j, b);
+      else tma_load_4d(&mPcol, bar, st, cv, j, 0, b);
+    }
+  };
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < TA_STAGES - 1; ++s) issue(s);
+  }
+  for (int j = 0; j < N; ++j) {
+    if (tid == 0) tma_store_wait_read();            // the output tile written two iterations ago has left smem
+    mbar_wait(bar_full + (j % TA_STAGES) * 8, (uint32_t)((j / TA_STAGES) & 1));
+    __syncthreads();                                // stage j landed; everyone is done with iteration j-1
+    if (tid == 0) {
+      issue(j + TA_STAGES - 1);
+      if (j > 0) {
+        tma_store_4d(&mVA, sOut + ((j - 1) & 1) * TILE_BYTES, co, j - 1, 0, b);
+        tma_store_commit();
+      }
+    }
+    const uint32_t sV = sbase + (j % TA_STAGES) * TILE_BYTES;
+    float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      uint32_t vb[4];
+      load_b_kn(vb, sV, t * 16, lane);
+      Mma<T>::run(o[0], pa[t], vb[0], vb[1]);
+      Mma<T>::run(o[1], pa[t], vb[2], vb[3]);
+    }
+    store_c_tile<T>(sOut + (j & 1) * TILE_BYTES, m0, lane, o, 1.f);
+    fence_proxy_async();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    tma_store_4d(&mVA, sOut + ((N - 1) & 1) * TILE_BYTES, co, N - 1, 0, b);
+    tma_store_commit();
+    tma_store_wait_all();
+  }
+}
+
+constexpr int TAB_STAGES = 4;
+constexpr int TAB_STAGE_BYTES = 2 * TILE_BYTES;               // V, dO
+constexpr int TAB_SMEM = TAB_STAGES * TAB_STAGE_BYTES + 2 * TILE_BYTES + 64 + 1024;
+
+template <typename T>
+__global__ void __launch_bounds__(128, 4)
+tri_aggr_bwd_tma(const tgt_triplet_aggr_desc D, const __grid_constant__ CUtensorMap mPcol,
+                 const __grid_constant__ CUtensorMap mProw, const __grid_constant__ CUtensorMap mDVA,
+                 const __grid_constant__ CUtensorMap mDPcol, const __grid_constant__ CUtensorMap mDProw,
+                 const float *__restrict__ aw, float *__restrict__ daw) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int N = D.N, H = D.H;
+  const int h = blockIdx.x, dir = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const int m0 = warp * 16;
+  const uint32_t sOut = sbase + TAB_STAGES * TAB_STAGE_BYTES;
+  const uint32_t bar_full = sOut + 2 * TILE_BYTES;
+  if (tid == 0) {
+    tma_prefetch_desc(&mPcol);
+    tma_prefetch_desc(&mProw);
+    tma_prefetch_desc(&mDVA);
+    tma_prefetch_desc(&mDPcol);
+    tma_prefetch_desc(&mDProw);
+    for (int s = 0; s < TAB_STAGES; ++s) mbar_init(bar_full + s * 8, 1);
+    fence_barrier_init();
+  }
+  const int64_t abase = ((int64_t)(b * 2 + dir) * H + h) * N * N;
+  uint32_t pat[4][4];                          // A^T: rows = keys m0.., columns = queries
+  load_aw_frags<T>(pat, aw + abase, N, m0, g, q, true);
+  float da[8][4];                              // dA[i = m0 + g (+8)][k]: sum over j of dO_j V_j^T
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) da[nt][0] = da[nt][1] = da[nt][2] = da[nt][3] = 0.f;
+  const int cv = D.off_v[dir] + h * HD, co = dir * H * HD + h * HD;
+  auto issue = [&](int j) {                   // thread 0 only
+    if (j < N) {
+      const uint32_t st = sbase + (j % TAB_STAGES) * TAB_STAGE_BYTES, bar = bar_full + (j % TAB_STAGES) * 8;
+      mbar_expect_tx(bar, TAB_STAGE_BYTES);
+      if (dir == 0) tma_load_4d(&mProw, bar, st, cv, 0, j, b);
+      else tma_load_4d(&mPcol, bar, st, cv, j, 0, b);
+      tma_load_4d(&mDVA, bar, st + TILE_BYTES, co, j, 0, b);
+    }
+  };
+  auto store_dv = [&](int j) {                // thread 0 only
+    if (dir == 0) tma_store_4d(&mDProw, sOut + (j & 1) * TILE_BYTES, cv, 0, j, b);
+    else tma_store_4d(&mDPcol, sOut + (j & 1) * TILE_BYTES, cv, j, 0, b);
+    tma_store_commit();
+  };
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < TAB_STAGES - 1; ++s) issue(s);
+  }
+  for (int j = 0; j < N; ++j) {
+    if (tid == 0) tma_store_wait_read();
+    mbar_wait(bar_full + (j % TAB_STAGES) * 8, (uint32_t)((j / TAB_STAGES) & 1));
+    __syncthreads();
+    if (tid == 0) {
+      issue(j + TAB_STAGES - 1);
+      if (j > 0) store_dv(j - 1);
+    }
+    const uint32_t sV = sbase + (j % TAB_STAGES) * TAB_STAGE_BYTES, sO = sV + TILE_BYTES;
+    // dA += dO_j V_j^T   (rows of this warp x all 64 keys)
+    uint32_t oa[4];
+    load_a_rows(oa, sO, m0, lane);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      uint32_t vb[4];
+      load_b_nk(vb, sV, p * 16, lane);
+      Mma<T>::run(da[2 * p], oa, vb[0], vb[1]);
+      Mma<T>::run(da[2 * p + 1], oa, vb[2], vb[3]);
+    }
+    // dV_j = A^T dO_j    (this warp owns keys m0 .. m0+15)
+    float dv[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      uint32_t ob[4];
+      load_b_kn(ob, sO, t * 16, lane);
+      Mma<T>::run(dv[0], pat[t], ob[0], ob[1]);
+      Mma<T>::run(dv[1], pat[t], ob[2], ob[3]);
+    }
+    store_c_tile<T>(sOut + (j & 1) * TILE_BYTES, m0, lane, dv, 1.f);
+    fence_proxy_async();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    store_dv(N - 1);
+    tma_store_wait_all();
+  }
+  float *o = daw + abase;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const int c = nt * 8 + 2 * q;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int i = m0 + g + (e >> 1) * 8, k = c + (e & 1);
+      if (i < N && k < N) o[(int64_t)i * N + k] = da[nt][e];
+    }
+  }
+}
+
+bool triplet_aggr_tma_supported(const tgt_triplet_aggr_desc &D) {
+  if (D.dtype != TGT_BF16 && D.dtype != TGT_F16) return false;
+  if (D.d != HD || D.N > TN || (D.ld % 8)) return false;
+  if ((D.off_v[0] % 8) || (D.off_v[1] % 8)) return false;
+  return encode_tiled_fn() != nullptr;
+}
+
+template <typename T>
+static int aggr_fwd_tma_impl(const tgt_triplet_aggr_desc &D, const void *proj, void *va, const float *aw, cudaStream_t st) {
+  CUtensorMap mPcol, mProw, mVA;
+  const int C = (int)D.ld, Cv = 2 * D.H * HD;
+  if (int e = make_tile_map(&mPcol, proj, D.B, D.N, C, D.ld, true, D.dtype)) return e;
+  if (int e = make_tile_map(&mProw, proj, D.B, D.N, C, D.ld, false, D.dtype)) return e;
+  if (int e = make_tile_map(&mVA, va, D.B, D.N, Cv, Cv, true, D.dtype)) return e;
+  static std::once_flag once;
+  std::call_once(once, [] { cudaFuncSetAttribute(tri_aggr_fwd_tma<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM); });
+  KernelTimerScope ts("tri_aggr_fwd_tma", st);
+  tri_aggr_fwd_tma<T><<<dim3(D.H, 2, D.B), 128, TA_SMEM, st>>>(D, mPcol, mProw, mVA, aw);
+  return check_launch("tri_aggr_fwd_tma");
+}
+
+template <typename T>
+static int aggr_bwd_tma_impl(const tgt_triplet_aggr_desc &D, const void *proj, const void *dva, const float *aw, float *daw,
+                             void *dproj, cudaStream_t st) {
+  CUtensorMap mPcol, mProw, mDVA, mDPcol, mDProw;
+  const int C = (int)D.ld, Cv = 2 * D.H * HD;
+  if (int e = make_tile_map(&mPcol, proj, D.B, D.N, C, D.ld, true, D.dtype)) return e;
+  if (int e = make_tile_map(&mProw, proj, D.B, D.N, C, D.ld, false, D.dtype)) return e;
+  if (int e = make_tile_map(&mDVA, dva, D.B, D.N, Cv, Cv, true, D.dtype)) return e;
+  if (int e = make_tile_map(&mDPcol, dproj, D.B, D.N, C, D.ld, true, D.dtype)) return e;
+  if (int e = make_tile_map(&mDProw, dproj, D.B, D.N, C, D.ld, false, D.dtype)) return e;
+  static std::once_flag once;
+  std::call_once(once, [] { cudaFuncSetAttribute(tri_aggr_bwd_tma<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAB_SMEM); });
+  KernelTimerScope ts("tri_aggr_bwd_tma", st);
+  tri_aggr_bwd_tma<T><<<dim3(D.H, 2, D.B), 128, TAB_SMEM, st>>>(D, mPcol, mProw, mDVA, mDPcol, mDProw, aw, daw);
+  return check_launch("tri_aggr_bwd_tma");
+}
+
+int triplet_aggr_fwd_tma_launch(const tgt_triplet_aggr_desc &D, const void *proj, void *va, const float *aw, cudaStream_t st) {
+  if (D.dtype == TGT_BF16) return aggr_fwd_tma_impl<__nv_bfloat16>(D, proj, va, aw, st);
+  return aggr_fwd_tma_impl<__half>(D, proj, va, aw, st);
+}
+int triplet_aggr_bwd_tma_launch(const tgt_triplet_aggr_desc &D, const void *proj, const void *dva, const float *aw, float *daw,
+                                void *dproj, cudaStream_t st) {
+  if (D.dtype == TGT_BF16) return aggr_bwd_tma_impl<__nv_bfloat16>(D, proj, dva, aw, daw, dproj, st);
+  return aggr_bwd_tma_impl<__half>(D, proj, dva, aw, daw, dproj, st);
+}
+
 int triplet_attn_fwd_tma_launch(const tgt_triplet_attn_desc &D, const void *proj, void *va, float *stats,
                                 const float *ws_e, const __half *ws_g, cudaStream_t st) {
   if (D.dtype == TGT_BF16) return fwd_tma_impl<__nv_bfloat16>(D, proj, va, stats, ws_e, ws_g, st);

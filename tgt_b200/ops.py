@@ -1055,3 +1055,23 @@ class GaussianBasisFn(Function):
                                                  _C.stream_ptr()), "gaussian_basis_bwd")
         d = ctx.dts
         return dx.to(d[0]), dms[0].to(d[1]), dms[1].to(d[2]), None
+
+
+# ------------------------------------------------------------------------------------------
+# two-stage inference: logits -> symmetrised argmax bins -> distances, one kernel
+# (dist_pred/scheme.py:186-194 + commons.py:72-82)
+# ------------------------------------------------------------------------------------------
+def bins_decode(logits: Tensor, range_bins: float = 8.0, shift_half: bool = True, zero_diag: bool = True,
+                want_bins: bool = True):
+    """logits [B,N,N,num_bins] (16-bit or fp32) -> (bins int16 [B,N,N] or None, dist_input fp32 [B,N,N])."""
+    _require_cuda(logits)
+    B, N, N2, nb = logits.shape
+    assert N == N2
+    lg = logits.detach().contiguous()
+    bins = torch.empty((B, N, N), dtype=torch.int16, device=lg.device) if want_bins else None
+    dist = torch.empty((B, N, N), dtype=torch.float32, device=lg.device)
+    with timed("bins_decode"):
+        _C.check(_C.lib().tgt_bins_decode(_C.ptr(lg), _C.ptr(bins), _C.ptr(dist), B, N, nb, range_bins / (nb - 1),
+                                          int(shift_half), int(zero_diag), _C.dtype_code(lg.dtype), _C.stream_ptr()),
+                 "bins_decode")
+    return bins, dist

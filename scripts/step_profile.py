@@ -22,6 +22,7 @@ ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--nodes", type=int, default=64)
 ap.add_argument("--layers", type=int, default=24)
 ap.add_argument("--top", type=int, default=70)
+ap.add_argument("--width", type=int, default=100)
 a = ap.parse_args()
 a.fp32_logits = False
 dev = torch.device("cuda", 0)
@@ -57,7 +58,7 @@ agg = defaultdict(lambda: [0, 0.0])
 for ev in prof.events():
     if ev.device_type == torch.autograd.DeviceType.CUDA:
         name = re.sub(r"^void ", "", ev.name)
-        name = re.sub(r"\(.*", "", name)[:100]
+        name = (re.sub(r"\(.*", "", name) if "tgt::" in name or "nvjet" in name else name)[:a.width]
         agg[name][0] += 1
         agg[name][1] += ev.device_time
 tot = sum(v[1] for v in agg.values()) / 1e3

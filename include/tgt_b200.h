@@ -248,8 +248,13 @@ typedef struct {
   float stat_eps;
   const void *res2;               /* TGT_EPI_LN_BWD | TGT_EPI_RES */
   int64_t ldres2;
+  void *stat_partial;             /* TGT_EPI_STATS with more than one column slice (tgt_gemm_tc_slices): workspace of
+                                   * slices * M * 8 bytes for the per-slice (sum, sum of squares); a tiny second kernel
+                                   * then writes stat_mean / stat_rstd                                              */
 } tgt_gemm_desc;
 int tgt_gemm_tc(const tgt_gemm_desc *desc, const void *A, const void *B, void *D, void *stream);
+/* number of column slices tgt_gemm_tc cuts an [M,N] output into for this K and epilogue */
+int tgt_gemm_tc_slices(int N, int K, int flags);
 
 /* per-row LayerNorm statistics of x:[rows,W] (16-bit, pitch ldx): mean, rstd = 1/sqrt(var + eps)   */
 int tgt_row_stats(const void *x, float *mean, float *rstd, int64_t rows, int W, int64_t ldx, float eps,

@@ -135,7 +135,7 @@ def test_linear_residual_bwd_matches_autograd():
     _close(db, b.grad, 8e-3)
 
 
-@pytest.mark.parametrize("N,K", [(256, 256), (256, 64), (64, 128)])
+@pytest.mark.parametrize("N,K", [(256, 256), (256, 64), (64, 128), (256, 512), (192, 448)])   # K > 256: two column slices
 def test_gemm_output_row_stats(N, K):
     """EPI_STATS: mean / rstd of the rows the residual GEMM writes == LayerNorm statistics of its (rounded) output."""
     ops = _ops()

@@ -269,6 +269,22 @@ def test_rowwise_kernels():
         dx, dg, db = ops.layernorm_bwd(dy, x, g, mean, rstd)
         assert max_rel(dx.float(), xr.grad) < (1e-5 if xdt == torch.float32 else 2e-2)
         assert max_rel(dg, gr.grad) < 1e-4 and max_rel(db, br.grad) < 1e-4
+    # LayerNorm backward that also emits the augmented y = [LN(x) | 1 | 0..] (tgt_layernorm_bwd_y, W = 256, 16-bit dy):
+    # same dx / dgamma / dbeta as the plain call, y equal to the forward kernel's output for the same statistics
+    for xdt in (torch.bfloat16, torch.float32):
+        x = torch.randn(777, 256, device=DEV).to(xdt)
+        g = torch.rand(256, device=DEV) + 0.5
+        b = torch.randn(256, device=DEV)
+        dy = torch.randn(777, 256, device=DEV).bfloat16()
+        dres = torch.randn(777, 256, device=DEV).to(xdt)
+        assert ops.ln_bwd_emits_y(x, torch.bfloat16)
+        yf, mean, rstd = ops.layernorm_fwd(x, g, b, torch.bfloat16, aug=True)
+        dx0, dg0, db0 = ops.layernorm_bwd(dy, x, g, mean, rstd, dres)
+        dx1, dg1, db1, y1 = ops.layernorm_bwd(dy, x, g, mean, rstd, dres, beta=b)
+        assert torch.equal(dx0, dx1) and max_rel(dg1, dg0) < 1e-5 and max_rel(db1, db0) < 1e-5
+        assert y1.shape == (777, 264) and torch.equal(y1, yf)
+    assert not ops.ln_bwd_emits_y(torch.empty(4, 768), torch.bfloat16)
+    assert not ops.ln_bwd_emits_y(torch.empty(4, 256), torch.float32)
     # gelu + dropout: p=0 equals F.gelu; p>0 keeps ~(1-p), scales by 1/(1-p), fwd/bwd masks agree
     u = torch.randn(4096, 256, device=DEV)
     y = torch.empty_like(u)

@@ -63,7 +63,7 @@ class GemmDesc(C.Structure):
                 ("U", C.c_void_p), ("ldu", C.c_int64),
                 ("p_drop", C.c_float), ("seed", C.c_uint64),
                 ("stat_mean", C.c_void_p), ("stat_rstd", C.c_void_p), ("stat_eps", C.c_float),
-                ("res2", C.c_void_p), ("ldres2", C.c_int64)]
+                ("res2", C.c_void_p), ("ldres2", C.c_int64), ("stat_partial", C.c_void_p)]
 
 
 EPI_LN, EPI_BIAS, EPI_GELU, EPI_RES, EPI_STORE_U, EPI_ROWSCALE, EPI_GELU_BWD, EPI_STATS, EPI_LN_BWD = 1, 2, 4, 8, 16, 64, 128, 256, 512
@@ -98,6 +98,7 @@ _SIGNATURES = {
     "tgt_gelu_dropout_fwd": (C.c_int, [_P, _P, C.c_int64, C.c_float, C.c_uint64, C.c_int, _P]),
     "tgt_gelu_dropout_bwd": (C.c_int, [_P, _P, _P, C.c_int64, C.c_float, C.c_uint64, C.c_int, _P]),
     "tgt_gemm_tc": (C.c_int, [C.POINTER(GemmDesc), _P, _P, _P, _P]),
+    "tgt_gemm_tc_slices": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "tgt_row_stats": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, C.c_int64, C.c_float, C.c_int, _P]),
     "tgt_gaussian_basis_fwd": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, _P]),
     "tgt_gaussian_basis_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, _P]),

@@ -549,10 +549,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const int64_t grow = row0 + it * 8 + crow;
               if (grow < p.M) {
                 const float2 o = other[it * 8 + crow];
-                const float mu = (st1[it] + o.x) * inv_n;
-                const float var = fmaxf((st2[it] + o.y) * inv_n - mu * mu, 0.f);
-                p.stat_mean[grow] = mu;
-                p.stat_rstd[grow] = rsqrtf(var + p.stat_eps);
+                if (p.n_slices > 1) {
+                  // the row spans several column slices (CTAs): emit this slice's (sum, sum of squares); stat_mean is a
+                  // [n_slices][M] float2 buffer here and stats_finalize_kernel turns the partials into mean / rstd
+                  reinterpret_cast<float2 *>(p.stat_mean)[(int64_t)slice * p.M + grow] = make_float2(st1[it] + o.x, st2[it] + o.y);
+                } else {
+                  const float mu = (st1[it] + o.x) * inv_n;
+                  const float var = fmaxf((st2[it] + o.y) * inv_n - mu * mu, 0.f);
+                  p.stat_mean[grow] = mu;
+                  p.stat_rstd[grow] = rsqrtf(var + p.stat_eps);
+                }
               }
             }
           }
@@ -567,6 +573,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 2) {
     tc_fence_after();
     tc_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// (sum, sum of squares) partials of the column slices of a multi-slice TGT_EPI_STATS GEMM -> mean / rstd
+__global__ void __launch_bounds__(256) stats_finalize_kernel(const float2 *__restrict__ part, int n_slices, int64_t M, float inv_n,
+                                                             float eps, float *__restrict__ mean, float *__restrict__ rstd) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < M; r += (int64_t)gridDim.x * blockDim.x) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int s = 0; s < n_slices; ++s) {
+      const float2 v = part[(int64_t)s * M + r];
+      s1 += v.x;
+      s2 += v.y;
+    }
+    const float mu = s1 * inv_n;
+    mean[r] = mu;
+    rstd[r] = rsqrtf(fmaxf(s2 * inv_n - mu * mu, 0.f) + eps);
   }
 }
 
@@ -764,9 +786,11 @@ extern "C" int tgt_gemm_tc(const tgt_gemm_desc *g, const void *A, const void *B,
     p.ldres2 = g->ldres2;
   }
   if (flags & EPI_STATS) {
-    if (p.n_slices != 1 || p.bn < g->N || !g->stat_mean || !g->stat_rstd)
-      return fail("gemm_tc: STATS epilogue needs N <= 256 (one column slice) and the two output vectors");
-    p.stat_mean = g->stat_mean;
+    if (!g->stat_mean || !g->stat_rstd) return fail("gemm_tc: STATS epilogue needs the two output vectors");
+    if (p.n_slices != 1 && !g->stat_partial)
+      return fail("gemm_tc: STATS epilogue over %d column slices needs the stat_partial workspace (%d x M float2)", p.n_slices,
+                  p.n_slices);
+    p.stat_mean = p.n_slices != 1 ? reinterpret_cast<float *>(g->stat_partial) : g->stat_mean;
     p.stat_rstd = g->stat_rstd;
     p.stat_eps = g->stat_eps;
   }
@@ -776,8 +800,21 @@ extern "C" int tgt_gemm_tc(const tgt_gemm_desc *g, const void *A, const void *B,
   if (int e = make_operand_map(&mb, B, g->N, g->K, g->ldb, p.bn, g->dtype)) return e;
   const size_t smem = (size_t)p.kblocks * p.bn * 128 + (size_t)p.stages * A_STAGE_BYTES + epi_stage_bytes(flags) + 2048 + 4096 + 256 + 1024;
   cudaStream_t st = (cudaStream_t)stream;
-  if (g->dtype == TGT_BF16) return dispatch_gemm<__nv_bfloat16>(ma, mb, p, smem, st);
-  return dispatch_gemm<__half>(ma, mb, p, smem, st);
+  const int rc = g->dtype == TGT_BF16 ? dispatch_gemm<__nv_bfloat16>(ma, mb, p, smem, st) : dispatch_gemm<__half>(ma, mb, p, smem, st);
+  if (rc || !(flags & EPI_STATS) || p.n_slices == 1) return rc;
+  const int blocks = (int)std::min<int64_t>((g->M + 255) / 256, (int64_t)num_sms() * 8);
+  stats_finalize_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float2 *>(g->stat_partial), p.n_slices, g->M,
+                                                1.f / (float)g->N, g->stat_eps, g->stat_mean, g->stat_rstd);
+  return check_launch("stats_finalize");
+}
+
+extern "C" int tgt_gemm_tc_slices(int N, int K, int flags) {
+  // number of column slices tgt_gemm_tc cuts N into (callers size the stat_partial workspace with it)
+  const int kblocks = (K + 63) / 64;
+  const int smem_budget = 232448 - 1024 - 2048 - 4096 - 256 - epi_stage_bytes(flags);
+  int bn_max = 256;
+  while (bn_max > 16 && kblocks * bn_max * 128 + 3 * A_STAGE_BYTES > smem_budget) bn_max -= 16;
+  return (N + bn_max - 1) / bn_max;
 }
 
 extern "C" int tgt_row_stats(const void *x, float *mean, float *rstd, int64_t rows, int W, int64_t ldx, float eps,

@@ -631,7 +631,7 @@ static int ln_bwd_launch(const void *dy, const void *x, const float *gamma, cons
     }
   }
   if (y) return fail("layernorm_bwd_y: only the W = 256, 16-bit gradient fast path can emit y");
-  int g = grid_for(rows, 8 * 16);
+  int g = grid_for(rows, 8 * 4);            // few rows per warp: node-side tensors have only B*N rows
   if (g > 148 * 4) g = 148 * 4;
   ln_bwd_kernel<XT, YT><<<g, 256, 2 * W * sizeof(float), st>>>((const YT *)dy, (const XT *)x, gamma, mean, rstd,
                                                                (const XT *)dres, (XT *)dx, dgamma, dbeta, rows, W);

@@ -61,7 +61,11 @@ class EGT_Attention(nn.Module):
         """(h_out, H_hat, alias of e): everything except the edge output projection."""
         cd = ops.compute_dtype(e)
         # node side: small [B*N, Wn] GEMMs -- plain library calls
-        qkv = self.lin_QKV(self.mha_ln_h(h))
+        if h.is_cuda:
+            qkv = ops.LNLinearFn.apply(h, self.mha_ln_h.weight, self.mha_ln_h.bias, self.lin_QKV.weight,
+                                       self.lin_QKV.bias, cd)[0]
+        else:
+            qkv = self.lin_QKV(self.mha_ln_h(h))
         # edge side: LN + projection to 2H channels (LN output recomputed in backward)
         eg, e_alias = ops.LNLinearFn.apply(e, self.mha_ln_e.weight, self.mha_ln_e.bias, self.lin_EG.weight,
                                            self.lin_EG.bias, cd)
@@ -105,7 +109,11 @@ class EdgeUpdate(nn.Module):
 
     def forward_parts(self, h, e, mask):
         cd = ops.compute_dtype(e)
-        qk = self.lin_QK(self.mha_ln_h(h))
+        if h.is_cuda:
+            qk = ops.LNLinearFn.apply(h, self.mha_ln_h.weight, self.mha_ln_h.bias, self.lin_QK.weight,
+                                      self.lin_QK.bias, cd)[0]
+        else:
+            qk = self.lin_QK(self.mha_ln_h(h))
         eb, e_alias = ops.LNLinearFn.apply(e, self.mha_ln_e.weight, self.mha_ln_e.bias, self.lin_E.weight,
                                            self.lin_E.bias, cd)
         hhat = ops.EGTCoreFn.apply(qk, eb, mask, None, self.num_heads, False, False, cd)

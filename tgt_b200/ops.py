@@ -225,9 +225,14 @@ def gemm_tc(a: Tensor, w: Tensor, *, bias: Optional[Tensor] = None, ln: Optional
         if len(ln_bwd) > 4 and ln_bwd[4] is not None:
             flags |= _C.EPI_RES
             g.res2, g.ldres2 = ln_bwd[4].data_ptr(), ln_bwd[4].stride(0)
+    part = None
     if stats_out is not None:
         flags |= _C.EPI_STATS
         g.stat_mean, g.stat_rstd, g.stat_eps = stats_out[0].data_ptr(), stats_out[1].data_ptr(), 1e-5
+        n_sl = _C.lib().tgt_gemm_tc_slices(N, K, flags | (_C.EPI_RES if res is not None else 0))
+        if n_sl > 1:            # rows span several column slices: per-slice partial sums + a finalize kernel (in the library)
+            part = torch.empty((n_sl, M, 2), dtype=torch.float32, device=a.device)
+            g.stat_partial = part.data_ptr()
     g.flags = flags
     with timed(name):
         _C.check(_C.lib().tgt_gemm_tc(g, _C.ptr(a), _C.ptr(w), _C.ptr(out), _C.stream_ptr()), "gemm_tc")
@@ -292,8 +297,9 @@ def linear_residual(a2: Tensor, Wc: Tensor, bias: Tensor, res2: Optional[Tensor]
             res2.dtype in (a2.dtype, torch.float32) and res2.stride(1) == 1 and res2.stride(0) % 8 == 0)):
         rps = M // scale.numel() if scale is not None else 0
         stats = None
-        # the statistics epilogue needs the whole output row in one CTA: the [N, K] weight panel must fit in smem
-        if want_stats and res2 is not None and N <= 256 and ((K + 63) // 64) * ((N + 15) // 16 * 16) * 128 <= 159000:
+        # statistics of the output rows from the epilogue (rows that span several column slices, e.g. lin_O with K = 512,
+        # go through per-slice partial sums and a finalize kernel: still no pass over the edge-sized tensor)
+        if want_stats and res2 is not None and N <= 256:
             stats = (torch.empty(M, dtype=torch.float32, device=a2.device),
                      torch.empty(M, dtype=torch.float32, device=a2.device))
         gemm_tc(a2, Wc, bias=bias.detach().float().contiguous(), res=res2,

@@ -63,13 +63,17 @@ int tgt_layernorm_bwd(const void *dy, const void *x, const float *gamma, const f
                       const float *rstd, const void *dres, void *dx, float *dgamma, float *dbeta,
                       int64_t rows, int W, int x_dtype, int y_dtype, void *stream);
 
-/* Same, and also emits y = LN(x) as [rows, ldy] in y_dtype (ldy = W or W + 8 with the augmentation columns of
- * tgt_layernorm_fwd): the normalised rows are in registers anyway, so the weight-gradient GEMM of the Linear that
- * follows the LayerNorm needs no separate recompute pass.  W = 256 and 16-bit y only (else an error).           */
+/* Same, with by-products of the pass (W = 256 and 16-bit dy only, else an error):
+ *  y (or NULL)          : y = LN(x) as [rows, ldy] in y_dtype (ldy = W or W + 8 with the augmentation columns of
+ *                         tgt_layernorm_fwd) -- the weight-gradient GEMM of the Linear behind the LayerNorm then needs
+ *                         no recompute pass; needs beta;
+ *  dres_colsum (or NULL): [W] f32, ZERO on entry: += sum_r w_r * dres[r,:], w_r = res_row_scale[r / rows_per_scale]
+ *                         (1 when res_row_scale is NULL) -- dres is the upstream gradient of the module this LayerNorm
+ *                         opens, so this is the (DropPath-weighted) bias gradient of the module's output projection.  */
 int tgt_layernorm_bwd_y(const void *dy, const void *x, const float *gamma, const float *beta,
                         const float *mean, const float *rstd, const void *dres, void *dx, float *dgamma,
                         float *dbeta, void *y, int64_t ldy, int64_t rows, int W, int x_dtype, int y_dtype,
-                        void *stream);
+                        const float *res_row_scale, int64_t rows_per_scale, float *dres_colsum, void *stream);
 
 /* ---- triplet attention core -------------------------------------------------------------
  * replaces lib/tgt/layers/triplet.py:213-227 and 232-246 (both einsums, bias add, masked

@@ -283,6 +283,14 @@ def test_rowwise_kernels():
         dx1, dg1, db1, y1 = ops.layernorm_bwd(dy, x, g, mean, rstd, dres, beta=b)
         assert torch.equal(dx0, dx1) and max_rel(dg1, dg0) < 1e-5 and max_rel(db1, db0) < 1e-5
         assert y1.shape == (777, 264) and torch.equal(y1, yf)
+        # ... and the DropPath-weighted column sum of the residual gradient (= bias gradient of the module's output Linear)
+        sc = torch.tensor([0., 1.25, 2.5, 0., 1., 1., 0.5], device=DEV)          # 7 graphs x 111 rows
+        dx2, dg2, db2, y2, cs = ops.layernorm_bwd(dy, x, g, mean, rstd, dres, beta=b, colsum=(sc,))
+        assert torch.equal(dx2, dx0) and torch.equal(y2, yf)
+        ref_cs = (dres.float().view(7, 111, 256) * sc.view(7, 1, 1)).sum((0, 1))
+        assert max_rel(cs, ref_cs) < 1e-5
+        cs1 = ops.layernorm_bwd(dy, x, g, mean, rstd, dres, colsum=(None,))[3]
+        assert max_rel(cs1, dres.float().sum(0)) < 1e-5
     assert not ops.ln_bwd_emits_y(torch.empty(4, 768), torch.bfloat16)
     assert not ops.ln_bwd_emits_y(torch.empty(4, 256), torch.float32)
     # gelu + dropout: p=0 equals F.gelu; p>0 keeps ~(1-p), scales by 1/(1-p), fwd/bwd masks agree

@@ -78,7 +78,8 @@ _SIGNATURES = {
     "tgt_kernel_timer_read": (C.c_int, [C.c_char_p, C.c_size_t]),
     "tgt_layernorm_fwd": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int64, C.c_float, C.c_int, C.c_int, _P]),
     "tgt_layernorm_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, _P]),
-    "tgt_layernorm_bwd_y": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, _P]),
+    "tgt_layernorm_bwd_y": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                      _P, C.c_int64, _P, _P]),
     "tgt_triplet_attn_workspace_bytes": (C.c_size_t, [C.POINTER(TripletAttnDesc), C.c_int]),
     "tgt_triplet_attn_fwd": (C.c_int, [C.POINTER(TripletAttnDesc), _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "tgt_triplet_attn_bwd": (C.c_int, [C.POINTER(TripletAttnDesc), _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),

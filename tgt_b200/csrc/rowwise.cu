@@ -295,19 +295,28 @@ ln_fwd_w256(const XT *__restrict__ x, const float *__restrict__ gamma, const flo
 
 // EMIT_Y: also write y = LN(x) (the normalised rows are in registers anyway) as [rows, ldy] with the augmentation columns
 // -- the weight-gradient GEMM of the Linear behind the LayerNorm then needs no separate LayerNorm recompute pass.
-template <typename XT, typename T, int RU, bool EMIT_Y = false>
+// COLSUM: also accumulate  dres_colsum[c] += sum_r w_r * dres[r, c],  w_r = res_row_scale[r / rows_per_scale] (1 if null):
+// the residual gradient dres IS the upstream gradient of the module whose LayerNorm this is, so this is the bias gradient
+// of the module's output projection (DropPath-weighted) -- it costs no pass of its own.
+template <typename XT, typename T, int RU, bool EMIT_Y = false, bool COLSUM = false>
 __global__ void __launch_bounds__(256)
 ln_bwd_w256(const T *__restrict__ dy, const XT *__restrict__ x, const float *__restrict__ gamma,
             const float *__restrict__ mean, const float *__restrict__ rstd, const XT *__restrict__ dres,
             XT *__restrict__ dx, float *__restrict__ dgamma, float *__restrict__ dbeta, int64_t rows,
-            const float *__restrict__ beta = nullptr, T *__restrict__ y = nullptr, int64_t ldy = 0) {
-  __shared__ float sm[2 * 256];
+            const float *__restrict__ beta = nullptr, T *__restrict__ y = nullptr, int64_t ldy = 0,
+            const float *__restrict__ res_row_scale = nullptr, int64_t rows_per_scale = 1,
+            float *__restrict__ dres_colsum = nullptr) {
+  __shared__ float sm[(COLSUM ? 3 : 2) * 256];
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int c = threadIdx.x; c < 512; c += blockDim.x) sm[c] = 0.f;
+  for (int c = threadIdx.x; c < (COLSUM ? 768 : 512); c += blockDim.x) sm[c] = 0.f;
   __syncthreads();
-  float g[8], ag[8], ab[8];
+  float g[8], ag[8], ab[8], ar[COLSUM ? 8 : 1];
+  if constexpr (COLSUM) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) ar[q] = 0.f;
+  }
   {
     const float4 g0 = *reinterpret_cast<const float4 *>(gamma + lane * 8), g1 = *reinterpret_cast<const float4 *>(gamma + lane * 8 + 4);
     g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
@@ -369,6 +378,11 @@ ln_bwd_w256(const T *__restrict__ dy, const XT *__restrict__ x, const float *__r
         V8<XT>::unpack(rr[u], rv);
 #pragma unroll
         for (int q = 0; q < 8; ++q) o[q] += rv[q];
+        if constexpr (COLSUM) {
+          const float w = res_row_scale ? res_row_scale[(r0 + u) / rows_per_scale] : 1.f;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) ar[q] = fmaf(w, rv[q], ar[q]);
+        }
       }
       V8<XT>::store(dx + (r0 + u) * 256 + lane * 8, o);
     }
@@ -377,11 +391,13 @@ ln_bwd_w256(const T *__restrict__ dy, const XT *__restrict__ x, const float *__r
   for (int q = 0; q < 8; ++q) {
     atomicAdd(&sm[lane * 8 + q], ag[q]);
     atomicAdd(&sm[256 + lane * 8 + q], ab[q]);
+    if constexpr (COLSUM) atomicAdd(&sm[512 + lane * 8 + q], ar[q]);
   }
   __syncthreads();
   for (int c = threadIdx.x; c < 256; c += blockDim.x) {
     atomicAdd(&dgamma[c], sm[c]);
     atomicAdd(&dbeta[c], sm[256 + c]);
+    if constexpr (COLSUM) atomicAdd(&dres_colsum[c], sm[512 + c]);
   }
 }
 
@@ -614,23 +630,36 @@ template <typename XT, typename YT>
 static int ln_bwd_launch(const void *dy, const void *x, const float *gamma, const float *mean,
                          const float *rstd, const void *dres, void *dx, float *dgamma, float *dbeta,
                          int64_t rows, int W, cudaStream_t st, const float *beta = nullptr, void *y = nullptr,
-                         int64_t ldy = 0) {
+                         int64_t ldy = 0, const float *res_row_scale = nullptr, int64_t rows_per_scale = 1,
+                         float *dres_colsum = nullptr) {
   if constexpr (sizeof(YT) == 2 && (std::is_same<XT, YT>::value || std::is_same<XT, float>::value)) {
     if (W == 256 && (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx | (uintptr_t)dres | (uintptr_t)y) & 15) == 0) {
       int g = grid_for(rows, 8 * 2 * 8);
       if (g > 148 * 8) g = 148 * 8;
+      if (dres_colsum && (!dres || rows_per_scale <= 0)) return fail("layernorm_bwd_y: dres_colsum needs dres and rows_per_scale > 0");
       if (y) {
         if (!beta || (ldy != 256 && ldy != 264)) return fail("layernorm_bwd_y: beta is required and ldy must be 256 or 264");
-        ln_bwd_w256<XT, YT, 2, true><<<g, 256, 0, st>>>((const YT *)dy, (const XT *)x, gamma, mean, rstd, (const XT *)dres,
-                                                        (XT *)dx, dgamma, dbeta, rows, beta, (YT *)y, ldy);
+        if (dres_colsum)
+          ln_bwd_w256<XT, YT, 2, true, true><<<g, 256, 0, st>>>((const YT *)dy, (const XT *)x, gamma, mean, rstd,
+                                                                (const XT *)dres, (XT *)dx, dgamma, dbeta, rows, beta, (YT *)y,
+                                                                ldy, res_row_scale, rows_per_scale, dres_colsum);
+        else
+          ln_bwd_w256<XT, YT, 2, true><<<g, 256, 0, st>>>((const YT *)dy, (const XT *)x, gamma, mean, rstd, (const XT *)dres,
+                                                          (XT *)dx, dgamma, dbeta, rows, beta, (YT *)y, ldy);
         return check_launch("ln_bwd_w256_y");
+      }
+      if (dres_colsum) {
+        ln_bwd_w256<XT, YT, 2, false, true><<<g, 256, 0, st>>>((const YT *)dy, (const XT *)x, gamma, mean, rstd,
+                                                               (const XT *)dres, (XT *)dx, dgamma, dbeta, rows, nullptr, nullptr, 0,
+                                                               res_row_scale, rows_per_scale, dres_colsum);
+        return check_launch("ln_bwd_w256_cs");
       }
       ln_bwd_w256<XT, YT, 2><<<g, 256, 0, st>>>((const YT *)dy, (const XT *)x, gamma, mean, rstd, (const XT *)dres, (XT *)dx,
                                             dgamma, dbeta, rows);
       return check_launch("ln_bwd_w256");
     }
   }
-  if (y) return fail("layernorm_bwd_y: only the W = 256, 16-bit gradient fast path can emit y");
+  if (y || dres_colsum) return fail("layernorm_bwd_y: only the W = 256, 16-bit gradient fast path can emit y / dres_colsum");
   int g = grid_for(rows, 8 * 4);            // few rows per warp: node-side tensors have only B*N rows
   if (g > 148 * 4) g = 148 * 4;
   ln_bwd_kernel<XT, YT><<<g, 256, 2 * W * sizeof(float), st>>>((const YT *)dy, (const XT *)x, gamma, mean, rstd,
@@ -678,13 +707,16 @@ extern "C" int tgt_layernorm_bwd(const void *dy, const void *x, const float *gam
 
 extern "C" int tgt_layernorm_bwd_y(const void *dy, const void *x, const float *gamma, const float *beta, const float *mean,
                                    const float *rstd, const void *dres, void *dx, float *dgamma, float *dbeta, void *y,
-                                   int64_t ldy, int64_t rows, int W, int x_dtype, int y_dtype, void *stream) {
-  if (!y || !beta) return fail("layernorm_bwd_y: y and beta are required");
+                                   int64_t ldy, int64_t rows, int W, int x_dtype, int y_dtype, const float *res_row_scale,
+                                   int64_t rows_per_scale, float *dres_colsum, void *stream) {
+  if (!y && !dres_colsum) return fail("layernorm_bwd_y: nothing extra to emit (use tgt_layernorm_bwd)");
+  if (y && !beta) return fail("layernorm_bwd_y: beta is required to emit y");
   if (rows <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-#define X(xc, yc, XT, YT)                   \
-  if (x_dtype == xc && y_dtype == yc)       \
-    return ln_bwd_launch<XT, YT>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, rows, W, st, beta, y, ldy);
+#define X(xc, yc, XT, YT)                                                                                         \
+  if (x_dtype == xc && y_dtype == yc)                                                                             \
+    return ln_bwd_launch<XT, YT>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, rows, W, st, beta, y, ldy,    \
+                                 res_row_scale, rows_per_scale, dres_colsum);
   LN_COMBOS(X)
 #undef X
   return fail("layernorm_bwd_y: unsupported dtype combination x=%d y=%d", x_dtype, y_dtype);

@@ -105,22 +105,32 @@ def ln_bwd_emits_y(x2: Tensor, cd: torch.dtype) -> bool:
 
 
 def layernorm_bwd(dy: Tensor, x2: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor,
-                  dres: Optional[Tensor] = None, beta: Optional[Tensor] = None):
-    """(dx, dgamma, dbeta[, y]).  With `beta` given (see ln_bwd_emits_y) the kernel also emits the augmented
-    y = [LN(x) | 1 | 0...] in dy's dtype, so callers order their weight-gradient GEMM after this call instead of
-    running a LayerNorm recompute pass for it."""
+                  dres: Optional[Tensor] = None, beta: Optional[Tensor] = None, colsum: Optional[tuple] = None):
+    """(dx, dgamma, dbeta[, y][, dres_colsum]).  By-products of the same pass (see ln_bwd_emits_y):
+    `beta` given   -> also the augmented y = [LN(x) | 1 | 0...] in dy's dtype, so callers order their weight-gradient
+                      GEMM after this call instead of running a LayerNorm recompute pass for it;
+    `colsum` = (scale [B] or None,) -> also sum_r scale[graph(r)] * dres[r, :]: dres is the upstream gradient of the module
+                      this LayerNorm opens, i.e. the DropPath-weighted bias gradient of the module's output projection."""
     rows, W = x2.shape
     dx = torch.empty_like(x2)
-    dgb = torch.zeros((2, W), dtype=torch.float32, device=x2.device)
-    if beta is not None:
-        y = torch.empty((rows, W + AUG), dtype=dy.dtype, device=x2.device)
+    dgb = torch.zeros((3 if colsum is not None else 2, W), dtype=torch.float32, device=x2.device)
+    if beta is not None or colsum is not None:
+        y = torch.empty((rows, W + AUG), dtype=dy.dtype, device=x2.device) if beta is not None else None
+        sc = colsum[0] if colsum is not None else None
+        rps = rows // sc.numel() if sc is not None else 1
         with timed(f"layernorm_bwd_W{W}"):
             _C.check(_C.lib().tgt_layernorm_bwd_y(_C.ptr(dy), _C.ptr(x2), _C.ptr(gamma), _C.ptr(beta), _C.ptr(mean),
                                                   _C.ptr(rstd), _C.ptr(dres), _C.ptr(dx), _C.ptr(dgb[0]),
                                                   _C.ptr(dgb[1]), _C.ptr(y), W + AUG, rows, W,
-                                                  _C.dtype_code(x2.dtype), _C.dtype_code(dy.dtype), _C.stream_ptr()),
+                                                  _C.dtype_code(x2.dtype), _C.dtype_code(dy.dtype), _C.ptr(sc), rps,
+                                                  _C.ptr(dgb[2]) if colsum is not None else None, _C.stream_ptr()),
                      "layernorm_bwd_y")
-        return dx, dgb[0], dgb[1], y
+        out = (dx, dgb[0], dgb[1])
+        if beta is not None:
+            out += (y,)
+        if colsum is not None:
+            out += (dgb[2],)
+        return out
     with timed(f"layernorm_bwd_W{W}"):
         _C.check(_C.lib().tgt_layernorm_bwd(_C.ptr(dy), _C.ptr(x2), _C.ptr(gamma), _C.ptr(mean), _C.ptr(rstd),
                                             _C.ptr(dres), _C.ptr(dx), _C.ptr(dgb[0]), _C.ptr(dgb[1]), rows, W,
@@ -335,7 +345,7 @@ def _bmm_f32(a: Tensor, b: Tensor) -> Tensor:
 
 
 def linear_residual_bwd(do2: Tensor, a2: Tensor, Wc: Tensor, scale: Optional[Tensor], gelu_bwd: Optional[tuple] = None,
-                        name: str = "gemm_tc_dx"):
+                        name: str = "gemm_tc_dx", want_db: bool = True):
     """Gradients of  out = res + scale[b] * (a2 Wc^T + bias)  given do2 = d out: (da2, dW, dbias).
     The DropPath scale never costs a pass over an edge-sized tensor: da2 = scale[b] * (do2 Wc) is the row-scale
     epilogue of the GEMM, dW = sum_b scale[b] * do2_b^T a2_b is a per-graph batched GEMM followed by a weighted sum.
@@ -354,7 +364,7 @@ def linear_residual_bwd(do2: Tensor, a2: Tensor, Wc: Tensor, scale: Optional[Ten
                                                    _C.dtype_code(da.dtype), _C.stream_ptr()), "gelu_dropout_bwd")
             da = du
     if scale is None:
-        return da, torch.mm(do2.t(), a2), do2.sum(0, dtype=torch.float32)
+        return da, torch.mm(do2.t(), a2), (do2.sum(0, dtype=torch.float32) if want_db else None)
     B = scale.numel()
     if B * N * K * 4 > M * (N + K):
         # few rows per graph (node-side tensors): the per-graph [B, N, K] intermediate would dwarf the operands --
@@ -364,7 +374,8 @@ def linear_residual_bwd(do2: Tensor, a2: Tensor, Wc: Tensor, scale: Optional[Ten
     dob = do2.view(B, M // B, N)
     dWb = _bmm_f32(dob.transpose(1, 2), a2.view(B, M // B, K))
     dW = torch.mv(dWb.view(B, N * K).t(), scale).view(N, K)
-    db = torch.mv(dob.sum(1, dtype=torch.float32).t(), scale)
+    # want_db=False: the caller gets the bias gradient as a by-product of its LayerNorm-backward kernel (layernorm_bwd)
+    db = torch.mv(dob.sum(1, dtype=torch.float32).t(), scale) if want_db else None
     return da, dW, db
 
 
@@ -415,8 +426,17 @@ import os as _os
 _LN_BWD_FUSED = _os.environ.get("TGT_LN_BWD_FUSED", "0") == "1"
 
 
+_LN_COLSUM = _os.environ.get("TGT_LN_COLSUM", "1") == "1"      # A/B switch for the bias-gradient by-product
+
+
+def ln_bwd_colsum_ok(x2: Tensor, cd: torch.dtype, dout_dtype: torch.dtype) -> bool:
+    """ln_linear_bwd(..., colsum=...) can deliver the weighted column sum of dres (see layernorm_bwd)."""
+    return _LN_COLSUM and ln_bwd_emits_y(x2, cd) and dout_dtype == cd and not _LN_BWD_FUSED
+
+
 def ln_linear_bwd(dout2: Tensor, x2: Tensor, g: Tensor, bt: Tensor, Wc: Tensor, mean: Tensor, rstd: Tensor,
-                  dres: Optional[Tensor], cd: torch.dtype, name: str = "gemm_tc_ln_bwd", fused: Optional[bool] = None):
+                  dres: Optional[Tensor], cd: torch.dtype, name: str = "gemm_tc_ln_bwd", fused: Optional[bool] = None,
+                  colsum: Optional[tuple] = None):
     """Backward of  out = LN(x2) Wc^T + b  given dout2 = d out [M, C]:  (dx, dgamma, dbeta, dW, db).
 
     16-bit x2 of width <= 256: ONE tcgen05 GEMM computes dy = dout2 Wc and applies the LayerNorm backward in its
@@ -444,10 +464,12 @@ def ln_linear_bwd(dout2: Tensor, x2: Tensor, g: Tensor, bt: Tensor, Wc: Tensor, 
         return dx, dg, dbt, dW, db
     if ln_bwd_emits_y(x2, cd) and dout2.dtype == cd:
         dy = torch.mm(dout2, Wc)
-        dx, dg, dbt, y = layernorm_bwd(dy, x2, g, mean, rstd, dres, beta=bt)
+        res = layernorm_bwd(dy, x2, g, mean, rstd, dres, beta=bt, colsum=colsum)
+        dx, dg, dbt, y = res[:4]
         del dy
         dWa = torch.mm(dout2.t(), y)
-        return dx, dg, dbt, dWa[:, :W], dWa[:, W]
+        return (dx, dg, dbt, dWa[:, :W], dWa[:, W]) + ((res[4],) if colsum is not None else ())
+    assert colsum is None, "colsum needs the y-emitting LayerNorm backward (check ln_bwd_colsum_ok first)"
     y, _, _ = layernorm_fwd(x2, g, bt, cd, aug=True)
     dWa = torch.mm(dout2.t(), y)
     dW, db = dWa[:, :W], dWa[:, W]
@@ -655,9 +677,12 @@ class TripletAttentionFn(Function):
             do = dout.reshape(-1, W).to(cd).contiguous()
             if ctx.fuse_res:
                 dalias = dout                               # residual branch: d(e) += dout, folded into the LN backward
-            dva, dWo, dbo = linear_residual_bwd(do, va, Woc, sc, name="gemm_tc_dva")
-            del do
             late_y = (kept_proj is not None or Wg is not None) and ln_bwd_emits_y(x2, cd)
+            # fused residual: dout is also the residual gradient the LayerNorm backward adds, so that kernel delivers the
+            # lin_O bias gradient (its DropPath-weighted column sum) as a by-product
+            cs_db = late_y and ctx.fuse_res and _LN_COLSUM
+            dva, dWo, dbo = linear_residual_bwd(do, va, Woc, sc, name="gemm_tc_dva", want_db=not cs_db)
+            del do
             y = None if late_y else layernorm_fwd(x2, g, bt, cd, aug=True)[0]
             if kept_proj is not None:   # one of the last layers: HBM had room to keep the projection (keep_projection)
                 proj = kept_proj
@@ -677,7 +702,11 @@ class TripletAttentionFn(Function):
             del proj, dva
             if late_y:                  # LN(x) comes out of the LayerNorm-backward kernel: no recompute pass
                 dy = torch.mm(dproj, Wc)
-                dx, dg, dbt, y = layernorm_bwd(dy, x2, g, mean, rstd, _dres_for(dalias, x2), beta=bt)
+                res = layernorm_bwd(dy, x2, g, mean, rstd, _dres_for(dalias, x2), beta=bt,
+                                    colsum=(sc,) if cs_db else None)
+                dx, dg, dbt, y = res[:4]
+                if cs_db:
+                    dbo = res[4]
                 del dy
                 dWa = torch.mm(dproj.t(), y)              # [C, W+8]: weight gradient | bias gradient (column W)
                 dWc, dbc = dWa[:, :W], dWa[:, W]
@@ -954,9 +983,15 @@ class FFNGeluFn(Function):
             if fuse_res:
                 dalias = dout
             # du = scale[b] * (do W2) * GELU'(u) * dropout mask in ONE GEMM; `a` was saved by the forward epilogue
-            du, dW2, db2 = linear_residual_bwd(do, a, W2c, sc, gelu_bwd=(u, p_drop, seed), name="gemm_tc_du")
-            dx, dg, dbt, dW1, db1 = ln_linear_bwd(du, x2, g, bt, W1c, mean, rstd, _dres_for(dalias, x2), cd,
-                                                  name="gemm_tc_ln_bwd_ffn")
+            # fused residual: W2's bias gradient is a by-product of the LayerNorm-backward kernel (its residual input is dout)
+            cs_db = bool(fuse_res) and ln_bwd_colsum_ok(x2, cd, do.dtype)
+            du, dW2, db2 = linear_residual_bwd(do, a, W2c, sc, gelu_bwd=(u, p_drop, seed), name="gemm_tc_du",
+                                               want_db=not cs_db)
+            res = ln_linear_bwd(du, x2, g, bt, W1c, mean, rstd, _dres_for(dalias, x2), cd, name="gemm_tc_ln_bwd_ffn",
+                                colsum=(sc,) if cs_db else None)
+            dx, dg, dbt, dW1, db1 = res[:5]
+            if cs_db:
+                db2 = res[5]
         return (dx.view(*dout.shape[:-1], x2.shape[-1]).to(in_dtype), dg.to(p[0]), dbt.to(p[0]), dW1.to(p[1]),
                 db1.to(p[2]), dW2.to(p[3]), db2.to(p[4]), None, None, None, None, None)
 

@@ -234,6 +234,10 @@ int tgt_egt_attn_bwd(const tgt_egt_desc *desc, const void *qkv, const void *eg, 
                                * N % 64 == 0): D = rstd*(g - mean(g) - xhat*mean(g*xhat)) [+ res2], g = dy*gamma;
                                * x = `res` (16-bit), gamma = col_sum, row_mean / row_rstd = forward statistics;
                                * with TGT_EPI_RES the residual gradient res2 (16-bit, pitch ldres2) is added          */
+#define TGT_EPI_STORE_GP 1024 /* with GELU | STORE_U: U receives GELU'(u) * dropout mask instead of the pre-activation u, so
+                               * that the backward epilogue is a plain multiply (TGT_EPI_MULRES)                        */
+#define TGT_EPI_MULRES   2048 /* D = value * res (16-bit, pitch ldres): backward of GELU + dropout for a STORE_GP forward;
+                               * combines with ROWSCALE, excludes RES / GELU_BWD                                        */
 #define TGT_EPI_GELU_BWD 128  /* D = value * GELU'(u) * dropout mask(p_drop, seed); u = `res` (16-bit, pitch ldres) */
 typedef struct {
   int64_t M;

@@ -117,6 +117,35 @@ def test_gemm_gelu_backward_epilogue(p_drop):
     _close(plain, da, 8e-3)
 
 
+@pytest.mark.parametrize("p_drop", [0.0, 0.1])
+def test_gemm_gelu_stored_derivative_and_multiply_epilogue(p_drop):
+    """STORE_GP: same activation as the plain GELU epilogue, U holds GELU'(u) * mask; MULRES (+ROWSCALE) multiplies by it:
+    together they equal the GELU_BWD epilogue on the stored pre-activation."""
+    ops = _ops()
+    Bb, rows_per = 6, 500
+    M, N, K = Bb * rows_per, 256, 256
+    a, w = _rand((M, K), torch.bfloat16, 15), _rand((N, K), torch.bfloat16, 16, K ** -0.5)
+    bias = _rand((N,), torch.float32, 17)
+    out0, u = ops.gemm_tc(a, w, bias=bias, gelu=(p_drop, 4242))
+    out1, gp = ops.gemm_tc(a, w, bias=bias, gelu=(p_drop, 4242), store_gp=True)
+    assert torch.equal(out0, out1)
+    uf = u.float().requires_grad_(True)
+    torch.nn.functional.gelu(uf).sum().backward()
+    keep = (out0 != 0) | (u == 0) if p_drop > 0 else torch.ones_like(u, dtype=torch.bool)
+    scale_keep = 1.0 / (1.0 - p_drop) if p_drop > 0 else 1.0
+    _close(gp.float()[keep], (uf.grad * scale_keep)[keep], 6e-3)
+    if p_drop > 0:
+        assert float((gp[~keep] != 0).float().sum()) == 0.0
+    do, w2 = _rand((M, N), torch.bfloat16, 21), _rand((K, N), torch.bfloat16, 22, N ** -0.5)
+    scale = torch.tensor([1.25, 0.0, 1.25, 1.25, 0.0, 1.25], device="cuda")
+    got = ops.gemm_tc(do, w2, row_scale=scale, rows_per_scale=rows_per, mul=gp)
+    want = ops.gemm_tc(do, w2, row_scale=scale, rows_per_scale=rows_per, gelu_bwd=(u, p_drop, 4242))
+    _close(got, want, 1.2e-2)
+    assert ((got == 0) == (want == 0)).float().mean().item() > 0.999
+    got2 = ops.gemm_tc(do, w2, mul=gp)                 # without the row scale
+    _close(got2, (do.float() @ w2.float().t()) * gp.float(), 8e-3)
+
+
 def test_linear_residual_bwd_matches_autograd():
     """DropPath-scaled linear backward (row-scale epilogue + per-graph batched weight gradient) vs autograd."""
     ops = _ops()

@@ -67,6 +67,7 @@ class GemmDesc(C.Structure):
 
 
 EPI_LN, EPI_BIAS, EPI_GELU, EPI_RES, EPI_STORE_U, EPI_ROWSCALE, EPI_GELU_BWD, EPI_STATS, EPI_LN_BWD = 1, 2, 4, 8, 16, 64, 128, 256, 512
+EPI_STORE_GP, EPI_MULRES = 1024, 2048
 
 _P = C.c_void_p
 _SIGNATURES = {

@@ -34,7 +34,7 @@ template <typename T> __device__ __forceinline__ uint32_t umma_idesc(int n) {
 
 // ---------------------------------------------------------------------------------------------- kernel
 enum : int { EPI_LN = 1, EPI_BIAS = 2, EPI_GELU = 4, EPI_RES = 8, EPI_STORE_U = 16, EPI_RES_F32 = 32, EPI_ROWSCALE = 64,
-              EPI_GELU_BWD = 128, EPI_STATS = 256, EPI_LN_BWD = 512 };
+              EPI_GELU_BWD = 128, EPI_STATS = 256, EPI_LN_BWD = 512, EPI_STORE_GP = 1024, EPI_MULRES = 2048 };
 
 struct GemmParams {
   int64_t M;
@@ -89,6 +89,24 @@ __device__ __forceinline__ float gelu_grad_fast(float u) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * ax * ax));
   const float h = 0.5f * poly * t * e;
   return fmaf(u * 0.39894228040143268f, e, u < 0.f ? h : 1.f - h);
+}
+
+// GELU(u) and d/du GELU(u) from one evaluation of the erfc approximation (the forward epilogue with EPI_STORE_GP stores
+// the derivative * dropout mask instead of the pre-activation, so the backward epilogue is a plain multiply)
+__device__ __forceinline__ void gelu_both_fast(float u, float &act, float &grad) {
+  const float ax = fabsf(u) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.f)));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * ax * ax));
+  const float h = 0.5f * poly * t * e;
+  const float cdf = u < 0.f ? h : 1.f - h;
+  act = u * cdf;
+  grad = fmaf(u * 0.39894228040143268f, e, cdf);
 }
 
 template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
@@ -304,7 +322,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         };
-        if (FLAGS & (EPI_RES | EPI_GELU_BWD)) res_load(half * 32, rcur);
+        if (FLAGS & (EPI_RES | EPI_GELU_BWD | EPI_MULRES)) res_load(half * 32, rcur);
         float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};   // EPI_STATS: sum / sum of squares per row
         // LN_BWD: this lane's row of x for the (up to 4) column groups of this warp, fetched before the accumulator wait
         uint32_t xh[LNB ? 4 : 1][16];
@@ -371,7 +389,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int k = 0; k < 8; ++k) bsv[k] = *reinterpret_cast<const float4 *>(vec_bias + c + k * 4);
           }
-          if ((FLAGS & (EPI_RES | EPI_GELU_BWD)) && c + 64 < bn) res_load(c + 64, rnext);
+          if ((FLAGS & (EPI_RES | EPI_GELU_BWD | EPI_MULRES)) && c + 64 < bn) res_load(c + 64, rnext);
           tc_ld_wait();
           // ---- TMEM domain (lane = row): LN fold, bias, activation; 16-bit results go to the staging tile
 #pragma unroll
@@ -419,18 +437,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               wu.y = pack2<T>(f[2], f[3]);
               wu.z = pack2<T>(f[4], f[5]);
               wu.w = pack2<T>(f[6], f[7]);
-              st_shared_v4(stage_addr(stU, lane, pc), wu);
+              if (!(FLAGS & EPI_STORE_GP)) st_shared_v4(stage_addr(stU, lane, pc), wu);
               const uint32_t wr[4] = {wu.x, wu.y, wu.z, wu.w};
               const uint64_t pair0 = (uint64_t)(row * p.ldu + col0 + c + pc * 8) >> 1;
+              uint32_t gpw[4];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 // the activation is computed from the ROUNDED pre-activation: backward recomputes from the stored U
                 float u0, u1, m0 = 1.f, m1 = 1.f;
                 unpack2<T>(wr[j], u0, u1);
                 if (p.p_drop > 0.f) drop_mask_pair(dc, pair0 + j, m0, m1);
-                f[2 * j] = gelu_fast(u0) * m0;
-                f[2 * j + 1] = gelu_fast(u1) * m1;
+                if (FLAGS & EPI_STORE_GP) {
+                  float a0, a1, g0, g1;
+                  gelu_both_fast(u0, a0, g0);
+                  gelu_both_fast(u1, a1, g1);
+                  f[2 * j] = a0 * m0;
+                  f[2 * j + 1] = a1 * m1;
+                  gpw[j] = pack2<T>(g0 * m0, g1 * m1);
+                } else {
+                  f[2 * j] = gelu_fast(u0) * m0;
+                  f[2 * j + 1] = gelu_fast(u1) * m1;
+                }
               }
+              if (FLAGS & EPI_STORE_GP) st_shared_v4(stage_addr(stU, lane, pc), make_uint4(gpw[0], gpw[1], gpw[2], gpw[3]));
             }
             uint4 w;
             w.x = pack2<T>(f[0], f[1]);
@@ -470,6 +499,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (p.p_drop > 0.f) drop_mask_pair(dc, pair0 + j, m0, m1);
                     f[2 * j] *= gelu_grad_fast(u0) * m0;
                     f[2 * j + 1] *= gelu_grad_fast(u1) * m1;
+                  }
+                  w.x = pack2<T>(f[0], f[1]);
+                  w.y = pack2<T>(f[2], f[3]);
+                  w.z = pack2<T>(f[4], f[5]);
+                  w.w = pack2<T>(f[6], f[7]);
+                }
+                if (FLAGS & EPI_MULRES) {
+                  // D = value * res: backward of GELU + dropout when the forward stored GELU'(u) * mask (EPI_STORE_GP)
+                  const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+                  const uint32_t gw[4] = {rcur[it][0].x, rcur[it][0].y, rcur[it][0].z, rcur[it][0].w};
+                  float f[8];
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    float g0, g1;
+                    unpack2<T>(ww[j], f[2 * j], f[2 * j + 1]);
+                    unpack2<T>(gw[j], g0, g1);
+                    f[2 * j] *= g0;
+                    f[2 * j + 1] *= g1;
                   }
                   w.x = pack2<T>(f[0], f[1]);
                   w.y = pack2<T>(f[2], f[3]);
@@ -517,7 +564,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           __syncwarp();
-          if (FLAGS & (EPI_RES | EPI_GELU_BWD)) {
+          if (FLAGS & (EPI_RES | EPI_GELU_BWD | EPI_MULRES)) {
 #pragma unroll
             for (int it = 0; it < 4; ++it)
 #pragma unroll
@@ -705,6 +752,10 @@ static int dispatch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const Gem
     TGT_GEMM_CASE(EPI_ROWSCALE)
     TGT_GEMM_CASE(EPI_GELU_BWD)
     TGT_GEMM_CASE(EPI_GELU_BWD | EPI_ROWSCALE)
+    TGT_GEMM_CASE(EPI_LN | EPI_BIAS | EPI_GELU | EPI_STORE_U | EPI_STORE_GP)
+    TGT_GEMM_CASE(EPI_BIAS | EPI_GELU | EPI_STORE_U | EPI_STORE_GP)
+    TGT_GEMM_CASE(EPI_MULRES)
+    TGT_GEMM_CASE(EPI_MULRES | EPI_ROWSCALE)
     TGT_GEMM_CASE(EPI_LN_BWD)
     TGT_GEMM_CASE(EPI_LN_BWD | EPI_RES)
 #undef TGT_GEMM_CASE
@@ -732,6 +783,10 @@ extern "C" int tgt_gemm_tc(const tgt_gemm_desc *g, const void *A, const void *B,
   if ((flags & EPI_GELU_BWD) && ((flags & EPI_RES) || !g->res || g->ldres % 8 || (reinterpret_cast<uintptr_t>(g->res) & 15) ||
                                  g->res_dtype != g->dtype))
     return fail("gemm_tc: GELU_BWD epilogue needs the 16-bit pre-activation in `res` (ldres %% 8 == 0) and excludes RES");
+  if ((flags & EPI_MULRES) && ((flags & (EPI_RES | EPI_GELU_BWD)) || !g->res || g->ldres % 8 ||
+                               (reinterpret_cast<uintptr_t>(g->res) & 15) || g->res_dtype != g->dtype))
+    return fail("gemm_tc: MULRES epilogue needs a 16-bit multiplier in `res` (ldres %% 8 == 0) and excludes RES / GELU_BWD");
+  if ((flags & EPI_STORE_GP) && !(flags & EPI_GELU)) return fail("gemm_tc: STORE_GP modifies the GELU epilogue");
   if ((flags & EPI_ROWSCALE) && !g->row_scale) return fail("gemm_tc: ROWSCALE epilogue without row_scale");
   if ((flags & (EPI_RES | EPI_ROWSCALE)) && g->row_scale && g->rows_per_scale <= 0) return fail("gemm_tc: rows_per_scale must be > 0");
   if (flags & EPI_STORE_U) {

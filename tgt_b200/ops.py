@@ -181,12 +181,15 @@ def row_stats(x2: Tensor, eps: float = 1e-5):
 def gemm_tc(a: Tensor, w: Tensor, *, bias: Optional[Tensor] = None, ln: Optional[tuple] = None,
             gelu: Optional[tuple] = None, res: Optional[Tensor] = None, row_scale: Optional[Tensor] = None,
             rows_per_scale: int = 0, gelu_bwd: Optional[tuple] = None, out: Optional[Tensor] = None,
-            stats_out: Optional[tuple] = None, ln_bwd: Optional[tuple] = None, name: str = "gemm_tc"):
+            stats_out: Optional[tuple] = None, ln_bwd: Optional[tuple] = None, name: str = "gemm_tc",
+            store_gp: bool = False, mul: Optional[Tensor] = None):
     """out[M,N] = epilogue(a[M,K] @ w[N,K]^T) on the tcgen05 kernel.
 
     ln   = (row_mean, row_rstd, col_sum): LayerNorm folded into the epilogue (`w` must already be W*gamma and
            `bias` = b + W beta);
-    gelu = (p_drop, seed): exact GELU + dropout; returns (out, u) with u the 16-bit pre-activation;
+    gelu = (p_drop, seed): exact GELU + dropout; returns (out, u) with u the 16-bit pre-activation -- or, with
+           store_gp=True, (out, gp) with gp = GELU'(u) * dropout mask, which makes the backward epilogue `mul=gp`;
+    mul: out = value * mul (16-bit [M, N]);
     row_scale / rows_per_scale: value *= row_scale[row // rows_per_scale] (DropPath);
     res: out = res + value;
     gelu_bwd = (u, p_drop, seed): out = value * GELU'(u) * dropout mask (backward of `gelu`);
@@ -215,6 +218,11 @@ def gemm_tc(a: Tensor, w: Tensor, *, bias: Optional[Tensor] = None, ln: Optional
         u = torch.empty((M, N), dtype=a.dtype, device=a.device)
         g.U, g.ldu = u.data_ptr(), u.stride(0)
         g.p_drop, g.seed = float(gelu[0]), int(gelu[1])
+        if store_gp:
+            flags |= _C.EPI_STORE_GP
+    if mul is not None:
+        flags |= _C.EPI_MULRES
+        g.res, g.ldres, g.res_dtype = mul.data_ptr(), mul.stride(0), _C.dtype_code(mul.dtype)
     if res is not None:
         flags |= _C.EPI_RES
         g.res, g.ldres, g.res_dtype = res.data_ptr(), res.stride(0), _C.dtype_code(res.dtype)
@@ -352,11 +360,16 @@ def linear_residual_bwd(do2: Tensor, a2: Tensor, Wc: Tensor, scale: Optional[Ten
     gelu_bwd = (u, p_drop, seed) additionally multiplies da2 by GELU'(u) * dropout mask in the same epilogue."""
     M, N = do2.shape
     K = a2.shape[1]
-    if tc_gemm_ok(do2, K, N) and Wc.dtype == do2.dtype and (scale is not None or gelu_bwd is not None):
+    gp = None
+    if gelu_bwd is not None and isinstance(gelu_bwd[0], str):      # ("gp", GELU'(u) * mask) stored by the forward epilogue
+        gp, gelu_bwd = gelu_bwd[1], None
+    if tc_gemm_ok(do2, K, N) and Wc.dtype == do2.dtype and (scale is not None or gelu_bwd is not None or gp is not None):
         rps = M // scale.numel() if scale is not None else 0
-        da = gemm_tc(do2, Wc.t().contiguous(), row_scale=scale, rows_per_scale=rps, gelu_bwd=gelu_bwd, name=name)
+        da = gemm_tc(do2, Wc.t().contiguous(), row_scale=scale, rows_per_scale=rps, gelu_bwd=gelu_bwd, mul=gp, name=name)
     else:
         da = _scale_rows(torch.mm(do2, Wc), scale)
+        if gp is not None:
+            da = da * gp
         if gelu_bwd is not None:
             u, p_drop, seed = gelu_bwd
             du = torch.empty_like(da)
@@ -930,6 +943,9 @@ class EGTCoreFn(Function):
 # ------------------------------------------------------------------------------------------
 # FFN: LN -> W1 -> gelu -> dropout -> W2   (saves the input, LN stats and the pre-activation only)
 # ------------------------------------------------------------------------------------------
+_STORE_GP = _os.environ.get("TGT_FFN_STORE_GP", "1") == "1"     # A/B switch: GELU' * mask stored by the forward epilogue
+
+
 class FFNGeluFn(Function):
     """fuse_res=False: (FFN(x), alias of x); fuse_res=True: x + res_scale[b] * FFN(x) in one pass (the DropPath +
     residual add is the epilogue of the W2 GEMM; LN, bias, GELU and dropout are the epilogue of the W1 GEMM)."""
@@ -947,9 +963,12 @@ class FFNGeluFn(Function):
                 st = take_stats(x, x2)
                 mean, rstd = st if st is not None else row_stats(x2)
                 W1g, b1p, cs = _ln_fold(W1, b1, g, bt, cdtype)
+                # the epilogue stores GELU'(u) * dropout mask in place of u: backward is then a multiply, not a re-evaluation
                 a, u = gemm_tc(x2, W1g, bias=b1p, ln=(mean, rstd, cs), gelu=(float(p_drop), int(seed)),
-                               name="gemm_tc_ln_gelu")
+                               name="gemm_tc_ln_gelu", store_gp=_STORE_GP)
+                u_is_gp = _STORE_GP
             else:
+                u_is_gp = False
                 y, mean, rstd = layernorm_fwd(x2, g, bt, cdtype)
                 u = torch.addmm(b1.detach().to(cdtype), y, W1c.t())
                 del y
@@ -965,6 +984,7 @@ class FFNGeluFn(Function):
             ctx.save_for_backward(x2, g, bt, W1c, W2c, mean, rstd, u, a, sc)
             ctx.meta = (float(p_drop), int(seed), cdtype, x.dtype,
                         (ln_w.dtype, W1.dtype, b1.dtype, W2.dtype, b2.dtype), fuse_res)
+            ctx.u_is_gp = u_is_gp
             ctx.set_materialize_grads(False)
         if fuse_res:
             return _with_stats(ctx, out, ostats)
@@ -985,8 +1005,8 @@ class FFNGeluFn(Function):
             # du = scale[b] * (do W2) * GELU'(u) * dropout mask in ONE GEMM; `a` was saved by the forward epilogue
             # fused residual: W2's bias gradient is a by-product of the LayerNorm-backward kernel (its residual input is dout)
             cs_db = bool(fuse_res) and ln_bwd_colsum_ok(x2, cd, do.dtype)
-            du, dW2, db2 = linear_residual_bwd(do, a, W2c, sc, gelu_bwd=(u, p_drop, seed), name="gemm_tc_du",
-                                               want_db=not cs_db)
+            du, dW2, db2 = linear_residual_bwd(do, a, W2c, sc, name="gemm_tc_du", want_db=not cs_db,
+                                               gelu_bwd=("gp", u) if ctx.u_is_gp else (u, p_drop, seed))
             res = ln_linear_bwd(du, x2, g, bt, W1c, mean, rstd, _dres_for(dalias, x2), cd, name="gemm_tc_ln_bwd_ffn",
                                 colsum=(sc,) if cs_db else None)
             dx, dg, dbt, dW1, db1 = res[:5]

@@ -87,6 +87,99 @@ tri_post_bias_gate(const tgt_triplet_attn_desc D, const float *__restrict__ ws_d
   }
 }
 
+// ---- H = 16 fast paths of the two kernels above: the E (and G) values of one edge row are 16 contiguous 16-bit channels =
+// two 16-byte vectors, so a thread moves 8 heads per load / store instead of 2 bytes, and the tile side moves float4 / uint4.
+// Thread t of 256: row k = t / 4, part = t % 4: parts 0,1 = heads 0-7 / 8-15 of E, parts 2,3 = the same of G.
+template <typename T>
+__global__ void __launch_bounds__(256)
+tri_prep_bias_gate_h16(const tgt_triplet_attn_desc D, const T *__restrict__ proj, const float *__restrict__ mask,
+                       float *__restrict__ ws_e, __half *__restrict__ ws_g) {
+  __shared__ float se[16 * 65], sg[16 * 65];
+  const int N = D.N;
+  const int i = blockIdx.x, dir = blockIdx.y, b = blockIdx.z;
+  const int off_e = D.off_e[dir], off_g = D.off_g[dir];
+  const int k = threadIdx.x >> 2, part = threadIdx.x & 3;
+  const bool is_g = part >= 2;
+  const int h0 = (part & 1) * 8;
+  float v[8];
+  if (i < N && k < N) {
+    const int64_t brow = dir == 0 ? ((int64_t)(b * N + i) * N + k) : ((int64_t)(b * N + k) * N + i);
+    const float mk = mask[brow];
+    const int off = is_g ? off_g : off_e;
+    float x[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) x[q] = 0.f;
+    if (off >= 0) load_vec<T, 8>(proj + brow * D.ld + off + h0, x);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (is_g) v[q] = off_g >= 0 ? 1.f / (1.f + __expf(-(x[q] + mk))) : 1.f;
+      else v[q] = fmaxf((x[q] + mk) * LOG2E, NEG_BIG);
+    }
+  } else {                              // tile padding (i or k >= N): excluded from every softmax
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = is_g ? 0.f : -INFINITY;
+  }
+  float *dst = is_g ? sg : se;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) dst[(h0 + q) * 65 + k] = v[q];
+  __syncthreads();
+  // tile rows: (h, i, :) = 64 fp32 (256 B) / 64 halfs (128 B)
+  const int64_t base = (((int64_t)(b * 2 + dir) * 16) * TN + i) * TN;        // + h * TN * TN + k
+  {
+    const int h = threadIdx.x >> 4, k4 = (threadIdx.x & 15) * 4;
+    const float *r = se + h * 65 + k4;
+    *reinterpret_cast<float4 *>(ws_e + base + (int64_t)h * TN * TN + k4) = make_float4(r[0], r[1], r[2], r[3]);
+  }
+  if (threadIdx.x < 128) {
+    const int h = threadIdx.x >> 3, k8 = (threadIdx.x & 7) * 8;
+    const float *r = sg + h * 65 + k8;
+    __half2 p[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) p[q] = __floats2half2_rn(r[2 * q], r[2 * q + 1]);
+    *reinterpret_cast<uint4 *>(ws_g + base + (int64_t)h * TN * TN + k8) = *reinterpret_cast<uint4 *>(p);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+tri_post_bias_gate_h16(const tgt_triplet_attn_desc D, const float *__restrict__ ws_de, const float *__restrict__ ws_dg,
+                       T *__restrict__ dproj) {
+  __shared__ float se[16 * 65], sg[16 * 65];
+  const int N = D.N;
+  const int i = blockIdx.x, dir = blockIdx.y, b = blockIdx.z;
+  const int off_e = D.off_e[dir], off_g = D.off_g[dir];
+  if (off_e < 0 && off_g < 0) return;
+  const int64_t base = (((int64_t)(b * 2 + dir) * 16) * TN + i) * TN;
+  {
+    const int h = threadIdx.x >> 4, k4 = (threadIdx.x & 15) * 4;
+    const float4 e = *reinterpret_cast<const float4 *>(ws_de + base + (int64_t)h * TN * TN + k4);
+    const float4 g = *reinterpret_cast<const float4 *>(ws_dg + base + (int64_t)h * TN * TN + k4);
+    float *r = se + h * 65 + k4, *t = sg + h * 65 + k4;
+    r[0] = e.x; r[1] = e.y; r[2] = e.z; r[3] = e.w;
+    t[0] = g.x; t[1] = g.y; t[2] = g.z; t[3] = g.w;
+  }
+  __syncthreads();
+  const int k = threadIdx.x >> 2, part = threadIdx.x & 3;
+  const bool is_g = part >= 2;
+  const int h0 = (part & 1) * 8;
+  const int off = is_g ? off_g : off_e;
+  if (k < N && off >= 0) {
+    const int64_t brow = dir == 0 ? ((int64_t)(b * N + i) * N + k) : ((int64_t)(b * N + k) * N + i);
+    const float *src = is_g ? sg : se;
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = src[(h0 + q) * 65 + k];
+    store_vec<T, 8>(dproj + brow * D.ld + off + h0, v);
+  }
+}
+
+static bool bias_gate_h16_ok(const tgt_triplet_attn_desc &D) {
+  if (D.H != 16 || (D.ld % 8)) return false;
+  for (int dir = 0; dir < 2; ++dir)
+    if ((D.off_e[dir] >= 0 && D.off_e[dir] % 8) || (D.off_g[dir] >= 0 && D.off_g[dir] % 8)) return false;
+  return true;
+}
+
 // ------------------------------------------------------------------------------------------------ forward
 constexpr int FWD_STAGES = 4;
 constexpr int FWD_STAGE_BYTES = 3 * TN * HD * 2;      // Q, K, V tiles: 6 KB
@@ -513,7 +606,8 @@ static int fwd_impl(const tgt_triplet_attn_desc &D, const void *proj, const floa
                     void *ws, cudaStream_t st) {
   const Ws w = carve_fwd(D, ws);
   const size_t psm = 2 * (size_t)D.H * 65 * sizeof(float);
-  tri_prep_bias_gate<T><<<dim3(TN, 2, D.B), 256, psm, st>>>(D, (const T *)proj, mask, w.e, w.g);
+  if (bias_gate_h16_ok(D)) tri_prep_bias_gate_h16<T><<<dim3(TN, 2, D.B), 256, 0, st>>>(D, (const T *)proj, mask, w.e, w.g);
+  else tri_prep_bias_gate<T><<<dim3(TN, 2, D.B), 256, psm, st>>>(D, (const T *)proj, mask, w.e, w.g);
   if (int e = check_launch("tri_prep_bias_gate")) return e;
   if (use_tma()) return triplet_attn_fwd_tma_launch(D, proj, va, stats, w.e, w.g, st);
   KernelTimerScope ts("tri_attn_fwd_mma", st);
@@ -532,12 +626,14 @@ static int bwd_impl(const tgt_triplet_attn_desc &D, const void *proj, const floa
     w.e = wf.e;
     w.g = wf.g;
   } else {
-    tri_prep_bias_gate<T><<<dim3(TN, 2, D.B), 256, psm, st>>>(D, (const T *)proj, mask, w.e, w.g);
+    if (bias_gate_h16_ok(D)) tri_prep_bias_gate_h16<T><<<dim3(TN, 2, D.B), 256, 0, st>>>(D, (const T *)proj, mask, w.e, w.g);
+    else tri_prep_bias_gate<T><<<dim3(TN, 2, D.B), 256, psm, st>>>(D, (const T *)proj, mask, w.e, w.g);
     if (int e = check_launch("tri_prep_bias_gate")) return e;
   }
   if (use_tma()) {
     if (int e = triplet_attn_bwd_tma_launch(D, proj, dva, stats, dproj, w.e, w.g, w.de, w.dg, st)) return e;
-    tri_post_bias_gate<T><<<dim3(D.N, 2, D.B), 256, psm, st>>>(D, w.de, w.dg, (T *)dproj);
+    if (bias_gate_h16_ok(D)) tri_post_bias_gate_h16<T><<<dim3(D.N, 2, D.B), 256, 0, st>>>(D, w.de, w.dg, (T *)dproj);
+    else tri_post_bias_gate<T><<<dim3(D.N, 2, D.B), 256, psm, st>>>(D, w.de, w.dg, (T *)dproj);
     return check_launch("tri_post_bias_gate");
   }
   static const int minb = [] { const char *v = getenv("TGT_TRI_BWD_MINB"); return v ? atoi(v) : 2; }();   // tuning knob
@@ -553,7 +649,8 @@ static int bwd_impl(const tgt_triplet_attn_desc &D, const void *proj, const floa
   }
 #undef L
   if (int e = check_launch("tri_attn_bwd_mma")) return e;
-  tri_post_bias_gate<T><<<dim3(D.N, 2, D.B), 256, psm, st>>>(D, w.de, w.dg, (T *)dproj);
+  if (bias_gate_h16_ok(D)) tri_post_bias_gate_h16<T><<<dim3(D.N, 2, D.B), 256, 0, st>>>(D, w.de, w.dg, (T *)dproj);
+  else tri_post_bias_gate<T><<<dim3(D.N, 2, D.B), 256, psm, st>>>(D, w.de, w.dg, (T *)dproj);
   return check_launch("tri_post_bias_gate");
 }
 

@@ -28,6 +28,8 @@ h = torch.randn(B, N, 768, device=dev).bfloat16().requires_grad_(True)
 mods = {}
 if "triplet" in a.what:
     mods["triplet"] = L.TripletAttention(256, 16).to(dev)
+if "aggregate" in a.what:
+    mods["aggregate"] = L.TripletAggregate(256, 16).to(dev)
 if "egt" in a.what:
     mods["egt"] = L.EGT_Attention(768, 256, 64).to(dev)
 if "ffn" in a.what:
@@ -36,6 +38,8 @@ for it in range(a.iters):
     with torch.autocast("cuda", dtype=torch.bfloat16):
         if "triplet" in mods:
             mods["triplet"](e, mask).float().sum().backward()
+        if "aggregate" in mods:
+            mods["aggregate"](e, mask).float().sum().backward()
         if "egt" in mods:
             ho, eo = mods["egt"](h, e, mask)
             (ho.float().sum() + eo.float().sum()).backward()

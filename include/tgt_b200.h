@@ -128,6 +128,16 @@ int tgt_triplet_attn_bwd_tiles(const tgt_triplet_attn_desc *desc, const void *pr
  * proj_eg: [R, desc->ld] the E|G columns (desc->off_e / off_g index THIS matrix; off_q/k/v are ignored)
  * va, stats, workspace: as tgt_triplet_attn_fwd (the backward is tgt_triplet_attn_bwd on a recomputed
  * projection; stats are interchangeable with the TMA / cp.async tensor-core kernels).                  */
+/* Same as ..._bwd_tiles, and -- when dbias is non-NULL -- also accumulates the column sums of dproj into dbias
+ * [desc->ld] f32 (ZERO on entry): the bias gradient of the projection (lin_QKV_in/out, lin_EG_in/out) as a by-product
+ * of the backward kernel, so the weight-gradient GEMM needs no augmented [LN(x) | 1] operand.  Only the pipelined
+ * TMA kernel provides it: ask tgt_triplet_attn_bwd_bias_supported first (1 = yes).                               */
+int tgt_triplet_attn_bwd_bias_supported(const tgt_triplet_attn_desc *desc);
+int tgt_triplet_attn_bwd_bias(const tgt_triplet_attn_desc *desc, const void *proj, const float *mask,
+                              const void *va, const void *dva, const float *stats, void *dproj,
+                              void *workspace, size_t workspace_bytes, const void *fwd_workspace,
+                              float *dbias, void *stream);
+
 int tgt_triplet_attn_fused_supported(const tgt_triplet_attn_desc *desc, int We);
 int tgt_triplet_attn_fused_fwd(const tgt_triplet_attn_desc *desc, const void *x, int64_t ldx, int We,
                                const float *row_mean, const float *row_rstd, const void *wf,

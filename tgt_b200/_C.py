@@ -85,6 +85,8 @@ _SIGNATURES = {
     "tgt_triplet_attn_fwd": (C.c_int, [C.POINTER(TripletAttnDesc), _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "tgt_triplet_attn_bwd": (C.c_int, [C.POINTER(TripletAttnDesc), _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "tgt_triplet_attn_bwd_tiles": (C.c_int, [C.POINTER(TripletAttnDesc), _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P, _P]),
+    "tgt_triplet_attn_bwd_bias_supported": (C.c_int, [C.POINTER(TripletAttnDesc)]),
+    "tgt_triplet_attn_bwd_bias": (C.c_int, [C.POINTER(TripletAttnDesc), _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P, _P, _P]),
     "tgt_triplet_attn_fused_supported": (C.c_int, [C.POINTER(TripletAttnDesc), C.c_int]),
     "tgt_triplet_attn_fused_fwd": (C.c_int, [C.POINTER(TripletAttnDesc), _P, C.c_int64, C.c_int, _P, _P, _P, _P, _P, _P, _P,
                                              _P, _P, _P, C.c_size_t, _P]),

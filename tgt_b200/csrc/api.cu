@@ -57,7 +57,8 @@ size_t triplet_attn_mma_workspace(const tgt_triplet_attn_desc &, int backward);
 int triplet_attn_fwd_mma(const tgt_triplet_attn_desc &, const void *, const float *, void *, float *, void *, size_t,
                          cudaStream_t);
 int triplet_attn_bwd_mma(const tgt_triplet_attn_desc &, const void *, const float *, const void *, const void *,
-                         const float *, void *, void *, size_t, const void *, cudaStream_t);
+                         const float *, void *, void *, size_t, const void *, float *, cudaStream_t);
+bool triplet_attn_bwd_bias_available(const tgt_triplet_attn_desc &);
 bool triplet_attn_fused_supported(const tgt_triplet_attn_desc &D, int We);
 int triplet_attn_fused_fwd(const tgt_triplet_attn_desc &D, int We, const void *x, int64_t ldx, const float *mean,
                            const float *rstd, const void *wf, const float *wcolsum, const float *wbias,
@@ -137,14 +138,26 @@ extern "C" int tgt_triplet_attn_fwd(const tgt_triplet_attn_desc *D, const void *
   return triplet_attn_fwd_simt(*D, proj, mask, va, stats, st);
 }
 
-extern "C" int tgt_triplet_attn_bwd_tiles(const tgt_triplet_attn_desc *D, const void *proj, const float *mask,
-                                          const void *va, const void *dva, const float *stats, void *dproj, void *ws,
-                                          size_t ws_bytes, const void *fwd_workspace, void *stream) {
+extern "C" int tgt_triplet_attn_bwd_bias_supported(const tgt_triplet_attn_desc *D) {
+  if (!D || attn_check(D)) return 0;
+  return (g_policy.load() != 1 && triplet_attn_bwd_bias_available(*D)) ? 1 : 0;
+}
+
+extern "C" int tgt_triplet_attn_bwd_bias(const tgt_triplet_attn_desc *D, const void *proj, const float *mask,
+                                         const void *va, const void *dva, const float *stats, void *dproj, void *ws,
+                                         size_t ws_bytes, const void *fwd_workspace, float *dbias, void *stream) {
   if (int e = attn_check(D)) return e;
   cudaStream_t st = (cudaStream_t)stream;
   if (g_policy.load() != 1 && triplet_attn_mma_supported(*D))
-    return triplet_attn_bwd_mma(*D, proj, mask, va, dva, stats, dproj, ws, ws_bytes, fwd_workspace, st);
+    return triplet_attn_bwd_mma(*D, proj, mask, va, dva, stats, dproj, ws, ws_bytes, fwd_workspace, dbias, st);
+  if (dbias) return fail("triplet_attn_bwd_bias: not available with the generic kernels (check ..._bias_supported)");
   return triplet_attn_bwd_simt(*D, proj, mask, va, dva, stats, dproj, st);
+}
+
+extern "C" int tgt_triplet_attn_bwd_tiles(const tgt_triplet_attn_desc *D, const void *proj, const float *mask,
+                                          const void *va, const void *dva, const float *stats, void *dproj, void *ws,
+                                          size_t ws_bytes, const void *fwd_workspace, void *stream) {
+  return tgt_triplet_attn_bwd_bias(D, proj, mask, va, dva, stats, dproj, ws, ws_bytes, fwd_workspace, nullptr, stream);
 }
 
 extern "C" int tgt_triplet_attn_bwd(const tgt_triplet_attn_desc *D, const void *proj, const float *mask,

@@ -568,8 +568,9 @@ bool triplet_attn_tma_available();
 int triplet_attn_fwd_tma_launch(const tgt_triplet_attn_desc &D, const void *proj, void *va, float *stats,
                                 const float *ws_e, const __half *ws_g, cudaStream_t st);
 int triplet_attn_bwd_tma_launch(const tgt_triplet_attn_desc &D, const void *proj, const void *dva, const float *stats,
-                                void *dproj, const float *ws_e, const __half *ws_g, float *ws_de, float *ws_dg,
+                                void *dproj, const float *ws_e, const __half *ws_g, float *ws_de, float *ws_dg, float *dbias,
                                 cudaStream_t st);
+bool triplet_attn_bwd_tma_has_bias();
 // triplet_fused.cu
 bool triplet_attn_fused_supported(const tgt_triplet_attn_desc &D, int We);
 int triplet_attn_fused_launch(const tgt_triplet_attn_desc &D, int We, const void *x, int64_t ldx, const float *mean,
@@ -617,7 +618,9 @@ static int fwd_impl(const tgt_triplet_attn_desc &D, const void *proj, const floa
 
 template <typename T>
 static int bwd_impl(const tgt_triplet_attn_desc &D, const void *proj, const float *mask, const void *dva,
-                    const float *stats, void *dproj, void *ws, const void *fwd_ws, cudaStream_t st) {
+                    const float *stats, void *dproj, void *ws, const void *fwd_ws, float *dbias, cudaStream_t st) {
+  if (dbias && !(use_tma() && triplet_attn_bwd_tma_has_bias()))
+    return fail("triplet_attn_bwd: the projection-bias by-product is not available with this kernel family");
   Ws w = carve(D, ws);
   const size_t psm = 2 * (size_t)D.H * 65 * sizeof(float);
   if (fwd_ws) {
@@ -631,7 +634,7 @@ static int bwd_impl(const tgt_triplet_attn_desc &D, const void *proj, const floa
     if (int e = check_launch("tri_prep_bias_gate")) return e;
   }
   if (use_tma()) {
-    if (int e = triplet_attn_bwd_tma_launch(D, proj, dva, stats, dproj, w.e, w.g, w.de, w.dg, st)) return e;
+    if (int e = triplet_attn_bwd_tma_launch(D, proj, dva, stats, dproj, w.e, w.g, w.de, w.dg, dbias, st)) return e;
     if (bias_gate_h16_ok(D)) tri_post_bias_gate_h16<T><<<dim3(D.N, 2, D.B), 256, 0, st>>>(D, w.de, w.dg, (T *)dproj);
     else tri_post_bias_gate<T><<<dim3(D.N, 2, D.B), 256, psm, st>>>(D, w.de, w.dg, (T *)dproj);
     return check_launch("tri_post_bias_gate");
@@ -688,15 +691,19 @@ int triplet_attn_fwd_mma(const tgt_triplet_attn_desc &D, const void *proj, const
 
 int triplet_attn_bwd_mma(const tgt_triplet_attn_desc &D, const void *proj, const float *mask, const void *va,
                          const void *dva, const float *stats, void *dproj, void *ws, size_t ws_bytes,
-                         const void *fwd_ws, cudaStream_t st) {
+                         const void *fwd_ws, float *dbias, cudaStream_t st) {
   (void)va;      // delta = rowsum(dP o P) is recomputed in registers; the forward output is not needed
   if (!ws || ws_bytes < triplet_attn_mma_workspace(D, 1))
     return fail("triplet_attn_bwd: workspace too small (%zu < %zu bytes)", ws_bytes, triplet_attn_mma_workspace(D, 1));
   if (((uintptr_t)proj | (uintptr_t)dva | (uintptr_t)dproj) & 15)
     return fail("triplet_attn_bwd: proj / dva / dproj must be 16-byte aligned");
   if (D.B > 65535) return fail("triplet_attn_bwd: B > 65535 unsupported");
-  if (D.dtype == TGT_BF16) return bwd_impl<__nv_bfloat16>(D, proj, mask, dva, stats, dproj, ws, fwd_ws, st);
-  return bwd_impl<__half>(D, proj, mask, dva, stats, dproj, ws, fwd_ws, st);
+  if (D.dtype == TGT_BF16) return bwd_impl<__nv_bfloat16>(D, proj, mask, dva, stats, dproj, ws, fwd_ws, dbias, st);
+  return bwd_impl<__half>(D, proj, mask, dva, stats, dproj, ws, fwd_ws, dbias, st);
+}
+
+bool triplet_attn_bwd_bias_available(const tgt_triplet_attn_desc &D) {
+  return triplet_attn_mma_supported(D) && use_tma() && triplet_attn_bwd_tma_has_bias();
 }
 
 }  // namespace tgt

@@ -105,7 +105,8 @@ def ln_bwd_emits_y(x2: Tensor, cd: torch.dtype) -> bool:
 
 
 def layernorm_bwd(dy: Tensor, x2: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor,
-                  dres: Optional[Tensor] = None, beta: Optional[Tensor] = None, colsum: Optional[tuple] = None):
+                  dres: Optional[Tensor] = None, beta: Optional[Tensor] = None, colsum: Optional[tuple] = None,
+                  aug: bool = True):
     """(dx, dgamma, dbeta[, y][, dres_colsum]).  By-products of the same pass (see ln_bwd_emits_y):
     `beta` given   -> also the augmented y = [LN(x) | 1 | 0...] in dy's dtype, so callers order their weight-gradient
                       GEMM after this call instead of running a LayerNorm recompute pass for it;
@@ -115,13 +116,14 @@ def layernorm_bwd(dy: Tensor, x2: Tensor, gamma: Tensor, mean: Tensor, rstd: Ten
     dx = torch.empty_like(x2)
     dgb = torch.zeros((3 if colsum is not None else 2, W), dtype=torch.float32, device=x2.device)
     if beta is not None or colsum is not None:
-        y = torch.empty((rows, W + AUG), dtype=dy.dtype, device=x2.device) if beta is not None else None
+        ldy = W + AUG if aug else W            # aug=False: plain LN(x) (the caller has the bias gradient from elsewhere)
+        y = torch.empty((rows, ldy), dtype=dy.dtype, device=x2.device) if beta is not None else None
         sc = colsum[0] if colsum is not None else None
         rps = rows // sc.numel() if sc is not None else 1
         with timed(f"layernorm_bwd_W{W}"):
             _C.check(_C.lib().tgt_layernorm_bwd_y(_C.ptr(dy), _C.ptr(x2), _C.ptr(gamma), _C.ptr(beta), _C.ptr(mean),
                                                   _C.ptr(rstd), _C.ptr(dres), _C.ptr(dx), _C.ptr(dgb[0]),
-                                                  _C.ptr(dgb[1]), _C.ptr(y), W + AUG, rows, W,
+                                                  _C.ptr(dgb[1]), _C.ptr(y), ldy, rows, W,
                                                   _C.dtype_code(x2.dtype), _C.dtype_code(dy.dtype), _C.ptr(sc), rps,
                                                   _C.ptr(dgb[2]) if colsum is not None else None, _C.stream_ptr()),
                      "layernorm_bwd_y")
@@ -615,6 +617,9 @@ def _fused_triplet_fwd(x2, mean, rstd, fold, m3, va, stats, B, N, H, d, W, off_e
     return ws
 
 
+_TRI_BWD_BIAS = _os.environ.get("TGT_TRI_BWD_BIAS", "1") == "1"   # A/B switch: projection bias gradient from the backward kernel
+
+
 class TripletAttentionFn(Function):
     """e:[B,N,N,W]; Wcat:[C,W] rows in kernel order (head-major q/k/v blocks, then bias/gate blocks);
     Wo:[W,2W] with columns in kernel order (dir, h, dd).  `layout` = (H, d, off_q, off_k, off_v, off_e, off_g).
@@ -707,22 +712,28 @@ class TripletAttentionFn(Function):
             ws, wsb = _workspace(_C.lib().tgt_triplet_attn_workspace_bytes(desc, 1), x2.device)
             if tiles is not None and ctx.tile_policy != _C.kernel_policy():
                 tiles = None                                # kernel family changed since the forward: recompute
+            # the pipelined backward kernel also sums the columns of dproj (= bias gradient of the projection): the
+            # weight-gradient GEMM then runs on the plain 256-column LN(x) instead of the augmented 264-column one
+            dbias = None
+            if late_y and _TRI_BWD_BIAS and _C.lib().tgt_triplet_attn_bwd_bias_supported(desc):
+                dbias = torch.zeros(proj.shape[1], dtype=torch.float32, device=x2.device)
             with timed("triplet_attn_bwd"):
-                _C.check(_C.lib().tgt_triplet_attn_bwd_tiles(desc, _C.ptr(proj), _C.ptr(m3), _C.ptr(va), _C.ptr(dva),
-                                                             _C.ptr(stats), _C.ptr(dproj), _C.ptr(ws), wsb,
-                                                             _C.ptr(tiles), _C.stream_ptr()), "triplet_attn_bwd")
+                _C.check(_C.lib().tgt_triplet_attn_bwd_bias(desc, _C.ptr(proj), _C.ptr(m3), _C.ptr(va), _C.ptr(dva),
+                                                            _C.ptr(stats), _C.ptr(dproj), _C.ptr(ws), wsb,
+                                                            _C.ptr(tiles), _C.ptr(dbias), _C.stream_ptr()),
+                         "triplet_attn_bwd")
             del ws
             del proj, dva
             if late_y:                  # LN(x) comes out of the LayerNorm-backward kernel: no recompute pass
                 dy = torch.mm(dproj, Wc)
                 res = layernorm_bwd(dy, x2, g, mean, rstd, _dres_for(dalias, x2), beta=bt,
-                                    colsum=(sc,) if cs_db else None)
+                                    colsum=(sc,) if cs_db else None, aug=dbias is None)
                 dx, dg, dbt, y = res[:4]
                 if cs_db:
                     dbo = res[4]
                 del dy
-                dWa = torch.mm(dproj.t(), y)              # [C, W+8]: weight gradient | bias gradient (column W)
-                dWc, dbc = dWa[:, :W], dWa[:, W]
+                dWa = torch.mm(dproj.t(), y)              # [C, W (+8)]: weight gradient (| bias gradient in column W)
+                dWc, dbc = (dWa, dbias) if dbias is not None else (dWa[:, :W], dWa[:, W])
                 del y, dproj
             else:
                 dWa = torch.mm(dproj.t(), y)

@@ -547,6 +547,9 @@ tri_attn_bwd_tma_pipe(const tgt_triplet_attn_desc D, const __grid_constant__ CUt
   float sa0, sa1, sb0, sb1;                  // lse of the next two junctions (fetched two iterations ahead)
   load_stats(0, sa0, sa1);
   load_stats(1, sb0, sb1);
+  // running pointers to the lse of junction j + 2 (rows i0 / i1): one add per junction instead of 64-bit index arithmetic
+  const float *pl0 = stb + 2 * (int64_t)N + (i0 < N ? i0 : 0), *pl1 = stb + 2 * (int64_t)N + (i1 < N ? i1 : 0);
+  const bool ok0 = i0 < N, ok1 = i1 < N;
 
   // Software pipeline over the junctions: iteration `it` runs the key pass (dK, dV) of junction it-1 and the score pass
   // (S, dA, P, dS, A, dQ) of junction it back to back, so ONE CTA barrier per junction separates "exchange tiles written"
@@ -597,7 +600,13 @@ tri_attn_bwd_tma_pipe(const tgt_triplet_attn_desc D, const __grid_constant__ CUt
       const float lse0 = sa0, lse1 = sa1;
       sa0 = sb0;
       sa1 = sb1;
-      load_stats(j + 2, sb0, sb1);
+      sb0 = sb1 = INFINITY;
+      if (j + 2 < N) {
+        if (ok0) sb0 = *pl0;
+        if (ok1) sb1 = *pl1;
+      }
+      pl0 += N;
+      pl1 += N;
       const uint32_t st = sbase + (j % TP_STAGES) * TB_STAGE_BYTES;
       const uint32_t sQ = st, sK = st + TILE_BYTES, sV = st + 2 * TILE_BYTES, sO = st + 3 * TILE_BYTES;
       const uint32_t xS = xbase + (j & 1) * 2 * TB_XCH_BYTES, xA = xS + TB_XCH_BYTES;

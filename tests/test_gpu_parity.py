@@ -485,3 +485,42 @@ def test_two_stage_inference_matches_oracle_pipeline():
         ref = gm(b2)
     assert torch.allclose(pred, ref.float(), rtol=1e-5, atol=1e-5)
     assert pred.shape == (3,) and bool(torch.isfinite(pred).all())
+
+
+def test_full_size_batch_invariance_and_padding_independence():
+    """BASELINE config-3 size (B = 256, N = 64, Wn = 768, We = 256, Hn = 64, Ht = 16, bf16 autocast) through two
+    size-independent properties of the reference path: (1) a graph's outputs and input gradients do not depend on which
+    other graphs share the batch -- the full batch must agree with the same graphs run four at a time (only cuBLAS's
+    node-side tile choice may differ: bf16-level tolerance, edge kernels never mix graphs); (2) for TripletAttention the
+    values on PADDED atoms of the input never reach real-pair outputs (unlike TripletAggregate, see the leak test)."""
+    torch.manual_seed(0)
+    B, N = 256, 64
+    layer = L.TGT_Layer(768, 256, 64, triplet_heads=16, triplet_type="attention").to(DEV).eval()
+    nn_ = [N] + [N // 2 + (i * 7) % (N // 2 + 1) for i in range(1, B)]
+    e, mask = make_edge_inputs(B, N, 256, nn_, seed=3)
+    gen = torch.Generator().manual_seed(9)
+    h = torch.randn(B, N, 768, generator=gen)
+    wh, we = torch.randn(B, N, 768, generator=gen), torch.randn(B, N, N, 256, generator=gen)
+
+    def run(sl, e_src=e):
+        hh = h[sl].to(DEV).requires_grad_(True)
+        ee = e_src[sl].to(DEV).requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            g = layer(Graph(h=hh, e=ee, mask=mask[sl].to(DEV)))
+        ((g.h.float() * wh[sl].to(DEV)).sum() + (g.e.float() * we[sl].to(DEV)).sum()).backward()
+        return g.h.float().detach().cpu(), g.e.float().detach().cpu(), hh.grad.cpu(), ee.grad.cpu()
+
+    full = run(slice(0, B))
+    assert all(bool(torch.isfinite(t).all()) for t in full)
+    for b0 in (0, 100, 252):
+        sub = run(slice(b0, b0 + 4))
+        for name, f, s_ in zip(("h", "e", "dh", "de"), full, sub):
+            assert rel_err(f[b0:b0 + 4], s_) < 5e-3, (name, b0, rel_err(f[b0:b0 + 4], s_))
+    # (2) perturb padded entries of e (graph 1 has nn_[1] < N real atoms): real-pair outputs must not move
+    n1 = nn_[1]
+    e2 = e.clone()
+    e2[1, n1:, :, :] += torch.randn(e2[1, n1:, :, :].shape, generator=gen)
+    e2[1, :, n1:, :] += torch.randn(e2[1, :, n1:, :].shape, generator=gen)
+    a = run(slice(0, 4))
+    b_ = run(slice(0, 4), e_src=e2)
+    assert torch.equal(a[1][1, :n1, :n1], b_[1][1, :n1, :n1]) and torch.equal(a[0][1, :n1], b_[0][1, :n1])

@@ -524,3 +524,42 @@ def test_full_size_batch_invariance_and_padding_independence():
     a = run(slice(0, 4))
     b_ = run(slice(0, 4), e_src=e2)
     assert torch.equal(a[1][1, :n1, :n1], b_[1][1, :n1, :n1]) and torch.equal(a[0][1, :n1], b_[0][1, :n1])
+
+
+def test_full_size_properties_config2_and_config5():
+    """Size-independent properties at the other BASELINE sizes.  Config 5 (B = 512, N = 48, 256 bins): the decoded bins /
+    distances are symmetric with a zero diagonal, invariant to a per-pair logit shift (softmax) and equivariant to
+    transposing the atom pair.  Config 2 (TripletAggregate, B = 256, N = 32, We = 256, Ht = 16, bf16): batch invariance of
+    outputs and input gradients (bit-exact: no library GEMM on this path depends on the batch size per row)."""
+    gen = torch.Generator(device=DEV).manual_seed(4)
+    lg = (torch.randn(512, 48, 48, 256, device=DEV, generator=gen) * 2).bfloat16()
+    bins, dist = ops.bins_decode(lg, range_bins=8.0)
+    assert torch.equal(bins, bins.transpose(1, 2)) and torch.equal(dist, dist.transpose(1, 2))
+    assert float(dist.diagonal(dim1=1, dim2=2).abs().max()) == 0.0 and int(bins.min()) >= 0 and int(bins.max()) <= 255
+    off = torch.arange(48, device=DEV).float()
+    assert torch.equal(dist[:, off.long(), off.long()], torch.zeros(512, 48, device=DEV))
+    b2, d2 = ops.bins_decode(lg.transpose(1, 2).contiguous(), range_bins=8.0)
+    assert torch.equal(b2, bins) and torch.equal(d2, dist)
+    shift = torch.randn(512, 48, 48, 1, device=DEV, generator=gen)
+    b3, _ = ops.bins_decode(lg.float() + shift, range_bins=8.0)
+    assert float((b3 == ops.bins_decode(lg.float(), range_bins=8.0)[0]).float().mean()) > 0.9999
+    del lg, shift
+
+    torch.manual_seed(0)
+    mod = L.TripletAggregate(256, 16).to(DEV)
+    B, N = 256, 32
+    nn_ = [N] + [N // 2 + (i * 5) % (N // 2 + 1) for i in range(1, B)]
+    e, mask = make_edge_inputs(B, N, 256, nn_, seed=6)
+    w = torch.randn(B, N, N, 256, generator=torch.Generator().manual_seed(2))
+
+    def run(sl):
+        ee = e[sl].to(DEV).requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = mod(ee, mask[sl].to(DEV))
+        (out.float() * w[sl].to(DEV)).sum().backward()
+        return out.detach().cpu(), ee.grad.cpu()
+
+    full = run(slice(0, B))
+    for b0 in (0, 77, 252):
+        sub = run(slice(b0, b0 + 4))
+        assert torch.equal(full[0][b0:b0 + 4], sub[0]) and rel_err(full[1][b0:b0 + 4], sub[1]) < 1e-3

@@ -88,7 +88,7 @@ def test_gemm_desc_mirrors_header():
         for part in decl.split(","):
             names.append(re.sub(r"[\*\s]", " ", part).split()[-1])
     assert names == [f[0] for f in _C.GemmDesc._fields_]
-    for flag in ("LN", "BIAS", "GELU", "RES", "STORE_U", "ROWSCALE", "GELU_BWD", "STATS", "LN_BWD"):
+    for flag in ("LN", "BIAS", "GELU", "RES", "STORE_U", "ROWSCALE", "GELU_BWD", "STATS", "LN_BWD", "STORE_GP", "MULRES"):
         val = int(re.search(rf"#define TGT_EPI_{flag}\s+(\d+)", hdr).group(1))
         assert getattr(_C, f"EPI_{flag}") == val
     assert C.sizeof(_C.GemmDesc) % 8 == 0
@@ -125,3 +125,36 @@ def test_keep_projection_policy(monkeypatch):
         out.append(ops.keep_projection(proj, "cuda:0", True))
     ops.set_layer_hint(None, None)
     assert not any(out)
+
+
+def test_other_descriptors_mirror_header():
+    """ctypes mirrors of the attention / aggregate / triangular / EGT descriptors: same field names in the same order."""
+    import os
+    hdr = open(os.path.join(os.path.dirname(__file__), "..", "include", "tgt_b200.h")).read()
+    for cname, cls in (("tgt_triplet_attn_desc", _C.TripletAttnDesc), ("tgt_triplet_aggr_desc", _C.TripletAggrDesc),
+                       ("tgt_triangular_desc", _C.TriangularDesc), ("tgt_egt_desc", _C.EgtDesc)):
+        body = re.search(r"typedef struct \{([^}]*)\} " + cname + ";", hdr, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            for part in decl.split(","):
+                names.append(re.sub(r"\[\d+\]", "", re.sub(r"[\*\s]", " ", part)).split()[-1])
+        assert names == [f[0] for f in cls._fields_], cname
+
+
+def test_two_stage_oracle_helpers():
+    """bins_from_logits / bins2dist (oracle): symmetry, zero diagonal, the (bin + 0.5) * range / (bins - 1) * 2 scale."""
+    from oracle import tgt_oracle as O
+    g = torch.Generator().manual_seed(0)
+    lg = torch.randn(2, 6, 6, 16, generator=g)
+    b = O.bins_from_logits(lg)
+    assert torch.equal(b, b.transpose(1, 2)) and b.dtype == torch.int64
+    d = O.bins2dist(b, 16, 8.0)
+    assert torch.equal(d, d.transpose(1, 2)) and float(d.diagonal(dim1=1, dim2=2).abs().max()) == 0.0
+    i, j = 0, 3
+    assert abs(float(d[0, i, j]) - 2 * (float(b[0, i, j]) + 0.5) * 8.0 / 15) < 1e-6
+    d2 = O.bins2dist(b, 16, 8.0, shift_half=False, zero_diag=False)
+    assert abs(float(d2[0, 2, 2]) - 2 * float(b[0, 2, 2]) * 8.0 / 15) < 1e-6

@@ -342,7 +342,7 @@ def run_ours(args):
                           parts={k: kernels[k]["ms_per_launch"] for k in names})
         base = None
         if not args.no_cpu_baseline:
-            base, _ = cpu_baseline(args, args.cpu_batch or 4, 1, 1 if args.cpu_warm else 0)
+            base, _ = cpu_baseline(args, args.cpu_batch or 4, 2, 1)       # bounded sample: 1 warm-up + 2 timed steps, ~18 s on 16 cores
         out = dict(metric=METRIC, value=world * B / (step_ms * 1e-3), unit=UNIT, n_gpus=world, steps=args.steps,
                    warmup=args.warmup, ms_per_step=step_ms, higher_is_better=True, scaling="weak", vs_baseline=None,
                    dtype="bf16", data="synthetic",

@@ -12,8 +12,11 @@ One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for the definitio
                  inside the timed region)
   roofline     : our kernel with the largest share of the step, timed with CUDA events INSIDE the step
   kernels      : the same for every one of our kernels (share of step, achieved vs bound)
-  cpu_baseline : the oracle port (oracle/tgt_oracle.py == the reference's PyTorch-CPU algorithm) on the host
-                 cores, on a bounded micro-batch of the same workload
+  cpu_baseline : the unmodified reference (oracle/_ref, staged by oracle/build_ref.py; kind "reference") on the host
+                 cores, on a bounded micro-batch of the same workload (falls back to the oracle port, kind "port")
+  gpu_eager_baseline : the same unmodified reference on this B200 under PyTorch-CUDA bf16 autocast at the largest
+                 micro-batch that fits (N = 1 only)
+  library_calls_per_step : every GEMM that still goes to cuBLAS through torch, by call site
   --impl reference : only the CPU path, K steps of a bounded micro-batch each.
 """
 from __future__ import annotations
@@ -54,8 +57,42 @@ def model_cfg(args):
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline
-def cpu_step_fn(args, B):
-    """Reference algorithm on CPU (oracle port), fp32, all host threads: fwd + loss + bwd + Adam."""
+def _reference_kwargs(cfg):
+    """TGT_AT_CONFIG -> kwargs of the reference's lib.models.pcqm.multitask.TGT_Multi (same names)."""
+    return dict(cfg)
+
+
+def reference_step_fn(args, B, device, autocast_dtype=None, fused_adam=False):
+    """The UNMODIFIED reference (oracle/_ref = lib.tgt + lib.models.pcqm + commons, staged by oracle/build_ref.py):
+    TGT_Multi forward + the pretrain loss of pretrain/scheme.py:78-88 + backward + Adam, train mode, shipped dropouts."""
+    from oracle import ref_loader as R                          # checker / baseline only
+    from tgt_b200.harness.synthetic import make_batch
+    cfg = model_cfg(args)
+    stack = R.reference()
+    ref = stack.__enter__()                                     # stays imported for the lifetime of the process
+    torch.manual_seed(0)
+    model = ref.TGT_Multi(**_reference_kwargs(cfg)).to(device).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-5, **(dict(fused=True) if fused_adam else {}))
+    batch = {k: v.to(device) for k, v in make_batch(B, args.nodes, seed=1).items()}
+    loss_fn = ref.commons.DiscreteDistLoss(cfg["num_dist_bins"], 8)
+
+    def step():
+        if autocast_dtype is not None:
+            with torch.autocast("cuda", dtype=autocast_dtype):
+                gap, logits = model(batch)
+        else:
+            gap, logits = model(batch)
+        loss = (torch.nn.functional.l1_loss(gap.float(), batch["target"].float())
+                + 0.1 * loss_fn(logits.float(), ref.commons.coords2dist(batch["dft_coords"]), batch["edge_mask"]))
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return float(loss.detach())
+    return step
+
+
+def port_step_fn(args, B):
+    """Fallback when oracle/_ref is not staged: the oracle port of the same step (oracle/tgt_oracle.py)."""
     from oracle import tgt_oracle as O                       # checker / baseline only
     from tgt_b200.harness.models import TGT_Multi
     from tgt_b200.harness.synthetic import make_batch
@@ -79,19 +116,59 @@ def cpu_step_fn(args, B):
 
 
 def cpu_baseline(args, B, steps, warmup):
+    from oracle import ref_loader as R
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    step = cpu_step_fn(args, B)
+    kind = "reference" if R.available() else "port"
+    step = reference_step_fn(args, B, "cpu") if kind == "reference" else port_step_fn(args, B)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    return dict(value=B / dt, unit=UNIT, cores=cores, kind="port",
-                sample=f"oracle port of lib.tgt + lib.models.pcqm (PyTorch-CPU fp32 eager), TGT-At {args.layers}L "
-                       f"N={args.nodes}, micro-batch {B} molecules/step, {steps} timed step(s) after {warmup} warm-up, "
-                       f"{dt:.2f} s/step"), dt
+    what = ("unmodified reference lib.models.pcqm.multitask.TGT_Multi on lib.tgt (oracle/_ref)" if kind == "reference"
+            else "oracle port of lib.tgt + lib.models.pcqm")
+    return dict(value=B / dt, unit=UNIT, cores=cores, kind=kind,
+                sample=f"{what}, PyTorch-CPU fp32 eager, train mode, TGT-At {args.layers}L N={args.nodes}, micro-batch "
+                       f"{B} molecules/step (fwd + pretrain loss + bwd + Adam), {steps} timed step(s) after {warmup} "
+                       f"warm-up, {dt:.2f} s/step"), dt
+
+
+def gpu_eager_baseline(args, dev):
+    """The reference itself on THIS B200 ('the bar to beat'): unmodified lib.tgt / lib.models.pcqm under
+    PyTorch-CUDA bf16 autocast, eager, fused Adam, at the largest micro-batch of the ladder that fits (the reference
+    materialises and saves several [B,N,N,N,H] tensors per layer, so batch 256 cannot fit: SURVEY 2.3 note)."""
+    from oracle import ref_loader as R
+    if not R.available():
+        return dict(unavailable="oracle/_ref not staged")
+    tried = []
+    for mb in (64, 48, 32, 24, 16, 8, 4):
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats(dev)
+        try:
+            step = reference_step_fn(args, mb, dev, torch.bfloat16, fused_adam=True)
+            step()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            n = 2
+            for _ in range(n):
+                step()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / n
+            return dict(value=mb / (ms * 1e-3), unit=UNIT, micro_batch=mb, ms_per_step=ms,
+                        peak_mem_gib=torch.cuda.max_memory_allocated(dev) / 2 ** 30, oom_at=tried,
+                        what=f"unmodified reference (oracle/_ref) TGT_Multi TGT-At {args.layers}L N={args.nodes}, "
+                             f"PyTorch-CUDA eager, bf16 autocast, train mode, fwd + pretrain loss + bwd + fused Adam, "
+                             f"micro-batch {mb} (largest of 64/48/32/24/16/8/4 that fits), 1 warm-up + {n} timed steps")
+        except torch.OutOfMemoryError:
+            tried.append(mb)
+            step = None
+            import gc
+            gc.collect()
+    return dict(unavailable=f"out of memory at every micro-batch tried {tried}")
 
 
 def run_reference(args):
@@ -160,7 +237,7 @@ def kernel_models(B, N, We, Ht, Wn, Hn, s=2):
     R = B * N * N
     d = {}
     d["triplet_attn_fwd"] = dict(bytes=(8 * R * We + 4 * R * Ht) * s + 4 * R, flops=8 * B * N ** 3 * We)
-    d["triplet_attn_bwd"] = dict(bytes=(16 * R * We + 8 * R * Ht) * s + 4 * R, flops=20 * B * N ** 3 * We)
+    d["triplet_attn_bwd"] = dict(bytes=(16 * R * We + 8 * R * Ht) * s + 4 * R, flops=16 * B * N ** 3 * We)   # dA, dV, dQ, dK per direction; the S recompute is not algorithmic work
     d["triplet_aggr_fwd"] = dict(bytes=(4 * R * We + 4 * R * Ht) * s + 4 * R, flops=4 * B * N ** 3 * We)
     d["triplet_aggr_bwd"] = dict(bytes=(8 * R * We + 8 * R * Ht) * s + 4 * R, flops=8 * B * N ** 3 * We)
     d["egt_attn_fwd"] = dict(bytes=(3 * R * Hn + 4 * B * N * Wn) * s + 4 * R, flops=4 * B * N * N * Wn)
@@ -282,9 +359,11 @@ def run_ours(args):
     _C.kernel_timer(True)
     barrier()
     ksteps = max(1, min(args.steps, 2))
+    ops.LIBRARY_CALLS.clear()
     for _ in range(ksteps):
         step(resident)
     barrier()
+    lib_calls_raw = dict(ops.LIBRARY_CALLS)
     ksum = ops.KernelTimer.summary()
     dsum = _C.kernel_timer_read()          # main kernels only, CUDA events recorded inside the library
     ops.KernelTimer.reset(False)
@@ -329,17 +408,38 @@ def run_ours(args):
                             tensor_tflops=e["tflops"], tensor_frac_of_sustained=e["tc_frac"],
                             note="HBM-bound O(N^3) core: algorithmic bytes / CUDA-event duration of the kernel alone, "
                                  "timed inside the 24-layer step")
-        # the triplet module forward (LN-folded projection GEMM + attention core + lin_O GEMM) against the tensor roofline
+        # the triplet MODULE (LayerNorm -> projection -> attention core -> lin_O; SURVEY 8d's fused boundary) against the
+        # tensor roofline: CUDA events around the whole autograd Function, forward and backward, inside the real step.
+        # F_mod = R*We*(16*We + 8*Ht) + 8*B*N^3*We forward, 2*F_mod backward (projection recompute is NOT counted).
         module = None
-        names = ("gemm_tc_ln_proj", "triplet_attn_fwd", "gemm_tc_lin_o")
-        if all(k in kernels for k in names):
-            t_mod = sum(kernels[k]["ms_per_launch"] for k in names)
+        if "triplet_module_fwd" in kernels and "triplet_module_bwd" in kernels:
             R_ = micro * N * N
             We_, Ht_ = cfg["edge_width"], cfg["triplet_heads"]
             f_mod = R_ * We_ * (16 * We_ + 8 * Ht_) + 8 * micro * N ** 3 * We_
-            module = dict(ms=t_mod, alg_flops=f_mod, tflops=f_mod / (t_mod * 1e-3) / 1e12,
-                          tc_frac_of_sustained=f_mod / (t_mod * 1e-3) / 1e12 / pk["tc_sustained"],
-                          parts={k: kernels[k]["ms_per_launch"] for k in names})
+            t_f, t_b = kernels["triplet_module_fwd"]["ms_per_launch"], kernels["triplet_module_bwd"]["ms_per_launch"]
+            frac = lambda fl, ms_: fl / (ms_ * 1e-3) / 1e12 / pk["tc_sustained"]
+            module = dict(fwd_ms=t_f, bwd_ms=t_b, alg_flops_fwd=f_mod, alg_flops_fwd_bwd=3 * f_mod,
+                          module_tc_frac_fwd=frac(f_mod, t_f), module_tc_frac_fwd_bwd=frac(3 * f_mod, t_f + t_b),
+                          parts_fwd={k: kernels[k]["ms_per_launch"] for k in
+                                     ("gemm_tc_ln_proj", "triplet_attn_fwd", "gemm_tc_lin_o") if k in kernels},
+                          parts_bwd={k: kernels[k]["ms_per_launch"] for k in kernels
+                                     if k in ("gemm_tc_dva", "triplet_attn_bwd", "layernorm_bwd_W%d" % We_, "gemm_wgrad_proj",
+                                              "gemm_tc_dy_proj", "lib:triplet.dy", "lib:triplet.dW",
+                                              "lib:linear_residual_bwd.dW(bmm)")})
+        if roofline and module:
+            roofline["module_tc_frac_fwd"] = module["module_tc_frac_fwd"]
+            roofline["module_tc_frac_fwd_bwd"] = module["module_tc_frac_fwd_bwd"]
+            # one TGT-At layer is ~1.77 TF forward at B = 256, N = 64 => 3 x 1.77 TF x layers per step
+            roofline["whole_step_tc_frac"] = (3 * 1.77e12 * cfg["model_height"] * (B / 256) / (step_ms * 1e-3) / 1e12
+                                              / pk["tc_sustained"]) if N == 64 else None
+        lib_calls = {k: v / ksteps for k, v in sorted(lib_calls_raw.items())}
+        eager = None
+        if not args.no_gpu_eager_baseline and world == 1:
+            del net, opt, model, resident
+            import gc
+            gc.collect()
+            eager = gpu_eager_baseline(args, dev)
+            torch.cuda.empty_cache()
         base = None
         if not args.no_cpu_baseline:
             base, _ = cpu_baseline(args, args.cpu_batch or 4, 2, 1)       # bounded sample: 1 warm-up + 2 timed steps, ~18 s on 16 cores
@@ -355,7 +455,8 @@ def run_ours(args):
                    e2e=dict(value=world * B / (ms_e2e / args.steps * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d_bytes,
                             d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps),
                    gpu_launches=int(launches), clocks=clk, roofline=roofline, device_kernels=dev_kernels,
-                   triplet_module_fwd=module, kernels=kernels, cpu_baseline=base, peak_mem_gib=peak_mem)
+                   triplet_module=module, library_calls_per_step=lib_calls, kernels=kernels, cpu_baseline=base,
+                   gpu_eager_baseline=eager, peak_mem_gib=peak_mem)
         emit(out)
     if world > 1:
         dist.destroy_process_group()
@@ -394,6 +495,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=0)
     ap.add_argument("--cpu-warm", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager-baseline", action="store_true")
     ap.add_argument("--fp32-logits", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -269,14 +269,22 @@ def tgt_layer(p: Params, h: Tensor, e: Tensor, mask: Tensor, *, num_heads: int,
     else:
         raise ValueError("At least one of node_update and edge_update must be True")
     if node_update:
-        h = h + dh
-        h = h + ffn(sub(p, "node_ffn"), h, activation)
+        h = _residual(dh, h)
+        h = _residual(ffn(sub(p, "node_ffn"), h, activation), h)
     if edge_update_:
-        e = e + de
+        e = _residual(de, e)
         if triplet_heads > 0:
-            e = e + TRIPLET_FNS[triplet_type](sub(p, "tria"), e, mask, triplet_heads)
-        e = e + ffn(sub(p, "edge_ffn"), e, activation)
+            e = _residual(TRIPLET_FNS[triplet_type](sub(p, "tria"), e, mask, triplet_heads), e)
+        e = _residual(ffn(sub(p, "edge_ffn"), e, activation), e)
     return h, e
+
+
+def _residual(x: Tensor, res: Tensor) -> Tensor:
+    """`x.add_(res)` of layers.py:270-290: the sum is formed in the promoted type and stored in x's dtype.  In a
+    uniform-precision run this is x + res; under autocast x is the 16-bit Linear output and res the (initially fp32)
+    stream, so the residual stream is 16-bit from the first add onwards -- kept here so that the
+    oracle run under CUDA autocast is the reference's arithmetic, not a more accurate one."""
+    return (x + res).to(x.dtype)
 
 
 def encoder(p: Params, h: Tensor, e: Tensor, mask: Tensor, *, model_height: int,

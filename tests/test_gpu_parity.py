@@ -1,8 +1,13 @@
 """GPU parity tests: tgt_b200 CUDA path (through the C ABI) vs the golden vectors of the real reference and vs
 the CPU oracle.  Tolerances (stated per BASELINE.json north_star):
   fp32 : max |ours - ref| / max |ref| <= 1e-5          (TF32 is off: torch default for matmul)
-  bf16 : relative L2 error <= 1e-2 on module outputs/grads, AND <= 1.5x the error the reference's own
-         bf16-autocast path makes on the same inputs (+1e-3 slack); bf16 storage alone costs ~1.1e-3.
+  bf16 : the binding criterion is  err(ours vs fp64 golden) <= 1.0 x err(reference algorithm under CUDA bf16 autocast
+         vs fp64 golden)  on the same inputs, with NO additive slack, for module outputs and input gradients
+         (relative L2; rounding a tensor to bf16 alone costs ~1.1e-3, so an element-wise 1e-3 is unreachable for ANY
+         bf16 implementation, the reference's included -- SURVEY.md section 7).  BF16_TOL = 1e-2 is only a sanity
+         ceiling.  The other half of SURVEY section 7's protocol -- the attention core with fp32 outputs on bf16-rounded
+         inputs within 1e-3 of the fp64 oracle -- is tests/test_gpu_triplet_tc.py; whole layers / encoders at the
+         shipped geometry are tests/test_gpu_shipped_geometry.py.
 """
 import glob
 import os
@@ -78,8 +83,9 @@ def test_triplet_bf16_vs_golden(name, policy):
     assert out.dtype == torch.bfloat16
     ref_eo, ref_ed = _oracle_autocast_error(fx, torch.bfloat16)
     eo, ed = rel_err(out.float().cpu(), fx["out"]), rel_err(de.cpu(), fx["de"])
-    assert eo < BF16_TOL and eo < 1.5 * ref_eo + 1e-3, (eo, ref_eo)
-    assert ed < 2 * BF16_TOL and ed < 1.5 * ref_ed + 1e-3, (ed, ref_ed)
+    print(f"bf16 {name} policy {policy}: out {eo:.3e} (reference autocast {ref_eo:.3e}), de {ed:.3e} ({ref_ed:.3e})")
+    assert eo < BF16_TOL and eo <= ref_eo, (eo, ref_eo)
+    assert ed < 2 * BF16_TOL and ed <= ref_ed, (ed, ref_ed)
     assert_grads_close(grads, fx["grads"], 3 * BF16_TOL, "l2")
 
 

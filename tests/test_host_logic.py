@@ -99,9 +99,10 @@ def test_keep_projection_policy(monkeypatch):
     live = {"v": 0}
     monkeypatch.setattr(torch.cuda, "memory_allocated", lambda dev=None: live["v"])
 
-    class P:
-        total_memory = 100 << 30
-    monkeypatch.setattr(torch.cuda, "get_device_properties", lambda dev=None: P)
+    # what the process can still get = free device memory + the allocator's cached blocks (100 GiB here, of which
+    # some other tenant of the GPU already holds the rest: it never enters the budget)
+    monkeypatch.setattr(torch.cuda, "mem_get_info", lambda dev=None: (60 << 30, 140 << 30))
+    monkeypatch.setattr(torch.cuda, "memory_reserved", lambda dev=None: 40 << 30)
     monkeypatch.delenv("TGT_KEEP_PROJ_LAYERS", raising=False)
     ops._KEEP_STATE.clear()
     L, per_layer, proj = 10, 4 << 30, 3 << 30

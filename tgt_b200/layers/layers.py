@@ -48,7 +48,7 @@ class EGT_Attention(nn.Module):
         then folded into the LayerNorm-backward kernel, see ops.LNLinearFn)."""
         h, hhat, e_alias = self.forward_parts(h, e, mask)
         if self.edge_update:
-            e = self.lin_O_e(hhat)
+            e = ops.lib_linear("egt.lin_O_e(unfused)", hhat, self.lin_O_e)
         return h, e, e_alias
 
     def edge_residual(self, hhat, e_alias, scale):
@@ -60,12 +60,9 @@ class EGT_Attention(nn.Module):
     def forward_parts(self, h, e, mask):
         """(h_out, H_hat, alias of e): everything except the edge output projection."""
         cd = ops.compute_dtype(e)
-        # node side: small [B*N, Wn] GEMMs -- plain library calls
-        if h.is_cuda:
-            qkv = ops.LNLinearFn.apply(h, self.mha_ln_h.weight, self.mha_ln_h.bias, self.lin_QKV.weight,
-                                       self.lin_QKV.bias, cd)[0]
-        else:
-            qkv = self.lin_QKV(self.mha_ln_h(h))
+        # node side: small [B*N, Wn] GEMMs -- plain library calls behind our LayerNorm kernels
+        qkv = ops.LNLinearFn.apply(h, self.mha_ln_h.weight, self.mha_ln_h.bias, self.lin_QKV.weight,
+                                   self.lin_QKV.bias, cd)[0]
         # edge side: LN + projection to 2H channels (LN output recomputed in backward)
         eg, e_alias = ops.LNLinearFn.apply(e, self.mha_ln_e.weight, self.mha_ln_e.bias, self.lin_EG.weight,
                                            self.lin_EG.bias, cd)
@@ -74,7 +71,7 @@ class EGT_Attention(nn.Module):
             src = torch.empty((h.shape[0], h.shape[1]), dtype=torch.float32, device=h.device) \
                        .bernoulli_(self.source_dropout) * torch.finfo(torch.float32).min
         hhat, vatt = ops.EGTCoreFn.apply(qkv, eg, mask, src, self.num_heads, True, self.scale_degree, cd)
-        h = self.lin_O_h(vatt)
+        h = ops.lib_linear("egt.lin_O_h", vatt, self.lin_O_h)
         return h, hhat, e_alias
 
 
@@ -103,17 +100,14 @@ class EdgeUpdate(nn.Module):
 
     def forward_alias(self, h, e, mask):
         h, hhat, e_alias = self.forward_parts(h, e, mask)
-        return h, self.lin_O_e(hhat), e_alias
+        return h, ops.lib_linear("edge_update.lin_O_e(unfused)", hhat, self.lin_O_e), e_alias
 
     edge_residual = EGT_Attention.edge_residual
 
     def forward_parts(self, h, e, mask):
         cd = ops.compute_dtype(e)
-        if h.is_cuda:
-            qk = ops.LNLinearFn.apply(h, self.mha_ln_h.weight, self.mha_ln_h.bias, self.lin_QK.weight,
-                                      self.lin_QK.bias, cd)[0]
-        else:
-            qk = self.lin_QK(self.mha_ln_h(h))
+        qk = ops.LNLinearFn.apply(h, self.mha_ln_h.weight, self.mha_ln_h.bias, self.lin_QK.weight,
+                                  self.lin_QK.bias, cd)[0]
         eb, e_alias = ops.LNLinearFn.apply(e, self.mha_ln_e.weight, self.mha_ln_e.bias, self.lin_E.weight,
                                            self.lin_E.bias, cd)
         hhat = ops.EGTCoreFn.apply(qk, eb, mask, None, self.num_heads, False, False, cd)

@@ -2,11 +2,13 @@
 
 Design rules:
   * outputs are never saved for backward -- the caller (TGT_Layer) adds residuals to them;
-  * nothing O(N^3) and no LayerNorm output / projection buffer is kept between forward and
-    backward: the backward recomputes LN(e) and the projection GEMM, so a 24-layer TGT-At step
-    at B=256, N=64 fits in one B200's HBM;
-  * plain projection GEMMs go through cuBLAS (torch.addmm / torch.mm); everything else on the
-    path is one of our kernels;
+  * nothing O(N^3) and no LayerNorm output is kept between forward and backward; the [R, 6We+4Ht]
+    projection is kept only for the last k layers that HBM has room for (keep_projection), the other
+    layers recompute it with the same LN-folded GEMM, so a 24-layer TGT-At step at B=256, N=64 fits
+    in one B200's HBM;
+  * GEMMs on the edge rows run on our tcgen05 kernels (csrc/gemm_tc.cu, csrc/gemm_wgrad.cu); what
+    still goes to cuBLAS (node-side [B*N, 768] projections, fp32 parity path) is counted per call
+    site in LIBRARY_CALLS and reported by bench.py;
   * no fallback: CPU tensors or a missing library raise.
 """
 from __future__ import annotations
@@ -74,6 +76,34 @@ def _f32c(t: Tensor) -> Tensor:
     if t.dtype != torch.float32:
         t = t.float()
     return t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------
+# library (cuBLAS via torch) GEMMs: every call site is named, counted and timed -- there is no silent dispatch.
+# bench.py prints LIBRARY_CALLS per step next to the launch count of our own kernels.
+# ------------------------------------------------------------------------------------------
+import collections
+
+LIBRARY_CALLS = collections.Counter()
+
+
+def lib_mm(site: str, a: Tensor, b: Tensor) -> Tensor:
+    LIBRARY_CALLS[site] += 1
+    with timed("lib:" + site):
+        return torch.mm(a, b)
+
+
+def lib_addmm(site: str, bias: Tensor, a: Tensor, b: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    LIBRARY_CALLS[site] += 1
+    with timed("lib:" + site):
+        return torch.addmm(bias, a, b, out=out) if out is not None else torch.addmm(bias, a, b)
+
+
+def lib_linear(site: str, x: Tensor, lin) -> Tensor:
+    """nn.Linear module call (node-side [B*N, Wn] projections: plain library GEMMs with no fusable neighbour)."""
+    LIBRARY_CALLS[site] += 1
+    with timed("lib:" + site):
+        return lin(x)
 
 
 # ------------------------------------------------------------------------------------------
@@ -265,12 +295,15 @@ def take_stats(x: Tensor, x2: Tensor) -> Optional[tuple]:
     st = getattr(x, "_tgt_ln_stats", None)
     if st is None or x2.data_ptr() != x.data_ptr() or x2.dtype != x.dtype or st[0].numel() != x2.shape[0]:
         return None
+    if getattr(x, "_tgt_ln_stats_version", None) != x._version:
+        return None                    # x was modified in place after the producing kernel ran: the statistics are stale
     return st
 
 
 def attach_stats(out: Tensor, mean: Optional[Tensor], rstd: Optional[Tensor]) -> Tensor:
     if mean is not None:
         out._tgt_ln_stats = (mean, rstd)
+        out._tgt_ln_stats_version = out._version
     return out
 
 
@@ -327,8 +360,8 @@ def linear_residual(a2: Tensor, Wc: Tensor, bias: Tensor, res2: Optional[Tensor]
                 name=name)
         return out2, stats
     if res2 is None:
-        return torch.addmm(bias.detach().to(a2.dtype), a2, Wc.t(), out=out2), None
-    y = torch.addmm(bias.detach().to(a2.dtype), a2, Wc.t())
+        return lib_addmm("linear_residual", bias.detach().to(a2.dtype), a2, Wc.t(), out=out2), None
+    y = lib_addmm("linear_residual", bias.detach().to(a2.dtype), a2, Wc.t())
     B = scale.numel() if scale is not None else 1
     rc = res2.contiguous()
     _C.check(_C.lib().tgt_scaled_residual(_C.ptr(y), _C.ptr(rc), _C.ptr(scale), _C.ptr(out2), B, y.numel() // B,
@@ -349,9 +382,11 @@ def _bmm_f32(a: Tensor, b: Tensor) -> Tensor:
             _BMM_OUT_F32[key] = True
         except (TypeError, RuntimeError):
             _BMM_OUT_F32[key] = False
-    if _BMM_OUT_F32[key] and a.dtype != torch.float32:
-        return torch.bmm(a, b, out_dtype=torch.float32)
-    return torch.bmm(a, b).float()
+    LIBRARY_CALLS["linear_residual_bwd.dW(bmm)"] += 1
+    with timed("lib:linear_residual_bwd.dW(bmm)"):
+        if _BMM_OUT_F32[key] and a.dtype != torch.float32:
+            return torch.bmm(a, b, out_dtype=torch.float32)
+        return torch.bmm(a, b).float()
 
 
 def linear_residual_bwd(do2: Tensor, a2: Tensor, Wc: Tensor, scale: Optional[Tensor], gelu_bwd: Optional[tuple] = None,
@@ -369,7 +404,7 @@ def linear_residual_bwd(do2: Tensor, a2: Tensor, Wc: Tensor, scale: Optional[Ten
         rps = M // scale.numel() if scale is not None else 0
         da = gemm_tc(do2, Wc.t().contiguous(), row_scale=scale, rows_per_scale=rps, gelu_bwd=gelu_bwd, mul=gp, name=name)
     else:
-        da = _scale_rows(torch.mm(do2, Wc), scale)
+        da = _scale_rows(lib_mm("linear_residual_bwd.dx", do2, Wc), scale)
         if gp is not None:
             da = da * gp
         if gelu_bwd is not None:
@@ -379,13 +414,13 @@ def linear_residual_bwd(do2: Tensor, a2: Tensor, Wc: Tensor, scale: Optional[Ten
                                                    _C.dtype_code(da.dtype), _C.stream_ptr()), "gelu_dropout_bwd")
             da = du
     if scale is None:
-        return da, torch.mm(do2.t(), a2), (do2.sum(0, dtype=torch.float32) if want_db else None)
+        return da, lib_mm("linear_residual_bwd.dW", do2.t(), a2), (do2.sum(0, dtype=torch.float32) if want_db else None)
     B = scale.numel()
     if B * N * K * 4 > M * (N + K):
         # few rows per graph (node-side tensors): the per-graph [B, N, K] intermediate would dwarf the operands --
         # scale the (small) gradient explicitly instead
         dos = _scale_rows(do2, scale)
-        return da, torch.mm(dos.t(), a2), dos.sum(0, dtype=torch.float32)
+        return da, lib_mm("linear_residual_bwd.dW", dos.t(), a2), dos.sum(0, dtype=torch.float32)
     dob = do2.view(B, M // B, N)
     dWb = _bmm_f32(dob.transpose(1, 2), a2.view(B, M // B, K))
     dW = torch.mv(dWb.view(B, N * K).t(), scale).view(N, K)
@@ -406,7 +441,7 @@ def ln_linear(x2: Tensor, g: Tensor, bt: Tensor, W: Tensor, b: Tensor, Wc: Tenso
         Wg, bp, cs = _ln_fold(W, b, g, bt, cd)
         return gemm_tc(x2, Wg, bias=bp, ln=(mean, rstd, cs), name=name), mean, rstd, (Wg, bp, cs)
     y, mean, rstd = layernorm_fwd(x2, g, bt, cd)
-    return torch.addmm(b.detach().to(cd), y, Wc.t()), mean, rstd, (None, None, None)
+    return lib_addmm("ln_linear", b.detach().to(cd), y, Wc.t()), mean, rstd, (None, None, None)
 
 
 def _with_stats(ctx, out: Tensor, stats: Optional[tuple]):
@@ -468,7 +503,7 @@ def ln_linear_bwd(dout2: Tensor, x2: Tensor, g: Tensor, bt: Tensor, Wc: Tensor, 
             and ((C + 63) // 64) * W * 128 <= 159000 and (dres is None or dres.dtype == cd)):
         ones = torch.ones(W, dtype=torch.float32, device=x2.device)
         xh, _, _ = layernorm_fwd(x2, ones, torch.zeros_like(ones), cd, aug=True)          # [xhat | 1 | 0...]
-        Ga = torch.mm(dout2.t(), xh).float()                                              # [C, W+8]
+        Ga = lib_mm("ln_linear_bwd.dW", dout2.t(), xh).float()                                              # [C, W+8]
         G, db = Ga[:, :W], Ga[:, W]
         del xh
         Wf = Wc.float()
@@ -478,17 +513,17 @@ def ln_linear_bwd(dout2: Tensor, x2: Tensor, g: Tensor, bt: Tensor, Wc: Tensor, 
         dx = gemm_tc(dout2, Wc.t().contiguous(), ln_bwd=(x2, mean, rstd, g, dres), name=name)
         return dx, dg, dbt, dW, db
     if ln_bwd_emits_y(x2, cd) and dout2.dtype == cd:
-        dy = torch.mm(dout2, Wc)
+        dy = lib_mm("ln_linear_bwd.dy", dout2, Wc)
         res = layernorm_bwd(dy, x2, g, mean, rstd, dres, beta=bt, colsum=colsum)
         dx, dg, dbt, y = res[:4]
         del dy
-        dWa = torch.mm(dout2.t(), y)
+        dWa = lib_mm("ln_linear_bwd.dW", dout2.t(), y)
         return (dx, dg, dbt, dWa[:, :W], dWa[:, W]) + ((res[4],) if colsum is not None else ())
     assert colsum is None, "colsum needs the y-emitting LayerNorm backward (check ln_bwd_colsum_ok first)"
     y, _, _ = layernorm_fwd(x2, g, bt, cd, aug=True)
-    dWa = torch.mm(dout2.t(), y)
+    dWa = lib_mm("ln_linear_bwd.dW", dout2.t(), y)
     dW, db = dWa[:, :W], dWa[:, W]
-    dy = torch.mm(dout2, Wc)
+    dy = lib_mm("ln_linear_bwd.dy", dout2, Wc)
     del y
     dx, dg, dbt = layernorm_bwd(dy, x2, g, mean, rstd, dres)
     return dx, dg, dbt, dW, db
@@ -567,12 +602,38 @@ def keep_projection(nbytes: int, device, needs_grad: bool) -> bool:
         if env is not None:
             st["k"] = max(0, min(int(env), L - 2))
         else:
-            total = torch.cuda.get_device_properties(device).total_memory
+            # what this process can still get: free device memory plus the allocator's cached-but-unused blocks
+            # (other processes on the GPU and the CUDA context are already excluded by mem_get_info)
+            free, _ = torch.cuda.mem_get_info(device)
+            total = free + torch.cuda.memory_reserved(device)
             predicted_end = live + (live - st["live0"]) * (L - 1)
             budget = 0.88 * total - predicted_end - 0.03 * total      # r1_21: k = 10 at config 3 (peak 151 GiB of 179)
             st["k"] = max(0, min(int(budget // (nbytes + (64 << 20))), L - 2))
         return False
     return i >= L - st.get("k", 0)
+
+
+def _used_cols(wide, narrow, H: int, d: int) -> int:
+    """One past the last projection column the core kernels write a gradient for: `wide` = offsets of the head-major
+    q/k/v blocks (H*d columns each), `narrow` = offsets of the bias / gate blocks (H columns each, -1 = absent)."""
+    hi = 0
+    for offs, width in ((wide, H * d), (narrow, H)):
+        for pair in offs:
+            for o in tuple(pair):
+                if o >= 0:
+                    hi = max(hi, o + width)
+    return hi
+
+
+def _alloc_dproj(proj: Tensor, used: int) -> Tensor:
+    """Gradient buffer of the projection.  The kernels write exactly the q/k/v/bias/gate columns; when the projection
+    was padded to a multiple of 8 columns (layers/triplet.py `pad`) the pad columns must be ZERO, not uninitialised:
+    they meet the zero pad rows of the weight in dy = dproj @ Wc, and NaN * 0 = NaN."""
+    dproj = torch.empty_like(proj)
+    if used < proj.shape[1]:
+        dproj[:, used:].zero_()
+    return dproj
+
 
 
 _PANEL_IDX = {}
@@ -633,7 +694,7 @@ class TripletAttentionFn(Function):
         H, d, off_q, off_k, off_v, off_e, off_g = layout
         B, N, _, W = e.shape
         R = B * N * N
-        with torch.autocast("cuda", enabled=False):
+        with timed("triplet_module_fwd"), torch.autocast("cuda", enabled=False):
             x2 = _x_for_ln(e, cdtype).view(R, W)
             g, bt = _f32c(ln_w), _f32c(ln_b)
             Wc, bc = Wcat.detach().to(cdtype).contiguous(), bcat.detach().to(cdtype).contiguous()
@@ -691,7 +752,7 @@ class TripletAttentionFn(Function):
             return (dalias,) + (None,) * 11
         cd, desc = ctx.cdtype, ctx.desc
         B, N, W = desc.B, desc.N, x2.shape[1]
-        with torch.autocast("cuda", enabled=False):
+        with timed("triplet_module_bwd"), torch.autocast("cuda", enabled=False):
             do = dout.reshape(-1, W).to(cd).contiguous()
             if ctx.fuse_res:
                 dalias = dout                               # residual branch: d(e) += dout, folded into the LN backward
@@ -707,8 +768,9 @@ class TripletAttentionFn(Function):
             elif Wg is not None:        # bit-identical recompute of the forward projection (same kernel, same inputs)
                 proj = gemm_tc(x2, Wg, bias=bp, ln=(mean, rstd, cs), name="gemm_tc_ln_proj")
             else:
-                proj = torch.addmm(bc, y[:, :W], Wc.t())
-            dproj = torch.empty_like(proj)
+                proj = lib_addmm("triplet.proj", bc, y[:, :W], Wc.t())
+            dproj = _alloc_dproj(proj, _used_cols((desc.off_q, desc.off_k, desc.off_v), (desc.off_e, desc.off_g),
+                                                  desc.H, desc.d))
             ws, wsb = _workspace(_C.lib().tgt_triplet_attn_workspace_bytes(desc, 1), x2.device)
             if tiles is not None and ctx.tile_policy != _C.kernel_policy():
                 tiles = None                                # kernel family changed since the forward: recompute
@@ -725,21 +787,21 @@ class TripletAttentionFn(Function):
             del ws
             del proj, dva
             if late_y:                  # LN(x) comes out of the LayerNorm-backward kernel: no recompute pass
-                dy = torch.mm(dproj, Wc)
+                dy = lib_mm("triplet.dy", dproj, Wc)
                 res = layernorm_bwd(dy, x2, g, mean, rstd, _dres_for(dalias, x2), beta=bt,
                                     colsum=(sc,) if cs_db else None, aug=dbias is None)
                 dx, dg, dbt, y = res[:4]
                 if cs_db:
                     dbo = res[4]
                 del dy
-                dWa = torch.mm(dproj.t(), y)              # [C, W (+8)]: weight gradient (| bias gradient in column W)
+                dWa = lib_mm("triplet.dW", dproj.t(), y)              # [C, W (+8)]: weight gradient (| bias gradient in column W)
                 dWc, dbc = (dWa, dbias) if dbias is not None else (dWa[:, :W], dWa[:, W])
                 del y, dproj
             else:
-                dWa = torch.mm(dproj.t(), y)
+                dWa = lib_mm("triplet.dW", dproj.t(), y)
                 dWc, dbc = dWa[:, :W], dWa[:, W]
                 del y
-                dy = torch.mm(dproj, Wc)
+                dy = lib_mm("triplet.dy", dproj, Wc)
                 del dproj
                 dx, dg, dbt = layernorm_bwd(dy, x2, g, mean, rstd, _dres_for(dalias, x2))
         p = ctx.pdt
@@ -807,8 +869,8 @@ class TripletAggregateFn(Function):
             if Wg is not None:          # bit-identical recompute of the forward projection (same kernel, same inputs)
                 proj = gemm_tc(x2, Wg, bias=bp, ln=(mean, rstd, cs), name="gemm_tc_ln_proj")
             else:
-                proj = torch.addmm(bc, y[:, :W], Wc.t())
-            dproj = torch.empty_like(proj)
+                proj = lib_addmm("triplet.proj", bc, y[:, :W], Wc.t())
+            dproj = _alloc_dproj(proj, _used_cols((desc.off_v,), (desc.off_e, desc.off_g), desc.H, desc.d))
             daw = torch.empty_like(aw)
             with timed("triplet_aggr_bwd"):
                 _C.check(_C.lib().tgt_triplet_aggr_bwd(desc, _C.ptr(proj), _C.ptr(m3), _C.ptr(dva), _C.ptr(aw),
@@ -816,17 +878,17 @@ class TripletAggregateFn(Function):
                          "triplet_aggr_bwd")
             del proj, dva, daw
             if late_y:                  # LN(x) comes out of the LayerNorm-backward kernel: no recompute pass
-                dy = torch.mm(dproj, Wc)
+                dy = lib_mm("triplet.dy", dproj, Wc)
                 dx, dg, dbt, y = layernorm_bwd(dy, x2, g, mean, rstd, _dres_for(dalias, x2), beta=bt)
                 del dy
-                dWa = torch.mm(dproj.t(), y)              # [C, W+8]: weight gradient | bias gradient (column W)
+                dWa = lib_mm("triplet.dW", dproj.t(), y)              # [C, W+8]: weight gradient | bias gradient (column W)
                 dWc, dbc = dWa[:, :W], dWa[:, W]
                 del y, dproj
             else:
-                dWa = torch.mm(dproj.t(), y)
+                dWa = lib_mm("triplet.dW", dproj.t(), y)
                 dWc, dbc = dWa[:, :W], dWa[:, W]
                 del y
-                dy = torch.mm(dproj, Wc)
+                dy = lib_mm("triplet.dy", dproj, Wc)
                 del dproj
                 dx, dg, dbt = layernorm_bwd(dy, x2, g, mean, rstd, _dres_for(dalias, x2))
         p = ctx.pdt
@@ -981,7 +1043,7 @@ class FFNGeluFn(Function):
             else:
                 u_is_gp = False
                 y, mean, rstd = layernorm_fwd(x2, g, bt, cdtype)
-                u = torch.addmm(b1.detach().to(cdtype), y, W1c.t())
+                u = lib_addmm("ffn.W1", b1.detach().to(cdtype), y, W1c.t())
                 del y
                 a = torch.empty_like(u)
                 _C.check(_C.lib().tgt_gelu_dropout_fwd(_C.ptr(u), _C.ptr(a), u.numel(), float(p_drop), int(seed),

@@ -39,7 +39,9 @@ uint64_t    tgt_launch_count(void);
 /* 0 = pick the fastest kernel that supports the shape (default); 1 = force the generic
  * SIMT kernels; 2 = tensor-core triplet kernels with cp.async staging instead of TMA; 3 = like 0
  * but the triplet-attention forward runs the fused projection + attention kernel
- * (tgt_triplet_attn_fused_fwd).  The tests cross-check the families. */
+ * (tgt_triplet_attn_fused_fwd); 4 = triplet-attention core on tcgen05 / TMEM (csrc/triplet_tc.cu: UMMA for
+ * Q K^T and P V, S / P / O in tensor memory); 5 = the TMA-staged mma.sync core (the round-1 default).
+ * The tests cross-check the families. */
 void        tgt_set_kernel_policy(int policy);
 
 /* optional device-side timing of the MAIN kernel of each call (prep / post helpers excluded): enable,
@@ -103,6 +105,12 @@ size_t tgt_triplet_attn_workspace_bytes(const tgt_triplet_attn_desc *desc, int b
 int tgt_triplet_attn_fwd(const tgt_triplet_attn_desc *desc, const void *proj, const float *mask,
                          void *va, float *stats, void *workspace, size_t workspace_bytes,
                          void *stream);
+/* Test hook for the bf16 parity protocol ("fp32 kernel outputs on 16-bit-rounded inputs within
+ * 1e-3 of the fp64 oracle"): the tcgen05 core with its Va written as fp32 [R, 2*H*d] (same channel order) instead
+ * of being rounded to 16 bit.  Errors unless the tcgen05 kernel supports desc (d = 16, N <= 64, even H, 16-bit proj). */
+int tgt_triplet_attn_fwd_f32out(const tgt_triplet_attn_desc *desc, const void *proj, const float *mask,
+                                float *va_f32, float *stats, void *workspace, size_t workspace_bytes,
+                                void *stream);
 /* dproj: [R, ld] out, same column layout as proj; every column named in desc is written.   */
 int tgt_triplet_attn_bwd(const tgt_triplet_attn_desc *desc, const void *proj, const float *mask,
                          const void *va, const void *dva, const float *stats, void *dproj,

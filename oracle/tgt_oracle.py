@@ -425,6 +425,47 @@ def bins2dist(bins: Tensor, num_bins: int, range_bins: float = 8.0, shift_half: 
 
 
 # --------------------------------------------------------------------------
+# the attention CORE alone, on a given projection buffer (what the CUDA core kernels see)
+# --------------------------------------------------------------------------
+def triplet_attention_core(proj: Tensor, mask: Tensor, H: int, d: int, off_q, off_k, off_v, off_e, off_g,
+                           scale: Optional[float] = None, round_a: Optional[torch.dtype] = None) -> Tensor:
+    """triplet.py:213-227 (inward) and :232-246 (outward) on an explicit projection `proj` [B,N,N,C] whose column blocks
+    are laid out the way the kernels want them (include/tgt_b200.h: HEAD-major q/k/v blocks of H*d columns at
+    off_q/off_k/off_v[dir], H-wide bias / gate blocks at off_e/off_g[dir], -1 = absent).  mask: [B,N,N] additive.
+    Returns Va [B,N,N,2*H*d] with channel = dir*H*d + h*d + dd.  Differentiable: autograd of this function is the
+    oracle of the core backward kernels.
+    round_a: round the attention weights A to this 16-bit dtype before the A.V contraction -- the ONE rounding a 16-bit
+    tensor-core implementation cannot avoid (the reference's own autocast path casts A to 16 bit for this einsum,
+    triplet.py:227 / SURVEY App. A "Autocast dtype flow"); used as the attainable-accuracy yardstick in the tests."""
+    B, N = proj.shape[0], proj.shape[1]
+    scale = d ** -0.5 if scale is None else scale
+    outs = []
+    for dirn in range(2):
+        blk = lambda o: proj[..., o[dirn]:o[dirn] + H * d].reshape(B, N, N, H, d)
+        Q, K, V = blk(off_q), blk(off_k), blk(off_v)
+        if dirn == 0:      # S[b,i,j,k,h] = <Q[b,i,j], K[b,j,k]> + E[b,i,k,h] + M[b,i,k]
+            S = scale * torch.einsum("bijhd,bjkhd->bijkh", Q, K)
+            tile = lambda t: t.unsqueeze(2)                          # [B,i,k,.] -> [B,i,1,k,.]
+        else:              # S[b,i,j,k,h] = <Q[b,i,j], K[b,k,j]> + E[b,k,i,h] + M[b,k,i]
+            S = scale * torch.einsum("bijhd,bkjhd->bijkh", Q, K)
+            tile = lambda t: t.transpose(1, 2).unsqueeze(2)          # [B,k,i,.] -> [B,i,1,k,.]
+        M = tile(mask.unsqueeze(-1))
+        if off_e[dirn] >= 0:
+            S = S + tile(proj[..., off_e[dirn]:off_e[dirn] + H])
+        A = torch.softmax(S + M, dim=3)
+        if off_g[dirn] >= 0:
+            A = A * torch.sigmoid(tile(proj[..., off_g[dirn]:off_g[dirn] + H]) + M)
+        if round_a is not None:
+            A = A.to(round_a).to(proj.dtype)
+        if dirn == 0:
+            Va = torch.einsum("bijkh,bjkhd->bijhd", A, V)
+        else:
+            Va = torch.einsum("bijkh,bkjhd->bijhd", A, V)
+        outs.append(Va.reshape(B, N, N, H * d))
+    return torch.cat(outs, dim=-1)
+
+
+# --------------------------------------------------------------------------
 # closed-form backward of the gated attention core (second oracle for the CUDA
 # backward; SURVEY.md Appendix A, verified against autograd in the tests)
 # --------------------------------------------------------------------------

@@ -144,3 +144,38 @@ def test_bins_decode_oracle_vs_golden():
     d = O.bins2dist(bins, fx["num_bins"], fx["range_bins"])
     assert torch.equal(d, fx["dist"])
     assert torch.equal(d, d.transpose(-1, -2)) and float(d.diagonal(dim1=-2, dim2=-1).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("kind", ["attention", "attention_ungated", "axial_attention"])
+def test_core_oracle_matches_module_oracle(kind):
+    """O.triplet_attention_core (the projection-level restatement the core-kernel tests use) composed with the
+    LayerNorm / projection / lin_O of the module equals the module-level oracle, which is pinned to the reference
+    above.  Also pins the host-side channel bookkeeping (head-major gather, Va -> lin_O column order)."""
+    from tgt_b200 import layers as L
+    from tgt_b200.layers.triplet import _head_major_perm, _out_perm
+    torch.manual_seed(0)
+    W, H, B, N = 32, 2, 2, 7
+    d = W // H
+    mod = L.get_triplet_layer(kind)(W, H).double()
+    p = {k: v.detach() for k, v in mod.state_dict().items()}
+    e = torch.randn(B, N, N, W, dtype=torch.float64)
+    m = (torch.arange(N)[None, :] < torch.tensor([7, 4])[:, None]).double()
+    mask = ((1 - m[:, :, None] * m[:, None, :]) * torch.finfo(torch.float32).min).unsqueeze(-1)
+    ref = O.TRIPLET_FNS[kind](p, e, mask, H)
+    x = torch.nn.functional.layer_norm(e, (W,), p["tri_ln_e.weight"], p["tri_ln_e.bias"])
+    hm = _head_major_perm(W, H, "cpu")
+    qp = torch.cat([hm, hm + W, hm + 2 * W])
+    ws, bs = [p["lin_QKV_in.weight"][qp], p["lin_QKV_out.weight"][qp]], [p["lin_QKV_in.bias"][qp], p["lin_QKV_out.bias"][qp]]
+    off_e, off_g, col = [-1, -1], [-1, -1], 6 * W
+    for dirn, name in enumerate(mod._bias_names):
+        if name is None:
+            continue
+        ws.append(p[name + ".weight"]); bs.append(p[name + ".bias"])
+        off_e[dirn] = col
+        if mod._gated:
+            off_g[dirn] = col + H
+        col += p[name + ".weight"].shape[0]
+    proj = x @ torch.cat(ws).t() + torch.cat(bs)
+    va = O.triplet_attention_core(proj, mask[..., 0], H, d, (0, 3 * W), (W, 4 * W), (2 * W, 5 * W), off_e, off_g)
+    out = va @ p["lin_O.weight"][:, _out_perm(W, H, "cpu")].t() + p["lin_O.bias"]
+    assert float((out - ref).abs().max()) < 1e-12

@@ -83,6 +83,7 @@ _SIGNATURES = {
                                       _P, C.c_int64, _P, _P]),
     "tgt_triplet_attn_workspace_bytes": (C.c_size_t, [C.POINTER(TripletAttnDesc), C.c_int]),
     "tgt_triplet_attn_fwd": (C.c_int, [C.POINTER(TripletAttnDesc), _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "tgt_triplet_attn_fwd_f32out": (C.c_int, [C.POINTER(TripletAttnDesc), _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "tgt_triplet_attn_bwd": (C.c_int, [C.POINTER(TripletAttnDesc), _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "tgt_triplet_attn_bwd_tiles": (C.c_int, [C.POINTER(TripletAttnDesc), _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P, _P]),
     "tgt_triplet_attn_bwd_bias_supported": (C.c_int, [C.POINTER(TripletAttnDesc)]),
@@ -174,7 +175,8 @@ _policy = 0
 
 def set_kernel_policy(policy: int) -> None:
     """0 = fastest supported kernel (default), 1 = generic SIMT kernels, 2 = cp.async-staged tensor-core triplet kernels,
-    3 = fused projection + attention forward (see include/tgt_b200.h)."""
+    3 = fused projection + attention forward, 4 = tcgen05 / TMEM triplet core, 5 = TMA-staged mma.sync core
+    (see include/tgt_b200.h)."""
     global _policy
     _policy = int(policy)
     lib().tgt_set_kernel_policy(int(policy))

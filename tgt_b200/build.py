@@ -10,7 +10,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libtgt_b200.so")
-SOURCES = ["api.cu", "rowwise.cu", "triplet_simt.cu", "triplet_mma.cu", "egt.cu", "egt_fast.cu", "gemm_tc.cu", "triplet_tma.cu", "triplet_fused.cu", "triangular.cu", "bins.cu"]
+SOURCES = ["api.cu", "rowwise.cu", "triplet_simt.cu", "triplet_mma.cu", "egt.cu", "egt_fast.cu", "gemm_tc.cu", "triplet_tma.cu", "triplet_tc.cu", "triplet_fused.cu", "triangular.cu", "bins.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "--use_fast_math", "-Xcompiler", "-fPIC", "-Xptxas", "-v",

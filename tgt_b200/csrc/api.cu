@@ -59,6 +59,8 @@ int triplet_attn_fwd_mma(const tgt_triplet_attn_desc &, const void *, const floa
 int triplet_attn_bwd_mma(const tgt_triplet_attn_desc &, const void *, const float *, const void *, const void *,
                          const float *, void *, void *, size_t, const void *, float *, cudaStream_t);
 bool triplet_attn_bwd_bias_available(const tgt_triplet_attn_desc &);
+int triplet_attn_fwd_tc_f32out(const tgt_triplet_attn_desc &, const void *, const float *, float *, float *, void *, size_t,
+                               cudaStream_t);
 bool triplet_attn_fused_supported(const tgt_triplet_attn_desc &D, int We);
 int triplet_attn_fused_fwd(const tgt_triplet_attn_desc &D, int We, const void *x, int64_t ldx, const float *mean,
                            const float *rstd, const void *wf, const float *wcolsum, const float *wbias,
@@ -136,6 +138,13 @@ extern "C" int tgt_triplet_attn_fwd(const tgt_triplet_attn_desc *D, const void *
   if (g_policy.load() != 1 && triplet_attn_mma_supported(*D))
     return triplet_attn_fwd_mma(*D, proj, mask, va, stats, ws, ws_bytes, st);
   return triplet_attn_fwd_simt(*D, proj, mask, va, stats, st);
+}
+
+extern "C" int tgt_triplet_attn_fwd_f32out(const tgt_triplet_attn_desc *D, const void *proj, const float *mask,
+                                           float *va_f32, float *stats, void *ws, size_t ws_bytes, void *stream) {
+  if (int e = attn_check(D)) return e;
+  if (!va_f32) return fail("triplet_attn_fwd_f32out: null output");
+  return triplet_attn_fwd_tc_f32out(*D, proj, mask, va_f32, stats, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int tgt_triplet_attn_bwd_bias_supported(const tgt_triplet_attn_desc *D) {

@@ -576,8 +576,21 @@ bool triplet_attn_fused_supported(const tgt_triplet_attn_desc &D, int We);
 int triplet_attn_fused_launch(const tgt_triplet_attn_desc &D, int We, const void *x, int64_t ldx, const float *mean,
                               const float *rstd, const void *wf, const float *wcolsum, const float *wbias, void *va,
                               float *stats, const float *ws_e, const __half *ws_g, cudaStream_t st);
-// kernel policy 0 (default): TMA-staged kernels; policy 2: the cp.async-staged kernels of this file
-static bool use_tma() { return (g_policy.load() == 0 || g_policy.load() == 3) && triplet_attn_tma_available(); }
+// triplet_tc.cu
+bool triplet_attn_tc_supported(const tgt_triplet_attn_desc &D);
+int triplet_attn_fwd_tc_launch(const tgt_triplet_attn_desc &D, const void *proj, void *va, float *va_f32, float *stats,
+                               const float *ws_e, const __half *ws_g, cudaStream_t st);
+int triplet_attn_bwd_tc_launch(const tgt_triplet_attn_desc &D, const void *proj, const void *dva, const float *stats,
+                               void *dproj, const float *ws_e, const __half *ws_g, float *ws_de, float *ws_dg,
+                               cudaStream_t st);
+// kernel policy 0 (default) / 3 / 4 / 5: TMA-staged kernels; policy 2: the cp.async-staged kernels of this file
+static bool use_tma() { return g_policy.load() != 2 && g_policy.load() != 1 && triplet_attn_tma_available(); }
+// tcgen05 / TMEM core: policy 4 (and the default once it is the measured winner, see TC_DEFAULT)
+constexpr bool TC_DEFAULT = false;
+static bool use_tc(const tgt_triplet_attn_desc &D) {
+  const int p = g_policy.load();
+  return (p == 4 || (TC_DEFAULT && (p == 0 || p == 3))) && triplet_attn_tc_supported(D);
+}
 
 struct Ws {
   float *e; __half *g; float *de; float *dg;
@@ -610,6 +623,7 @@ static int fwd_impl(const tgt_triplet_attn_desc &D, const void *proj, const floa
   if (bias_gate_h16_ok(D)) tri_prep_bias_gate_h16<T><<<dim3(TN, 2, D.B), 256, 0, st>>>(D, (const T *)proj, mask, w.e, w.g);
   else tri_prep_bias_gate<T><<<dim3(TN, 2, D.B), 256, psm, st>>>(D, (const T *)proj, mask, w.e, w.g);
   if (int e = check_launch("tri_prep_bias_gate")) return e;
+  if (use_tc(D)) return triplet_attn_fwd_tc_launch(D, proj, va, nullptr, stats, w.e, w.g, st);
   if (use_tma()) return triplet_attn_fwd_tma_launch(D, proj, va, stats, w.e, w.g, st);
   KernelTimerScope ts("tri_attn_fwd_mma", st);
   tri_attn_fwd_mma<T><<<dim3(D.H, 2, D.B), 128, 0, st>>>(D, (const T *)proj, w.e, w.g, (T *)va, stats);
@@ -619,7 +633,7 @@ static int fwd_impl(const tgt_triplet_attn_desc &D, const void *proj, const floa
 template <typename T>
 static int bwd_impl(const tgt_triplet_attn_desc &D, const void *proj, const float *mask, const void *dva,
                     const float *stats, void *dproj, void *ws, const void *fwd_ws, float *dbias, cudaStream_t st) {
-  if (dbias && !(use_tma() && triplet_attn_bwd_tma_has_bias()))
+  if (dbias && (use_tc(D) || !(use_tma() && triplet_attn_bwd_tma_has_bias())))
     return fail("triplet_attn_bwd: the projection-bias by-product is not available with this kernel family");
   Ws w = carve(D, ws);
   const size_t psm = 2 * (size_t)D.H * 65 * sizeof(float);
@@ -632,6 +646,13 @@ static int bwd_impl(const tgt_triplet_attn_desc &D, const void *proj, const floa
     if (bias_gate_h16_ok(D)) tri_prep_bias_gate_h16<T><<<dim3(TN, 2, D.B), 256, 0, st>>>(D, (const T *)proj, mask, w.e, w.g);
     else tri_prep_bias_gate<T><<<dim3(TN, 2, D.B), 256, psm, st>>>(D, (const T *)proj, mask, w.e, w.g);
     if (int e = check_launch("tri_prep_bias_gate")) return e;
+  }
+  if (use_tc(D)) {
+    if (dbias) return fail("triplet_attn_bwd: the projection-bias by-product is not produced by the tcgen05 kernel");
+    if (int e = triplet_attn_bwd_tc_launch(D, proj, dva, stats, dproj, w.e, w.g, w.de, w.dg, st)) return e;
+    if (bias_gate_h16_ok(D)) tri_post_bias_gate_h16<T><<<dim3(D.N, 2, D.B), 256, 0, st>>>(D, w.de, w.dg, (T *)dproj);
+    else tri_post_bias_gate<T><<<dim3(D.N, 2, D.B), 256, psm, st>>>(D, w.de, w.dg, (T *)dproj);
+    return check_launch("tri_post_bias_gate");
   }
   if (use_tma()) {
     if (int e = triplet_attn_bwd_tma_launch(D, proj, dva, stats, dproj, w.e, w.g, w.de, w.dg, dbias, st)) return e;
@@ -702,8 +723,25 @@ int triplet_attn_bwd_mma(const tgt_triplet_attn_desc &D, const void *proj, const
   return bwd_impl<__half>(D, proj, mask, dva, stats, dproj, ws, fwd_ws, dbias, st);
 }
 
+int triplet_attn_fwd_tc_f32out(const tgt_triplet_attn_desc &D, const void *proj, const float *mask, float *va_f32,
+                               float *stats, void *ws, size_t ws_bytes, cudaStream_t st) {
+  if (!triplet_attn_mma_supported(D) || !triplet_attn_tc_supported(D))
+    return fail("triplet_attn_fwd_f32out: shape / dtype not supported by the tcgen05 kernel");
+  if (!ws || ws_bytes < triplet_attn_mma_workspace(D, 0))
+    return fail("triplet_attn_fwd_f32out: workspace too small (%zu < %zu bytes)", ws_bytes, triplet_attn_mma_workspace(D, 0));
+  if (((uintptr_t)proj | (uintptr_t)va_f32) & 15) return fail("triplet_attn_fwd_f32out: proj / va must be 16-byte aligned");
+  const Ws w = carve_fwd(D, ws);
+  const size_t psm = 2 * (size_t)D.H * 65 * sizeof(float);
+  if (D.dtype == TGT_BF16)
+    tri_prep_bias_gate<__nv_bfloat16><<<dim3(TN, 2, D.B), 256, psm, st>>>(D, (const __nv_bfloat16 *)proj, mask, w.e, w.g);
+  else
+    tri_prep_bias_gate<__half><<<dim3(TN, 2, D.B), 256, psm, st>>>(D, (const __half *)proj, mask, w.e, w.g);
+  if (int e = check_launch("tri_prep_bias_gate")) return e;
+  return triplet_attn_fwd_tc_launch(D, proj, nullptr, va_f32, stats, w.e, w.g, st);
+}
+
 bool triplet_attn_bwd_bias_available(const tgt_triplet_attn_desc &D) {
-  return triplet_attn_mma_supported(D) && use_tma() && triplet_attn_bwd_tma_has_bias();
+  return triplet_attn_mma_supported(D) && !use_tc(D) && use_tma() && triplet_attn_bwd_tma_has_bias();
 }
 
 }  // namespace tgt

@@ -551,7 +551,7 @@ size_t triplet_attn_mma_workspace(const tgt_triplet_attn_desc &D, int backward) 
   const size_t n = tile_elems(D);
   size_t bytes = n * sizeof(float) + n * sizeof(__half);
   if (backward) bytes += 2 * n * sizeof(float);
-  return bytes + 1024;
+  return bytes + 1024 + 256;          // + alignment slack + the work-item counter of the persistent tcgen05 backward
 }
 
 bool triplet_attn_mma_supported(const tgt_triplet_attn_desc &D) {
@@ -580,9 +580,9 @@ int triplet_attn_fused_launch(const tgt_triplet_attn_desc &D, int We, const void
 bool triplet_attn_tc_supported(const tgt_triplet_attn_desc &D);
 int triplet_attn_fwd_tc_launch(const tgt_triplet_attn_desc &D, const void *proj, void *va, float *va_f32, float *stats,
                                const float *ws_e, const __half *ws_g, cudaStream_t st);
-int triplet_attn_bwd_tc_launch(const tgt_triplet_attn_desc &D, const void *proj, const void *dva, const float *stats,
-                               void *dproj, const float *ws_e, const __half *ws_g, float *ws_de, float *ws_dg,
-                               cudaStream_t st);
+int triplet_attn_bwd_tc_launch(const tgt_triplet_attn_desc &D, const void *proj, const void *va, const void *dva,
+                               const float *stats, void *dproj, const float *ws_e, const __half *ws_g, float *ws_de,
+                               float *ws_dg, int *counter, cudaStream_t st);
 // kernel policy 0 (default) / 3 / 4 / 5: TMA-staged kernels; policy 2: the cp.async-staged kernels of this file
 static bool use_tma() { return g_policy.load() != 2 && g_policy.load() != 1 && triplet_attn_tma_available(); }
 // tcgen05 / TMEM core: policy 4 (and the default once it is the measured winner, see TC_DEFAULT)
@@ -594,6 +594,7 @@ static bool use_tc(const tgt_triplet_attn_desc &D) {
 
 struct Ws {
   float *e; __half *g; float *de; float *dg;
+  int *counter;
 };
 static Ws carve(const tgt_triplet_attn_desc &D, void *ws) {
   const size_t n = tile_elems(D);
@@ -603,6 +604,7 @@ static Ws carve(const tgt_triplet_attn_desc &D, void *ws) {
   w.de = w.e + n;
   w.dg = w.de + n;
   w.g = (__half *)(w.dg + n);
+  w.counter = (int *)(((uintptr_t)(w.g + n) + 15) & ~(uintptr_t)15);
   return w;
 }
 static Ws carve_fwd(const tgt_triplet_attn_desc &D, void *ws) {
@@ -612,6 +614,7 @@ static Ws carve_fwd(const tgt_triplet_attn_desc &D, void *ws) {
   w.e = (float *)p;
   w.g = (__half *)(w.e + n);
   w.de = w.dg = nullptr;
+  w.counter = nullptr;
   return w;
 }
 
@@ -631,7 +634,7 @@ static int fwd_impl(const tgt_triplet_attn_desc &D, const void *proj, const floa
 }
 
 template <typename T>
-static int bwd_impl(const tgt_triplet_attn_desc &D, const void *proj, const float *mask, const void *dva,
+static int bwd_impl(const tgt_triplet_attn_desc &D, const void *proj, const float *mask, const void *va, const void *dva,
                     const float *stats, void *dproj, void *ws, const void *fwd_ws, float *dbias, cudaStream_t st) {
   if (dbias && (use_tc(D) || !(use_tma() && triplet_attn_bwd_tma_has_bias())))
     return fail("triplet_attn_bwd: the projection-bias by-product is not available with this kernel family");
@@ -649,7 +652,7 @@ static int bwd_impl(const tgt_triplet_attn_desc &D, const void *proj, const floa
   }
   if (use_tc(D)) {
     if (dbias) return fail("triplet_attn_bwd: the projection-bias by-product is not produced by the tcgen05 kernel");
-    if (int e = triplet_attn_bwd_tc_launch(D, proj, dva, stats, dproj, w.e, w.g, w.de, w.dg, st)) return e;
+    if (int e = triplet_attn_bwd_tc_launch(D, proj, va, dva, stats, dproj, w.e, w.g, w.de, w.dg, w.counter, st)) return e;
     if (bias_gate_h16_ok(D)) tri_post_bias_gate_h16<T><<<dim3(D.N, 2, D.B), 256, 0, st>>>(D, w.de, w.dg, (T *)dproj);
     else tri_post_bias_gate<T><<<dim3(D.N, 2, D.B), 256, psm, st>>>(D, w.de, w.dg, (T *)dproj);
     return check_launch("tri_post_bias_gate");
@@ -713,14 +716,13 @@ int triplet_attn_fwd_mma(const tgt_triplet_attn_desc &D, const void *proj, const
 int triplet_attn_bwd_mma(const tgt_triplet_attn_desc &D, const void *proj, const float *mask, const void *va,
                          const void *dva, const float *stats, void *dproj, void *ws, size_t ws_bytes,
                          const void *fwd_ws, float *dbias, cudaStream_t st) {
-  (void)va;      // delta = rowsum(dP o P) is recomputed in registers; the forward output is not needed
   if (!ws || ws_bytes < triplet_attn_mma_workspace(D, 1))
     return fail("triplet_attn_bwd: workspace too small (%zu < %zu bytes)", ws_bytes, triplet_attn_mma_workspace(D, 1));
   if (((uintptr_t)proj | (uintptr_t)dva | (uintptr_t)dproj) & 15)
     return fail("triplet_attn_bwd: proj / dva / dproj must be 16-byte aligned");
   if (D.B > 65535) return fail("triplet_attn_bwd: B > 65535 unsupported");
-  if (D.dtype == TGT_BF16) return bwd_impl<__nv_bfloat16>(D, proj, mask, dva, stats, dproj, ws, fwd_ws, dbias, st);
-  return bwd_impl<__half>(D, proj, mask, dva, stats, dproj, ws, fwd_ws, dbias, st);
+  if (D.dtype == TGT_BF16) return bwd_impl<__nv_bfloat16>(D, proj, mask, va, dva, stats, dproj, ws, fwd_ws, dbias, st);
+  return bwd_impl<__half>(D, proj, mask, va, dva, stats, dproj, ws, fwd_ws, dbias, st);
 }
 
 int triplet_attn_fwd_tc_f32out(const tgt_triplet_attn_desc &D, const void *proj, const float *mask, float *va_f32,

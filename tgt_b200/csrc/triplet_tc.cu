@@ -280,12 +280,13 @@ tri_attn_fwd_tc(const tgt_triplet_attn_desc D, const __grid_constant__ CUtensorM
 // ------------------------------------------------------------------------------------------------ host
 // 4-D map over a [B, N, N, C] 16-bit tensor (row pitch ld elements): box = 64 rows x `ch` channels along the
 // second-to-last index ("row" tiles: fixed first index) or along the first index ("column" tiles: fixed second index)
-static int make_map(CUtensorMap *map, const void *base, int B, int N, int C, int64_t ld, bool column, int ch, int dtype) {
+static int make_map(CUtensorMap *map, const void *base, int B, int N, int C, int64_t ld, bool column, int ch, int dtype,
+                    int rows = TN) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return fail("triplet_attn_tc: cuTensorMapEncodeTiled is not available from the driver");
   const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)N, (cuuint64_t)N, (cuuint64_t)B};
   const cuuint64_t gstride[3] = {(cuuint64_t)ld * 2, (cuuint64_t)N * ld * 2, (cuuint64_t)N * N * ld * 2};
-  const cuuint32_t box[4] = {(cuuint32_t)ch, column ? 1u : (cuuint32_t)TN, column ? (cuuint32_t)TN : 1u, 1u};
+  const cuuint32_t box[4] = {(cuuint32_t)ch, column ? 1u : (cuuint32_t)rows, column ? (cuuint32_t)rows : 1u, 1u};
   const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
   const CUtensorMapDataType dt = dtype == TGT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   const CUtensorMapSwizzle sw = ch == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : (ch == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
@@ -330,51 +331,89 @@ int triplet_attn_fwd_tc_launch(const tgt_triplet_attn_desc &D, const void *proj,
 //      P = exp2(S c + E - lse),  g = gate,  A = P g,  dP = dA g,  delta = rowsum(dP P),  dS = P (dP - delta)
 //      dQ = c dS K,   dK = c dS^T Q,   dV = A^T dO,   dE = sum_j dS,   dG = g (1 - g) sum_j dA P
 //
-// One PERSISTENT CTA per SM, 384 threads = two compute warpgroups + one control warpgroup.  Each compute warpgroup owns a
-// stream of work items (head h, direction, graph b) and loops over the junction j; it never synchronises with the other
-// warpgroup, nor its four warps with each other (mbarrier arrivals only).
-//   thread <-> (query row i = 16 q + lane % 16, key half kh = lane / 16) with q = warp % 4: the M = 64 accumulators of
-//   S and dA are issued as TWO N = 32 UMMAs (keys 0-31 -> lanes 32q + 0..15, keys 32-63 -> lanes 32q + 16..31, the
-//   interleaved half of each TMEM sub-partition), so a thread tcgen05.ld's 32 S and 32 dA values of ONE row, the row
-//   reduction (delta) is one shuffle, and dE / dG accumulate in 2 x 32 registers for all N junctions (no atomics).
-//   dS and A leave as 16-bit rows of two 64 x 64 shared-memory tiles (128-byte rows, 128B swizzle) that the tensor core
-//   reads BOTH ways: K-major for dQ = dS K, MN-major (transposed, no data movement) for dK = dS^T Q and dV = A^T dO;
-//   the Q / K / dO tiles TMA delivered are their MN-major B operands.  dQ | dV (lanes 0-15) and dK (lanes 16-31) come
-//   back with one tcgen05.ld and leave with 32-byte global stores.
-//   control warpgroup: warps 8, 9 = TMA producers (Q, K, V, dO tiles of a junction, 4-stage ring per compute warpgroup),
-//   warps 10, 11 = tcgen05.mma issuers (4 + 12 UMMAs per junction).
-// TMEM (512 columns = the SM): per warpgroup S|dA 2 x 64 (double buffered) + dQ/dK|dV 2 x 32.
-// setmaxnreg: 240 registers per compute thread, 24 per control thread.
-constexpr int TCB_THREADS = 384;
-constexpr int TCB_REGS_WORK = 240, TCB_REGS_CTRL = 24;      // 2 * 128 * 240 + 128 * 24 = 64512
+// One PERSISTENT CTA per SM, 512 threads = four warpgroups with four roles:
+//   warps 0-3, 4-7   two COMPUTE warpgroups.  Each owns a stream of work items (head h, direction, graph b), drawn in
+//                    id order from a global counter, and loops over the junction j.  thread <-> (query row
+//                    i = 16 q + lane % 16, key half kh = lane / 16), q = warp % 4: the M = 64 accumulators of S and dA
+//                    are issued as TWO N = 32 UMMAs (keys 0-31 -> TMEM lanes 32q + 0..15, keys 32-63 -> lanes
+//                    32q + 16..31, the interleaved half of each sub-partition), so a thread tcgen05.ld's 32 S and 32
+//                    dA values of ONE row, the row reduction (delta) is one shuffle, dE / dG accumulate in 2 x 32
+//                    registers for all N junctions (no atomics), bias and gate rows stay packed in 2 x 16 registers.
+//                    delta = rowsum(dP P) is taken as dO . O from the dO / Va tiles (one pass over the scores).  dS and A leave as 16-bit rows of two 64 x 64 shared-memory tiles (128-byte
+//                    rows, 128B swizzle) that the tensor core reads BOTH ways: K-major for dQ = dS K, MN-major
+//                    (transposed, no data movement) for dK = dS^T Q and dV = A^T dO; the Q / K / dO tiles TMA
+//                    delivered are their MN-major B operands.  The compute warps never wait for each other.
+//   warps 8-11       CONTROL: 8, 9 = TMA producers (Q, K, V, dO tiles, 4-stage ring per compute warpgroup; they also draw
+//                    the work items), 10, 11 = tcgen05.mma issuers (4 + 12 UMMAs per junction).
+//   warps 12-15      EPILOGUE: warp 12 + q drains TMEM lane quadrant q of BOTH compute warpgroups' output accumulators
+//                    (dQ | dV rows on lanes 0-15, dK rows on lanes 16-31), scales, rounds and stores them, so neither the
+//                    TMEM round trip nor the global stores sit in the compute warps' instruction streams.
+// TMEM (512 columns = the SM): per compute warpgroup S|dA 2 x 64 (double buffered) + dQ/dK|dV 2 x 32.
+// setmaxnreg: 208 registers per compute thread, 40 per control thread, 56 per epilogue thread.
+constexpr int TCB_THREADS = 512;
+constexpr int TCB_REGS_WORK = 208, TCB_REGS_CTRL = 40, TCB_REGS_EPI = 56;     // 128 * (2 * 208 + 40 + 56) = 65536
 constexpr int TCB_STAGES = 4;
-constexpr int TCB_STAGE_BYTES = 4 * TCF_TILE;               // Q, K, V, dO
+constexpr int TCB_STAGE_BYTES = 5 * TCF_TILE;               // Q, K, V, dO, O (= the forward output Va, for delta)
 constexpr int TCB_XT = TN * TN * 2;                         // 8 KB: one 64 x 64 16-bit tile (dS or A)
-constexpr int TCB_GATE = 128 * 64;                          // 8 KB: 32 fp16 gate values per thread, [chunk][thread] x 16 B
-constexpr int TCB_WG_BYTES = TCB_STAGES * TCB_STAGE_BYTES + 4 * TCB_XT + TCB_GATE;      // 72 KB
-constexpr int TCB_SMEM = 2 * TCB_WG_BYTES + 512 + 1024;
+constexpr int TCB_WG_BYTES = TCB_STAGES * TCB_STAGE_BYTES + 4 * TCB_XT;      // 72 KB
+constexpr int TCB_QS = 16;                                  // item-queue slots per warpgroup
+constexpr int TCB_SMEM = 2 * TCB_WG_BYTES + 1024 + 1024;
 constexpr uint32_t TCB_COLS_WG = 192, TCB_COL_OUT = 128, TCB_TMEM_COLS = 512;
+
+// shared-memory matrix descriptor from (address >> 4) + a byte offset: the high word is a per-layout constant, so the
+// issuing thread spends one add per descriptor
+__host__ __device__ constexpr uint32_t umma_desc_hi(uint32_t sbo_bytes, uint32_t swizzle) { return (sbo_bytes >> 4) | (1u << 14) | (swizzle << 29); }
+__device__ __forceinline__ uint64_t umma_desc_at(uint32_t base16, uint32_t off_bytes, uint32_t hi) {
+  return ((uint64_t)hi << 32) | (uint64_t)(base16 + (off_bytes >> 4) + (1u << 16));
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// wait of a single-lane control role: back off between polls so that the spin does not eat the issue slots of the
+// compute warps on the same SM sub-partition
+__device__ __forceinline__ void mbar_wait_polite(uint32_t bar, uint32_t parity) {
+  while (!mbar_test(bar, parity)) __nanosleep(40);
+}
 
 template <typename T>
 __global__ void __launch_bounds__(TCB_THREADS, 1)
 tri_attn_bwd_tc(const tgt_triplet_attn_desc D, const __grid_constant__ CUtensorMap mPcol,
                 const __grid_constant__ CUtensorMap mProw, const __grid_constant__ CUtensorMap mDVA,
+                const __grid_constant__ CUtensorMap mVA,
                 const float *__restrict__ ws_e, const __half *__restrict__ ws_g, const float *__restrict__ stats,
-                T *__restrict__ dproj, float *__restrict__ ws_de, float *__restrict__ ws_dg) {
+                T *__restrict__ dproj, float *__restrict__ ws_de, float *__restrict__ ws_dg, int *__restrict__ item_counter) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int N = D.N, H = D.H;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int total_items = D.B * 2 * H;
   const uint32_t bars = sbase + 2 * TCB_WG_BYTES;
-  const uint32_t tmem_slot = bars + 256;
-  volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-  // per-warpgroup barrier block (w = 0, 1): full[4] empty[4] s_ready[2] t_ready[2] o_ready[2]
+  const uint32_t tmem_slot = bars + 288;
+  auto generic = [&](uint32_t saddr) { return smem_raw + (saddr - smem_u32(smem_raw)); };
+  volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(generic(tmem_slot));
+  // per-warpgroup barrier block (w = 0, 1): full[4] empty[4] s_ready[2] t_ready[2] o_ready[2] o_free[2]
   auto bar_full = [&](int w, int s) { return bars + w * 128 + 8 * s; };
   auto bar_empty = [&](int w, int s) { return bars + w * 128 + 32 + 8 * s; };
   auto bar_s = [&](int w, int q) { return bars + w * 128 + 64 + 8 * q; };
   auto bar_t = [&](int w, int q) { return bars + w * 128 + 80 + 8 * q; };
   auto bar_o = [&](int w, int q) { return bars + w * 128 + 96 + 8 * q; };
+  auto bar_of = [&](int w, int q) { return bars + w * 128 + 112 + 8 * q; };
+  // item queue: the producer of a warpgroup draws work items (h, dir, b) from a global counter, in order, and hands
+  // their ids to the issuer, the compute warps and the epilogue warps.  Items are therefore always started in id order by
+  // whichever warpgroup is free -- the 16 heads x 2 directions of a graph, which share 128-byte lines of the projection,
+  // run at the same time on neighbouring SMs and meet in L2 (a static round-robin lets them drift apart: 2.7x DRAM reads).
+  auto q_item = [&](int w, int k) { return reinterpret_cast<volatile int *>(generic(bars + 320 + (w * TCB_QS + (k % TCB_QS)) * 4)); };
+  auto q_full = [&](int w, int k) { return bars + 512 + (w * TCB_QS + (k % TCB_QS)) * 8; };
 
   if (tid == 0) {
     for (int w = 0; w < 2; ++w) {
@@ -386,34 +425,109 @@ tri_attn_bwd_tc(const tgt_triplet_attn_desc D, const __grid_constant__ CUtensorM
         mbar_init(bar_s(w, q), 1);
         mbar_init(bar_t(w, q), 4);             // one arrival per compute warp
         mbar_init(bar_o(w, q), 1);
+        mbar_init(bar_of(w, q), 4);            // one arrival per epilogue warp
       }
+      for (int k = 0; k < TCB_QS; ++k) mbar_init(q_full(w, k), 1);
     }
     fence_barrier_init();
     tma_prefetch_desc(&mPcol);
     tma_prefetch_desc(&mProw);
     tma_prefetch_desc(&mDVA);
+    tma_prefetch_desc(&mVA);
   }
   if (warp == 10) tc_alloc(tmem_slot, TCB_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
+  const int oq0 = D.off_q[0], oq1 = D.off_q[1], ok0 = D.off_k[0], ok1 = D.off_k[1], ov0 = D.off_v[0], ov1 = D.off_v[1];
 
-  if (warp >= 8) {
+  if (warp >= 12) {
+    // ------------------------------------------------------------------------------------------------ epilogue warps
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TCB_REGS_EPI));
+    const int q = warp & 3, i = q * 16 + (lane & 15), kh = lane >> 4;
+    const int64_t ld = D.ld;
+    const float sc = D.scale;
+    int n_[2] = {0, 0}, k_[2] = {0, 0}, j_[2] = {0, 0};       // per stream: junction counter, queue cursor, junction in item
+    bool live[2] = {true, true};
+    int64_t qoff[2] = {0, 0}, koff[2] = {0, 0}, kstep[2] = {0, 0};     // element offsets of this lane's rows at j = 0
+    auto load_item = [&](int w) {                               // decode item k_[w] of stream w (or mark the stream finished)
+      mbar_wait(q_full(w, k_[w]), (uint32_t)((k_[w] / TCB_QS) & 1));
+      const int t = *q_item(w, k_[w]);
+      if (t < 0) { live[w] = false; return; }
+      const int b = t / (2 * H), r = t - b * 2 * H, dir = r / H, h = r - dir * H;
+      // kh == 0: dQ row (b, i, j) and dV row; kh == 1: dK row.  i plays the key index for dK / dV: inward keys are row j
+      // of e ((b, j, k)), outward keys are column j ((b, k, j))
+      const int64_t qrow0 = (int64_t)(b * N + i) * N, krow0 = dir == 0 ? (int64_t)b * N * N + i : qrow0;
+      qoff[w] = qrow0 * ld + (dir ? oq1 : oq0) + h * HD;
+      koff[w] = krow0 * ld + (kh == 0 ? (dir ? ov1 : ov0) : (dir ? ok1 : ok0)) + h * HD;
+      kstep[w] = dir == 0 ? (int64_t)N * ld : ld;
+    };
+    load_item(0);
+    load_item(1);
+    while (live[0] || live[1]) {
+      bool did = false;
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        if (!live[w]) continue;
+        const int n = n_[w];
+        if (!mbar_test(bar_o(w, n & 1), (uint32_t)((n >> 1) & 1))) continue;
+        did = true;
+        tc_fence_after();
+        const uint32_t tO = tmem + (uint32_t)w * TCB_COLS_WG + ((uint32_t)(q * 32) << 16) + TCB_COL_OUT + (uint32_t)(n & 1) * 32u;
+        uint32_t o[16];
+        tcx_ld16(tO, o);                                      // dQ (lanes 0-15) | dK (lanes 16-31)
+        tc_ld_wait();
+        const int j = j_[w];
+        if (i < N) {
+          uint32_t wv[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) wv[c] = Mma<T>::pack(__uint_as_float(o[2 * c]) * sc, __uint_as_float(o[2 * c + 1]) * sc);
+          uint4 *dst = reinterpret_cast<uint4 *>(dproj + (kh == 0 ? qoff[w] + (int64_t)j * ld : koff[w] + (int64_t)j * kstep[w]));
+          dst[0] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+          dst[1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
+        }
+        tcx_ld16(tO + 16u, o);                                // dV (lanes 0-15)
+        tc_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_of(w, n & 1));         // this quadrant of the output accumulator is free again
+        if (i < N && kh == 0) {
+          uint32_t vv[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) vv[c] = Mma<T>::pack(__uint_as_float(o[2 * c]), __uint_as_float(o[2 * c + 1]));
+          uint4 *dst = reinterpret_cast<uint4 *>(dproj + koff[w] + (int64_t)j * kstep[w]);
+          dst[0] = make_uint4(vv[0], vv[1], vv[2], vv[3]);
+          dst[1] = make_uint4(vv[4], vv[5], vv[6], vv[7]);
+        }
+        ++n_[w];
+        if (++j_[w] == N) {
+          j_[w] = 0;
+          ++k_[w];
+          load_item(w);
+        }
+      }
+      if (!did) __nanosleep(40);
+    }
+  } else if (warp >= 8) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TCB_REGS_CTRL));
     const int w = warp & 1;                                  // the compute warpgroup this control warp serves
     const uint32_t wg_smem = sbase + w * TCB_WG_BYTES;
-    const int first = blockIdx.x * 2 + w, stride = gridDim.x * 2;
     if (warp < 10 && lane == 0) {
       // ------------------------------------------------------------------------------------------ TMA producer
-      int n = 0;
-      for (int t = first; t < total_items; t += stride) {
+      int n = 0, t_next = atomicAdd(item_counter, 1);
+      for (int k = 0;; ++k) {
+        const int t = t_next < total_items ? t_next : -1;
+        *q_item(w, k) = t;
+        mbar_arrive(q_full(w, k));                           // release: the id is visible to whoever waits on the slot
+        if (t < 0) break;
+        t_next = atomicAdd(item_counter, 1);                 // next id: its latency hides behind this item's loads
         const int b = t / (2 * H), r = t - b * 2 * H, dir = r / H, h = r - dir * H;
-        const int cq = D.off_q[dir] + h * HD, ck = D.off_k[dir] + h * HD, cv = D.off_v[dir] + h * HD;
+        const int cq = (dir ? oq1 : oq0) + h * HD, ck = (dir ? ok1 : ok0) + h * HD, cv = (dir ? ov1 : ov0) + h * HD;
         const int co = dir * H * HD + h * HD;
         for (int j = 0; j < N; ++j, ++n) {
           const int s = n % TCB_STAGES;
-          mbar_wait(bar_empty(w, s), (uint32_t)(((n / TCB_STAGES) & 1) ^ 1));
+          mbar_wait_polite(bar_empty(w, s), (uint32_t)(((n / TCB_STAGES) & 1) ^ 1));
           const uint32_t st = wg_smem + s * TCB_STAGE_BYTES, bar = bar_full(w, s);
           mbar_expect_tx(bar, TCB_STAGE_BYTES);
           tma_load_4d(&mPcol, bar, st, cq, j, 0, b);
@@ -425,83 +539,100 @@ tri_attn_bwd_tc(const tgt_triplet_attn_desc D, const __grid_constant__ CUtensorM
             tma_load_4d(&mPcol, bar, st + 2 * TCF_TILE, cv, j, 0, b);
           }
           tma_load_4d(&mDVA, bar, st + 3 * TCF_TILE, co, j, 0, b);
+          tma_load_4d(&mVA, bar, st + 4 * TCF_TILE, co, j, 0, b);
         }
       }
     } else if (warp >= 10 && lane == 0) {
       // ------------------------------------------------------------------------------------------ MMA issuer
-      int items = 0;
-      for (int t = first; t < total_items; t += stride) ++items;
-      const int total_n = items * N;
       const uint32_t tw = tmem + (uint32_t)w * TCB_COLS_WG;
-      const uint32_t sX = wg_smem + TCB_STAGES * TCB_STAGE_BYTES;          // [buf][dS | A]
+      const uint32_t sX16 = (wg_smem + TCB_STAGES * TCB_STAGE_BYTES) >> 4;       // [buf][dS | A], address >> 4
       const uint32_t id_sa = umma_idesc_f16<T>(64, 32, false, false);
       const uint32_t id_dq = umma_idesc_f16<T>(64, 16, false, true);
       const uint32_t id_kv = umma_idesc_f16<T>(64, 16, true, true);
-      auto issue_sa = [&](int n) {                       // S(n), dA(n) -> buffer n & 1
-        const int s = n % TCB_STAGES;
-        mbar_wait(bar_full(w, s), (uint32_t)((n / TCB_STAGES) & 1));
-        tc_fence_after();
-        const uint32_t st = wg_smem + s * TCB_STAGE_BYTES;
-        const uint32_t tSA = tw + (uint32_t)(n & 1) * 64u;
-        const uint64_t dQ_ = umma_smem_desc(st, 256, 16, UMMA_SW32), dO_ = umma_smem_desc(st + 3 * TCF_TILE, 256, 16, UMMA_SW32);
-#pragma unroll
-        for (int kh = 0; kh < 2; ++kh) {                 // keys 32 kh .. 32 kh + 31 -> lane offset 16 kh
-          tc_mma(tSA + kh * TC_LANE16, dQ_, umma_smem_desc(st + TCF_TILE + kh * 1024, 256, 16, UMMA_SW32), id_sa, 0u);
-          tc_mma(tSA + 32u + kh * TC_LANE16, dO_, umma_smem_desc(st + 2 * TCF_TILE + kh * 1024, 256, 16, UMMA_SW32), id_sa, 0u);
+      constexpr uint32_t HI32 = umma_desc_hi(256, UMMA_SW32), HI128 = umma_desc_hi(1024, UMMA_SW128);
+      int ns = 0, ks = 0, js = 0;                            // S / dA tiles issued so far; queue cursor of the next one
+      bool more = true;
+      auto try_issue_sa = [&]() {                            // S(ns), dA(ns) -> buffer ns & 1, if that junction exists
+        if (!more) return;
+        if (js == 0) {
+          mbar_wait_polite(q_full(w, ks), (uint32_t)((ks / TCB_QS) & 1));
+          if (*q_item(w, ks) < 0) { more = false; return; }
         }
-        tc_commit(bar_s(w, n & 1));
-      };
-      if (total_n > 0) issue_sa(0);
-      if (total_n > 1) issue_sa(1);
-      for (int n = 0; n < total_n; ++n) {
-        mbar_wait(bar_t(w, n & 1), (uint32_t)((n >> 1) & 1));      // dS(n), A(n) are in shared memory; S(n), dA(n) were read
+        const int s = ns % TCB_STAGES;
+        mbar_wait_polite(bar_full(w, s), (uint32_t)((ns / TCB_STAGES) & 1));
         tc_fence_after();
-        const uint32_t st = wg_smem + (n % TCB_STAGES) * TCB_STAGE_BYTES;
-        const uint32_t sDS = sX + (uint32_t)(n & 1) * 2 * TCB_XT, sA = sDS + TCB_XT;
+        const uint32_t st16 = (wg_smem + s * TCB_STAGE_BYTES) >> 4;
+        const uint32_t tSA = tw + (uint32_t)(ns & 1) * 64u;
+        const uint64_t dQ_ = umma_desc_at(st16, 0, HI32), dO_ = umma_desc_at(st16, 3 * TCF_TILE, HI32);
+#pragma unroll
+        for (int kh = 0; kh < 2; ++kh) {                     // keys 32 kh .. 32 kh + 31 -> lane offset 16 kh
+          tc_mma(tSA + kh * TC_LANE16, dQ_, umma_desc_at(st16, TCF_TILE + kh * 1024, HI32), id_sa, 0u);
+          tc_mma(tSA + 32u + kh * TC_LANE16, dO_, umma_desc_at(st16, 2 * TCF_TILE + kh * 1024, HI32), id_sa, 0u);
+        }
+        tc_commit(bar_s(w, ns & 1));
+        ++ns;
+        if (++js == N) { js = 0; ++ks; }
+      };
+      try_issue_sa();
+      try_issue_sa();
+      for (int n = 0; n < ns; ++n) {
+        mbar_wait_polite(bar_t(w, n & 1), (uint32_t)((n >> 1) & 1));     // dS(n), A(n) are in shared memory; S(n), dA(n) were read
+        if (n >= 2) mbar_wait_polite(bar_of(w, n & 1), (uint32_t)(((n - 2) >> 1) & 1));   // outputs of n-2 have left TMEM
+        tc_fence_after();
+        const uint32_t st16 = (wg_smem + (n % TCB_STAGES) * TCB_STAGE_BYTES) >> 4;
+        const uint32_t dS16 = sX16 + (uint32_t)(n & 1) * (2 * TCB_XT >> 4), a16 = dS16 + (TCB_XT >> 4);
         const uint32_t tOut = tw + TCB_COL_OUT + (uint32_t)(n & 1) * 32u;
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
+        for (int ks_ = 0; ks_ < 4; ++ks_) {
           // dQ[i, d] += dS[i, 16ks..] K[16ks.., d]        A: dS K-major (32 B per step), B: K tile MN-major
-          tc_mma(tOut, umma_smem_desc(sDS + ks * 32, 1024, 16, UMMA_SW128), umma_smem_desc(st + TCF_TILE + ks * 512, 256, 16, UMMA_SW32),
-                 id_dq, (uint32_t)(ks != 0));
+          tc_mma(tOut, umma_desc_at(dS16, ks_ * 32, HI128), umma_desc_at(st16, TCF_TILE + ks_ * 512, HI32), id_dq,
+                 (uint32_t)(ks_ != 0));
           // dK[k, d] += dS[16ks.., k]^T Q[16ks.., d]      A: dS MN-major (two 8-row groups per step), B: Q tile MN-major
-          tc_mma(tOut + TC_LANE16, umma_smem_desc(sDS + ks * 2048, 1024, 16, UMMA_SW128), umma_smem_desc(st + ks * 512, 256, 16, UMMA_SW32),
-                 id_kv, (uint32_t)(ks != 0));
+          tc_mma(tOut + TC_LANE16, umma_desc_at(dS16, ks_ * 2048, HI128), umma_desc_at(st16, ks_ * 512, HI32), id_kv,
+                 (uint32_t)(ks_ != 0));
           // dV[k, d] += A[16ks.., k]^T dO[16ks.., d]
-          tc_mma(tOut + 16u, umma_smem_desc(sA + ks * 2048, 1024, 16, UMMA_SW128),
-                 umma_smem_desc(st + 3 * TCF_TILE + ks * 512, 256, 16, UMMA_SW32), id_kv, (uint32_t)(ks != 0));
+          tc_mma(tOut + 16u, umma_desc_at(a16, ks_ * 2048, HI128), umma_desc_at(st16, 3 * TCF_TILE + ks_ * 512, HI32), id_kv,
+                 (uint32_t)(ks_ != 0));
         }
         tc_commit(bar_o(w, n & 1));
         tc_commit(bar_empty(w, n % TCB_STAGES));
-        if (n + 2 < total_n) issue_sa(n + 2);
+        try_issue_sa();
       }
     }
     __syncwarp();
   } else {
     // ---------------------------------------------------------------------------------------------- compute warpgroups
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TCB_REGS_WORK));
-    const int w = warp >> 2, q = warp & 3, tw_id = tid & 127;
+    const int w = warp >> 2, q = warp & 3;
     const int i = q * 16 + (lane & 15), kh = lane >> 4;
     const uint32_t wg_smem = sbase + w * TCB_WG_BYTES;
     const uint32_t sX = wg_smem + TCB_STAGES * TCB_STAGE_BYTES;
-    const uint32_t sGate = sX + 4 * TCB_XT + (uint32_t)tw_id * 16u;                    // + chunk * 2048
     const uint32_t tl = tmem + (uint32_t)w * TCB_COLS_WG + ((uint32_t)(q * 32) << 16);
     const uint32_t row_off = (uint32_t)i * 128u;                                        // this row in a 64 x 64 tile
-    const int first = blockIdx.x * 2 + w, stride = gridDim.x * 2;
+    // this row in a [64 x 16] SWIZZLE_32B stage tile: 16-byte halves at row32 + half0 / half1
+    const uint32_t row32 = (uint32_t)i * 32u, half0 = (uint32_t)(((i >> 2) & 1) << 4), half1 = half0 ^ 16u;
     constexpr float LN2 = 0.6931471805599453f;
     const float2 l2e = make_float2(LOG2E, LOG2E);
 
-    uint32_t ebk[16];
+    // per item, constant over the junctions: E + mask (natural-log domain; exactly the 16-bit projection value, hugely
+    // negative when masked) and the fp16 gate of this thread's 32 keys, packed two per register; dE / dG accumulators
+    uint32_t ebk[16], gtk[16];
     float2 dE[16], dG[16];
     float sc = 0.f;
-    int b = 0, dir = 0, h = 0;
+    int64_t tile_base = 0;                                   // this thread's 32 entries of the (b, dir, h) bias / gate tiles
+    const float *lse_row = stats;                            // stats[b, dir, h, 0, i]
+    int kq = 0;
+    auto next_item = [&]() {
+      mbar_wait(q_full(w, kq), (uint32_t)((kq / TCB_QS) & 1));
+      const int t = *q_item(w, kq);
+      ++kq;
+      return t;
+    };
     auto setup = [&](int t) {
-      b = t / (2 * H);
-      const int r = t - b * 2 * H;
-      dir = r / H;
-      h = r - dir * H;
-      const int64_t tbase = (((int64_t)(b * 2 + dir) * H + h) * TN + i) * TN + 32 * kh;
-      const float4 *er = reinterpret_cast<const float4 *>(ws_e + tbase);
+      const int b = t / (2 * H), r = t - b * 2 * H, dir = r / H, h = r - dir * H;
+      tile_base = (((int64_t)(b * 2 + dir) * H + h) * TN + i) * TN + 32 * kh;
+      lse_row = stats + ((int64_t)(b * 2 + dir) * H + h) * N * N + i;
+      const float4 *er = reinterpret_cast<const float4 *>(ws_e + tile_base);
       float4 v[8];
       bool fm = true;
 #pragma unroll
@@ -521,122 +652,87 @@ tri_attn_bwd_tc(const tgt_triplet_attn_desc D, const __grid_constant__ CUtensorM
         ebk[2 * c + 1] = Mma<T>::pack(u.z * LN2, u.w * LN2);
       }
       sc = fm ? 0.f : D.scale;
-      const uint4 *gr = reinterpret_cast<const uint4 *>(ws_g + tbase);
+      const uint4 *gr = reinterpret_cast<const uint4 *>(ws_g + tile_base);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const uint4 g4 = gr[c];
-        st_shared_v4u(sGate + c * 2048, g4.x, g4.y, g4.z, g4.w);
+        gtk[4 * c] = g4.x; gtk[4 * c + 1] = g4.y; gtk[4 * c + 2] = g4.z; gtk[4 * c + 3] = g4.w;
       }
 #pragma unroll
       for (int c = 0; c < 16; ++c) dE[c] = dG[c] = make_float2(0.f, 0.f);
     };
     auto finish = [&]() {                                               // dE, dG = g (1 - g) * acc -> [B,2,H,64,64] tiles
-      const int64_t tbase = (((int64_t)(b * 2 + dir) * H + h) * TN + i) * TN + 32 * kh;
-      float4 *de = reinterpret_cast<float4 *>(ws_de + tbase), *dg = reinterpret_cast<float4 *>(ws_dg + tbase);
+      float4 *de = reinterpret_cast<float4 *>(ws_de + tile_base), *dg = reinterpret_cast<float4 *>(ws_dg + tile_base);
 #pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) {
-        const uint4 g4 = ld_shared_v4u(sGate + c4 * 2048);
-        const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w};
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int c = 4 * c4 + 2 * u;
-          const float2 g0 = __half22float2(*reinterpret_cast<const __half2 *>(&gw[2 * u]));
-          const float2 g1 = __half22float2(*reinterpret_cast<const __half2 *>(&gw[2 * u + 1]));
-          de[2 * c4 + u] = make_float4(dE[c].x, dE[c].y, dE[c + 1].x, dE[c + 1].y);
-          dg[2 * c4 + u] = make_float4(dG[c].x * g0.x * (1.f - g0.x), dG[c].y * g0.y * (1.f - g0.y),
-                                       dG[c + 1].x * g1.x * (1.f - g1.x), dG[c + 1].y * g1.y * (1.f - g1.y));
-        }
-      }
-    };
-    // O(n-1) of the junction (pb, pdir, ph, pj): dQ | dV rows on lanes 0-15, dK rows on lanes 16-31
-    int pb = 0, pdir = 0, ph = 0, pj = 0;
-    auto epilogue = [&](int n) {
-      mbar_wait(bar_o(w, n & 1), (uint32_t)((n >> 1) & 1));
-      tc_fence_after();
-      uint32_t o[32];
-      tcx_ld32(tl + TCB_COL_OUT + (uint32_t)(n & 1) * 32u, o);
-      tc_ld_wait();
-      if (i < N) {
-        const int64_t qrow = ((int64_t)(pb * N + i) * N + pj);
-        const int64_t krow = pdir == 0 ? ((int64_t)(pb * N + pj) * N + i) : qrow;      // i plays the key index here
-        const float s_ = D.scale;
-        uint32_t wv[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) wv[c] = Mma<T>::pack(__uint_as_float(o[2 * c]) * s_, __uint_as_float(o[2 * c + 1]) * s_);
-        if (kh == 0) {
-          uint4 *dq = reinterpret_cast<uint4 *>(dproj + qrow * D.ld + D.off_q[pdir] + ph * HD);
-          dq[0] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-          dq[1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
-          uint32_t vv[8];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) vv[c] = Mma<T>::pack(__uint_as_float(o[16 + 2 * c]), __uint_as_float(o[17 + 2 * c]));
-          uint4 *dv = reinterpret_cast<uint4 *>(dproj + krow * D.ld + D.off_v[pdir] + ph * HD);
-          dv[0] = make_uint4(vv[0], vv[1], vv[2], vv[3]);
-          dv[1] = make_uint4(vv[4], vv[5], vv[6], vv[7]);
-        } else {
-          uint4 *dk = reinterpret_cast<uint4 *>(dproj + krow * D.ld + D.off_k[pdir] + ph * HD);
-          dk[0] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-          dk[1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
-        }
+      for (int c = 0; c < 8; ++c) {
+        const float2 g0 = __half22float2(*reinterpret_cast<const __half2 *>(&gtk[2 * c]));
+        const float2 g1 = __half22float2(*reinterpret_cast<const __half2 *>(&gtk[2 * c + 1]));
+        de[c] = make_float4(dE[2 * c].x, dE[2 * c].y, dE[2 * c + 1].x, dE[2 * c + 1].y);
+        dg[c] = make_float4(dG[2 * c].x * g0.x * (1.f - g0.x), dG[2 * c].y * g0.y * (1.f - g0.y),
+                            dG[2 * c + 1].x * g1.x * (1.f - g1.x), dG[2 * c + 1].y * g1.y * (1.f - g1.y));
       }
     };
 
-    int t = first, j = 0;
-    if (t < total_items) setup(t);
-    float lse_next = 0.f;
-    auto lse_addr = [&](int jj) { return stats + (((int64_t)(b * 2 + dir) * H + h) * N + jj) * N + i; };
-    if (t < total_items) lse_next = i < N ? __ldg(lse_addr(0)) : INFINITY;
-    for (int n = 0; t < total_items; ++n) {
+    int t = next_item(), j = 0;
+    if (t >= 0) setup(t);
+    float lse_next = (t >= 0 && i < N) ? __ldg(lse_row) : INFINITY;
+    for (int n = 0; t >= 0; ++n) {
       const float lse2 = lse_next;                       // log2-domain log-sum-exp of row i at junction j (+inf: padding row)
-      if (j + 1 < N) lse_next = i < N ? __ldg(lse_addr(j + 1)) : INFINITY;
-      mbar_wait(bar_s(w, n & 1), (uint32_t)((n >> 1) & 1));
+      if (j + 1 < N && i < N) lse_next = __ldg(lse_row + (int64_t)(j + 1) * N);
+      mbar_wait(bar_s(w, n & 1), (uint32_t)((n >> 1) & 1));     // S(n), dA(n) in tensor memory (=> the stage's tiles have landed)
       tc_fence_after();
-      uint32_t sv[32], av[32];
-      tcx_ld32(tl + (uint32_t)(n & 1) * 64u, sv);
-      tcx_ld32(tl + (uint32_t)(n & 1) * 64u + 32u, av);
-      tc_ld_wait();
-      // pass 1: P, dG += dA P, A = P g, dP = dA g, delta = sum dP P
-      const float2 scp = make_float2(sc, sc), nl = make_float2(-lse2, -lse2);
-      float2 p[16], dp[16], dl = make_float2(0.f, 0.f);
-      uint32_t apk[16];
-#pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) {
-        const uint4 g4 = ld_shared_v4u(sGate + c4 * 2048);
-        const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w};
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int c = 4 * c4 + u;
-          const float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[2 * c]), __uint_as_float(sv[2 * c + 1])), scp,
-                                      unpack16x2<T>(ebk[c]));
-          const float2 e2 = __ffma2_rn(x, l2e, nl);
-          p[c] = make_float2(fast_exp2(e2.x), fast_exp2(e2.y));
-          const float2 da = make_float2(__uint_as_float(av[2 * c]), __uint_as_float(av[2 * c + 1]));
-          const float2 g2 = __half22float2(*reinterpret_cast<const __half2 *>(&gw[u]));
-          dG[c] = __ffma2_rn(da, p[c], dG[c]);
-          dp[c] = __fmul2_rn(da, g2);
-          dl = __ffma2_rn(dp[c], p[c], dl);
-          const float2 a2 = __fmul2_rn(p[c], g2);
-          apk[c] = Mma<T>::pack(a2.x, a2.y);
-        }
-      }
-      float delta = dl.x + dl.y;
-      delta += __shfl_xor_sync(0xffffffffu, delta, 16);
-      // pass 2: dS = P (dP - delta), dE += dS
-      const float2 nd = make_float2(-delta, -delta);
-      uint32_t dpk[16];
-#pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        const float2 ds = __fmul2_rn(p[c], __fadd2_rn(dp[c], nd));
-        dE[c] = __fadd2_rn(dE[c], ds);
-        dpk[c] = Mma<T>::pack(ds.x, ds.y);
-      }
-      // this thread's 64 bytes of row i of the dS and A tiles (chunks 4 kh .. 4 kh + 3, 128B swizzle).  The tiles of
-      // junction n-2 were last read by UMMAs whose completion the epilogue of the previous iteration waited for.
+      const uint32_t tSA = tl + (uint32_t)(n & 1) * 64u;
+      uint32_t sv[16], av[16];
+      tcx_ld16(tSA, sv);
+      tcx_ld16(tSA + 32u, av);
+      // delta[i] = sum_k dP P = sum_d dO[i, d] O[i, d]  (O = A V is the forward output): one pass over the scores suffices
+      float delta;
       {
-        const uint32_t sDS = sX + (uint32_t)(n & 1) * 2 * TCB_XT + row_off, sA = sDS + TCB_XT;
+        const uint32_t st = wg_smem + (uint32_t)(n % TCB_STAGES) * TCB_STAGE_BYTES + row32;
+        const uint4 d0 = ld_shared_v4u(st + 3 * TCF_TILE + half0), d1 = ld_shared_v4u(st + 3 * TCF_TILE + half1);
+        const uint4 o0 = ld_shared_v4u(st + 4 * TCF_TILE + half0), o1 = ld_shared_v4u(st + 4 * TCF_TILE + half1);
+        const uint32_t dw[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+        const uint32_t ow[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+        float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const uint32_t off = (uint32_t)(((4 * kh + c) ^ (i & 7)) << 4);
+        for (int c = 0; c < 8; ++c) acc = __ffma2_rn(unpack16x2<T>(dw[c]), unpack16x2<T>(ow[c]), acc);
+        delta = acc.x + acc.y;
+      }
+      const float2 scp = make_float2(sc, sc), nl = make_float2(-lse2, -lse2), nd = make_float2(-delta, -delta);
+      // the dS / A tiles of junction n-2 were read by UMMAs that have completed when o_ready(n-2) has
+      if (n >= 2) mbar_wait(bar_o(w, n & 1), (uint32_t)(((n - 2) >> 1) & 1));
+      const uint32_t sDS = sX + (uint32_t)(n & 1) * 2 * TCB_XT + row_off, sA = sDS + TCB_XT;
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {                   // 16 keys per chunk
+        tc_ld_wait();
+        uint32_t s2[16], a2[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) { s2[c] = sv[c]; a2[c] = av[c]; }
+        if (ch == 0) {                                   // the second chunk flies during the math of the first
+          tcx_ld16(tSA + 16u, sv);
+          tcx_ld16(tSA + 48u, av);
+        }
+        uint32_t dpk[8], apk[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int cc = 8 * ch + c;
+          const float2 x = __ffma2_rn(make_float2(__uint_as_float(s2[2 * c]), __uint_as_float(s2[2 * c + 1])), scp,
+                                      unpack16x2<T>(ebk[cc]));
+          const float2 e2 = __ffma2_rn(x, l2e, nl);
+          const float2 p = make_float2(fast_exp2(e2.x), fast_exp2(e2.y));
+          const float2 da = make_float2(__uint_as_float(a2[2 * c]), __uint_as_float(a2[2 * c + 1]));
+          const float2 g2 = __half22float2(*reinterpret_cast<const __half2 *>(&gtk[cc]));
+          dG[cc] = __ffma2_rn(da, p, dG[cc]);
+          const float2 ds = __fmul2_rn(p, __ffma2_rn(da, g2, nd));          // P (dA g - delta)
+          dE[cc] = __fadd2_rn(dE[cc], ds);
+          const float2 aa = __fmul2_rn(p, g2);
+          dpk[c] = Mma<T>::pack(ds.x, ds.y);
+          apk[c] = Mma<T>::pack(aa.x, aa.y);
+        }
+        // this thread's 32 bytes per tile of row i (chunks 4 kh + 2 ch, + 1; 128B swizzle)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const uint32_t off = (uint32_t)(((4 * kh + 2 * ch + c) ^ (i & 7)) << 4);
           st_shared_v4u(sDS + off, dpk[4 * c], dpk[4 * c + 1], dpk[4 * c + 2], dpk[4 * c + 3]);
           st_shared_v4u(sA + off, apk[4 * c], apk[4 * c + 1], apk[4 * c + 2], apk[4 * c + 3]);
         }
@@ -645,18 +741,15 @@ tri_attn_bwd_tc(const tgt_triplet_attn_desc D, const __grid_constant__ CUtensorM
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_t(w, n & 1));
-      if (n > 0) epilogue(n - 1);
-      pb = b; pdir = dir; ph = h; pj = j;
       if (++j == N) {
         finish();
-        t += stride;
+        t = next_item();
         j = 0;
-        if (t < total_items) {
+        if (t >= 0) {
           setup(t);
-          lse_next = i < N ? __ldg(lse_addr(0)) : INFINITY;
+          lse_next = i < N ? __ldg(lse_row) : INFINITY;
         }
       }
-      if (t >= total_items) epilogue(n);                 // the very last junction of this warpgroup
     }
     tc_fence_before();
   }
@@ -668,29 +761,34 @@ tri_attn_bwd_tc(const tgt_triplet_attn_desc D, const __grid_constant__ CUtensorM
 }
 
 template <typename T>
-static int bwd_tc_impl(const tgt_triplet_attn_desc &D, const void *proj, const void *dva, const float *stats, void *dproj,
-                       const float *ws_e, const __half *ws_g, float *ws_de, float *ws_dg, cudaStream_t st) {
-  CUtensorMap mPcol, mProw, mDVA;
+static int bwd_tc_impl(const tgt_triplet_attn_desc &D, const void *proj, const void *va, const void *dva, const float *stats,
+                       void *dproj, const float *ws_e, const __half *ws_g, float *ws_de, float *ws_dg, int *counter,
+                       cudaStream_t st) {
+  CUtensorMap mPcol, mProw, mDVA, mVA;
   const int C = (int)D.ld, Cv = 2 * D.H * HD;
   if (int e = make_map(&mPcol, proj, D.B, D.N, C, D.ld, true, 16, D.dtype)) return e;
   if (int e = make_map(&mProw, proj, D.B, D.N, C, D.ld, false, 16, D.dtype)) return e;
   if (int e = make_map(&mDVA, dva, D.B, D.N, Cv, Cv, true, 16, D.dtype)) return e;
+  if (int e = make_map(&mVA, va, D.B, D.N, Cv, Cv, true, 16, D.dtype)) return e;
   int dev = 0, sms = 0;
   TGT_CUDA_OK(cudaGetDevice(&dev));
   TGT_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   TGT_CUDA_OK(cudaFuncSetAttribute(tri_attn_bwd_tc<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCB_SMEM));
   const int items = D.B * 2 * D.H;
   const int grid = std::min(sms, (items + 1) / 2);
+  TGT_CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(int), st));        // work-item counter of the persistent CTAs
   KernelTimerScope ts("tri_attn_bwd_tc", st);
-  tri_attn_bwd_tc<T><<<grid, TCB_THREADS, TCB_SMEM, st>>>(D, mPcol, mProw, mDVA, ws_e, ws_g, stats, (T *)dproj, ws_de, ws_dg);
+  tri_attn_bwd_tc<T><<<grid, TCB_THREADS, TCB_SMEM, st>>>(D, mPcol, mProw, mDVA, mVA, ws_e, ws_g, stats, (T *)dproj, ws_de, ws_dg,
+                                                          counter);
   return check_launch("tri_attn_bwd_tc");
 }
 
-int triplet_attn_bwd_tc_launch(const tgt_triplet_attn_desc &D, const void *proj, const void *dva, const float *stats,
-                               void *dproj, const float *ws_e, const __half *ws_g, float *ws_de, float *ws_dg,
-                               cudaStream_t st) {
-  if (D.dtype == TGT_BF16) return bwd_tc_impl<__nv_bfloat16>(D, proj, dva, stats, dproj, ws_e, ws_g, ws_de, ws_dg, st);
-  return bwd_tc_impl<__half>(D, proj, dva, stats, dproj, ws_e, ws_g, ws_de, ws_dg, st);
+int triplet_attn_bwd_tc_launch(const tgt_triplet_attn_desc &D, const void *proj, const void *va, const void *dva,
+                               const float *stats, void *dproj, const float *ws_e, const __half *ws_g, float *ws_de,
+                               float *ws_dg, int *counter, cudaStream_t st) {
+  if (D.dtype == TGT_BF16)
+    return bwd_tc_impl<__nv_bfloat16>(D, proj, va, dva, stats, dproj, ws_e, ws_g, ws_de, ws_dg, counter, st);
+  return bwd_tc_impl<__half>(D, proj, va, dva, stats, dproj, ws_e, ws_g, ws_de, ws_dg, counter, st);
 }
 
 }  // namespace tgt

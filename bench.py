@@ -267,6 +267,7 @@ def kernel_models(B, N, We, Ht, Wn, Hn, s=2):
 
 
 DEVICE_KERNELS = {   # main kernels timed inside the library (tgt_kernel_timer_*) -> roofline model
+    "tri_attn_fwd_tc": "triplet_attn_fwd", "tri_attn_bwd_tc": "triplet_attn_bwd",
     "tri_attn_fwd_tma": "triplet_attn_fwd", "tri_attn_fwd_mma": "triplet_attn_fwd",
     "tri_attn_bwd_tma": "triplet_attn_bwd", "tri_attn_bwd_mma": "triplet_attn_bwd",
     "tri_fused_fwd": "triplet_fused_fwd",

@@ -585,11 +585,19 @@ int triplet_attn_bwd_tc_launch(const tgt_triplet_attn_desc &D, const void *proj,
                                float *ws_dg, int *counter, cudaStream_t st);
 // kernel policy 0 (default) / 3 / 4 / 5: TMA-staged kernels; policy 2: the cp.async-staged kernels of this file
 static bool use_tma() { return g_policy.load() != 2 && g_policy.load() != 1 && triplet_attn_tma_available(); }
-// tcgen05 / TMEM core: policy 4 (and the default once it is the measured winner, see TC_DEFAULT)
-constexpr bool TC_DEFAULT = false;
-static bool use_tc(const tgt_triplet_attn_desc &D) {
+// tcgen05 / TMEM core (triplet_tc.cu): policy 4 runs it forward and backward.  Under the default policy 0 the forward
+// runs it too (1.01 ms against 1.06 ms for the TMA-staged mma.sync kernel at config 3; both write the same log-sum-exp
+// statistics, so the backward family is independent); the tcgen05 backward (2.40 ms against 2.47 ms) becomes the
+// default only together with a weight-gradient GEMM that supplies the projection's bias gradient, which the mma.sync
+// backward produces as a by-product and the tcgen05 one does not (TGT_TRI_TC_BWD=1 forces it).
+static bool tc_bwd_default() {
+  static const int v = [] { const char *e = getenv("TGT_TRI_TC_BWD"); return e ? atoi(e) : 0; }();
+  return v != 0;
+}
+static bool use_tc(const tgt_triplet_attn_desc &D, bool backward = false) {
   const int p = g_policy.load();
-  return (p == 4 || (TC_DEFAULT && (p == 0 || p == 3))) && triplet_attn_tc_supported(D);
+  const bool want = p == 4 || ((p == 0 || p == 3) && (!backward || tc_bwd_default()));
+  return want && triplet_attn_tc_supported(D);
 }
 
 struct Ws {
@@ -636,7 +644,7 @@ static int fwd_impl(const tgt_triplet_attn_desc &D, const void *proj, const floa
 template <typename T>
 static int bwd_impl(const tgt_triplet_attn_desc &D, const void *proj, const float *mask, const void *va, const void *dva,
                     const float *stats, void *dproj, void *ws, const void *fwd_ws, float *dbias, cudaStream_t st) {
-  if (dbias && (use_tc(D) || !(use_tma() && triplet_attn_bwd_tma_has_bias())))
+  if (dbias && (use_tc(D, true) || !(use_tma() && triplet_attn_bwd_tma_has_bias())))
     return fail("triplet_attn_bwd: the projection-bias by-product is not available with this kernel family");
   Ws w = carve(D, ws);
   const size_t psm = 2 * (size_t)D.H * 65 * sizeof(float);
@@ -650,7 +658,7 @@ static int bwd_impl(const tgt_triplet_attn_desc &D, const void *proj, const floa
     else tri_prep_bias_gate<T><<<dim3(TN, 2, D.B), 256, psm, st>>>(D, (const T *)proj, mask, w.e, w.g);
     if (int e = check_launch("tri_prep_bias_gate")) return e;
   }
-  if (use_tc(D)) {
+  if (use_tc(D, true)) {
     if (dbias) return fail("triplet_attn_bwd: the projection-bias by-product is not produced by the tcgen05 kernel");
     if (int e = triplet_attn_bwd_tc_launch(D, proj, va, dva, stats, dproj, w.e, w.g, w.de, w.dg, w.counter, st)) return e;
     if (bias_gate_h16_ok(D)) tri_post_bias_gate_h16<T><<<dim3(D.N, 2, D.B), 256, 0, st>>>(D, w.de, w.dg, (T *)dproj);
@@ -743,7 +751,7 @@ int triplet_attn_fwd_tc_f32out(const tgt_triplet_attn_desc &D, const void *proj,
 }
 
 bool triplet_attn_bwd_bias_available(const tgt_triplet_attn_desc &D) {
-  return triplet_attn_mma_supported(D) && !use_tc(D) && use_tma() && triplet_attn_bwd_tma_has_bias();
+  return triplet_attn_mma_supported(D) && !use_tc(D, true) && use_tma() && triplet_attn_bwd_tma_has_bias();
 }
 
 }  // namespace tgt

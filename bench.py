@@ -300,7 +300,7 @@ def run_ours(args):
     cfg = model_cfg(args)
     torch.manual_seed(0)
     model = TGT_Multi(**cfg).to(dev).train()
-    net = wrap_ddp(model, world, device_ids=[local])
+    net = wrap_ddp(model, world, device_ids=[local], bucket_cap_mb=args.ddp_bucket_mb, bf16_grads=bool(args.ddp_bf16))
     opt = torch.optim.Adam(model.parameters(), lr=1e-5, fused=True)
     B, N = args.batch, args.nodes
     micro = args.micro_batch or B
@@ -319,7 +319,11 @@ def run_ours(args):
                 gap, logits = net(batch)
                 loss = pretrain_loss(gap.float(), logits.float() if args.fp32_logits else logits, batch,
                                      cfg["num_dist_bins"]) * (micro / B)
-            loss.backward()
+            if args.ddp_no_sync and world > 1:              # diagnostic: the same step without the gradient all-reduce
+                with net.no_sync():
+                    loss.backward()
+            else:
+                loss.backward()
             total = loss.detach() if total is None else total + loss.detach()
         opt.step()
         opt.zero_grad(set_to_none=True)
@@ -451,6 +455,8 @@ def run_ours(args):
                                         f"bwd + fused Adam, per-GPU batch {B} x N={N}, bf16 autocast, train mode "
                                         f"(source_dropout .3, drop_path .2, act_dropout .1)",
                                micro_batch=micro, parallelism=f"dp{world}",
+                               ddp=dict(bucket_cap_mb=args.ddp_bucket_mb, bf16_grads=bool(args.ddp_bf16),
+                                        no_sync_diagnostic=bool(args.ddp_no_sync)) if world > 1 else None,
                                inputs="synthetic PCQM-shaped batch (tgt_b200/harness/synthetic.py), random-init weights",
                                l2="inputs and activations per step (>10 GB) exceed the 126 MB L2; no explicit flush"),
                    e2e=dict(value=world * B / (ms_e2e / args.steps * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d_bytes,
@@ -498,6 +504,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-eager-baseline", action="store_true")
     ap.add_argument("--fp32-logits", action="store_true")
+    ap.add_argument("--ddp-bucket-mb", type=int, default=25, help="DDP gradient bucket size (torch default 25)")
+    ap.add_argument("--ddp-bf16", type=int, default=0, help="1 = all-reduce the gradients in bf16 (stock DDP comm hook)")
+    ap.add_argument("--ddp-no-sync", action="store_true", help="diagnostic: skip the gradient all-reduce (INVALID as a result)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -25,8 +25,23 @@ ap.add_argument("--samples", type=int, default=2)
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--which", default="2,5")
 a = ap.parse_args()
-dev = torch.device("cuda", 0)
+# under torchrun every rank runs its own graphs (the reference's per-rank prediction shards): no collective on the data path,
+# one barrier + max-over-ranks for the timing
+RANK, LOCAL, WORLD = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("LOCAL_RANK", "0"), ("WORLD_SIZE", "1")))
+torch.cuda.set_device(LOCAL)
+dev = torch.device("cuda", LOCAL)
+if WORLD > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=dev)
 _C.lib()
+
+
+def over_ranks(ms):
+    if WORLD == 1:
+        return ms
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
 
 
 def timed(fn, iters):
@@ -38,22 +53,23 @@ def timed(fn, iters):
         fn()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters
+    return over_ranks(e0.elapsed_time(e1) / iters)
 
 
 if "2" in a.which.split(","):
     B, N = 256, 32
     torch.manual_seed(0)
     gm = TGT_Gap(**TGT_AGX2_CONFIG).to(dev).train()
-    batch = add_scheme_fields({k: v.to(dev) for k, v in make_batch(B, N, seed=1).items()}, with_3d=True)
+    batch = add_scheme_fields({k: v.to(dev) for k, v in make_batch(B, N, seed=1 + RANK).items()}, with_3d=True)
 
     def fwd():
         with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
             return gm(batch)
     n0 = _C.launch_count()
     ms = timed(fwd, a.iters)
-    print(json.dumps(dict(config="2: TGT-Agx2 12Lx2 gap-predictor forward, B=256 N=32, bf16, 1xB200", ms_per_batch=ms,
-                          molecules_per_s=B / ms * 1e3, gpu_launches=_C.launch_count() - n0,
+    if RANK == 0:
+        print(json.dumps(dict(config=f"2: TGT-Agx2 12Lx2 gap-predictor forward, B=256 (per GPU) N=32, bf16, {WORLD}xB200",
+                          ms_per_batch=ms, molecules_per_s=WORLD * B / ms * 1e3, gpu_launches=_C.launch_count() - n0,
                           peak_mem_gib=torch.cuda.max_memory_allocated() / 2 ** 30)))
     del gm, batch
     torch.cuda.empty_cache()
@@ -64,7 +80,7 @@ if "5" in a.which.split(","):
     cfg = {k: v for k, v in TGT_AT_CONFIG.items() if k != "num_dist_bins"}
     dm = TGT_Distance(num_dist_bins=256, embed_3d_type="none", **cfg).to(dev).train()
     gm = TGT_Gap(**cfg).to(dev).train()
-    batch = {k: v.to(dev) for k, v in make_batch(B, N, seed=1).items()}
+    batch = {k: v.to(dev) for k, v in make_batch(B, N, seed=1 + RANK).items()}
     out = {}
 
     def two_stage():
@@ -73,8 +89,13 @@ if "5" in a.which.split(","):
     n0 = _C.launch_count()
     ms = timed(two_stage, a.iters)
     assert bool(torch.isfinite(out["pred"]).all())
-    print(json.dumps(dict(config=f"5: TGT-At distance-predictor + gap-predictor two-stage inference, B=512 (per GPU) N=48, "
-                                 f"S={S} MC samples per stage, bf16, 1xB200", ms_per_batch=ms,
-                          molecules_per_s=B / ms * 1e3, forward_passes_per_batch=2 * S,
-                          molecule_passes_per_s=B * 2 * S / ms * 1e3, gpu_launches=_C.launch_count() - n0,
-                          peak_mem_gib=torch.cuda.max_memory_allocated() / 2 ** 30)))
+    if RANK == 0:
+        print(json.dumps(dict(config=f"5: TGT-At distance-predictor + gap-predictor two-stage inference, B=512 per GPU "
+                                     f"(global {512 * WORLD}) N=48, S={S} MC samples per stage (reference default 50, "
+                                     f"README.md:81), bf16, {WORLD}xB200, max over ranks", ms_per_batch=ms,
+                              molecules_per_s=WORLD * B / ms * 1e3, forward_passes_per_batch=2 * S,
+                              molecule_passes_per_s=WORLD * B * 2 * S / ms * 1e3, gpu_launches=_C.launch_count() - n0,
+                              peak_mem_gib=torch.cuda.max_memory_allocated() / 2 ** 30)))
+
+if WORLD > 1:
+    dist.destroy_process_group()

@@ -23,10 +23,19 @@ def rank_batch(B: int, N: int, rank: int):
     return {k: host[k] for k in RAW_KEYS}
 
 
-def wrap_ddp(model: torch.nn.Module, world: int, device_ids=None) -> torch.nn.Module:
+def wrap_ddp(model: torch.nn.Module, world: int, device_ids=None, bucket_cap_mb: int = 25,
+             bf16_grads: bool = False) -> torch.nn.Module:
+    """torch DDP exactly as the reference wraps its model (training.py:148-153) plus the in-library knobs SURVEY 5.9
+    lists: buckets as views of the gradients, bucket size, and the stock bf16 gradient-compression hook (the all-reduce
+    moves half the bytes; gradients are decompressed back to fp32 before the optimizer sees them)."""
     if world <= 1:
         return model
-    return torch.nn.parallel.DistributedDataParallel(model, device_ids=device_ids, gradient_as_bucket_view=True)
+    ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=device_ids, gradient_as_bucket_view=True,
+                                                    bucket_cap_mb=bucket_cap_mb)
+    if bf16_grads:
+        from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+        ddp.register_comm_hook(state=None, hook=default_hooks.bf16_compress_hook)
+    return ddp
 
 
 def max_over_ranks(value: float, world: int, device) -> float:

@@ -36,12 +36,11 @@ int         tgt_version(void);
 const char *tgt_last_error(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 uint64_t    tgt_launch_count(void);
-/* 0 = pick the fastest kernel that supports the shape (default); 1 = force the generic
- * SIMT kernels; 2 = tensor-core triplet kernels with cp.async staging instead of TMA; 3 = like 0
- * but the triplet-attention forward runs the fused projection + attention kernel
- * (tgt_triplet_attn_fused_fwd); 4 = triplet-attention core on tcgen05 / TMEM (csrc/triplet_tc.cu: UMMA for
- * Q K^T and P V, S / P / O in tensor memory); 5 = the TMA-staged mma.sync core (the round-1 default).
- * The tests cross-check the families. */
+/* 0 = default: the fastest measured kernel per op (triplet attention: tcgen05 / TMEM forward + software-pipelined mma.sync
+ * backward); 1 = force the generic SIMT kernels; 3 = like 0 but the triplet-attention forward runs the fused projection +
+ * attention kernel (tgt_triplet_attn_fused_fwd); 4 = triplet-attention core on tcgen05 / TMEM forward AND backward
+ * (csrc/triplet_tc.cu); 5 (and 2, kept as an alias of the removed cp.async family) = the TMA-staged mma.sync core forward
+ * and backward (csrc/triplet_tma.cu).  The tests cross-check the families. */
 void        tgt_set_kernel_policy(int policy);
 
 /* optional device-side timing of the MAIN kernel of each call (prep / post helpers excluded): enable,

@@ -10,8 +10,8 @@
 //   * results (Va; dQ, dK, dV) go from mma accumulators to shared memory with stmatrix and leave with TMA tensor
 //     stores (full 32-byte rows instead of 4-byte scattered stores); the dS / A exchange tiles use stmatrix too.
 // Net effect: ~100 fewer issue slots per thread and iteration (no address arithmetic, no cp.async, no predicated
-// 4-byte stores) and sector-exact HBM writes.  The cp.async kernels remain available (kernel policy 2) and the tests
-// cross-check the two families.
+// 4-byte stores) and sector-exact HBM writes.  The tests cross-check this family against the tcgen05 / TMEM family
+// (triplet_tc.cu) and the generic SIMT kernels.
 #include "triplet_common.cuh"
 #include <stdlib.h>
 
@@ -180,259 +180,8 @@ tri_attn_fwd_tma(const tgt_triplet_attn_desc D, const __grid_constant__ CUtensor
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-constexpr int TB_STAGES = 3;
 constexpr int TB_STAGE_BYTES = 4 * TILE_BYTES;               // Q, K, V, dO
 constexpr int TB_XCH_BYTES = TN * TN * 2;                    // one 64x64 16-bit exchange tile: 8 KB
-constexpr int TB_SMEM = TB_STAGES * TB_STAGE_BYTES + 4 * TB_XCH_BYTES + 3 * TILE_BYTES + 64 + 1024;
-
-template <typename T>
-__global__ void __launch_bounds__(128, 2)
-tri_attn_bwd_tma(const tgt_triplet_attn_desc D, const __grid_constant__ CUtensorMap mPcol,
-                 const __grid_constant__ CUtensorMap mProw, const __grid_constant__ CUtensorMap mDVA,
-                 const __grid_constant__ CUtensorMap mDPcol, const __grid_constant__ CUtensorMap mDProw,
-                 const float *__restrict__ ws_e, const __half *__restrict__ ws_g, const float *__restrict__ stats,
-                 float *__restrict__ ws_de, float *__restrict__ ws_dg) {
-  extern __shared__ unsigned char smem_raw[];
-  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int N = D.N, H = D.H;
-  const int h = blockIdx.x, dir = blockIdx.y, b = blockIdx.z;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = lane >> 2, q = lane & 3;
-  const int m0 = warp * 16;
-  const uint32_t xbase = sbase + TB_STAGES * TB_STAGE_BYTES;
-  const uint32_t sOut = xbase + 4 * TB_XCH_BYTES;             // dQ, dK, dV staging tiles
-  const uint32_t bar_full = sOut + 3 * TILE_BYTES;
-
-  if (tid == 0) {
-    tma_prefetch_desc(&mPcol);
-    tma_prefetch_desc(&mProw);
-    tma_prefetch_desc(&mDVA);
-    tma_prefetch_desc(&mDPcol);
-    tma_prefetch_desc(&mDProw);
-    for (int s = 0; s < TB_STAGES; ++s) mbar_init(bar_full + s * 8, 1);
-    fence_barrier_init();
-  }
-
-  float eb[8][4];
-  uint32_t gt[8][2];
-  const int64_t tbase = ((int64_t)(b * 2 + dir) * H + h) * TN * TN;
-#pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
-    const int col = nt * 8 + 2 * q;
-    const float2 e0 = *reinterpret_cast<const float2 *>(ws_e + tbase + (m0 + g) * TN + col);
-    const float2 e1 = *reinterpret_cast<const float2 *>(ws_e + tbase + (m0 + g + 8) * TN + col);
-    eb[nt][0] = e0.x; eb[nt][1] = e0.y; eb[nt][2] = e1.x; eb[nt][3] = e1.y;
-    gt[nt][0] = *reinterpret_cast<const uint32_t *>(ws_g + tbase + (m0 + g) * TN + col);
-    gt[nt][1] = *reinterpret_cast<const uint32_t *>(ws_g + tbase + (m0 + g + 8) * TN + col);
-  }
-  float de[8][4], dg[8][4];          // sum_j dS   and   sum_j dA * P
-#pragma unroll
-  for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) de[nt][c] = dg[nt][c] = 0.f;
-
-  float c1r0, c1r1;
-  fix_fully_masked_rows(eb, D.scale * LOG2E, c1r0, c1r1);
-  const int cq = D.off_q[dir] + h * HD, ck = D.off_k[dir] + h * HD, cv = D.off_v[dir] + h * HD;
-  const int co = dir * H * HD + h * HD;
-  const int i0 = m0 + g, i1 = m0 + g + 8;
-  const float *stb = stats + (((int64_t)(b * 2 + dir) * H + h) * N) * N;
-
-  auto issue = [&](int j) {                   // thread 0 only
-    if (j < N) {
-      const uint32_t st = sbase + (j % TB_STAGES) * TB_STAGE_BYTES, bar = bar_full + (j % TB_STAGES) * 8;
-      mbar_expect_tx(bar, TB_STAGE_BYTES);
-      tma_load_4d(&mPcol, bar, st, cq, j, 0, b);
-      if (dir == 0) {
-        tma_load_4d(&mProw, bar, st + TILE_BYTES, ck, 0, j, b);
-        tma_load_4d(&mProw, bar, st + 2 * TILE_BYTES, cv, 0, j, b);
-      } else {
-        tma_load_4d(&mPcol, bar, st + TILE_BYTES, ck, j, 0, b);
-        tma_load_4d(&mPcol, bar, st + 2 * TILE_BYTES, cv, j, 0, b);
-      }
-      tma_load_4d(&mDVA, bar, st + 3 * TILE_BYTES, co, j, 0, b);
-    }
-  };
-  auto store_kv = [&](int j) {                // thread 0 only: dK / dV tiles of junction j
-    if (dir == 0) {
-      tma_store_4d(&mDProw, sOut + TILE_BYTES, ck, 0, j, b);
-      tma_store_4d(&mDProw, sOut + 2 * TILE_BYTES, cv, 0, j, b);
-    } else {
-      tma_store_4d(&mDPcol, sOut + TILE_BYTES, ck, j, 0, b);
-      tma_store_4d(&mDPcol, sOut + 2 * TILE_BYTES, cv, j, 0, b);
-    }
-    tma_store_commit();
-  };
-  // rows beyond N (tile padding) get lse2 = +inf  ->  P = exp2(-inf) = 0 for the whole row
-  auto load_stats = [&](int j, float &a, float &c) {
-    a = INFINITY;
-    c = INFINITY;
-    if (j < N) {
-      if (i0 < N) a = stb[(int64_t)j * N + i0];
-      if (i1 < N) c = stb[(int64_t)j * N + i1];
-    }
-  };
-
-  __syncthreads();
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < TB_STAGES - 1; ++s) issue(s);
-  }
-  float sa0, sa1, sb0, sb1;                  // lse of the next two junctions (fetched two iterations ahead)
-  load_stats(0, sa0, sa1);
-  load_stats(1, sb0, sb1);
-
-  for (int j = 0; j < N; ++j) {
-    if (tid == 0) tma_store_wait_read();             // dQ(j-1) has left its staging tile
-    mbar_wait(bar_full + (j % TB_STAGES) * 8, (uint32_t)((j / TB_STAGES) & 1));
-    __syncthreads();                                   // (A) stage j landed; everyone is done with iteration j-1
-    if (tid == 0) {
-      issue(j + TB_STAGES - 1);
-      if (j > 0) store_kv(j - 1);
-    }
-    const float lse0 = sa0, lse1 = sa1;
-    sa0 = sb0;
-    sa1 = sb1;
-    load_stats(j + 2, sb0, sb1);
-    const uint32_t st = sbase + (j % TB_STAGES) * TB_STAGE_BYTES;
-    const uint32_t sQ = st, sK = st + TILE_BYTES, sV = st + 2 * TILE_BYTES, sO = st + 3 * TILE_BYTES;
-    const uint32_t xS = xbase + (j & 1) * 2 * TB_XCH_BYTES, xA = xS + TB_XCH_BYTES;
-
-    uint32_t qa[4], oa[4];
-    load_a_rows(qa, sQ, m0, lane);
-    load_a_rows(oa, sO, m0, lane);
-    float s[8][4], da[8][4];
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      uint32_t kb[4], vb[4];
-      load_b_nk(kb, sK, p * 16, lane);
-      load_b_nk(vb, sV, p * 16, lane);
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int nt = 2 * p + u;
-        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-        da[nt][0] = da[nt][1] = da[nt][2] = da[nt][3] = 0.f;
-        Mma<T>::run(s[nt], qa, kb[2 * u], kb[2 * u + 1]);
-        Mma<T>::run(da[nt], oa, vb[2 * u], vb[2 * u + 1]);
-      }
-    }
-    // P (normalised), t = dA*g*P, delta = rowsum(t).  The element-wise math runs on packed f32x2 instructions
-    // (fma/add/mul.rn.f32x2: two accumulator columns of one row per issue slot); results are identical to scalar fp32.
-    const float2 c1p0 = make_float2(c1r0, c1r0), c1p1 = make_float2(c1r1, c1r1);
-    const float2 nl0 = make_float2(-lse0, -lse0), nl1 = make_float2(-lse1, -lse1);
-    float2 dlp0 = make_float2(0.f, 0.f), dlp1 = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const float2 g0 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][0]));
-      const float2 g1 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][1]));
-      float2 &s01 = *reinterpret_cast<float2 *>(&s[nt][0]), &s23 = *reinterpret_cast<float2 *>(&s[nt][2]);
-      float2 &a01 = *reinterpret_cast<float2 *>(&da[nt][0]), &a23 = *reinterpret_cast<float2 *>(&da[nt][2]);
-      float2 &e01 = *reinterpret_cast<float2 *>(&eb[nt][0]), &e23 = *reinterpret_cast<float2 *>(&eb[nt][2]);
-      float2 &q01 = *reinterpret_cast<float2 *>(&dg[nt][0]), &q23 = *reinterpret_cast<float2 *>(&dg[nt][2]);
-      const float2 x01 = __ffma2_rn(s01, c1p0, __fadd2_rn(e01, nl0));
-      const float2 x23 = __ffma2_rn(s23, c1p1, __fadd2_rn(e23, nl1));
-      const float2 p01 = make_float2(fast_exp2(x01.x), fast_exp2(x01.y));
-      const float2 p23 = make_float2(fast_exp2(x23.x), fast_exp2(x23.y));
-      const float2 dap01 = __fmul2_rn(a01, p01), dap23 = __fmul2_rn(a23, p23);
-      q01 = __fadd2_rn(q01, dap01);
-      q23 = __fadd2_rn(q23, dap23);
-      s01 = p01;                             // P
-      s23 = p23;
-      a01 = __fmul2_rn(dap01, g0);           // t = dA * g * P
-      a23 = __fmul2_rn(dap23, g1);
-      dlp0 = __fadd2_rn(dlp0, a01);
-      dlp1 = __fadd2_rn(dlp1, a23);
-    }
-    float dl0 = dlp0.x + dlp0.y, dl1 = dlp1.x + dlp1.y;
-    dl0 += __shfl_xor_sync(0xffffffffu, dl0, 1);
-    dl0 += __shfl_xor_sync(0xffffffffu, dl0, 2);
-    dl1 += __shfl_xor_sync(0xffffffffu, dl1, 1);
-    dl1 += __shfl_xor_sync(0xffffffffu, dl1, 2);
-    // dS = t - P*delta ; A = P*g ; exchange through shared memory (stmatrix) ; dS also as A-fragments for dQ
-    const float2 nd0 = make_float2(-dl0, -dl0), nd1 = make_float2(-dl1, -dl1);
-    uint32_t dsa[4][4];
-#pragma unroll
-    for (int np = 0; np < 4; ++np) {
-      uint32_t aa[4];
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int nt = 2 * np + u;
-        const float2 g0 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][0]));
-        const float2 g1 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][1]));
-        const float2 p01 = *reinterpret_cast<float2 *>(&s[nt][0]), p23 = *reinterpret_cast<float2 *>(&s[nt][2]);
-        const float2 d01 = __ffma2_rn(p01, nd0, *reinterpret_cast<float2 *>(&da[nt][0]));
-        const float2 d23 = __ffma2_rn(p23, nd1, *reinterpret_cast<float2 *>(&da[nt][2]));
-        float2 &f01 = *reinterpret_cast<float2 *>(&de[nt][0]), &f23 = *reinterpret_cast<float2 *>(&de[nt][2]);
-        f01 = __fadd2_rn(f01, d01);
-        f23 = __fadd2_rn(f23, d23);
-        dsa[np][u * 2 + 0] = Mma<T>::pack(d01.x, d01.y);
-        dsa[np][u * 2 + 1] = Mma<T>::pack(d23.x, d23.y);
-        const float2 w01 = __fmul2_rn(p01, g0), w23 = __fmul2_rn(p23, g1);
-        aa[u * 2 + 0] = Mma<T>::pack(w01.x, w01.y);
-        aa[u * 2 + 1] = Mma<T>::pack(w23.x, w23.y);
-      }
-      store_xch_pair(xS, m0, lane, 2 * np, dsa[np][0], dsa[np][1], dsa[np][2], dsa[np][3]);
-      store_xch_pair(xA, m0, lane, 2 * np, aa[0], aa[1], aa[2], aa[3]);
-    }
-    // dQ = scale * dS K   (rows of this warp)
-    {
-      float dq[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        uint32_t kb[4];
-        load_b_kn(kb, sK, t * 16, lane);
-        Mma<T>::run(dq[0], dsa[t], kb[0], kb[1]);
-        Mma<T>::run(dq[1], dsa[t], kb[2], kb[3]);
-      }
-      store_c_tile<T>(sOut, m0, lane, dq, D.scale);
-    }
-    fence_proxy_async();
-    if (tid == 0) tma_store_wait_read();               // dK / dV (j-1) have left their staging tiles
-    __syncthreads();                                   // (B) dS / A / dQ tiles complete
-    if (tid == 0) {
-      tma_store_4d(&mDPcol, sOut, cq, j, 0, b);
-      tma_store_commit();
-    }
-    // dK = scale * dS^T Q ; dV = A^T dO   (this warp owns keys m0 .. m0+15)
-    {
-      float dk[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-      float dv[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        uint32_t at[4], qb[4], ob[4];
-        load_a_xt(at, xS, m0, t * 16, lane);
-        load_b_kn(qb, sQ, t * 16, lane);
-        Mma<T>::run(dk[0], at, qb[0], qb[1]);
-        Mma<T>::run(dk[1], at, qb[2], qb[3]);
-        load_a_xt(at, xA, m0, t * 16, lane);
-        load_b_kn(ob, sO, t * 16, lane);
-        Mma<T>::run(dv[0], at, ob[0], ob[1]);
-        Mma<T>::run(dv[1], at, ob[2], ob[3]);
-      }
-      store_c_tile<T>(sOut + TILE_BYTES, m0, lane, dk, D.scale);
-      store_c_tile<T>(sOut + 2 * TILE_BYTES, m0, lane, dv, 1.f);
-    }
-    fence_proxy_async();
-  }
-  __syncthreads();
-  if (tid == 0) {
-    store_kv(N - 1);
-    tma_store_wait_all();
-  }
-  // dE = sum_j dS ; dG = g (1 - g) sum_j dA P
-#pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
-    const int col = nt * 8 + 2 * q;
-    const float2 g0 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][0]));
-    const float2 g1 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][1]));
-    *reinterpret_cast<float2 *>(ws_de + tbase + (m0 + g) * TN + col) = make_float2(de[nt][0], de[nt][1]);
-    *reinterpret_cast<float2 *>(ws_de + tbase + (m0 + g + 8) * TN + col) = make_float2(de[nt][2], de[nt][3]);
-    *reinterpret_cast<float2 *>(ws_dg + tbase + (m0 + g) * TN + col) =
-        make_float2(dg[nt][0] * g0.x * (1.f - g0.x), dg[nt][1] * g0.y * (1.f - g0.y));
-    *reinterpret_cast<float2 *>(ws_dg + tbase + (m0 + g + 8) * TN + col) =
-        make_float2(dg[nt][2] * g1.x * (1.f - g1.x), dg[nt][3] * g1.y * (1.f - g1.y));
-  }
-}
 
 // ------------------------------------------------------------------------------------------------ backward, pipelined
 constexpr int TP_STAGES = 4;
@@ -765,673 +514,6 @@ tri_attn_bwd_tma_pipe(const tgt_triplet_attn_desc D, const __grid_constant__ CUt
 }
 
 
-// ------------------------------------------------------------------------------------------------ backward, warp-specialised
-// Same arithmetic as tri_attn_bwd_tma, re-organised so that more warps hide the latency of the register-heavy part:
-// one CTA per SM (head, direction, graph) with three warpgroups
-//   WG0 / WG1  "score" warpgroups: junctions j = 0,2,4,.. / 1,3,5,..  (each holds the bias / gate tiles and its own partial
-//              dE / dG sums in registers): S, dA, P, dS, dQ; dS and A go to this warpgroup's exchange tiles
-//   WG2        "key" warpgroup: for every j, dK = dS^T Q and dV = A^T dO from the exchange tiles; its first thread is
-//              also the TMA producer (4-stage ring: a stage is re-filled as soon as the key pass of its junction is done)
-// setmaxnreg gives the score warpgroups 224 registers and leaves 56 to the key warpgroup.  Hand-over between warpgroups
-// uses mbarriers (xch_ready / xch_free), results leave with stmatrix + TMA tensor stores as in tri_attn_bwd_tma.
-constexpr int TW_STAGES = 4;
-constexpr int TW_SMEM = TW_STAGES * TB_STAGE_BYTES + 4 * TB_XCH_BYTES + 4 * TILE_BYTES + 128 + 1024;
-constexpr int TW_REGS_SCORE = 224, TW_REGS_KEY = 56;
-
-template <typename T>
-__global__ void __launch_bounds__(384, 1)
-tri_attn_bwd_ws(const tgt_triplet_attn_desc D, const __grid_constant__ CUtensorMap mPcol,
-                const __grid_constant__ CUtensorMap mProw, const __grid_constant__ CUtensorMap mDVA,
-                const __grid_constant__ CUtensorMap mDPcol, const __grid_constant__ CUtensorMap mDProw,
-                const float *__restrict__ ws_e, const __half *__restrict__ ws_g, const float *__restrict__ stats,
-                float *__restrict__ ws_de, float *__restrict__ ws_dg) {
-  extern __shared__ unsigned char smem_raw[];
-  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int N = D.N, H = D.H;
-  const int h = blockIdx.x, dir = blockIdx.y, b = blockIdx.z;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wgrp = warp >> 2;                      // 0, 1: score warpgroups; 2: key warpgroup
-  const int wl = warp & 3;
-  const int g = lane >> 2, q = lane & 3;
-  const int m0 = wl * 16;
-  const uint32_t xbase = sbase + TW_STAGES * TB_STAGE_BYTES;        // [wg][dS, A] exchange tiles
-  const uint32_t sOut = xbase + 4 * TB_XCH_BYTES;                   // dQ(wg0), dQ(wg1), dK, dV staging tiles
-  const uint32_t bar_full = sOut + 4 * TILE_BYTES;                  // 4 x full
-  const uint32_t bar_ready = bar_full + 8 * TW_STAGES;              // 2 x xch_ready
-  const uint32_t bar_free = bar_ready + 16;                         // 2 x xch_free
-
-  if (tid == 0) {
-    tma_prefetch_desc(&mPcol);
-    tma_prefetch_desc(&mProw);
-    tma_prefetch_desc(&mDVA);
-    tma_prefetch_desc(&mDPcol);
-    tma_prefetch_desc(&mDProw);
-    for (int s = 0; s < TW_STAGES; ++s) mbar_init(bar_full + s * 8, 1);
-    for (int w = 0; w < 2; ++w) {
-      mbar_init(bar_ready + w * 8, 128);
-      mbar_init(bar_free + w * 8, 128);
-    }
-    fence_barrier_init();
-  }
-  __syncthreads();
-
-  const int cq = D.off_q[dir] + h * HD, ck = D.off_k[dir] + h * HD, cv = D.off_v[dir] + h * HD;
-  const int co = dir * H * HD + h * HD;
-  const int64_t tbase = ((int64_t)(b * 2 + dir) * H + h) * TN * TN;
-
-  if (wgrp == 2) {
-    // ====================================================================================== key warpgroup + TMA producer
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TW_REGS_KEY));
-    auto issue = [&](int j) {                   // first thread of the warpgroup only
-      if (j < N) {
-        const uint32_t st = sbase + (j % TW_STAGES) * TB_STAGE_BYTES, bar = bar_full + (j % TW_STAGES) * 8;
-        mbar_expect_tx(bar, TB_STAGE_BYTES);
-        tma_load_4d(&mPcol, bar, st, cq, j, 0, b);
-        if (dir == 0) {
-          tma_load_4d(&mProw, bar, st + TILE_BYTES, ck, 0, j, b);
-          tma_load_4d(&mProw, bar, st + 2 * TILE_BYTES, cv, 0, j, b);
-        } else {
-          tma_load_4d(&mPcol, bar, st + TILE_BYTES, ck, j, 0, b);
-          tma_load_4d(&mPcol, bar, st + 2 * TILE_BYTES, cv, j, 0, b);
-        }
-        tma_load_4d(&mDVA, bar, st + 3 * TILE_BYTES, co, j, 0, b);
-      }
-    };
-    const bool first = (wl == 0 && lane == 0);
-    if (first) {
-#pragma unroll
-      for (int s = 0; s < TW_STAGES; ++s) issue(s);
-    }
-    for (int j = 0; j < N; ++j) {
-      const int w = j & 1, k = j >> 1;
-      const uint32_t st = sbase + (j % TW_STAGES) * TB_STAGE_BYTES;
-      const uint32_t sQ = st, sO = st + 3 * TILE_BYTES;
-      const uint32_t xS = xbase + w * 2 * TB_XCH_BYTES, xA = xS + TB_XCH_BYTES;
-      mbar_wait(bar_ready + w * 8, (uint32_t)(k & 1));           // dS / A of junction j are in the exchange tiles
-      float dk[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-      float dv[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        uint32_t at[4], qb[4], ob[4];
-        load_a_xt(at, xS, m0, t * 16, lane);
-        load_b_kn(qb, sQ, t * 16, lane);
-        Mma<T>::run(dk[0], at, qb[0], qb[1]);
-        Mma<T>::run(dk[1], at, qb[2], qb[3]);
-        load_a_xt(at, xA, m0, t * 16, lane);
-        load_b_kn(ob, sO, t * 16, lane);
-        Mma<T>::run(dv[0], at, ob[0], ob[1]);
-        Mma<T>::run(dv[1], at, ob[2], ob[3]);
-      }
-      mbar_arrive(bar_free + w * 8);                               // this thread no longer reads the exchange tiles
-      if (first) tma_store_wait_read();                           // dK / dV (j-1) have left their staging tiles
-      asm volatile("bar.sync 3, 128;" ::: "memory");
-      store_c_tile<T>(sOut + 2 * TILE_BYTES, m0, lane, dk, D.scale);
-      store_c_tile<T>(sOut + 3 * TILE_BYTES, m0, lane, dv, 1.f);
-      fence_proxy_async();
-      asm volatile("bar.sync 3, 128;" ::: "memory");
-      if (first) {
-        if (dir == 0) {
-          tma_store_4d(&mDProw, sOut + 2 * TILE_BYTES, ck, 0, j, b);
-          tma_store_4d(&mDProw, sOut + 3 * TILE_BYTES, cv, 0, j, b);
-        } else {
-          tma_store_4d(&mDPcol, sOut + 2 * TILE_BYTES, ck, j, 0, b);
-          tma_store_4d(&mDPcol, sOut + 3 * TILE_BYTES, cv, j, 0, b);
-        }
-        tma_store_commit();
-        issue(j + TW_STAGES);                                      // stage j is free: both warpgroups are done with it
-      }
-    }
-    if (first) tma_store_wait_all();
-  } else {
-    // ====================================================================================== score warpgroups
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TW_REGS_SCORE));
-    const int w = wgrp;
-    const int bar_id = 1 + w;
-    const bool first = (wl == 0 && lane == 0);
-    float eb[8][4];
-    uint32_t gt[8][2];
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const int col = nt * 8 + 2 * q;
-      const float2 e0 = *reinterpret_cast<const float2 *>(ws_e + tbase + (m0 + g) * TN + col);
-      const float2 e1 = *reinterpret_cast<const float2 *>(ws_e + tbase + (m0 + g + 8) * TN + col);
-      eb[nt][0] = e0.x; eb[nt][1] = e0.y; eb[nt][2] = e1.x; eb[nt][3] = e1.y;
-      gt[nt][0] = *reinterpret_cast<const uint32_t *>(ws_g + tbase + (m0 + g) * TN + col);
-      gt[nt][1] = *reinterpret_cast<const uint32_t *>(ws_g + tbase + (m0 + g + 8) * TN + col);
-    }
-    float de[8][4], dg[8][4];          // partial sums over this warpgroup's junctions
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) de[nt][c] = dg[nt][c] = 0.f;
-    float c1r0, c1r1;
-    fix_fully_masked_rows(eb, D.scale * LOG2E, c1r0, c1r1);
-    const int i0 = m0 + g, i1 = m0 + g + 8;
-    const float *stb = stats + (((int64_t)(b * 2 + dir) * H + h) * N) * N;
-    auto load_stats = [&](int j, float &a, float &c) {
-      a = INFINITY;
-      c = INFINITY;
-      if (j < N) {
-        if (i0 < N) a = stb[(int64_t)j * N + i0];
-        if (i1 < N) c = stb[(int64_t)j * N + i1];
-      }
-    };
-    float sa0, sa1, sb0, sb1;
-    load_stats(w, sa0, sa1);
-    load_stats(w + 2, sb0, sb1);
-    const uint32_t xS = xbase + w * 2 * TB_XCH_BYTES, xA = xS + TB_XCH_BYTES;
-    const uint32_t sDQ = sOut + w * TILE_BYTES;
-
-    for (int j = w, k = 0; j < N; j += 2, ++k) {
-      const float lse0 = sa0, lse1 = sa1;
-      sa0 = sb0;
-      sa1 = sb1;
-      load_stats(j + 4, sb0, sb1);
-      const uint32_t st = sbase + (j % TW_STAGES) * TB_STAGE_BYTES;
-      const uint32_t sQ = st, sK = st + TILE_BYTES, sV = st + 2 * TILE_BYTES, sO = st + 3 * TILE_BYTES;
-      mbar_wait(bar_full + (j % TW_STAGES) * 8, (uint32_t)((j / TW_STAGES) & 1));
-
-      uint32_t qa[4], oa[4];
-      load_a_rows(qa, sQ, m0, lane);
-      load_a_rows(oa, sO, m0, lane);
-      float s[8][4], da[8][4];
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        uint32_t kb[4], vb[4];
-        load_b_nk(kb, sK, p * 16, lane);
-        load_b_nk(vb, sV, p * 16, lane);
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int nt = 2 * p + u;
-          s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-          da[nt][0] = da[nt][1] = da[nt][2] = da[nt][3] = 0.f;
-          Mma<T>::run(s[nt], qa, kb[2 * u], kb[2 * u + 1]);
-          Mma<T>::run(da[nt], oa, vb[2 * u], vb[2 * u + 1]);
-        }
-      }
-      const float2 c1p0 = make_float2(c1r0, c1r0), c1p1 = make_float2(c1r1, c1r1);
-      const float2 nl0 = make_float2(-lse0, -lse0), nl1 = make_float2(-lse1, -lse1);
-      float2 dlp0 = make_float2(0.f, 0.f), dlp1 = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        const float2 g0 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][0]));
-        const float2 g1 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][1]));
-        float2 &s01 = *reinterpret_cast<float2 *>(&s[nt][0]), &s23 = *reinterpret_cast<float2 *>(&s[nt][2]);
-        float2 &a01 = *reinterpret_cast<float2 *>(&da[nt][0]), &a23 = *reinterpret_cast<float2 *>(&da[nt][2]);
-        float2 &e01 = *reinterpret_cast<float2 *>(&eb[nt][0]), &e23 = *reinterpret_cast<float2 *>(&eb[nt][2]);
-        float2 &q01 = *reinterpret_cast<float2 *>(&dg[nt][0]), &q23 = *reinterpret_cast<float2 *>(&dg[nt][2]);
-        const float2 x01 = __ffma2_rn(s01, c1p0, __fadd2_rn(e01, nl0));
-        const float2 x23 = __ffma2_rn(s23, c1p1, __fadd2_rn(e23, nl1));
-        const float2 p01 = make_float2(fast_exp2(x01.x), fast_exp2(x01.y));
-        const float2 p23 = make_float2(fast_exp2(x23.x), fast_exp2(x23.y));
-        const float2 dap01 = __fmul2_rn(a01, p01), dap23 = __fmul2_rn(a23, p23);
-        q01 = __fadd2_rn(q01, dap01);
-        q23 = __fadd2_rn(q23, dap23);
-        s01 = p01;
-        s23 = p23;
-        a01 = __fmul2_rn(dap01, g0);
-        a23 = __fmul2_rn(dap23, g1);
-        dlp0 = __fadd2_rn(dlp0, a01);
-        dlp1 = __fadd2_rn(dlp1, a23);
-      }
-      float dl0 = dlp0.x + dlp0.y, dl1 = dlp1.x + dlp1.y;
-      dl0 += __shfl_xor_sync(0xffffffffu, dl0, 1);
-      dl0 += __shfl_xor_sync(0xffffffffu, dl0, 2);
-      dl1 += __shfl_xor_sync(0xffffffffu, dl1, 1);
-      dl1 += __shfl_xor_sync(0xffffffffu, dl1, 2);
-      // the key warpgroup must be done with this warpgroup's previous exchange tiles, the previous dQ store must have
-      // left its staging tile
-      if (k > 0) mbar_wait(bar_free + w * 8, (uint32_t)((k - 1) & 1));
-      if (first) tma_store_wait_read();
-      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-      const float2 nd0 = make_float2(-dl0, -dl0), nd1 = make_float2(-dl1, -dl1);
-      uint32_t dsa[4][4];
-#pragma unroll
-      for (int np = 0; np < 4; ++np) {
-        uint32_t aa[4];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int nt = 2 * np + u;
-          const float2 g0 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][0]));
-          const float2 g1 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][1]));
-          const float2 p01 = *reinterpret_cast<float2 *>(&s[nt][0]), p23 = *reinterpret_cast<float2 *>(&s[nt][2]);
-          const float2 d01 = __ffma2_rn(p01, nd0, *reinterpret_cast<float2 *>(&da[nt][0]));
-          const float2 d23 = __ffma2_rn(p23, nd1, *reinterpret_cast<float2 *>(&da[nt][2]));
-          float2 &f01 = *reinterpret_cast<float2 *>(&de[nt][0]), &f23 = *reinterpret_cast<float2 *>(&de[nt][2]);
-          f01 = __fadd2_rn(f01, d01);
-          f23 = __fadd2_rn(f23, d23);
-          dsa[np][u * 2 + 0] = Mma<T>::pack(d01.x, d01.y);
-          dsa[np][u * 2 + 1] = Mma<T>::pack(d23.x, d23.y);
-          const float2 w01 = __fmul2_rn(p01, g0), w23 = __fmul2_rn(p23, g1);
-          aa[u * 2 + 0] = Mma<T>::pack(w01.x, w01.y);
-          aa[u * 2 + 1] = Mma<T>::pack(w23.x, w23.y);
-        }
-        store_xch_pair(xS, m0, lane, 2 * np, dsa[np][0], dsa[np][1], dsa[np][2], dsa[np][3]);
-        store_xch_pair(xA, m0, lane, 2 * np, aa[0], aa[1], aa[2], aa[3]);
-      }
-      {
-        float dq[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          uint32_t kb[4];
-          load_b_kn(kb, sK, t * 16, lane);
-          Mma<T>::run(dq[0], dsa[t], kb[0], kb[1]);
-          Mma<T>::run(dq[1], dsa[t], kb[2], kb[3]);
-        }
-        store_c_tile<T>(sDQ, m0, lane, dq, D.scale);
-      }
-      fence_proxy_async();
-      mbar_arrive(bar_ready + w * 8);           // exchange tiles written and this thread is done with stage j
-      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-      if (first) {
-        tma_store_4d(&mDPcol, sDQ, cq, j, 0, b);
-        tma_store_commit();
-      }
-    }
-    if (first) tma_store_wait_all();
-    // dE = sum_j dS ; dG = g (1 - g) sum_j dA P : warpgroup 0 stores its partial sums, warpgroup 1 adds its own
-    if (w == 0) {
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        const int col = nt * 8 + 2 * q;
-        *reinterpret_cast<float2 *>(ws_de + tbase + (m0 + g) * TN + col) = make_float2(de[nt][0], de[nt][1]);
-        *reinterpret_cast<float2 *>(ws_de + tbase + (m0 + g + 8) * TN + col) = make_float2(de[nt][2], de[nt][3]);
-        *reinterpret_cast<float2 *>(ws_dg + tbase + (m0 + g) * TN + col) = make_float2(dg[nt][0], dg[nt][1]);
-        *reinterpret_cast<float2 *>(ws_dg + tbase + (m0 + g + 8) * TN + col) = make_float2(dg[nt][2], dg[nt][3]);
-      }
-      __threadfence_block();
-    }
-    asm volatile("bar.sync 4, 256;" ::: "memory");          // both score warpgroups
-    if (w == 1) {
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        const int col = nt * 8 + 2 * q;
-        const float2 g0 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][0]));
-        const float2 g1 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][1]));
-        float2 *pe0 = reinterpret_cast<float2 *>(ws_de + tbase + (m0 + g) * TN + col);
-        float2 *pe1 = reinterpret_cast<float2 *>(ws_de + tbase + (m0 + g + 8) * TN + col);
-        float2 *pg0 = reinterpret_cast<float2 *>(ws_dg + tbase + (m0 + g) * TN + col);
-        float2 *pg1 = reinterpret_cast<float2 *>(ws_dg + tbase + (m0 + g + 8) * TN + col);
-        const float2 a0 = *pe0, a1 = *pe1, b0 = *pg0, b1 = *pg1;
-        *pe0 = make_float2(a0.x + de[nt][0], a0.y + de[nt][1]);
-        *pe1 = make_float2(a1.x + de[nt][2], a1.y + de[nt][3]);
-        *pg0 = make_float2((b0.x + dg[nt][0]) * g0.x * (1.f - g0.x), (b0.y + dg[nt][1]) * g0.y * (1.f - g0.y));
-        *pg1 = make_float2((b1.x + dg[nt][2]) * g1.x * (1.f - g1.x), (b1.y + dg[nt][3]) * g1.y * (1.f - g1.y));
-      }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------ backward, key-split
-// Same arithmetic and byte movement as tri_attn_bwd_tma, but the 64 x 64 score tile of a junction is owned by EIGHT warps:
-// warp (mr, kh) holds query rows 16 mr .. 16 mr + 15 and keys 32 kh .. 32 kh + 31.  The per-(i,k) state that must stay in
-// registers for all N junctions (bias, gate, dE and dG partial sums) is halved per thread, so the kernel fits 128
-// registers and runs 2 CTAs x 8 warps = 16 warps per SM instead of 8 -- the 4-warp kernel is latency-bound at 42 % issue
-// utilisation (profiles/r1_09_*).  What the split costs:
-//   * delta = rowsum(dA g P) spans both key halves: the two warps of a row block swap their partial sums through shared
-//     memory and a 64-thread named barrier;
-//   * dQ = dS K needs all 64 keys: it moves to the second phase and is read back from the dS exchange tile, so the second
-//     phase is 12 mma per warp for everyone (kh = 0: dK block + dQ columns 0-7; kh = 1: dV block + dQ columns 8-15);
-//   * dQ / dK / dV staging tiles are double-buffered and leave together with one TMA store group per junction.
-constexpr int T8_STAGES = 4;
-constexpr int T8_OFF_XCH = T8_STAGES * TB_STAGE_BYTES;
-constexpr int T8_OFF_OUT = T8_OFF_XCH + 2 * TB_XCH_BYTES;
-constexpr int T8_OFF_BAR = T8_OFF_OUT + 6 * TILE_BYTES;
-constexpr int T8_OFF_DLX = T8_OFF_BAR + 64;                   // [2][64] f32 partial deltas
-constexpr int T8_OFF_FMX = T8_OFF_DLX + 512;                  // [2][64] i32 fully-masked flags
-constexpr int T8_OFF_EB = T8_OFF_FMX + 512;                   // [4][256] float4: bias tile, thread-private slots
-constexpr int T8_OFF_GT = T8_OFF_EB + 4 * 256 * 16;           // [2][256] uint4 : gate tile (half2), thread-private slots
-constexpr int T8_SMEM = T8_OFF_GT + 2 * 256 * 16 + 1024;
-
-// keep a loop-invariant, lane-dependent shared-memory offset in ONE register: without this ptxas re-derives every
-// swizzled ldmatrix / stmatrix address from %tid in every iteration (~100 integer instructions per junction)
-__device__ __forceinline__ uint32_t pin(uint32_t v) {
-  asm volatile("" : "+r"(v));
-  return v;
-}
-__device__ __forceinline__ void ldsm_x2_t(uint32_t (&r)[2], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];\n" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
-}
-__device__ __forceinline__ float4 lds128f(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ uint4 lds128u(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-  return v;
-}
-
-template <typename T>
-__global__ void __launch_bounds__(256, 2)
-tri_attn_bwd_tma8(const tgt_triplet_attn_desc D, const __grid_constant__ CUtensorMap mPcol,
-                  const __grid_constant__ CUtensorMap mProw, const __grid_constant__ CUtensorMap mDVA,
-                  const __grid_constant__ CUtensorMap mDPcol, const __grid_constant__ CUtensorMap mDProw,
-                  const float *__restrict__ ws_e, const __half *__restrict__ ws_g, const float *__restrict__ stats,
-                  float *__restrict__ ws_de, float *__restrict__ ws_dg) {
-  extern __shared__ unsigned char smem_raw[];
-  const uint32_t sraw = smem_u32(smem_raw);
-  const uint32_t sbase = (sraw + 1023u) & ~1023u;
-  unsigned char *sgen = smem_raw + (sbase - sraw);
-  const int N = D.N, H = D.H;
-  const int h = blockIdx.x, dir = blockIdx.y, b = blockIdx.z;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int mr = warp & 3, kh = warp >> 2;
-  const int g = lane >> 2, q = lane & 3;
-  const int m0 = mr * 16;
-  const uint32_t xS = sbase + T8_OFF_XCH;
-  const uint32_t sOut = sbase + T8_OFF_OUT;                    // 2 x (dQ, dK, dV) staging tiles
-  const uint32_t bar_full = sbase + T8_OFF_BAR;
-  int *fmx = reinterpret_cast<int *>(sgen + T8_OFF_FMX);
-
-  if (tid == 0) {
-    tma_prefetch_desc(&mPcol);
-    tma_prefetch_desc(&mProw);
-    tma_prefetch_desc(&mDVA);
-    tma_prefetch_desc(&mDPcol);
-    tma_prefetch_desc(&mDProw);
-    for (int s = 0; s < T8_STAGES; ++s) mbar_init(bar_full + s * 8, 1);
-    fence_barrier_init();
-  }
-
-  const int64_t tbase = ((int64_t)(b * 2 + dir) * H + h) * TN * TN;
-  const int i0 = m0 + g, i1 = m0 + g + 8;
-  const uint32_t aEB = pin(sbase + T8_OFF_EB + tid * 16);      // + nt * 4096 : {eb[nt][0..3]}
-  const uint32_t aGT = pin(sbase + T8_OFF_GT + tid * 16);      // + np * 4096 : {gt[2np][0,1], gt[2np+1][0,1]}
-  float c1r0, c1r1;
-  {
-    // bias (log2 domain) and gate tiles of this thread's 16 rows x 32 keys -> thread-private shared-memory slots
-    float eb[4][4];
-    uint32_t gt[4][2];
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      const int col = (kh * 4 + nt) * 8 + 2 * q;
-      const float2 e0 = *reinterpret_cast<const float2 *>(ws_e + tbase + i0 * TN + col);
-      const float2 e1 = *reinterpret_cast<const float2 *>(ws_e + tbase + i1 * TN + col);
-      eb[nt][0] = e0.x; eb[nt][1] = e0.y; eb[nt][2] = e1.x; eb[nt][3] = e1.y;
-      gt[nt][0] = *reinterpret_cast<const uint32_t *>(ws_g + tbase + i0 * TN + col);
-      gt[nt][1] = *reinterpret_cast<const uint32_t *>(ws_g + tbase + i1 * TN + col);
-    }
-    // fully-masked rows (see fix_fully_masked_rows): the row's 64 keys are spread over the two key halves
-    int fm0 = 1, fm1 = 1;
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      fm0 &= (eb[nt][0] <= -1e37f) & (eb[nt][1] <= -1e37f);
-      fm1 &= (eb[nt][2] <= -1e37f) & (eb[nt][3] <= -1e37f);
-    }
-    fm0 &= __shfl_xor_sync(0xffffffffu, fm0, 1);
-    fm0 &= __shfl_xor_sync(0xffffffffu, fm0, 2);
-    fm1 &= __shfl_xor_sync(0xffffffffu, fm1, 1);
-    fm1 &= __shfl_xor_sync(0xffffffffu, fm1, 2);
-    if (q == 0) {
-      fmx[kh * 64 + i0] = fm0;
-      fmx[kh * 64 + i1] = fm1;
-    }
-    __syncthreads();                                   // also publishes the mbarrier initialisation
-    fm0 &= fmx[(kh ^ 1) * 64 + i0];
-    fm1 &= fmx[(kh ^ 1) * 64 + i1];
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      if (fm0) {
-        eb[nt][0] = eb[nt][0] == -INFINITY ? -INFINITY : 0.f;
-        eb[nt][1] = eb[nt][1] == -INFINITY ? -INFINITY : 0.f;
-      }
-      if (fm1) {
-        eb[nt][2] = eb[nt][2] == -INFINITY ? -INFINITY : 0.f;
-        eb[nt][3] = eb[nt][3] == -INFINITY ? -INFINITY : 0.f;
-      }
-      asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};\n" ::"r"(aEB + nt * 4096), "f"(eb[nt][0]), "f"(eb[nt][1]),
-                   "f"(eb[nt][2]), "f"(eb[nt][3]) : "memory");
-    }
-#pragma unroll
-    for (int np = 0; np < 2; ++np)
-      asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};\n" ::"r"(aGT + np * 4096), "r"(gt[2 * np][0]), "r"(gt[2 * np][1]),
-                   "r"(gt[2 * np + 1][0]), "r"(gt[2 * np + 1][1]) : "memory");
-    c1r0 = fm0 ? 0.f : D.scale * LOG2E;
-    c1r1 = fm1 ? 0.f : D.scale * LOG2E;
-  }
-  float de[4][4], dg[4][4];          // sum_j dS   and   sum_j dA * P   (this warp's 16 rows x 32 keys)
-#pragma unroll
-  for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) de[nt][c] = dg[nt][c] = 0.f;
-
-  const int cq = D.off_q[dir] + h * HD, ck = D.off_k[dir] + h * HD, cv = D.off_v[dir] + h * HD;
-  const int co = dir * H * HD + h * HD;
-
-  auto issue = [&](int j) {                   // thread 0 only
-    if (j < N) {
-      const uint32_t st = sbase + (j % T8_STAGES) * TB_STAGE_BYTES, bar = bar_full + (j % T8_STAGES) * 8;
-      mbar_expect_tx(bar, TB_STAGE_BYTES);
-      tma_load_4d(&mPcol, bar, st, cq, j, 0, b);
-      if (dir == 0) {
-        tma_load_4d(&mProw, bar, st + TILE_BYTES, ck, 0, j, b);
-        tma_load_4d(&mProw, bar, st + 2 * TILE_BYTES, cv, 0, j, b);
-      } else {
-        tma_load_4d(&mPcol, bar, st + TILE_BYTES, ck, j, 0, b);
-        tma_load_4d(&mPcol, bar, st + 2 * TILE_BYTES, cv, j, 0, b);
-      }
-      tma_load_4d(&mDVA, bar, st + 3 * TILE_BYTES, co, j, 0, b);
-    }
-  };
-  auto store_out = [&](int j) {               // thread 0 only: dQ / dK / dV tiles of junction j, one store group
-    const uint32_t so = sOut + (j & 1) * 3 * TILE_BYTES;
-    tma_store_4d(&mDPcol, so, cq, j, 0, b);
-    if (dir == 0) {
-      tma_store_4d(&mDProw, so + TILE_BYTES, ck, 0, j, b);
-      tma_store_4d(&mDProw, so + 2 * TILE_BYTES, cv, 0, j, b);
-    } else {
-      tma_store_4d(&mDPcol, so + TILE_BYTES, ck, j, 0, b);
-      tma_store_4d(&mDPcol, so + 2 * TILE_BYTES, cv, j, 0, b);
-    }
-    tma_store_commit();
-  };
-
-  // log-sum-exp of (junction j, rows i0 / i1): running pointers, fetched two junctions ahead.  Rows beyond N (tile padding)
-  // and junctions beyond N get lse2 = +inf  ->  P = exp2(-inf) = 0 for the whole row
-  const float *pl0 = stats + (((int64_t)(b * 2 + dir) * H + h) * N) * N + (i0 < N ? i0 : 0);
-  const float *pl1 = stats + (((int64_t)(b * 2 + dir) * H + h) * N) * N + (i1 < N ? i1 : 0);
-  const bool ok0 = i0 < N, ok1 = i1 < N;
-  float sa0 = INFINITY, sa1 = INFINITY, sb0 = INFINITY, sb1 = INFINITY;
-  if (ok0) sa0 = pl0[0];
-  if (ok1) sa1 = pl1[0];
-  if (N > 1) {
-    if (ok0) sb0 = pl0[N];
-    if (ok1) sb1 = pl1[N];
-  }
-  pl0 += 2 * (int64_t)N;
-  pl1 += 2 * (int64_t)N;
-
-  // loop-invariant lane-dependent offsets (relative to the stage base / absolute for the exchange and staging tiles)
-  const int r8 = (lane & 7) + ((lane >> 3) & 1) * 8;           // ldmatrix row pattern "rows 0-7, 8-15 | second chunk"
-  const int r8b = (lane & 7) + (lane >> 4) * 8;                // "rows 0-7 | second chunk | rows 8-15"
-  const uint32_t oA = pin(tile_off(m0 + r8, lane >> 4));                        // A rows of Q / dO
-  const uint32_t oBnk = pin(tile_off(kh * 32 + r8b, (lane >> 3) & 1));          // + p * 512 : K / V as [n][k]
-  const uint32_t oBkn = pin(tile_off(r8, lane >> 4) + (kh ? 3 * TILE_BYTES : 0));   // + t * 512 : Q (kh=0) / dO (kh=1) as [k][n]
-  const uint32_t oBh = pin(tile_off(r8, kh) + TILE_BYTES);                     // + t * 512 : K columns 8 kh.. as [k][n] (x2)
-  const uint32_t aXT = pin(xS + (kh ? TB_XCH_BYTES : 0) + xch_off(r8b, (m0 >> 3) + ((lane >> 3) & 1)));   // + t * 2048
-  const uint32_t aX = pin(xS + xch_off(m0 + r8, lane >> 4));                    // ^ (t << 5)
-  const uint32_t aSX = pin(xS + xch_off(m0 + r8, kh * 4 + (lane >> 4)));        // ^ (np << 5) ; + TB_XCH_BYTES for A
-  const uint32_t aOT = pin(sOut + (1 + kh) * TILE_BYTES + tile_off(m0 + r8, lane >> 4));
-  const uint32_t aOH = pin(sOut + tile_off(m0 + r8, kh));
-  const uint32_t aDL = pin(sbase + T8_OFF_DLX + (kh * 64 + i0) * 4);            // own partial delta of row i0 (+32: i1)
-  const uint32_t aDP = pin(sbase + T8_OFF_DLX + ((kh ^ 1) * 64 + i0) * 4);      // the partner's
-  const float sc_kv = kh ? 1.f : D.scale;
-
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < T8_STAGES - 1; ++s) issue(s);
-  }
-
-  for (int j = 0; j < N; ++j) {
-    mbar_wait(bar_full + (j % T8_STAGES) * 8, (uint32_t)((j / T8_STAGES) & 1));
-    __syncthreads();                                   // (A) stage j landed; everyone is done with iteration j-1
-    if (tid == 0) {
-      issue(j + T8_STAGES - 1);
-      if (j > 0) store_out(j - 1);
-    }
-    const float lse0 = sa0, lse1 = sa1;
-    sa0 = sb0;
-    sa1 = sb1;
-    sb0 = sb1 = INFINITY;
-    if (j + 2 < N) {
-      if (ok0) sb0 = *pl0;
-      if (ok1) sb1 = *pl1;
-    }
-    pl0 += N;
-    pl1 += N;
-    const uint32_t st = sbase + (j % T8_STAGES) * TB_STAGE_BYTES;     // Q | K | V | dO tiles of junction j
-
-    // ---- phase 1: S, dA, P, dS, A for rows m0.. x keys 32 kh ..
-    float s[4][4], da[4][4];
-    {
-      uint32_t qa[4], oa[4];
-      ldsm_x4(qa, st + oA);
-      ldsm_x4(oa, st + oA + 3 * TILE_BYTES);
-#pragma unroll
-      for (int p = 0; p < 2; ++p) {
-        uint32_t kb[4], vb[4];
-        ldsm_x4(kb, st + oBnk + TILE_BYTES + p * 512);
-        ldsm_x4(vb, st + oBnk + 2 * TILE_BYTES + p * 512);
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int nt = 2 * p + u;
-          s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-          da[nt][0] = da[nt][1] = da[nt][2] = da[nt][3] = 0.f;
-          Mma<T>::run(s[nt], qa, kb[2 * u], kb[2 * u + 1]);
-          Mma<T>::run(da[nt], oa, vb[2 * u], vb[2 * u + 1]);
-        }
-      }
-    }
-    uint32_t gt[4][2];
-    {
-      const uint4 ga = lds128u(aGT), gb = lds128u(aGT + 4096);
-      gt[0][0] = ga.x; gt[0][1] = ga.y; gt[1][0] = ga.z; gt[1][1] = ga.w;
-      gt[2][0] = gb.x; gt[2][1] = gb.y; gt[3][0] = gb.z; gt[3][1] = gb.w;
-    }
-    const float2 c1p0 = make_float2(c1r0, c1r0), c1p1 = make_float2(c1r1, c1r1);
-    const float2 nl0 = make_float2(-lse0, -lse0), nl1 = make_float2(-lse1, -lse1);
-    float2 dlp0 = make_float2(0.f, 0.f), dlp1 = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      const float4 ebv = lds128f(aEB + nt * 4096);
-      const float2 g0 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][0]));
-      const float2 g1 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][1]));
-      float2 &s01 = *reinterpret_cast<float2 *>(&s[nt][0]), &s23 = *reinterpret_cast<float2 *>(&s[nt][2]);
-      float2 &a01 = *reinterpret_cast<float2 *>(&da[nt][0]), &a23 = *reinterpret_cast<float2 *>(&da[nt][2]);
-      float2 &q01 = *reinterpret_cast<float2 *>(&dg[nt][0]), &q23 = *reinterpret_cast<float2 *>(&dg[nt][2]);
-      const float2 x01 = __ffma2_rn(s01, c1p0, __fadd2_rn(make_float2(ebv.x, ebv.y), nl0));
-      const float2 x23 = __ffma2_rn(s23, c1p1, __fadd2_rn(make_float2(ebv.z, ebv.w), nl1));
-      const float2 p01 = make_float2(fast_exp2(x01.x), fast_exp2(x01.y));
-      const float2 p23 = make_float2(fast_exp2(x23.x), fast_exp2(x23.y));
-      const float2 dap01 = __fmul2_rn(a01, p01), dap23 = __fmul2_rn(a23, p23);
-      q01 = __fadd2_rn(q01, dap01);
-      q23 = __fadd2_rn(q23, dap23);
-      s01 = p01;                             // P
-      s23 = p23;
-      a01 = __fmul2_rn(dap01, g0);           // t = dA * g * P
-      a23 = __fmul2_rn(dap23, g1);
-      dlp0 = __fadd2_rn(dlp0, a01);
-      dlp1 = __fadd2_rn(dlp1, a23);
-    }
-    float dl0 = dlp0.x + dlp0.y, dl1 = dlp1.x + dlp1.y;
-    dl0 += __shfl_xor_sync(0xffffffffu, dl0, 1);
-    dl1 += __shfl_xor_sync(0xffffffffu, dl1, 1);
-    dl0 += __shfl_xor_sync(0xffffffffu, dl0, 2);
-    dl1 += __shfl_xor_sync(0xffffffffu, dl1, 2);
-    // delta over all 64 keys: swap partial sums with the warp that holds the other key half of these rows
-    if (q == 0) {
-      asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(aDL), "f"(dl0) : "memory");
-      asm volatile("st.shared.f32 [%0+32], %1;\n" ::"r"(aDL), "f"(dl1) : "memory");
-    }
-    switch (mr) {                                      // immediate barrier ids (a register id makes ptxas reserve all 16)
-      case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
-      case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
-      case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
-      default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
-    }
-    {
-      float p0, p1;
-      asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(p0) : "r"(aDP) : "memory");
-      asm volatile("ld.shared.f32 %0, [%1+32];\n" : "=f"(p1) : "r"(aDP) : "memory");
-      dl0 += p0;
-      dl1 += p1;
-    }
-    // dS = t - P*delta ; A = P*g  -> exchange tiles (stmatrix)
-    const float2 nd0 = make_float2(-dl0, -dl0), nd1 = make_float2(-dl1, -dl1);
-#pragma unroll
-    for (int np = 0; np < 2; ++np) {
-      uint32_t ds[4], aa[4];
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int nt = 2 * np + u;
-        const float2 g0 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][0]));
-        const float2 g1 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][1]));
-        const float2 p01 = *reinterpret_cast<float2 *>(&s[nt][0]), p23 = *reinterpret_cast<float2 *>(&s[nt][2]);
-        const float2 d01 = __ffma2_rn(p01, nd0, *reinterpret_cast<float2 *>(&da[nt][0]));
-        const float2 d23 = __ffma2_rn(p23, nd1, *reinterpret_cast<float2 *>(&da[nt][2]));
-        float2 &f01 = *reinterpret_cast<float2 *>(&de[nt][0]), &f23 = *reinterpret_cast<float2 *>(&de[nt][2]);
-        f01 = __fadd2_rn(f01, d01);
-        f23 = __fadd2_rn(f23, d23);
-        ds[u * 2 + 0] = Mma<T>::pack(d01.x, d01.y);
-        ds[u * 2 + 1] = Mma<T>::pack(d23.x, d23.y);
-        const float2 w01 = __fmul2_rn(p01, g0), w23 = __fmul2_rn(p23, g1);
-        aa[u * 2 + 0] = Mma<T>::pack(w01.x, w01.y);
-        aa[u * 2 + 1] = Mma<T>::pack(w23.x, w23.y);
-      }
-      stsm_x4(aSX ^ (np << 5), ds[0], ds[1], ds[2], ds[3]);
-      stsm_x4((aSX ^ (np << 5)) + TB_XCH_BYTES, aa[0], aa[1], aa[2], aa[3]);
-    }
-    if (tid == 0) tma_store_wait_read1();              // the staging buffer of junction j-2 has been read
-    __syncthreads();                                   // (B) dS / A tiles complete
-    // ---- phase 2: kh = 0: dK = scale dS^T Q ; kh = 1: dV = A^T dO  (keys m0..m0+15) ; dQ = scale dS K, columns 8 kh ..
-    {
-      float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-      float dq[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        uint32_t at[4], bb[4], ax[4], kb[2];
-        ldsm_x4_t(at, aXT + t * 2048);
-        ldsm_x4_t(bb, st + oBkn + t * 512);
-        Mma<T>::run(acc[0], at, bb[0], bb[1]);
-        Mma<T>::run(acc[1], at, bb[2], bb[3]);
-        ldsm_x4(ax, aX ^ (t << 5));
-        ldsm_x2_t(kb, st + oBh + t * 512);
-        Mma<T>::run(dq, ax, kb[0], kb[1]);
-      }
-      const uint32_t ob = (j & 1) * 3 * TILE_BYTES;
-      stsm_x4(aOT + ob, Mma<T>::pack(acc[0][0] * sc_kv, acc[0][1] * sc_kv), Mma<T>::pack(acc[0][2] * sc_kv, acc[0][3] * sc_kv),
-              Mma<T>::pack(acc[1][0] * sc_kv, acc[1][1] * sc_kv), Mma<T>::pack(acc[1][2] * sc_kv, acc[1][3] * sc_kv));
-      const uint32_t r0 = Mma<T>::pack(dq[0] * D.scale, dq[1] * D.scale), r1 = Mma<T>::pack(dq[2] * D.scale, dq[3] * D.scale);
-      asm volatile("stmatrix.sync.aligned.m8n8.x2.shared.b16 [%0], {%1,%2};\n" ::"r"(aOH + ob), "r"(r0), "r"(r1) : "memory");
-    }
-    fence_proxy_async();
-  }
-  __syncthreads();
-  if (tid == 0) {
-    store_out(N - 1);
-    tma_store_wait_all();
-  }
-  // dE = sum_j dS ; dG = g (1 - g) sum_j dA P
-  {
-    const uint4 ga = lds128u(aGT), gb = lds128u(aGT + 4096);
-    const uint32_t gt[4][2] = {{ga.x, ga.y}, {ga.z, ga.w}, {gb.x, gb.y}, {gb.z, gb.w}};
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      const int col = (kh * 4 + nt) * 8 + 2 * q;
-      const float2 g0 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][0]));
-      const float2 g1 = __half22float2(*reinterpret_cast<const __half2 *>(&gt[nt][1]));
-      *reinterpret_cast<float2 *>(ws_de + tbase + i0 * TN + col) = make_float2(de[nt][0], de[nt][1]);
-      *reinterpret_cast<float2 *>(ws_de + tbase + i1 * TN + col) = make_float2(de[nt][2], de[nt][3]);
-      *reinterpret_cast<float2 *>(ws_dg + tbase + i0 * TN + col) =
-          make_float2(dg[nt][0] * g0.x * (1.f - g0.x), dg[nt][1] * g0.y * (1.f - g0.y));
-      *reinterpret_cast<float2 *>(ws_dg + tbase + i1 * TN + col) =
-          make_float2(dg[nt][2] * g1.x * (1.f - g1.x), dg[nt][3] * g1.y * (1.f - g1.y));
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------------ host
 // 4-D map over a [B, N, N, C] 16-bit tensor (row pitch ld elements): box = 64 rows of 16 channels taken along the
 // second-to-last index ("row" tiles, fixed first index) or along the first index ("column" tiles, fixed second index)
@@ -1468,12 +550,10 @@ static int fwd_tma_impl(const tgt_triplet_attn_desc &D, const void *proj, void *
   return check_launch("tri_attn_fwd_tma");
 }
 
-static int bwd_tma_variant() {
-  static const int variant = [] { const char *v = getenv("TGT_TRI_BWD_KERNEL"); return v ? atoi(v) : 2; }();
-  return variant;
-}
-bool triplet_attn_bwd_tma_has_bias() { return bwd_tma_variant() == 2 && !getenv("TGT_TRI_BWD_WS"); }
+bool triplet_attn_bwd_tma_has_bias() { return true; }
 
+// The software-pipelined kernel is the only mma.sync backward kept: the two-barrier, key-split (8 warps) and warp-specialised
+// variants of round 1 all measured slower (profiles/r1_18_*, r1_20_*) and were removed in round 2 (git history has them).
 template <typename T>
 static int bwd_tma_impl(const tgt_triplet_attn_desc &D, const void *proj, const void *dva, const float *stats,
                         void *dproj, const float *ws_e, const __half *ws_g, float *ws_de, float *ws_dg, float *dbias,
@@ -1485,56 +565,19 @@ static int bwd_tma_impl(const tgt_triplet_attn_desc &D, const void *proj, const 
   if (int e = make_tile_map(&mDVA, dva, D.B, D.N, Cv, Cv, true, D.dtype)) return e;
   if (int e = make_tile_map(&mDPcol, dproj, D.B, D.N, C, D.ld, true, D.dtype)) return e;
   if (int e = make_tile_map(&mDProw, dproj, D.B, D.N, C, D.ld, false, D.dtype)) return e;
-  // warp-specialised variant (three warpgroups, one CTA per SM): correct (tests) but measured slower than two 4-warp CTAs
-  // per SM (3.1 vs 2.55 ms at config 3, profiles/r1_18_*), so it is opt-in: TGT_TRI_BWD_WS=1
-  static const int use_ws = [] { const char *v = getenv("TGT_TRI_BWD_WS"); return v ? atoi(v) : 0; }();
-  if (use_ws) {
-    static std::once_flag once_ws;
-    std::call_once(once_ws, [] {
-      cudaFuncSetAttribute(tri_attn_bwd_ws<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM);
-    });
-    KernelTimerScope ts("tri_attn_bwd_ws", st);
-    tri_attn_bwd_ws<T><<<dim3(D.H, 2, D.B), 384, TW_SMEM, st>>>(D, mPcol, mProw, mDVA, mDPcol, mDProw, ws_e, ws_g, stats,
-                                                              ws_de, ws_dg);
-    return check_launch("tri_attn_bwd_ws");
-  }
-  // TGT_TRI_BWD_KERNEL: 0 = two barriers per junction (the first TMA kernel), 1 = key-split over 8 warps (16 warps per SM;
-  // measured slower: shared-memory traffic +60 %, profiles/r1_20_*), 2 = software-pipelined, one barrier per junction
-  const int variant = bwd_tma_variant();
-  if (variant == 1) {
-    static std::once_flag once8;
-    std::call_once(once8, [] {
-      cudaFuncSetAttribute(tri_attn_bwd_tma8<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, T8_SMEM);
-    });
-    KernelTimerScope ts("tri_attn_bwd_tma", st);
-    tri_attn_bwd_tma8<T><<<dim3(D.H, 2, D.B), 256, T8_SMEM, st>>>(D, mPcol, mProw, mDVA, mDPcol, mDProw, ws_e, ws_g, stats,
-                                                                ws_de, ws_dg);
-    return check_launch("tri_attn_bwd_tma8");
-  }
-  if (variant == 2) {
-    static std::once_flag oncep;
-    std::call_once(oncep, [] {
-      cudaFuncSetAttribute(tri_attn_bwd_tma_pipe<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_SMEM);
-      cudaFuncSetAttribute(tri_attn_bwd_tma_pipe<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_SMEM);
-    });
-    KernelTimerScope ts("tri_attn_bwd_tma", st);
-    if (dbias)
-      tri_attn_bwd_tma_pipe<T, true><<<dim3(D.H, 2, D.B), 128, TP_SMEM, st>>>(D, mPcol, mProw, mDVA, mDPcol, mDProw, ws_e,
-                                                                            ws_g, stats, ws_de, ws_dg, dbias);
-    else
-      tri_attn_bwd_tma_pipe<T, false><<<dim3(D.H, 2, D.B), 128, TP_SMEM, st>>>(D, mPcol, mProw, mDVA, mDPcol, mDProw, ws_e,
-                                                                             ws_g, stats, ws_de, ws_dg, nullptr);
-    return check_launch("tri_attn_bwd_tma_pipe");
-  }
-  if (dbias) return fail("triplet_attn_bwd: the projection-bias by-product needs the pipelined kernel (TGT_TRI_BWD_KERNEL=2)");
-  static std::once_flag once;
-  std::call_once(once, [] {
-    cudaFuncSetAttribute(tri_attn_bwd_tma<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM);
+  static std::once_flag oncep;
+  std::call_once(oncep, [] {
+    cudaFuncSetAttribute(tri_attn_bwd_tma_pipe<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_SMEM);
+    cudaFuncSetAttribute(tri_attn_bwd_tma_pipe<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_SMEM);
   });
   KernelTimerScope ts("tri_attn_bwd_tma", st);
-  tri_attn_bwd_tma<T><<<dim3(D.H, 2, D.B), 128, TB_SMEM, st>>>(D, mPcol, mProw, mDVA, mDPcol, mDProw, ws_e, ws_g, stats,
-                                                              ws_de, ws_dg);
-  return check_launch("tri_attn_bwd_tma");
+  if (dbias)
+    tri_attn_bwd_tma_pipe<T, true><<<dim3(D.H, 2, D.B), 128, TP_SMEM, st>>>(D, mPcol, mProw, mDVA, mDPcol, mDProw, ws_e,
+                                                                          ws_g, stats, ws_de, ws_dg, dbias);
+  else
+    tri_attn_bwd_tma_pipe<T, false><<<dim3(D.H, 2, D.B), 128, TP_SMEM, st>>>(D, mPcol, mProw, mDVA, mDPcol, mDProw, ws_e,
+                                                                           ws_g, stats, ws_de, ws_dg, nullptr);
+  return check_launch("tri_attn_bwd_tma_pipe");
 }
 
 // ------------------------------------------------------------------------------------------------ TripletAggregate (TGT-Agx2)

@@ -276,6 +276,9 @@ typedef struct {
   void *stat_partial;             /* TGT_EPI_STATS with more than one column slice (tgt_gemm_tc_slices): workspace of
                                    * slices * M * 8 bytes for the per-slice (sum, sum of squares); a tiny second kernel
                                    * then writes stat_mean / stat_rstd                                              */
+  const uint64_t *seed_ptr;       /* TGT_EPI_GELU / _GELU_BWD: if non-NULL the dropout seed is READ FROM DEVICE MEMORY when
+                                   * the kernel runs (and `seed` is ignored), so that a captured CUDA graph draws a fresh
+                                   * mask on every replay (Monte-Carlo-dropout inference, tgt_training.py:42)          */
 } tgt_gemm_desc;
 int tgt_gemm_tc(const tgt_gemm_desc *desc, const void *A, const void *B, void *D, void *stream);
 /* number of column slices tgt_gemm_tc cuts an [M,N] output into for this K and epilogue */

@@ -569,3 +569,29 @@ def test_full_size_properties_config2_and_config5():
     for b0 in (0, 77, 252):
         sub = run(slice(b0, b0 + 4))
         assert torch.equal(full[0][b0:b0 + 4], sub[0]) and rel_err(full[1][b0:b0 + 4], sub[1]) < 1e-3
+
+
+def test_cuda_graph_replay_of_mc_dropout_forward():
+    """harness.inference.GraphedForward: a train-mode (MC-dropout) forward of TGT_Gap captured once as a CUDA graph.  With the
+    dropouts off the replay reproduces the eager forward bit for bit; with them on, every replay draws fresh masks (device-
+    resident seed of the fused GELU + dropout epilogue, torch's graph-safe generator for source dropout / DropPath) and the
+    sample mean approaches the eager sample mean."""
+    from tgt_b200.harness import inference as INF
+    from tgt_b200.harness.synthetic import add_scheme_fields
+    torch.manual_seed(0)
+    cfg = dict(model_height=2, node_width=64, edge_width=32, num_heads=4, triplet_heads=2, triplet_type="aggregate")
+    batch = add_scheme_fields({k: v.to(DEV) for k, v in make_batch(4, 12, seed=2).items()}, with_3d=True)
+    det = HM.TGT_Gap(**cfg).to(DEV).train()                    # every dropout defaults to 0
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        want = det(batch).float()
+    gf = INF.GraphedForward(det, batch)
+    assert torch.equal(gf().float(), want) and torch.equal(gf().float(), want)
+    mc = HM.TGT_Gap(**cfg, source_dropout=0.3, drop_path=0.2, node_act_dropout=0.1, edge_act_dropout=0.1).to(DEV).train()
+    mc.load_state_dict(det.state_dict())
+    gf = INF.GraphedForward(mc, batch)
+    a, b_ = gf().float().clone(), gf().float().clone()
+    assert bool(torch.isfinite(a).all()) and not torch.equal(a, b_)
+    mean_g = torch.stack([gf().float().clone() for _ in range(64)]).mean(0)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        mean_e = torch.stack([mc(batch).float() for _ in range(64)]).mean(0)
+    assert float((mean_g - mean_e).abs().max()) < 0.35 * float(mean_e.abs().max() + 1.0)

@@ -63,7 +63,8 @@ class GemmDesc(C.Structure):
                 ("U", C.c_void_p), ("ldu", C.c_int64),
                 ("p_drop", C.c_float), ("seed", C.c_uint64),
                 ("stat_mean", C.c_void_p), ("stat_rstd", C.c_void_p), ("stat_eps", C.c_float),
-                ("res2", C.c_void_p), ("ldres2", C.c_int64), ("stat_partial", C.c_void_p)]
+                ("res2", C.c_void_p), ("ldres2", C.c_int64), ("stat_partial", C.c_void_p),
+                ("seed_ptr", C.c_void_p)]
 
 
 EPI_LN, EPI_BIAS, EPI_GELU, EPI_RES, EPI_STORE_U, EPI_ROWSCALE, EPI_GELU_BWD, EPI_STATS, EPI_LN_BWD = 1, 2, 4, 8, 16, 64, 128, 256, 512

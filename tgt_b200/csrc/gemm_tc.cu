@@ -49,6 +49,7 @@ struct GemmParams {
   int rows_per_scale;
   float p_drop;
   unsigned long long seed;
+  const unsigned long long *seed_ptr;   // device-resident seed (CUDA-graph replays), overrides `seed` when non-null
   int flags;
   float *stat_mean, *stat_rstd;      // EPI_STATS: LayerNorm statistics of the OUTPUT rows (needs one column slice)
   float stat_eps;
@@ -269,7 +270,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         vec_bias[et] = ((FLAGS & EPI_BIAS) && et < bn && gc < p.N) ? p.bias[gc] : 0.f;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      const DropCfg dc = make_drop_cfg(p.p_drop, p.seed);
+      const DropCfg dc = make_drop_cfg(p.p_drop, p.seed_ptr ? *p.seed_ptr : p.seed);
       constexpr uint32_t STAGE_PER_WARP = (FLAGS & EPI_STORE_U) ? 4096u : 2048u;
       const uint32_t stD = sStage + (uint32_t)(warp - 2) * STAGE_PER_WARP, stU = stD + 2048;
       const int crow = lane >> 2, cpiece = lane & 3;     // coalesced phase: 8 rows x 4 pieces per instruction
@@ -828,6 +829,7 @@ extern "C" int tgt_gemm_tc(const tgt_gemm_desc *g, const void *A, const void *B,
   p.rows_per_scale = g->rows_per_scale;
   p.p_drop = g->p_drop;
   p.seed = g->seed;
+  p.seed_ptr = reinterpret_cast<const unsigned long long *>(g->seed_ptr);
   if ((flags & EPI_RES) && !(flags & EPI_LN_BWD) && g->res_dtype == TGT_F32) flags |= EPI_RES_F32;
   else if ((flags & EPI_RES) && g->res_dtype != g->dtype) return fail("gemm_tc: residual dtype must be fp32 or the operand dtype");
   p.flags = flags;

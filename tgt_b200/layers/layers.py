@@ -146,7 +146,12 @@ class FFN(nn.Module):
     def _run(self, x, scale, fuse_res):
         if self.activation == 'gelu':
             p = self.act_dropout if self.training else 0.
-            seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0 else 0      # CPU generator: no sync
+            if p > 0 and x.is_cuda and torch.cuda.is_current_stream_capturing():
+                # CUDA-graph capture (MC-dropout inference): the seed lives on the device and comes from torch's
+                # graph-safe generator, so every replay of the graph draws a fresh dropout mask
+                seed = torch.randint(0, 2 ** 62, (1,), device=x.device, dtype=torch.int64)
+            else:
+                seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0 else 0      # CPU generator: no sync
             res = ops.FFNGeluFn.apply(x, self.ffn_ln.weight, self.ffn_ln.bias, self.lin_W1.weight,
                                       self.lin_W1.bias, self.lin_W2.weight, self.lin_W2.bias, p, seed,
                                       ops.compute_dtype(x), scale, fuse_res)

@@ -71,6 +71,31 @@ def _require_cuda(*ts: Optional[Tensor]) -> None:
             raise RuntimeError("tgt_b200 kernels need CUDA tensors (there is no CPU fallback)")
 
 
+def _guarded(fn):
+    """Run a Function.forward / backward with the device of its first CUDA tensor argument current: every launch takes
+    `torch.cuda.current_stream()` of the CURRENT device, so a model on cuda:1 in a process whose current device is cuda:0
+    would otherwise launch on the wrong device.  No-op (one attribute check) when the device is already current."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(ctx, *args):
+        dev = None
+        for a in args:
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                dev = a.device
+                break
+        if dev is None:
+            for a in getattr(ctx, "saved_tensors", ()) if fn.__name__ == "backward" else ():
+                if isinstance(a, torch.Tensor) and a.is_cuda:
+                    dev = a.device
+                    break
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(ctx, *args)
+        with torch.cuda.device(dev):
+            return fn(ctx, *args)
+    return wrapper
+
+
 def _f32c(t: Tensor) -> Tensor:
     t = t.detach()
     if t.dtype != torch.float32:
@@ -249,7 +274,11 @@ def gemm_tc(a: Tensor, w: Tensor, *, bias: Optional[Tensor] = None, ln: Optional
         flags |= _C.EPI_GELU | _C.EPI_STORE_U
         u = torch.empty((M, N), dtype=a.dtype, device=a.device)
         g.U, g.ldu = u.data_ptr(), u.stride(0)
-        g.p_drop, g.seed = float(gelu[0]), int(gelu[1])
+        g.p_drop = float(gelu[0])
+        if isinstance(gelu[1], torch.Tensor):        # device-resident seed: read by the kernel (CUDA-graph replays)
+            g.seed, g.seed_ptr = 0, gelu[1].data_ptr()
+        else:
+            g.seed = int(gelu[1])
         if store_gp:
             flags |= _C.EPI_STORE_GP
     if mul is not None:
@@ -534,6 +563,7 @@ def ln_linear_bwd(dout2: Tensor, x2: Tensor, g: Tensor, bt: Tensor, Wc: Tensor, 
 # ------------------------------------------------------------------------------------------
 class LNLinearFn(Function):
     @staticmethod
+    @_guarded
     def forward(ctx, x, ln_w, ln_b, W, b, cdtype):
         _require_cuda(x, W)
         with torch.autocast("cuda", enabled=False):
@@ -555,6 +585,7 @@ class LNLinearFn(Function):
         return out, x
 
     @staticmethod
+    @_guarded
     def backward(ctx, dout, dalias=None):
         x2, g, bt, Wc, mean, rstd = ctx.saved_tensors
         cd = ctx.cdtype
@@ -689,6 +720,7 @@ class TripletAttentionFn(Function):
     fuse_res=True : returns e + res_scale[b] * module(e) (DropPath + residual fused into the lin_O GEMM epilogue)."""
 
     @staticmethod
+    @_guarded
     def forward(ctx, e, mask, ln_w, ln_b, Wcat, bcat, Wo, bo, layout, cdtype, res_scale=None, fuse_res=False):
         _require_cuda(e, mask, Wcat)
         H, d, off_q, off_k, off_v, off_e, off_g = layout
@@ -744,6 +776,7 @@ class TripletAttentionFn(Function):
         return out, e                   # (result, alias of the input for the caller's residual add: see LNLinearFn)
 
     @staticmethod
+    @_guarded
     def backward(ctx, dout, dalias=None, _unused=None):
         if ctx_fused(ctx):
             dalias = None               # slots 2 and 3 are the (non-differentiable) statistics
@@ -813,6 +846,7 @@ class TripletAggregateFn(Function):
     """`layout` = (H, d, off_v, off_e, off_g, mask_dir)."""
 
     @staticmethod
+    @_guarded
     def forward(ctx, e, mask, ln_w, ln_b, Wcat, bcat, Wo, bo, layout, cdtype, res_scale=None, fuse_res=False):
         _require_cuda(e, mask, Wcat)
         H, d, off_v, off_e, off_g, mask_dir = layout
@@ -850,6 +884,7 @@ class TripletAggregateFn(Function):
         return out, e                   # (result, alias of the input for the caller's residual add: see LNLinearFn)
 
     @staticmethod
+    @_guarded
     def backward(ctx, dout, dalias=None, _unused=None):
         if ctx_fused(ctx):
             dalias = None               # slots 2 and 3 are the (non-differentiable) statistics
@@ -904,6 +939,7 @@ class TriangularCoreFn(Function):
     shared memory; backward recomputes them from `proj` (saved: it is the module's smallest tensor)."""
 
     @staticmethod
+    @_guarded
     def forward(ctx, proj, mask, H, cdtype):
         _require_cuda(proj, mask)
         B, N = proj.shape[0], proj.shape[1]
@@ -921,6 +957,7 @@ class TriangularCoreFn(Function):
         return va
 
     @staticmethod
+    @_guarded
     def backward(ctx, dva):
         pc, m3 = ctx.saved_tensors
         with torch.autocast("cuda", enabled=False):
@@ -936,6 +973,7 @@ class SigLinFn(Function):
     """x [..., 2W] = (gates | lins) -> sigmoid(gates) * lins [..., W]; backward recomputes the sigmoid from x."""
 
     @staticmethod
+    @_guarded
     def forward(ctx, x):
         _require_cuda(x)
         xc = x.detach().contiguous()
@@ -948,6 +986,7 @@ class SigLinFn(Function):
         return y
 
     @staticmethod
+    @_guarded
     def backward(ctx, dy):
         (xc,) = ctx.saved_tensors
         W = xc.shape[-1] // 2
@@ -965,6 +1004,7 @@ class EGTCoreFn(Function):
     """qkv:[B,N,3*Wn] (or [B,N,2*Wn] when attend=False), eg:[B,N,N,2H] (or [..,H]); returns (hhat, vatt)."""
 
     @staticmethod
+    @_guarded
     def forward(ctx, qkv, eg, mask, src_mask, H, attend, scale_degree, cdtype):
         _require_cuda(qkv, eg, mask)
         B, N = qkv.shape[0], qkv.shape[1]
@@ -993,6 +1033,7 @@ class EGTCoreFn(Function):
         return hhat
 
     @staticmethod
+    @_guarded
     def backward(ctx, dhhat, dvatt=None):
         q2, eg2, m3, src, stats, vatt = ctx.saved_tensors
         desc = ctx.desc
@@ -1024,6 +1065,7 @@ class FFNGeluFn(Function):
     residual add is the epilogue of the W2 GEMM; LN, bias, GELU and dropout are the epilogue of the W1 GEMM)."""
 
     @staticmethod
+    @_guarded
     def forward(ctx, x, ln_w, ln_b, W1, b1, W2, b2, p_drop, seed, cdtype, res_scale=None, fuse_res=False):
         _require_cuda(x, W1)
         with torch.autocast("cuda", enabled=False):
@@ -1037,11 +1079,15 @@ class FFNGeluFn(Function):
                 mean, rstd = st if st is not None else row_stats(x2)
                 W1g, b1p, cs = _ln_fold(W1, b1, g, bt, cdtype)
                 # the epilogue stores GELU'(u) * dropout mask in place of u: backward is then a multiply, not a re-evaluation
-                a, u = gemm_tc(x2, W1g, bias=b1p, ln=(mean, rstd, cs), gelu=(float(p_drop), int(seed)),
+                a, u = gemm_tc(x2, W1g, bias=b1p, ln=(mean, rstd, cs),
+                               gelu=(float(p_drop), seed if isinstance(seed, torch.Tensor) else int(seed)),
                                name="gemm_tc_ln_gelu", store_gp=_STORE_GP)
                 u_is_gp = _STORE_GP
             else:
                 u_is_gp = False
+                if isinstance(seed, torch.Tensor):
+                    raise RuntimeError("tgt_b200: a device-resident dropout seed (CUDA-graph capture) needs the tcgen05 "
+                                       "FFN path (16-bit activations, width <= 512)")
                 y, mean, rstd = layernorm_fwd(x2, g, bt, cdtype)
                 u = lib_addmm("ffn.W1", b1.detach().to(cdtype), y, W1c.t())
                 del y
@@ -1055,7 +1101,7 @@ class FFNGeluFn(Function):
             _, ostats = linear_residual(a, W2c, b2, x2 if fuse_res else None, sc, out2=out.view(-1, W2.shape[0]),
                                         want_stats=fuse_res, name="gemm_tc_w2")
             ctx.save_for_backward(x2, g, bt, W1c, W2c, mean, rstd, u, a, sc)
-            ctx.meta = (float(p_drop), int(seed), cdtype, x.dtype,
+            ctx.meta = (float(p_drop), 0 if isinstance(seed, torch.Tensor) else int(seed), cdtype, x.dtype,
                         (ln_w.dtype, W1.dtype, b1.dtype, W2.dtype, b2.dtype), fuse_res)
             ctx.u_is_gp = u_is_gp
             ctx.set_materialize_grads(False)
@@ -1064,6 +1110,7 @@ class FFNGeluFn(Function):
         return out, x                   # (result, alias of the input for the caller's residual add: see LNLinearFn)
 
     @staticmethod
+    @_guarded
     def backward(ctx, dout, dalias=None, _unused=None):
         if ctx_fused(ctx):
             dalias = None               # slots 2 and 3 are the (non-differentiable) statistics
@@ -1094,6 +1141,7 @@ class LinearResidualFn(Function):
     (lin_O_e, reference layers.py:82,126) with the caller's DropPath + residual add (layers.py:278-279) fused in."""
 
     @staticmethod
+    @_guarded
     def forward(ctx, a, W, bias, res, scale, cdtype):
         _require_cuda(a, W, res)
         with torch.autocast("cuda", enabled=False):
@@ -1112,6 +1160,7 @@ class LinearResidualFn(Function):
         return _with_stats(ctx, out, ostats)
 
     @staticmethod
+    @_guarded
     def backward(ctx, dout, _m=None, _r=None):
         a2, Wc, sc = ctx.saved_tensors
         with torch.autocast("cuda", enabled=False):
@@ -1126,6 +1175,7 @@ class LinearResidualFn(Function):
 # ------------------------------------------------------------------------------------------
 class ScaledResidualFn(Function):
     @staticmethod
+    @_guarded
     def forward(ctx, x, res, scale):
         _require_cuda(x, res)
         B = x.shape[0]
@@ -1141,6 +1191,7 @@ class ScaledResidualFn(Function):
         return out
 
     @staticmethod
+    @_guarded
     def backward(ctx, dout):
         dres = dout if dout.dtype == ctx.res_dtype else dout.to(ctx.res_dtype)
         if ctx.scale is None:
@@ -1166,6 +1217,7 @@ class GaussianBasisFn(Function):
     """x:[...] f32 (scaled distances), mu, sd:[K] f32  ->  [..., K] in `out_dtype`; backward recomputes the basis."""
 
     @staticmethod
+    @_guarded
     def forward(ctx, x, mu, sd, out_dtype):
         _require_cuda(x, mu, sd)
         xc, muc, sdc = _f32c(x), _f32c(mu), _f32c(sd)
@@ -1178,6 +1230,7 @@ class GaussianBasisFn(Function):
         return out
 
     @staticmethod
+    @_guarded
     def backward(ctx, dout):
         xc, muc, sdc = ctx.saved_tensors
         K = muc.numel()

@@ -295,6 +295,10 @@ int tgt_gelu_dropout_fwd(const void *u, void *y, int64_t n, float p_drop, uint64
                          int dtype, void *stream);
 int tgt_gelu_dropout_bwd(const void *u, const void *dy, void *du, int64_t n, float p_drop,
                          uint64_t seed, int dtype, void *stream);
+/* forward only, seed read from device memory at kernel start: a captured CUDA graph resamples
+ * the mask on every replay once the 8-byte seed is refreshed (inference, MC dropout).         */
+int tgt_gelu_dropout_fwd_dseed(const void *u, void *y, int64_t n, float p_drop,
+                               const uint64_t *seed_ptr, int dtype, void *stream);
 
 /* ---- residual: out = res + scale[b] * x  (per-sample DropPath + in-place add) --------------
  * replaces DropPath + add_ at lib/tgt/layers/layers.py:163-177, 269-290.

@@ -102,6 +102,7 @@ _SIGNATURES = {
     "tgt_egt_attn_workspace_bytes": (C.c_size_t, [C.POINTER(EgtDesc)]),
     "tgt_egt_attn_bwd": (C.c_int, [C.POINTER(EgtDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "tgt_gelu_dropout_fwd": (C.c_int, [_P, _P, C.c_int64, C.c_float, C.c_uint64, C.c_int, _P]),
+    "tgt_gelu_dropout_fwd_dseed": (C.c_int, [_P, _P, C.c_int64, C.c_float, _P, C.c_int, _P]),
     "tgt_gelu_dropout_bwd": (C.c_int, [_P, _P, _P, C.c_int64, C.c_float, C.c_uint64, C.c_int, _P]),
     "tgt_gemm_tc": (C.c_int, [C.POINTER(GemmDesc), _P, _P, _P, _P]),
     "tgt_gemm_tc_slices": (C.c_int, [C.c_int, C.c_int, C.c_int]),

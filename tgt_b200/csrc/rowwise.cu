@@ -412,9 +412,9 @@ __device__ __forceinline__ float gelu_grad(float u) {
 template <typename T, bool BWD>
 __global__ void __launch_bounds__(256)
 gelu_dropout_kernel(const T *__restrict__ u, const T *__restrict__ dy, T *__restrict__ out, int64_t n,
-                    float p_drop, uint64_t seed) {
+                    float p_drop, uint64_t seed, const uint64_t *__restrict__ seed_ptr) {
   constexpr int NV = 16 / sizeof(T);
-  const DropCfg dc = make_drop_cfg(p_drop, seed);
+  const DropCfg dc = make_drop_cfg(p_drop, seed_ptr ? *seed_ptr : seed);
   const int64_t nvec = n / NV;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
@@ -729,9 +729,21 @@ extern "C" int tgt_gelu_dropout_fwd(const void *u, void *y, int64_t n, float p_d
   cudaStream_t st = (cudaStream_t)stream;
   TGT_DISPATCH_DTYPE(dtype, T, {
     gelu_dropout_kernel<T, false><<<grid_for(n / (16 / sizeof(T)) + 1, 256 * 4), 256, 0, st>>>(
-        (const T *)u, nullptr, (T *)y, n, p_drop, seed);
+        (const T *)u, nullptr, (T *)y, n, p_drop, seed, nullptr);
   });
   return check_launch("gelu_dropout_fwd");
+}
+extern "C" int tgt_gelu_dropout_fwd_dseed(const void *u, void *y, int64_t n, float p_drop, const uint64_t *seed_ptr,
+                                          int dtype, void *stream) {
+  if (n <= 0) return 0;
+  if (p_drop < 0.f || p_drop >= 1.f) return fail("gelu_dropout: p_drop=%f out of range", p_drop);
+  if (!seed_ptr) return fail("gelu_dropout_fwd_dseed: null seed pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  TGT_DISPATCH_DTYPE(dtype, T, {
+    gelu_dropout_kernel<T, false><<<grid_for(n / (16 / sizeof(T)) + 1, 256 * 4), 256, 0, st>>>(
+        (const T *)u, nullptr, (T *)y, n, p_drop, 0, seed_ptr);
+  });
+  return check_launch("gelu_dropout_fwd_dseed");
 }
 extern "C" int tgt_gelu_dropout_bwd(const void *u, const void *dy, void *du, int64_t n, float p_drop, uint64_t seed,
                                     int dtype, void *stream) {
@@ -740,7 +752,7 @@ extern "C" int tgt_gelu_dropout_bwd(const void *u, const void *dy, void *du, int
   cudaStream_t st = (cudaStream_t)stream;
   TGT_DISPATCH_DTYPE(dtype, T, {
     gelu_dropout_kernel<T, true><<<grid_for(n / (16 / sizeof(T)) + 1, 256 * 4), 256, 0, st>>>(
-        (const T *)u, (const T *)dy, (T *)du, n, p_drop, seed);
+        (const T *)u, (const T *)dy, (T *)du, n, p_drop, seed, nullptr);
   });
   return check_launch("gelu_dropout_bwd");
 }

@@ -1085,15 +1085,17 @@ class FFNGeluFn(Function):
                 u_is_gp = _STORE_GP
             else:
                 u_is_gp = False
-                if isinstance(seed, torch.Tensor):
-                    raise RuntimeError("tgt_b200: a device-resident dropout seed (CUDA-graph capture) needs the tcgen05 "
-                                       "FFN path (16-bit activations, width <= 512)")
                 y, mean, rstd = layernorm_fwd(x2, g, bt, cdtype)
                 u = lib_addmm("ffn.W1", b1.detach().to(cdtype), y, W1c.t())
                 del y
                 a = torch.empty_like(u)
-                _C.check(_C.lib().tgt_gelu_dropout_fwd(_C.ptr(u), _C.ptr(a), u.numel(), float(p_drop), int(seed),
-                                                       _C.dtype_code(cdtype), _C.stream_ptr()), "gelu_dropout_fwd")
+                if isinstance(seed, torch.Tensor):      # CUDA-graph capture: the kernel reads the seed at replay time
+                    _C.check(_C.lib().tgt_gelu_dropout_fwd_dseed(_C.ptr(u), _C.ptr(a), u.numel(), float(p_drop),
+                                                                 _C.ptr(seed), _C.dtype_code(cdtype), _C.stream_ptr()),
+                             "gelu_dropout_fwd_dseed")
+                else:
+                    _C.check(_C.lib().tgt_gelu_dropout_fwd(_C.ptr(u), _C.ptr(a), u.numel(), float(p_drop), int(seed),
+                                                           _C.dtype_code(cdtype), _C.stream_ptr()), "gelu_dropout_fwd")
             sc = None
             if fuse_res and res_scale is not None:
                 sc = _f32c(res_scale).view(-1)

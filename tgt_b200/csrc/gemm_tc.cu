@@ -53,14 +53,21 @@ struct GemmParams {
   int flags;
   float *stat_mean, *stat_rstd;      // EPI_STATS: LayerNorm statistics of the OUTPUT rows (needs one column slice)
   float stat_eps;
+  int debug;                         // TGT_GEMM_DEBUG (profiling only): 1 = skip the bulk stores, 2 = skip the MMAs
   const void *res2;                  // EPI_LN_BWD: residual gradient added to dx (16-bit, pitch ldres2); `res` is x
   int64_t ldres2;
 };
 
-constexpr int GEMM_THREADS = 320;      // warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: epilogue
-constexpr int EPI_WARPS = 8;           // two per TMEM lane quadrant (they interleave 32-column groups)
+// warp 0: TMA producer, warp 1: MMA issuer, warps 2..: epilogue, WQ per TMEM lane quadrant (they interleave 32-column
+// groups).  WQ = 2 for the epilogues with coalesced-domain work, up to 4 for the TMA-store epilogues, whose per-group
+// chain (tcgen05.ld -> FMA -> st.shared -> bulk store) is latency- and not issue-bound.
 constexpr int A_STAGE_BYTES = 128 * 128;
-__host__ __device__ constexpr int epi_stage_bytes(int flags) { return EPI_WARPS * ((flags & 16) ? 4096 : 2048); }
+// Epilogues whose work is all in the TMEM domain (lane = row) hand their 32x32 output tiles to the TMA store engine: no
+// LDS / STG / address arithmetic in the epilogue warps, two staging tiles per warp so a store drains while the next fills.
+__host__ __device__ constexpr bool epi_tma_store(int flags) { return (flags & (8 | 128 | 2048 | 256 | 4 | 512)) == 0; }
+__host__ __device__ constexpr int epi_stage_bytes(int flags, int wq) {
+  return 4 * wq * (((flags & 16) || epi_tma_store(flags)) ? 4096 : 2048);
+}
 
 // GELU(u) = u * Phi(u) with Phi from the Abramowitz-Stegun 7.1.26 erfc approximation (|error| < 2e-7 in Phi): two MUFU
 // ops and ~10 FMA-pipe instructions per element -- the epilogue is issue-bound, CUDA's erff costs 3x as much.
@@ -157,13 +164,16 @@ __device__ __forceinline__ uint32_t stage_addr(uint32_t base, int row, int piece
   return base + row * 64 + ((piece ^ ((row >> 1) & 3)) << 4);
 }
 
-template <typename T, int FLAGS>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+template <typename T, int FLAGS, int WQ>
+__global__ void __launch_bounds__(64 + WQ * 128, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmD, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: provably warp-uniform, so tile / column-group bookkeeping and the TMA operands stay in
+  // uniform registers
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
   const int slice = blockIdx.x % p.n_slices;
   const int q = blockIdx.x / p.n_slices;
@@ -174,7 +184,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t sB = smem_base;                                           // kblocks x [bn rows x 128 B]
   const uint32_t sA = sB + (uint32_t)p.kblocks * bn * 128;                 // stages x 16 KB
   const uint32_t sStage = sA + (uint32_t)p.stages * A_STAGE_BYTES;         // 8 warps x (D 2 KB [+ U 2 KB])
-  const uint32_t sVec = sStage + epi_stage_bytes(FLAGS);                         // colsum[256], bias[256] fp32
+  static_assert(WQ == 2 || epi_tma_store(FLAGS), "the pair exchanges of the STATS / LN_BWD epilogues assume two warps per quadrant");
+  constexpr int EPI_WARPS = 4 * WQ;
+  const uint32_t sVec = sStage + epi_stage_bytes(FLAGS, WQ);                         // colsum[256], bias[256] fp32
   const uint32_t sPart = sVec + 2048;                                      // EPI_STATS: [2 buffers][8 warps][32 rows] float2
   const uint32_t sBar = sPart + 4096;                                      // mbarriers
   float2 *part = reinterpret_cast<float2 *>(smem_gen + (sPart - smem_base));
@@ -245,7 +257,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int k = 0; k < ksteps; ++k) {
               const uint64_t ad = umma_desc_sw128(sA + stage * A_STAGE_BYTES + k * 32);
               const uint64_t bd = umma_desc_sw128(sB + kb * bn * 128 + k * 32);
-              tc_mma(tmem_d, ad, bd, idesc, (uint32_t)((kb | k) != 0));
+              if (!(p.debug & 2)) tc_mma(tmem_d, ad, bd, idesc, (uint32_t)((kb | k) != 0));
             }
             tc_commit(bar_empty + stage * 8);
             if (++stage == p.stages) {
@@ -264,15 +276,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int half = (warp - 2) >> 2;  // which 32-column groups this warp drains: half, half + 2, ...
       const int et = threadIdx.x - 64;   // 0..255
       const int col0 = slice * bn;
-      {
+      if (et < 256) {
         const int gc = col0 + et;
         vec_colsum[et] = ((FLAGS & (EPI_LN | EPI_LN_BWD)) && et < bn && gc < p.N) ? p.col_sum[gc] : 0.f;
         vec_bias[et] = ((FLAGS & EPI_BIAS) && et < bn && gc < p.N) ? p.bias[gc] : 0.f;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(WQ * 128) : "memory");
       const DropCfg dc = make_drop_cfg(p.p_drop, p.seed_ptr ? *p.seed_ptr : p.seed);
-      constexpr uint32_t STAGE_PER_WARP = (FLAGS & EPI_STORE_U) ? 4096u : 2048u;
-      const uint32_t stD = sStage + (uint32_t)(warp - 2) * STAGE_PER_WARP, stU = stD + 2048;
+      constexpr bool TMA_ST = epi_tma_store(FLAGS);
+      constexpr uint32_t STAGE_PER_WARP = ((FLAGS & EPI_STORE_U) || TMA_ST) ? 4096u : 2048u;
+      const uint32_t stD0 = sStage + (uint32_t)(warp - 2) * STAGE_PER_WARP, stU = stD0 + 2048;
+      uint32_t st_buf = 0;               // TMA_ST: which of the two staging tiles the next group fills
+      if (TMA_ST && lane == 0) tma_prefetch_desc(&tmD);
       const int crow = lane >> 2, cpiece = lane & 3;     // coalesced phase: 8 rows x 4 pieces per instruction
       constexpr int RW = (FLAGS & EPI_RES_F32) ? 2 : 1;
       constexpr bool LNB = (FLAGS & EPI_LN_BWD) != 0;
@@ -347,7 +362,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(bar_tfull + acc * 8, acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * bn);
-        uint32_t v[32];
+        uint32_t v[32], v2[32];
         float lnb_s1 = 0.f, lnb_s2 = 0.f;     // LN_BWD: mean_c(g), mean_c(g * xhat) of this lane's row, g = dy * gamma
         if (LNB) {
           // pass 1 over the accumulators: row sums; pass 2 (the main loop below) re-reads them from tensor memory
@@ -377,9 +392,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           lnb_s2 = (lnb_s2 + o.y) * inv_n;
         }
         if (half * 32 < bn) tc_ld32(taddr + half * 32, v);
-#pragma unroll
-        for (int kq = 0; kq < (LNB ? 4 : 1); ++kq)
-        for (int c = half * 32 + kq * 64; c < bn; c += (LNB ? (1 << 20) : 64)) {
+        constexpr int CSTRIDE = WQ * 32;                     // column distance between two groups of one warp
+        // one 32-column group: accumulators in vc; with the TMA-store epilogues the next group's accumulators are
+        // requested into vn as soon as vc has landed, so the tcgen05.ld latency hides behind this group's arithmetic
+        auto group = [&](uint32_t(&v)[32], uint32_t(&vn)[32], const int c, const int kq) {
           // per-column epilogue vectors of this group (shared-memory broadcasts), issued before the TMEM wait
           float4 csv[8], bsv[8];
           if (FLAGS & EPI_LN) {
@@ -391,7 +407,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int k = 0; k < 8; ++k) bsv[k] = *reinterpret_cast<const float4 *>(vec_bias + c + k * 4);
           }
           if ((FLAGS & (EPI_RES | EPI_GELU_BWD | EPI_MULRES)) && c + 64 < bn) res_load(c + 64, rnext);
+          const bool tma_group = TMA_ST && c + 32 <= bn;      // a slice's ragged last group takes the vector-store path
+          const uint32_t stD = stD0 + (TMA_ST ? st_buf * 2048u : 0u);
+          if (TMA_ST) {
+            // the bulk store committed two groups ago has finished reading this staging tile
+            if (elect_one()) tma_store_wait_read1();
+            __syncwarp();
+            st_buf ^= 1u;
+          }
           tc_ld_wait();
+          if (TMA_ST && c + CSTRIDE < bn) tc_ld32(taddr + c + CSTRIDE, vn);
           // ---- TMEM domain (lane = row): LN fold, bias, activation; 16-bit results go to the staging tile
 #pragma unroll
           for (int pc = 0; pc < 4; ++pc) {
@@ -410,21 +435,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 f[2 * j + 1] = rstd * (g1 - lnb_s1 - fmaf(x1, rstd, nmr) * lnb_s2);
               }
             }
+            // packed fp32 pairs (fma.rn.f32x2: two columns per issue slot, bit-identical to the scalar FMAs)
             if (FLAGS & EPI_LN) {
-              const float cs[8] = {csv[2 * pc].x, csv[2 * pc].y, csv[2 * pc].z, csv[2 * pc].w,
-                                   csv[2 * pc + 1].x, csv[2 * pc + 1].y, csv[2 * pc + 1].z, csv[2 * pc + 1].w};
+              const float2 rstd2 = make_float2(rstd, rstd), nmr2 = make_float2(nmr, nmr);
+              const float4 cq[2] = {csv[2 * pc], csv[2 * pc + 1]};
+              const float2 cs2[4] = {make_float2(cq[0].x, cq[0].y), make_float2(cq[0].z, cq[0].w), make_float2(cq[1].x, cq[1].y),
+                                     make_float2(cq[1].z, cq[1].w)};
+              float2 t2[4];
               if (FLAGS & EPI_BIAS) {
-                const float bs[8] = {bsv[2 * pc].x, bsv[2 * pc].y, bsv[2 * pc].z, bsv[2 * pc].w,
-                                     bsv[2 * pc + 1].x, bsv[2 * pc + 1].y, bsv[2 * pc + 1].z, bsv[2 * pc + 1].w};
+                const float4 bq[2] = {bsv[2 * pc], bsv[2 * pc + 1]};
+                const float2 bs2[4] = {make_float2(bq[0].x, bq[0].y), make_float2(bq[0].z, bq[0].w), make_float2(bq[1].x, bq[1].y),
+                                       make_float2(bq[1].z, bq[1].w)};
 #pragma unroll
-                for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], rstd, fmaf(nmr, cs[i], bs[i]));
+                for (int j = 0; j < 4; ++j) t2[j] = __ffma2_rn(nmr2, cs2[j], bs2[j]);
               } else {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], rstd, nmr * cs[i]);
+                for (int j = 0; j < 4; ++j) t2[j] = __fmul2_rn(nmr2, cs2[j]);
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 r2 = __ffma2_rn(make_float2(f[2 * j], f[2 * j + 1]), rstd2, t2[j]);
+                f[2 * j] = r2.x;
+                f[2 * j + 1] = r2.y;
               }
             } else if (FLAGS & EPI_BIAS) {
-              const float bs[8] = {bsv[2 * pc].x, bsv[2 * pc].y, bsv[2 * pc].z, bsv[2 * pc].w,
-                                   bsv[2 * pc + 1].x, bsv[2 * pc + 1].y, bsv[2 * pc + 1].z, bsv[2 * pc + 1].w};
+              const float4 bq[2] = {bsv[2 * pc], bsv[2 * pc + 1]};
+              const float bs[8] = {bq[0].x, bq[0].y, bq[0].z, bq[0].w, bq[1].x, bq[1].y, bq[1].z, bq[1].w};
 #pragma unroll
               for (int i = 0; i < 8; ++i) f[i] += bs[i];
             }
@@ -469,8 +505,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             w.w = pack2<T>(f[6], f[7]);
             st_shared_v4(stage_addr(stD, lane, pc), w);
           }
-          if (c + 64 < bn) tc_ld32(taddr + c + 64, v);      // next group's accumulators fly during the store phase
+          if (!TMA_ST && c + 64 < bn) tc_ld32(taddr + c + 64, v);      // next group's accumulators fly during the store phase
+          if (TMA_ST) fence_proxy_async();
           __syncwarp();
+          if (TMA_ST) {
+            if (elect_one()) {
+              if (tma_group && !(p.debug & 1)) tma_store_2d(&tmD, stD, col0 + c, (int)row0);
+              tma_store_commit();                           // (an empty group on the ragged path keeps the 2-deep accounting)
+            }
+            if (tma_group) return;
+          }
           // ---- coalesced domain: each instruction moves 8 rows x 64 contiguous bytes
           const int gc = col0 + c + cpiece * 8;
           uint4 wst[4], ust[4];
@@ -571,6 +615,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int k = 0; k < RW; ++k) rcur[it][k] = rnext[it][k];
           }
+        };
+        if constexpr (TMA_ST) {
+          for (int c = half * 32; c < bn; c += 2 * CSTRIDE) {
+            group(v, v2, c, 0);
+            if (c + CSTRIDE < bn) group(v2, v, c + CSTRIDE, 0);
+          }
+        } else {
+#pragma unroll
+          for (int kq = 0; kq < (LNB ? 4 : 1); ++kq)
+            for (int c = half * 32 + kq * 64; c < bn; c += (LNB ? (1 << 20) : 64)) group(v, v, c, kq);
         }
         tc_fence_before();
         if (lane == 0) mbar_arrive(bar_tempty + acc * 8);
@@ -613,6 +667,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
+      }
+      if (TMA_ST) {
+        __syncwarp();
+        if (elect_one()) tma_store_wait_all();
       }
     }
   }
@@ -714,6 +772,21 @@ static int make_operand_map(CUtensorMap *map, const void *base, int64_t rows, in
   return 0;
 }
 
+// output map of the TMA-store epilogues: 32 columns x 32 rows per box, 64B swizzle (= stage_addr's xor pattern)
+static int make_store_map(CUtensorMap *map, const void *base, int64_t rows, int N, int64_t ld, int dtype) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return fail("gemm_tc: cuTensorMapEncodeTiled is not available from the driver");
+  const cuuint64_t gdim[2] = {(cuuint64_t)N, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {32u, 32u};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUtensorMapDataType dt = dtype == TGT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = enc(map, dt, 2, const_cast<void *>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("gemm_tc: cuTensorMapEncodeTiled (store map) failed (%d)", (int)r);
+  return 0;
+}
+
 static int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -724,22 +797,33 @@ static int num_sms() {
   return n;
 }
 
-template <typename T, int FLAGS>
-static int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const GemmParams &p, size_t smem, cudaStream_t st) {
+// epilogue warps per TMEM lane quadrant.  Measured (scripts/bench_gemm_flavors.py, r2): 3 or 4 warps per quadrant lose --
+// their staging tiles cost activation-ring stages (232 KB is shared with the weight panel) -- so every flavour runs 2.
+static constexpr int epi_wq(int) { return 2; }
+
+template <typename T, int FLAGS, int WQ>
+static int launch_gemm_wq(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &md, const GemmParams &p, size_t smem,
+                          cudaStream_t st) {
   static std::once_flag once;
   std::call_once(once, [] {
-    cudaFuncSetAttribute(gemm_tc_kernel<T, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaFuncSetAttribute(gemm_tc_kernel<T, FLAGS, WQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   });
-  gemm_tc_kernel<T, FLAGS><<<p.n_slices * p.ctas_per_slice, GEMM_THREADS, smem, st>>>(ma, mb, p);
+  gemm_tc_kernel<T, FLAGS, WQ><<<p.n_slices * p.ctas_per_slice, 64 + WQ * 128, smem, st>>>(ma, mb, md, p);
   return check_launch("gemm_tc");
 }
 
+template <typename T, int FLAGS>
+static int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &md, const GemmParams &p, size_t smem,
+                       cudaStream_t st) {
+  return launch_gemm_wq<T, FLAGS, 2>(ma, mb, md, p, smem, st);
+}
+
 template <typename T>
-static int dispatch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const GemmParams &p, size_t smem,
+static int dispatch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &md, const GemmParams &p, size_t smem,
                          cudaStream_t st) {
   switch (p.flags) {
 #define TGT_GEMM_CASE(F) \
-  case (F): return launch_gemm<T, (F)>(ma, mb, p, smem, st);
+  case (F): return launch_gemm<T, (F)>(ma, mb, md, p, smem, st);
     TGT_GEMM_CASE(0)
     TGT_GEMM_CASE(EPI_BIAS)
     TGT_GEMM_CASE(EPI_LN | EPI_BIAS)
@@ -803,7 +887,7 @@ extern "C" int tgt_gemm_tc(const tgt_gemm_desc *g, const void *A, const void *B,
   p.K = g->K;
   p.kblocks = (g->K + 63) / 64;
   // widest slice whose weight panel leaves room for >= 3 activation stages
-  const int smem_budget = 232448 - 1024 - 2048 - 4096 - 256 - epi_stage_bytes(flags);
+  const int smem_budget = 232448 - 1024 - 2048 - 4096 - 256 - epi_stage_bytes(flags, epi_wq(flags));
   int bn_max = 256;
   while (bn_max > 16 && p.kblocks * bn_max * 128 + 3 * A_STAGE_BYTES > smem_budget) bn_max -= 16;
   p.n_slices = (g->N + bn_max - 1) / bn_max;
@@ -830,6 +914,7 @@ extern "C" int tgt_gemm_tc(const tgt_gemm_desc *g, const void *A, const void *B,
   p.p_drop = g->p_drop;
   p.seed = g->seed;
   p.seed_ptr = reinterpret_cast<const unsigned long long *>(g->seed_ptr);
+  if (const char *dbg = getenv("TGT_GEMM_DEBUG")) p.debug = atoi(dbg);
   if ((flags & EPI_RES) && !(flags & EPI_LN_BWD) && g->res_dtype == TGT_F32) flags |= EPI_RES_F32;
   else if ((flags & EPI_RES) && g->res_dtype != g->dtype) return fail("gemm_tc: residual dtype must be fp32 or the operand dtype");
   p.flags = flags;
@@ -852,12 +937,17 @@ extern "C" int tgt_gemm_tc(const tgt_gemm_desc *g, const void *A, const void *B,
     p.stat_eps = g->stat_eps;
   }
 
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, md;
   if (int e = make_operand_map(&ma, A, g->M, g->K, g->lda, 128, g->dtype)) return e;
   if (int e = make_operand_map(&mb, B, g->N, g->K, g->ldb, p.bn, g->dtype)) return e;
-  const size_t smem = (size_t)p.kblocks * p.bn * 128 + (size_t)p.stages * A_STAGE_BYTES + epi_stage_bytes(flags) + 2048 + 4096 + 256 + 1024;
+  if (epi_tma_store(flags)) {
+    if (int e = make_store_map(&md, D, g->M, g->N, g->ldd, g->dtype)) return e;
+  } else {
+    md = ma;
+  }
+  const size_t smem = (size_t)p.kblocks * p.bn * 128 + (size_t)p.stages * A_STAGE_BYTES + epi_stage_bytes(flags, epi_wq(flags)) + 2048 + 4096 + 256 + 1024;
   cudaStream_t st = (cudaStream_t)stream;
-  const int rc = g->dtype == TGT_BF16 ? dispatch_gemm<__nv_bfloat16>(ma, mb, p, smem, st) : dispatch_gemm<__half>(ma, mb, p, smem, st);
+  const int rc = g->dtype == TGT_BF16 ? dispatch_gemm<__nv_bfloat16>(ma, mb, md, p, smem, st) : dispatch_gemm<__half>(ma, mb, md, p, smem, st);
   if (rc || !(flags & EPI_STATS) || p.n_slices == 1) return rc;
   const int blocks = (int)std::min<int64_t>((g->M + 255) / 256, (int64_t)num_sms() * 8);
   stats_finalize_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float2 *>(g->stat_partial), p.n_slices, g->M,
@@ -868,7 +958,7 @@ extern "C" int tgt_gemm_tc(const tgt_gemm_desc *g, const void *A, const void *B,
 extern "C" int tgt_gemm_tc_slices(int N, int K, int flags) {
   // number of column slices tgt_gemm_tc cuts N into (callers size the stat_partial workspace with it)
   const int kblocks = (K + 63) / 64;
-  const int smem_budget = 232448 - 1024 - 2048 - 4096 - 256 - epi_stage_bytes(flags);
+  const int smem_budget = 232448 - 1024 - 2048 - 4096 - 256 - epi_stage_bytes(flags, epi_wq(flags));
   int bn_max = 256;
   while (bn_max > 16 && kblocks * bn_max * 128 + 3 * A_STAGE_BYTES > smem_budget) bn_max -= 16;
   return (N + bn_max - 1) / bn_max;

@@ -3,7 +3,9 @@
 import json, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from tgt_b200 import ops
+from tgt_b200 import _C, ops
+if os.environ.get("TGT_LIB"):          # A/B builds of the library (scripts only)
+    _C.LIB_PATH = os.path.abspath(os.environ["TGT_LIB"])
 
 
 def timeit(fn, iters=10):
@@ -44,4 +46,8 @@ a5 = torch.randn(R, 512, device="cuda").bfloat16()
 w5 = (torch.randn(256, 512, device="cuda") / 22).bfloat16()
 res["bias_res_K512"] = timeit(lambda: ops.gemm_tc(a5, w5, bias=b, res=r, out=out))
 res["plain_K512"] = timeit(lambda: ops.gemm_tc(a5, w5, out=out))
+a6 = torch.randn(R, 64, device="cuda").bfloat16()
+w6 = (torch.randn(256, 64, device="cuda") / 8).bfloat16()
+res["bias_res_K64"] = timeit(lambda: ops.gemm_tc(a6, w6, bias=b, res=r, row_scale=sc, rows_per_scale=4096, out=out))
+res["lib"] = os.environ.get("TGT_LIB", "in-tree")
 print(json.dumps(res))

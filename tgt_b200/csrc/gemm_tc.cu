@@ -436,7 +436,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
             // packed fp32 pairs (fma.rn.f32x2: two columns per issue slot, bit-identical to the scalar FMAs)
-            if (FLAGS & EPI_LN) {
+            // (measured, scripts/bench_gemm_flavors.py: the issue-bound GELU epilogues are 12 % faster with scalar FMAs --
+            //  their values are consumed one by one -- everything else gains from the packed form)
+            constexpr bool PACKED_LN = !(FLAGS & EPI_GELU);
+            if ((FLAGS & EPI_LN) && !PACKED_LN) {
+              const float4 cq[2] = {csv[2 * pc], csv[2 * pc + 1]};
+              const float cs[8] = {cq[0].x, cq[0].y, cq[0].z, cq[0].w, cq[1].x, cq[1].y, cq[1].z, cq[1].w};
+              if (FLAGS & EPI_BIAS) {
+                const float4 bq[2] = {bsv[2 * pc], bsv[2 * pc + 1]};
+                const float bs[8] = {bq[0].x, bq[0].y, bq[0].z, bq[0].w, bq[1].x, bq[1].y, bq[1].z, bq[1].w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], rstd, fmaf(nmr, cs[i], bs[i]));
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], rstd, nmr * cs[i]);
+              }
+            } else if (FLAGS & EPI_LN) {
               const float2 rstd2 = make_float2(rstd, rstd), nmr2 = make_float2(nmr, nmr);
               const float4 cq[2] = {csv[2 * pc], csv[2 * pc + 1]};
               const float2 cs2[4] = {make_float2(cq[0].x, cq[0].y), make_float2(cq[0].z, cq[0].w), make_float2(cq[1].x, cq[1].y),
@@ -623,8 +638,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         } else {
 #pragma unroll
-          for (int kq = 0; kq < (LNB ? 4 : 1); ++kq)
+          for (int kq = 0; kq < (LNB ? 4 : 1); ++kq) {
+#pragma unroll((FLAGS & EPI_GELU) ? 1 : 2)      // two groups in flight hide the residual loads; the GELU bodies are too big
             for (int c = half * 32 + kq * 64; c < bn; c += (LNB ? (1 << 20) : 64)) group(v, v, c, kq);
+          }
         }
         tc_fence_before();
         if (lane == 0) mbar_arrive(bar_tempty + acc * 8);

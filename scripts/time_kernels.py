@@ -8,7 +8,9 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from tgt_b200 import layers as L, ops          # noqa: E402
+from tgt_b200 import layers as L, ops, _C          # noqa: E402
+if os.environ.get("TGT_LIB"):          # A/B builds of the library
+    _C.LIB_PATH = os.path.abspath(os.environ["TGT_LIB"])
 from tgt_b200.harness.synthetic import make_edge_inputs   # noqa: E402
 
 ap = argparse.ArgumentParser()

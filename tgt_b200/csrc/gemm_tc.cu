@@ -53,7 +53,7 @@ struct GemmParams {
   int flags;
   float *stat_mean, *stat_rstd;      // EPI_STATS: LayerNorm statistics of the OUTPUT rows (needs one column slice)
   float stat_eps;
-  int debug;                         // TGT_GEMM_DEBUG (profiling only): 1 = skip the bulk stores, 2 = skip the MMAs
+  int debug;                         // TGT_GEMM_DEBUG (profiling only): 1 = skip the bulk stores, 2 = skip the MMAs, 4 = skip the accumulator reads, 8 = skip the activation loads
   const void *res2;                  // EPI_LN_BWD: residual gradient added to dx (16-bit, pitch ldres2); `res` is x
   int64_t ldres2;
 };
@@ -230,8 +230,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int64_t mt = q; mt < num_m_tiles; mt += p.ctas_per_slice) {
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(bar_empty + stage * 8, phase ^ 1);
-            mbar_expect_tx(bar_full + stage * 8, A_STAGE_BYTES);
-            tma_load_2d(&tmA, bar_full + stage * 8, sA + stage * A_STAGE_BYTES, kb * 64, (int)(mt * 128));
+            if (p.debug & 8) {
+              mbar_arrive(bar_full + stage * 8);
+            } else {
+              mbar_expect_tx(bar_full + stage * 8, A_STAGE_BYTES);
+              tma_load_2d(&tmA, bar_full + stage * 8, sA + stage * A_STAGE_BYTES, kb * 64, (int)(mt * 128));
+            }
             if (++stage == p.stages) {
               stage = 0;
               phase ^= 1;
@@ -391,7 +395,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           lnb_s1 = (lnb_s1 + o.x) * inv_n;
           lnb_s2 = (lnb_s2 + o.y) * inv_n;
         }
-        if (half * 32 < bn) tc_ld32(taddr + half * 32, v);
+        if (half * 32 < bn && !(p.debug & 4)) tc_ld32(taddr + half * 32, v);
         constexpr int CSTRIDE = WQ * 32;                     // column distance between two groups of one warp
         // one 32-column group: accumulators in vc; with the TMA-store epilogues the next group's accumulators are
         // requested into vn as soon as vc has landed, so the tcgen05.ld latency hides behind this group's arithmetic
@@ -416,7 +420,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             st_buf ^= 1u;
           }
           tc_ld_wait();
-          if (TMA_ST && c + CSTRIDE < bn) tc_ld32(taddr + c + CSTRIDE, vn);
+          if (TMA_ST && c + CSTRIDE < bn && !(p.debug & 4)) tc_ld32(taddr + c + CSTRIDE, vn);
           // ---- TMEM domain (lane = row): LN fold, bias, activation; 16-bit results go to the staging tile
 #pragma unroll
           for (int pc = 0; pc < 4; ++pc) {
@@ -818,6 +822,18 @@ static int num_sms() {
 // their staging tiles cost activation-ring stages (232 KB is shared with the weight panel) -- so every flavour runs 2.
 static constexpr int epi_wq(int) { return 2; }
 
+static int gemm_smem_budget(int flags) { return 232448 - 1024 - 2048 - 4096 - 256 - epi_stage_bytes(flags, epi_wq(flags)); }
+// Widest column slice whose weight panel leaves room for >= 3 activation stages.  Measured (r2, K = 512, N = 256): trading
+// slice width for ring depth loses -- 2 slices x 4 stages 0.43 ms, 3 slices x 6 stages 0.60 ms, 4 slices x 8 stages 0.77 ms
+// -- because a narrower UMMA re-reads the activation tile from shared memory once per slice width.
+static int gemm_bn_max(int kblocks, int flags) {
+  const int budget = gemm_smem_budget(flags);
+  const int min_stages = 3;
+  int bn_max = 256;
+  while (bn_max > 16 && kblocks * bn_max * 128 + min_stages * A_STAGE_BYTES > budget) bn_max -= 16;
+  return bn_max;
+}
+
 template <typename T, int FLAGS, int WQ>
 static int launch_gemm_wq(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &md, const GemmParams &p, size_t smem,
                           cudaStream_t st) {
@@ -903,10 +919,8 @@ extern "C" int tgt_gemm_tc(const tgt_gemm_desc *g, const void *A, const void *B,
   p.N = g->N;
   p.K = g->K;
   p.kblocks = (g->K + 63) / 64;
-  // widest slice whose weight panel leaves room for >= 3 activation stages
-  const int smem_budget = 232448 - 1024 - 2048 - 4096 - 256 - epi_stage_bytes(flags, epi_wq(flags));
-  int bn_max = 256;
-  while (bn_max > 16 && p.kblocks * bn_max * 128 + 3 * A_STAGE_BYTES > smem_budget) bn_max -= 16;
+  const int smem_budget = gemm_smem_budget(flags);
+  const int bn_max = gemm_bn_max(p.kblocks, flags);
   p.n_slices = (g->N + bn_max - 1) / bn_max;
   p.bn = (((g->N + p.n_slices - 1) / p.n_slices) + 15) / 16 * 16;
   const int64_t m_tiles = (g->M + 127) / 128;
@@ -974,10 +988,7 @@ extern "C" int tgt_gemm_tc(const tgt_gemm_desc *g, const void *A, const void *B,
 
 extern "C" int tgt_gemm_tc_slices(int N, int K, int flags) {
   // number of column slices tgt_gemm_tc cuts N into (callers size the stat_partial workspace with it)
-  const int kblocks = (K + 63) / 64;
-  const int smem_budget = 232448 - 1024 - 2048 - 4096 - 256 - epi_stage_bytes(flags, epi_wq(flags));
-  int bn_max = 256;
-  while (bn_max > 16 && kblocks * bn_max * 128 + 3 * A_STAGE_BYTES > smem_budget) bn_max -= 16;
+  const int bn_max = gemm_bn_max((K + 63) / 64, flags);
   return (N + bn_max - 1) / bn_max;
 }
 

@@ -47,6 +47,20 @@ def test_gemm_strided_operands():
     assert out[:, :256].abs().max().item() == 0
 
 
+@pytest.mark.parametrize("M,N", [(1000, 72), (333, 200), (4097, 1608)])
+def test_gemm_bulk_store_epilogue_clips_to_the_output_window(M, N):
+    """The TMEM-domain epilogues leave through TMA bulk stores of 32 x 32 tiles (and vector stores for a slice's ragged
+    last column group): rows >= M and the columns on either side of the [M, N] window must stay untouched."""
+    ops = _ops()
+    K = 256
+    a, w = _rand((M, K), torch.bfloat16, 21), _rand((N, K), torch.bfloat16, 22, K ** -0.5)
+    bias = _rand((N,), torch.float32, 23)
+    big = torch.full((M + 40, N + 24), 7.0, dtype=torch.bfloat16, device="cuda")
+    ops.gemm_tc(a, w, bias=bias, out=big[:M, 8:8 + N])
+    _close(big[:M, 8:8 + N], a.float() @ w.float().t() + bias, 6e-3)
+    assert (big[:, :8] == 7).all() and (big[:, 8 + N:] == 7).all() and (big[M:] == 7).all()
+
+
 @pytest.mark.parametrize("W,N", [(256, 1600), (256, 128), (64, 256)])
 def test_gemm_layernorm_fold(W, N):
     ops = _ops()

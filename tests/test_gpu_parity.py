@@ -260,7 +260,8 @@ def test_padding_leak_of_aggregate_is_reproduced():
 def test_rowwise_kernels():
     torch.manual_seed(0)
     for W, xdt, ydt in [(256, torch.float32, torch.float32), (256, torch.bfloat16, torch.bfloat16),
-                        (768, torch.float32, torch.bfloat16), (36, torch.float32, torch.float32)]:
+                        (768, torch.float32, torch.bfloat16), (768, torch.bfloat16, torch.bfloat16),
+                        (36, torch.float32, torch.float32)]:
         x = torch.randn(1000, W, device=DEV).to(xdt)
         g = torch.rand(W, device=DEV) + 0.5
         b = torch.randn(W, device=DEV)
@@ -275,6 +276,11 @@ def test_rowwise_kernels():
         dx, dg, db = ops.layernorm_bwd(dy, x, g, mean, rstd)
         assert max_rel(dx.float(), xr.grad) < (1e-5 if xdt == torch.float32 else 2e-2)
         assert max_rel(dg, gr.grad) < 1e-4 and max_rel(db, br.grad) < 1e-4
+        if xdt == ydt:                                       # residual gradient folded in (node rows: ln_bwd_wide at W = 768)
+            dres = torch.randn(1000, W, device=DEV).to(xdt)
+            dx2, dg2, db2 = ops.layernorm_bwd(dy, x, g, mean, rstd, dres)
+            assert max_rel(dx2.float(), xr.grad + dres.float()) < (1e-5 if xdt == torch.float32 else 2e-2)
+            assert max_rel(dg2, gr.grad) < 1e-4 and max_rel(db2, br.grad) < 1e-4
     # LayerNorm backward that also emits the augmented y = [LN(x) | 1 | 0..] (tgt_layernorm_bwd_y, W = 256, 16-bit dy):
     # same dx / dgamma / dbeta as the plain call, y equal to the forward kernel's output for the same statistics
     for xdt in (torch.bfloat16, torch.float32):

@@ -401,6 +401,100 @@ ln_bwd_w256(const T *__restrict__ dy, const XT *__restrict__ x, const float *__r
   }
 }
 
+// ------------------------------------------------------------------ W = 256*NV (node rows, W = 768), 16-bit in/out
+// The node-side tensors have only B*N rows (16 K at config 3), far too few to hide the memory latency by occupancy: one
+// warp per row, NV 16-byte vectors of dy / x / dres per lane, and the NEXT row's vectors are requested before the current
+// row is reduced.  One persistent CTA per SM, so the per-CTA reduction of dgamma / dbeta (shared-memory atomics, then
+// 2*W global atomics) is paid 148 times, not once per 32 rows.
+template <typename T, int NV>
+__global__ void __launch_bounds__(256)
+ln_bwd_wide(const T *__restrict__ dy, const T *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ mean,
+            const float *__restrict__ rstd, const T *__restrict__ dres, T *__restrict__ dx, float *__restrict__ dgamma,
+            float *__restrict__ dbeta, int64_t rows) {
+  constexpr int W = 256 * NV;
+  __shared__ float sm[2 * W];
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int c = threadIdx.x; c < 2 * W; c += blockDim.x) sm[c] = 0.f;
+  __syncthreads();
+  float g[NV][8], ag[NV][8], ab[NV][8];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const float *gp = gamma + (v * 32 + lane) * 8;
+    const float4 g0 = *reinterpret_cast<const float4 *>(gp), g1 = *reinterpret_cast<const float4 *>(gp + 4);
+    g[v][0] = g0.x; g[v][1] = g0.y; g[v][2] = g0.z; g[v][3] = g0.w; g[v][4] = g1.x; g[v][5] = g1.y; g[v][6] = g1.z; g[v][7] = g1.w;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) ag[v][q] = ab[v][q] = 0.f;
+  }
+  uint4 nx[NV], nd[NV], nr[NV];
+  float nmu = 0.f, nrs = 0.f;
+  auto fetch = [&](int64_t r) {
+    if (r < rows) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int64_t o = r * W + (v * 32 + lane) * 8;
+        nx[v] = *reinterpret_cast<const uint4 *>(x + o);
+        nd[v] = *reinterpret_cast<const uint4 *>(dy + o);
+        if (dres) nr[v] = *reinterpret_cast<const uint4 *>(dres + o);
+      }
+      nmu = mean[r];
+      nrs = rstd[r];
+    }
+  };
+  fetch(warp0);
+  for (int64_t r = warp0; r < rows; r += nwarps) {
+    uint4 cx[NV], cd[NV], cr[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) { cx[v] = nx[v]; cd[v] = nd[v]; cr[v] = nr[v]; }
+    const float mu = nmu, rs = nrs;
+    fetch(r + nwarps);
+    float xh[NV][8], gd[NV][8], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      float dv[8];
+      V8<T>::unpack(cx[v], xh[v]);
+      V8<T>::unpack(cd[v], dv);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        xh[v][q] = (xh[v][q] - mu) * rs;
+        ag[v][q] += dv[q] * xh[v][q];
+        ab[v][q] += dv[q];
+        gd[v][q] = dv[q] * g[v][q];
+        s1 += gd[v][q];
+        s2 += gd[v][q] * xh[v][q];
+      }
+    }
+    s1 = warp_sum(s1) * (1.f / W);
+    s2 = warp_sum(s2) * (1.f / W);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      float o[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) o[q] = rs * (gd[v][q] - s1 - xh[v][q] * s2);
+      if (dres) {
+        float rv[8];
+        V8<T>::unpack(cr[v], rv);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) o[q] += rv[q];
+      }
+      V8<T>::store(dx + r * W + (v * 32 + lane) * 8, o);
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      atomicAdd(&sm[(v * 32 + lane) * 8 + q], ag[v][q]);
+      atomicAdd(&sm[W + (v * 32 + lane) * 8 + q], ab[v][q]);
+    }
+  __syncthreads();
+  for (int c = threadIdx.x; c < W; c += blockDim.x) {
+    atomicAdd(&dgamma[c], sm[c]);
+    atomicAdd(&dbeta[c], sm[W + c]);
+  }
+}
+
 // ------------------------------------------------------------------ gelu + dropout
 __device__ __forceinline__ float gelu_f(float u) { return 0.5f * u * (1.f + erff(u * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_grad(float u) {
@@ -660,6 +754,14 @@ static int ln_bwd_launch(const void *dy, const void *x, const float *gamma, cons
     }
   }
   if (y || dres_colsum) return fail("layernorm_bwd_y: only the W = 256, 16-bit gradient fast path can emit y / dres_colsum");
+  if constexpr (sizeof(YT) == 2 && std::is_same<XT, YT>::value) {
+    if (W == 768 && (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx | (uintptr_t)dres) & 15) == 0) {
+      const int g = (int)std::min<int64_t>((rows + 7) / 8, 148);
+      ln_bwd_wide<YT, 3><<<g, 256, 0, st>>>((const YT *)dy, (const YT *)x, gamma, mean, rstd, (const YT *)dres, (YT *)dx, dgamma,
+                                          dbeta, rows);
+      return check_launch("ln_bwd_wide");
+    }
+  }
   int g = grid_for(rows, 8 * 4);            // few rows per warp: node-side tensors have only B*N rows
   if (g > 148 * 4) g = 148 * 4;
   ln_bwd_kernel<XT, YT><<<g, 256, 2 * W * sizeof(float), st>>>((const YT *)dy, (const XT *)x, gamma, mean, rstd,

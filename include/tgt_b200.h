@@ -306,6 +306,18 @@ int tgt_gelu_dropout_fwd_dseed(const void *u, void *y, int64_t n, float p_drop,
 int tgt_scaled_residual(const void *x, const void *res, const float *scale, void *out,
                         int64_t B, int64_t inner, int dtype, int res_dtype, void *stream);
 
+/* ---- cross-entropy over distance bins ("next" row 8f-3: the loss end of the distance head) -------
+ * replaces F.cross_entropy(dist_logits, dist_targ, reduction='none') of DiscreteDistLoss
+ * (lib/training_schemes/pcqm/commons.py:26-48); the masked mean stays in the caller ([R] vectors).
+ * logits:[rows, nbins] (dtype, row pitch ld), target:[rows] int64 bin index; nbins % 8 == 0, <= 1024.
+ * fwd: xent[r] = lse_r - logits[r, target_r], lse[r] = log sum_c exp(logits[r, c])   (fp32)
+ * bwd: dlogits[r, c] = (exp(logits[r,c] - lse_r) - [c == target_r]) * gx[r]   (dense [rows, nbins], dtype);
+ *      rows with gx[r] == 0 (masked pairs) are written as zeros without being read.              */
+int tgt_xent_rows_fwd(const void *logits, int64_t ld, const int64_t *target, float *xent, float *lse,
+                      int64_t rows, int nbins, int dtype, void *stream);
+int tgt_xent_rows_bwd(const void *logits, int64_t ld, const int64_t *target, const float *lse,
+                      const float *gx, void *dlogits, int64_t rows, int nbins, int dtype, void *stream);
+
 /* ---- Gaussian basis of the 3-D distance embedding ("next" row 8f-3) ---------------------------
  * replaces the element-wise chain of lib/models/pcqm/layers.py:25-48 (GaussianLayer):
  * out[r,k] = exp(-0.5 ((x_r - mu_k)/sd_k)^2) / (sqrt(2*3.14159) sd_k),  x:[rows] f32, mu,sd:[K] f32,

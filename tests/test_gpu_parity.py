@@ -601,3 +601,26 @@ def test_cuda_graph_replay_of_mc_dropout_forward():
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
         mean_e = torch.stack([mc(batch).float() for _ in range(64)]).mean(0)
     assert float((mean_g - mean_e).abs().max()) < 0.35 * float(mean_e.abs().max() + 1.0)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("nbins,pitch", [(512, 512), (128, 128), (264, 272), (1024, 1024), (8, 16)])
+def test_cross_entropy_rows_matches_torch(dtype, nbins, pitch):
+    """DiscreteDistLoss's F.cross_entropy(..., reduction='none') (commons.py:38) and its gradient, incl. masked rows
+    (zero upstream gradient: written as zeros without being read) and a strided logits view."""
+    torch.manual_seed(3)
+    R = 3001
+    big = (torch.randn(R, pitch, device=DEV) * 3).to(dtype)
+    logits = big[:, :nbins].detach().requires_grad_(True)
+    target = torch.randint(0, nbins, (R,), device=DEV)
+    w = torch.rand(R, device=DEV) * (torch.rand(R, device=DEV) > 0.4)
+    assert ops.xent_rows_ok(logits, target)
+    x = ops.cross_entropy_rows(logits, target)
+    ref_in = big[:, :nbins].detach().float().requires_grad_(True)
+    xr = torch.nn.functional.cross_entropy(ref_in, target, reduction='none')
+    assert x.dtype == torch.float32 and max_rel(x, xr) < 2e-6
+    (x * w).sum().backward()
+    (xr * w).sum().backward()
+    tol = 1e-5 if dtype == torch.float32 else (1e-2 if dtype == torch.bfloat16 else 2e-3)
+    assert max_rel(logits.grad.float(), ref_in.grad) < tol
+    assert (logits.grad[w == 0] == 0).all()

@@ -159,3 +159,11 @@ def test_two_stage_oracle_helpers():
     assert abs(float(d[0, i, j]) - 2 * (float(b[0, i, j]) + 0.5) * 8.0 / 15) < 1e-6
     d2 = O.bins2dist(b, 16, 8.0, shift_half=False, zero_diag=False)
     assert abs(float(d2[0, 2, 2]) - 2 * float(b[0, 2, 2]) * 8.0 / 15) < 1e-6
+
+
+def test_cross_entropy_rows_falls_back_to_torch_off_gpu():
+    import torch
+    from tgt_b200 import ops
+    logits, target = torch.randn(7, 16), torch.randint(0, 16, (7,))
+    assert not ops.xent_rows_ok(logits, target)
+    assert torch.allclose(ops.cross_entropy_rows(logits, target), torch.nn.functional.cross_entropy(logits, target, reduction='none'))

@@ -110,6 +110,8 @@ _SIGNATURES = {
     "tgt_gaussian_basis_fwd": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, _P]),
     "tgt_gaussian_basis_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, _P]),
     "tgt_bins_decode": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, _P]),
+    "tgt_xent_rows_fwd": (C.c_int, [_P, C.c_int64, _P, _P, _P, C.c_int64, C.c_int, C.c_int, _P]),
+    "tgt_xent_rows_bwd": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, _P]),
     "tgt_scaled_residual": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int, C.c_int, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -495,6 +495,95 @@ ln_bwd_wide(const T *__restrict__ dy, const T *__restrict__ x, const float *__re
   }
 }
 
+// ------------------------------------------------------------------ cross-entropy over distance bins, one warp per row
+// F.cross_entropy(logits, target, reduction='none') of DiscreteDistLoss (training_schemes/pcqm/commons.py:26-48) on the
+// [R, nbins] logits of the distance head, R = B*N*N.  The torch path converts the 16-bit logits to fp32 (2 passes), keeps
+// fp32 log-probabilities for backward and runs log-softmax backward over them: 8 GB of traffic for 1 GB of logits.  Here
+// the forward reads the logits once (row max, log-sum-exp in fp32; xent and lse are [R] vectors) and the backward writes
+// d logits = (softmax - onehot) * g_r straight from the logits; rows whose upstream gradient is zero (masked pairs) are
+// neither read nor exponentiated.  NCH = nbins / 256 chunks of 8 columns per lane.
+template <typename T, int NCH>
+__global__ void __launch_bounds__(256)
+xent_rows_fwd(const T *__restrict__ logits, int64_t ld, const int64_t *__restrict__ target, float *__restrict__ xent,
+              float *__restrict__ lse, int64_t rows, int nbins) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = warp0; r < rows; r += nwarps) {
+    typename V8<T>::Raw raw[NCH];
+    const T *row = logits + r * ld;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+      if ((c * 32 + lane) * 8 < nbins) raw[c] = V8<T>::load(row + (c * 32 + lane) * 8);
+    const int64_t t = target[r];
+    float v[NCH][8], mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      if ((c * 32 + lane) * 8 < nbins) {
+        V8<T>::unpack(raw[c], v[c]);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) mx = fmaxf(mx, v[c][q]);
+      }
+    }
+    mx = warp_max(mx);
+    float sum = 0.f, at = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      if ((c * 32 + lane) * 8 < nbins) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          sum += __expf(v[c][q] - mx);
+          if ((c * 32 + lane) * 8 + q == t) at = v[c][q];
+        }
+      }
+    }
+    sum = warp_sum(sum);
+    at = warp_sum(at);                         // exactly one lane holds the target column
+    if (lane == 0) {
+      const float l = mx + __logf(sum);
+      lse[r] = l;
+      xent[r] = (t >= 0 && t < nbins) ? l - at : 0.f;
+    }
+  }
+}
+
+template <typename T, int NCH>
+__global__ void __launch_bounds__(256)
+xent_rows_bwd(const T *__restrict__ logits, int64_t ld, const int64_t *__restrict__ target, const float *__restrict__ lse,
+              const float *__restrict__ gx, T *__restrict__ dlogits, int64_t rows, int nbins) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = warp0; r < rows; r += nwarps) {
+    const float g = gx[r];
+    T *out = dlogits + r * (int64_t)nbins;
+    if (g == 0.f) {                            // masked pair: no read, no exp
+      const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < NCH; ++c)
+        if ((c * 32 + lane) * 8 < nbins) V8<T>::store(out + (c * 32 + lane) * 8, z);
+      continue;
+    }
+    typename V8<T>::Raw raw[NCH];
+    const T *row = logits + r * ld;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+      if ((c * 32 + lane) * 8 < nbins) raw[c] = V8<T>::load(row + (c * 32 + lane) * 8);
+    const int64_t t = target[r];
+    const float l = lse[r];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      if ((c * 32 + lane) * 8 < nbins) {
+        float v[8], o[8];
+        V8<T>::unpack(raw[c], v);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) o[q] = (__expf(v[q] - l) - ((c * 32 + lane) * 8 + q == t ? 1.f : 0.f)) * g;
+        V8<T>::store(out + (c * 32 + lane) * 8, o);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ gelu + dropout
 __device__ __forceinline__ float gelu_f(float u) { return 0.5f * u * (1.f + erff(u * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_grad(float u) {
@@ -877,6 +966,53 @@ extern "C" int tgt_scaled_residual(const void *x, const void *res, const float *
     return fail("scaled_residual: unsupported dtype combination %d/%d", dtype, res_dtype);
   }
   return check_launch("scaled_residual");
+}
+
+template <typename T>
+static int xent_launch(bool bwd, const void *logits, int64_t ld, const int64_t *target, float *xent, float *lse, const float *gx,
+                       void *dlogits, int64_t rows, int nbins, cudaStream_t st) {
+  const int nch = (nbins + 255) / 256;
+  const int g = grid_for(rows, 8 * 4);
+#define X(N)                                                                                                             \
+  do {                                                                                                                   \
+    if (bwd)                                                                                                             \
+      xent_rows_bwd<T, N><<<g, 256, 0, st>>>((const T *)logits, ld, target, lse, gx, (T *)dlogits, rows, nbins);           \
+    else                                                                                                                 \
+      xent_rows_fwd<T, N><<<g, 256, 0, st>>>((const T *)logits, ld, target, xent, lse, rows, nbins);                      \
+  } while (0)
+  switch (nch) {
+    case 1: X(1); break;
+    case 2: X(2); break;
+    case 3: X(3); break;
+    default: X(4); break;
+  }
+#undef X
+  return check_launch(bwd ? "xent_rows_bwd" : "xent_rows_fwd");
+}
+static int xent_check(const void *logits, int64_t ld, int64_t rows, int nbins) {
+  if (nbins <= 0 || nbins % 8 || nbins > 1024) return fail("xent_rows: nbins=%d must be a multiple of 8 and <= 1024", nbins);
+  if (ld % 8 || ld < nbins || (reinterpret_cast<uintptr_t>(logits) & 15)) return fail("xent_rows: logits rows must be 16-byte aligned");
+  (void)rows;
+  return 0;
+}
+extern "C" int tgt_xent_rows_fwd(const void *logits, int64_t ld, const int64_t *target, float *xent, float *lse, int64_t rows,
+                                 int nbins, int dtype, void *stream) {
+  if (rows <= 0) return 0;
+  if (!logits || !target || !xent || !lse) return fail("xent_rows_fwd: null argument");
+  if (int e = xent_check(logits, ld, rows, nbins)) return e;
+  TGT_DISPATCH_DTYPE(dtype, T, return xent_launch<T>(false, logits, ld, target, xent, lse, nullptr, nullptr, rows, nbins,
+                                                     (cudaStream_t)stream));
+  return 0;
+}
+extern "C" int tgt_xent_rows_bwd(const void *logits, int64_t ld, const int64_t *target, const float *lse, const float *gx,
+                                 void *dlogits, int64_t rows, int nbins, int dtype, void *stream) {
+  if (rows <= 0) return 0;
+  if (!logits || !target || !lse || !gx || !dlogits) return fail("xent_rows_bwd: null argument");
+  if (int e = xent_check(logits, ld, rows, nbins)) return e;
+  if (reinterpret_cast<uintptr_t>(dlogits) & 15) return fail("xent_rows_bwd: dlogits must be 16-byte aligned");
+  TGT_DISPATCH_DTYPE(dtype, T, return xent_launch<T>(true, logits, ld, target, nullptr, const_cast<float *>(lse), gx, dlogits,
+                                                     rows, nbins, (cudaStream_t)stream));
+  return 0;
 }
 
 extern "C" int tgt_gaussian_basis_fwd(const float *x, const float *mu, const float *sd, void *out, int64_t rows, int K,

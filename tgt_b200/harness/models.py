@@ -191,7 +191,7 @@ def pretrain_loss(gap, logits, batch, num_bins, range_bins=8.0, dist_loss_weight
     """L1(gap) + w * masked cross-entropy over distance bins (pretrain/scheme.py:78-88, commons.py:19-48)."""
     prim = F.l1_loss(gap, batch['target'].to(gap.dtype))
     tgt = (coords2dist(batch['dft_coords']) * ((num_bins - 1) / range_bins)).long().clamp(0, num_bins - 1)
-    xent = F.cross_entropy(logits.reshape(-1, num_bins), tgt.reshape(-1), reduction='none')
+    xent = ops.cross_entropy_rows(logits.reshape(-1, num_bins), tgt.reshape(-1))      # fp32 rows; one pass each way
     bsz = logits.size(0)
     m = batch['edge_mask'].to(xent.dtype).view(bsz, -1)
     dist = (xent.view(bsz, -1) * m).sum() / (m.sum() + 1e-9)

@@ -1247,6 +1247,54 @@ class GaussianBasisFn(Function):
 
 
 # ------------------------------------------------------------------------------------------
+# cross-entropy over distance bins (training_schemes/pcqm/commons.py:26-48): one read of the logits forward,
+# d logits straight from the logits backward
+# ------------------------------------------------------------------------------------------
+class XentRowsFn(Function):
+    """logits [R, nbins] (16-bit or fp32), target [R] int64  ->  xent [R] fp32 = F.cross_entropy(..., reduction='none')."""
+
+    @staticmethod
+    @_guarded
+    def forward(ctx, logits, target):
+        _require_cuda(logits, target)
+        R, nb = logits.shape
+        tg = target.contiguous()
+        xent = torch.empty(R, dtype=torch.float32, device=logits.device)
+        lse = torch.empty_like(xent)
+        with timed("xent_rows_fwd"):
+            _C.check(_C.lib().tgt_xent_rows_fwd(_C.ptr(logits), logits.stride(0), _C.ptr(tg), _C.ptr(xent), _C.ptr(lse), R, nb,
+                                                _C.dtype_code(logits.dtype), _C.stream_ptr()), "xent_rows_fwd")
+        ctx.save_for_backward(logits, tg, lse)
+        return xent
+
+    @staticmethod
+    @_guarded
+    def backward(ctx, gx):
+        logits, tg, lse = ctx.saved_tensors
+        R, nb = logits.shape
+        dl = torch.empty((R, nb), dtype=logits.dtype, device=logits.device)
+        with timed("xent_rows_bwd"):
+            _C.check(_C.lib().tgt_xent_rows_bwd(_C.ptr(logits), logits.stride(0), _C.ptr(tg), _C.ptr(lse), _C.ptr(_f32c(gx)),
+                                                _C.ptr(dl), R, nb, _C.dtype_code(logits.dtype), _C.stream_ptr()), "xent_rows_bwd")
+        return dl, None
+
+
+def xent_rows_ok(logits: Tensor, target: Tensor) -> bool:
+    return (logits.is_cuda and logits.dim() == 2 and target.dim() == 1 and target.dtype == torch.int64
+            and logits.dtype in (torch.float32, torch.bfloat16, torch.float16) and logits.shape[1] % 8 == 0
+            and logits.shape[1] <= 1024 and logits.stride(1) == 1 and logits.stride(0) % 8 == 0 and logits.data_ptr() % 16 == 0)
+
+
+def cross_entropy_rows(logits: Tensor, target: Tensor) -> Tensor:
+    """Drop-in for `F.cross_entropy(logits, target, reduction='none')` on the [R, num_bins] distance-bin logits
+    (DiscreteDistLoss, commons.py:38): fp32 row losses from logits of any supported dtype, no fp32 copy of the logits,
+    no saved log-probabilities.  Shapes / dtypes the kernels do not take (and CPU tensors) go to torch."""
+    if xent_rows_ok(logits, target):
+        return XentRowsFn.apply(logits, target)
+    return torch.nn.functional.cross_entropy(logits.float(), target, reduction='none')
+
+
+# ------------------------------------------------------------------------------------------
 # two-stage inference: logits -> symmetrised argmax bins -> distances, one kernel
 # (dist_pred/scheme.py:186-194 + commons.py:72-82)
 # ------------------------------------------------------------------------------------------

@@ -30,8 +30,16 @@ class _GaussianBasis(nn.Module):
         nn.init.constant_(self.mul.weight, 1)
 
     def forward(self, dist, types):
-        scale = self.mul(types).sum(dim=-2)
-        shift = self.bias(types).sum(dim=-2)
+        if isinstance(types, tuple):
+            # (row types [B,N], column types [B,N]) of the pair-type tensor types[b,i,j] = (row[b,i], col[b,j]): the two
+            # lookups per pair become two lookups per NODE plus a broadcast add -- same values, and the embedding
+            # backward sees B*N indices instead of sorting 2*B*N^2 of them
+            row, col = types
+            scale = (self.mul(row).unsqueeze(2) + self.mul(col).unsqueeze(1))
+            shift = (self.bias(row).unsqueeze(2) + self.bias(col).unsqueeze(1))
+        else:
+            scale = self.mul(types).sum(dim=-2)
+            shift = self.bias(types).sum(dim=-2)
         mu = self.means.weight.float().view(-1)
         sd = self.stds.weight.float().view(-1).abs() + 1e-2
         if dist.is_cuda and self.K % 4 == 0 and self.K <= 128:
@@ -62,7 +70,7 @@ class _Gaussian3D(nn.Module):
         self.gbf_proj = _TwoLayer(K, width)
 
     def forward(self, dist, types):
-        return self.gbf_proj(self.gbf(dist, types.long()))
+        return self.gbf_proj(self.gbf(dist, types if isinstance(types, tuple) else types.long()))
 
 
 class _EdgeEmbedFn(torch.autograd.Function):
@@ -113,11 +121,9 @@ class EmbedInput(nn.Module):
         hops = g.distance_matrix.long().clamp(max=self.upto_hop + 1)
         e = _EdgeEmbedFn.apply(hops, g.feature_matrix.long(), self.dist_embed.weight, self.featm_embed.weight)
         if self.uses_3d:
-            n = nf.size(1)
             a = nf[:, :, 0]
-            types = torch.stack([a.unsqueeze(2).expand(-1, -1, n),
-                                 (a + NODE_FEATURES_OFFSET).unsqueeze(1).expand(-1, n, -1)], dim=-1)
-            e = e + self.m3d_embed(g.dist_input, types)
+            # reference layers.py:74-77 stacks [a_i, a_j + offset] per pair; the factored form is passed instead
+            e = e + self.m3d_embed(g.dist_input, (a, a + NODE_FEATURES_OFFSET))
         em = g.edge_mask.unsqueeze(-1).to(e.dtype)
         g.h, g.e, g.mask = h, e, (1 - em) * torch.finfo(e.dtype).min
         return g

@@ -15,7 +15,7 @@ res = {}
 for N in (1600,):
     w = (torch.randn(N, 256, device="cuda") / 16).bfloat16()
     out = torch.empty(R, N, device="cuda", dtype=torch.bfloat16)
-    for d in (0, 7, 8, 9, 10, 11, 15):
+    for d in (0, 1, 2, 3, 4, 8, 9, 10, 11, 12, 15):
         os.environ["TGT_GEMM_DEBUG"] = str(d)
         res[f"N{N}_dbg{d}"] = timeit(lambda: ops.gemm_tc(a, w, out=out))
 print(json.dumps(res))

@@ -222,57 +222,73 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (q < p.ctas_per_slice) {
     if (warp == 0) {
       // ------------------------------------------------------------------ TMA producer
-      if (lane == 0) {
+      // The whole warp runs the loop (uniform control flow, addresses in uniform registers) and one elected lane issues:
+      // a `lane == 0` branch makes every operand a per-thread value that the compiler has to move to the uniform
+      // datapath with a vote loop around each TMA / MMA / commit instruction.
+      if (elect_one()) {
         mbar_expect_tx(bar_bfull, (uint32_t)p.kblocks * bn * 128);
         for (int kb = 0; kb < p.kblocks; ++kb) tma_load_2d(&tmB, bar_bfull, sB + kb * bn * 128, kb * 64, slice * bn);
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int64_t mt = q; mt < num_m_tiles; mt += p.ctas_per_slice) {
-          for (int kb = 0; kb < p.kblocks; ++kb) {
-            mbar_wait(bar_empty + stage * 8, phase ^ 1);
-            if (p.debug & 8) {
+      }
+      __syncwarp();
+      int stage = 0;
+      uint32_t phase = 0;
+      const bool no_loads = (p.debug & 8) != 0;
+      for (int64_t mt = q; mt < num_m_tiles; mt += p.ctas_per_slice) {
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(bar_empty + stage * 8, phase ^ 1);
+          if (elect_one()) {
+            if (no_loads) {
               mbar_arrive(bar_full + stage * 8);
             } else {
               mbar_expect_tx(bar_full + stage * 8, A_STAGE_BYTES);
               tma_load_2d(&tmA, bar_full + stage * 8, sA + stage * A_STAGE_BYTES, kb * 64, (int)(mt * 128));
             }
-            if (++stage == p.stages) {
-              stage = 0;
-              phase ^= 1;
-            }
+          }
+          __syncwarp();
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
           }
         }
       }
     } else if (warp == 1) {
-      // ------------------------------------------------------------------ MMA issuer (one thread)
-      if (lane == 0) {
-        const uint32_t idesc = umma_idesc<T>(bn);
-        mbar_wait(bar_bfull, 0);
-        int stage = 0, acc = 0;
-        uint32_t phase = 0, acc_phase = 0;
-        for (int64_t mt = q; mt < num_m_tiles; mt += p.ctas_per_slice) {
-          mbar_wait(bar_tempty + acc * 8, acc_phase ^ 1);
+      // ------------------------------------------------------------------ MMA issuer (one elected lane, see above)
+      // The issuing thread is the critical resource of small-K GEMMs: a 64-wide K block is 4 instructions of 120 tensor
+      // cycles each, so everything it does between two blocks (barrier poll, descriptors, commit) must stay well under
+      // 480 cycles.  Descriptors are built once per block and advanced by 2 (= 32 bytes >> 4) per K step.
+      const uint32_t idesc = umma_idesc<T>(bn);
+      const bool do_mma = !(p.debug & 2);
+      const int last_ksteps = (p.K - (p.kblocks - 1) * 64 + 15) / 16;      // K steps of the last (possibly partial) block
+      mbar_wait(bar_bfull, 0);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int64_t mt = q; mt < num_m_tiles; mt += p.ctas_per_slice) {
+        mbar_wait(bar_tempty + acc * 8, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * bn);
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(bar_full + stage * 8, phase);
           tc_fence_after();
-          const uint32_t tmem_d = tmem_base + (uint32_t)(acc * bn);
-          for (int kb = 0; kb < p.kblocks; ++kb) {
-            mbar_wait(bar_full + stage * 8, phase);
-            tc_fence_after();
-            const int ksteps = min(4, (p.K - kb * 64 + 15) / 16);
-            for (int k = 0; k < ksteps; ++k) {
-              const uint64_t ad = umma_desc_sw128(sA + stage * A_STAGE_BYTES + k * 32);
-              const uint64_t bd = umma_desc_sw128(sB + kb * bn * 128 + k * 32);
-              if (!(p.debug & 2)) tc_mma(tmem_d, ad, bd, idesc, (uint32_t)((kb | k) != 0));
+          if (elect_one()) {
+            const uint64_t ad = umma_desc_sw128(sA + stage * A_STAGE_BYTES), bd = umma_desc_sw128(sB + kb * bn * 128);
+            const int ksteps = kb + 1 < p.kblocks ? 4 : last_ksteps;
+            if (do_mma) {
+              tc_mma(tmem_d, ad, bd, idesc, (uint32_t)(kb != 0));
+              if (ksteps > 1) tc_mma(tmem_d, ad + 2, bd + 2, idesc, 1u);
+              if (ksteps > 2) tc_mma(tmem_d, ad + 4, bd + 4, idesc, 1u);
+              if (ksteps > 3) tc_mma(tmem_d, ad + 6, bd + 6, idesc, 1u);
             }
             tc_commit(bar_empty + stage * 8);
-            if (++stage == p.stages) {
-              stage = 0;
-              phase ^= 1;
-            }
+            if (kb + 1 == p.kblocks) tc_commit(bar_tfull + acc * 8);
           }
-          tc_commit(bar_tfull + acc * 8);
-          acc ^= 1;
-          if (acc == 0) acc_phase ^= 1;
+          __syncwarp();
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
       }
     } else {
       // ------------------------------------------------------------------ epilogue warps (TMEM lane quadrant = warp % 4)

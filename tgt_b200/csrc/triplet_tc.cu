@@ -62,7 +62,9 @@ tri_attn_fwd_tc(const tgt_triplet_attn_desc D, const __grid_constant__ CUtensorM
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int N = D.N, H = D.H;
   const int hp = blockIdx.x, dir = blockIdx.y, b = blockIdx.z;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // (warp index through a shuffle: provably warp-uniform, so the single-lane roles below keep their operands in uniform
+  //  registers and issue TMA / UMMA / commit without a vote loop around every instruction -- see gemm_tc.cu)
+  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const uint32_t bars = sbase + TCF_STAGES * TCF_STAGE_BYTES;
   const uint32_t bar_full = bars, bar_empty = bars + 8 * TCF_STAGES;
   const uint32_t bar_s = bars + 16 * TCF_STAGES, bar_p = bar_s + 16, bar_o = bar_s + 32;   // two barriers each
@@ -93,29 +95,33 @@ tri_attn_fwd_tc(const tgt_triplet_attn_desc D, const __grid_constant__ CUtensorM
 
   if (warp >= 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_CTRL));
-    if (warp == 4 && lane == 0) {
+    if (warp == 4) {
       // ------------------------------------------------------------------------------------------ TMA producer
+      // (the whole warp walks the loop, one elected lane issues)
       const int cq = D.off_q[dir] + hp * 2 * HD, ck = D.off_k[dir] + hp * 2 * HD, cv = D.off_v[dir] + hp * 2 * HD;
       for (int j = 0; j < N; ++j) {
         const int s = j % TCF_STAGES;
         mbar_wait(bar_empty + 8 * s, (uint32_t)(((j / TCF_STAGES) & 1) ^ 1));
         const uint32_t st = sbase + s * TCF_STAGE_BYTES, bar = bar_full + 8 * s;
-        mbar_expect_tx(bar, TCF_STAGE_BYTES);
-        tma_load_4d(&mC16, bar, st, cq, j, 0, b);                       // queries: column j of e, head 2hp
-        tma_load_4d(&mC16, bar, st + TCF_TILE, cq + HD, j, 0, b);       //                         head 2hp + 1
-        if (dir == 0) {                                                 // keys / values: row j of e
-          tma_load_4d(&mR16, bar, st + 2 * TCF_TILE, ck, 0, j, b);
-          tma_load_4d(&mR16, bar, st + 3 * TCF_TILE, ck + HD, 0, j, b);
-          tma_load_4d(&mR16, bar, st + 4 * TCF_TILE, cv, 0, j, b);
-          tma_load_4d(&mR16, bar, st + 5 * TCF_TILE, cv + HD, 0, j, b);
-        } else {                                                        // keys / values: column j of e
-          tma_load_4d(&mC16, bar, st + 2 * TCF_TILE, ck, j, 0, b);
-          tma_load_4d(&mC16, bar, st + 3 * TCF_TILE, ck + HD, j, 0, b);
-          tma_load_4d(&mC16, bar, st + 4 * TCF_TILE, cv, j, 0, b);
-          tma_load_4d(&mC16, bar, st + 5 * TCF_TILE, cv + HD, j, 0, b);
+        if (elect_one()) {
+          mbar_expect_tx(bar, TCF_STAGE_BYTES);
+          tma_load_4d(&mC16, bar, st, cq, j, 0, b);                       // queries: column j of e, head 2hp
+          tma_load_4d(&mC16, bar, st + TCF_TILE, cq + HD, j, 0, b);       //                         head 2hp + 1
+          if (dir == 0) {                                                 // keys / values: row j of e
+            tma_load_4d(&mR16, bar, st + 2 * TCF_TILE, ck, 0, j, b);
+            tma_load_4d(&mR16, bar, st + 3 * TCF_TILE, ck + HD, 0, j, b);
+            tma_load_4d(&mR16, bar, st + 4 * TCF_TILE, cv, 0, j, b);
+            tma_load_4d(&mR16, bar, st + 5 * TCF_TILE, cv + HD, 0, j, b);
+          } else {                                                        // keys / values: column j of e
+            tma_load_4d(&mC16, bar, st + 2 * TCF_TILE, ck, j, 0, b);
+            tma_load_4d(&mC16, bar, st + 3 * TCF_TILE, ck + HD, j, 0, b);
+            tma_load_4d(&mC16, bar, st + 4 * TCF_TILE, cv, j, 0, b);
+            tma_load_4d(&mC16, bar, st + 5 * TCF_TILE, cv + HD, j, 0, b);
+          }
         }
+        __syncwarp();
       }
-    } else if (warp == 5 && lane == 0) {
+    } else if (warp == 5) {
       // ------------------------------------------------------------------------------------------ MMA issuer
       const uint32_t idesc_s = umma_idesc_f16<T>(64, 64, false, false);
       const uint32_t idesc_o = umma_idesc_f16<T>(64, 16, false, true);
@@ -125,11 +131,14 @@ tri_attn_fwd_tc(const tgt_triplet_attn_desc D, const __grid_constant__ CUtensorM
         tc_fence_after();
         const uint32_t st = sbase + s * TCF_STAGE_BYTES;
         const uint32_t tS = tmem + TCF_COL_S + (uint32_t)(j & 1) * 64u;
+        if (elect_one()) {
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh)                  // 64 rows x 32 B, 8-row groups 256 B apart
-          tc_mma(tS + hh * TC_LANE16, umma_smem_desc(st + hh * TCF_TILE, 256, 16, UMMA_SW32),
-                 umma_smem_desc(st + (2 + hh) * TCF_TILE, 256, 16, UMMA_SW32), idesc_s, 0u);
-        tc_commit(bar_s + 8 * (j & 1));
+          for (int hh = 0; hh < 2; ++hh)                  // 64 rows x 32 B, 8-row groups 256 B apart
+            tc_mma(tS + hh * TC_LANE16, umma_smem_desc(st + hh * TCF_TILE, 256, 16, UMMA_SW32),
+                   umma_smem_desc(st + (2 + hh) * TCF_TILE, 256, 16, UMMA_SW32), idesc_s, 0u);
+          tc_commit(bar_s + 8 * (j & 1));
+        }
+        __syncwarp();
       };
       issue_s(0);
       if (N > 1) issue_s(1);
@@ -138,14 +147,18 @@ tri_attn_fwd_tc(const tgt_triplet_attn_desc D, const __grid_constant__ CUtensorM
         tc_fence_after();
         const uint32_t sV = sbase + (j % TCF_STAGES) * TCF_STAGE_BYTES + 4 * TCF_TILE;
         const uint32_t tO = tmem + TCF_COL_O + (uint32_t)(j & 1) * 16u, tP = tmem + TCF_COL_P + (uint32_t)(j & 1) * 32u;
+        if (elect_one()) {
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh)
+          for (int hh = 0; hh < 2; ++hh) {
+            const uint64_t vd = umma_smem_desc(sV + hh * TCF_TILE, 256, 16, UMMA_SW32);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)                // 16 keys per step: 8 packed columns of P, two 8-row groups of V
-            tc_mma_ts(tO + hh * TC_LANE16, tP + hh * TC_LANE16 + 8u * ks,
-                      umma_smem_desc(sV + hh * TCF_TILE + ks * 512, 256, 16, UMMA_SW32), idesc_o, (uint32_t)(ks != 0));
-        tc_commit(bar_o + 8 * (j & 1));                 // O(j) complete
-        tc_commit(bar_empty + 8 * (j % TCF_STAGES));    // ... and stage j's tiles are no longer read
+            for (int ks = 0; ks < 4; ++ks)              // 16 keys per step: 8 packed columns of P, two 8-row groups of V (+512 B)
+              tc_mma_ts(tO + hh * TC_LANE16, tP + hh * TC_LANE16 + 8u * ks, vd + (uint64_t)(ks * 32), idesc_o, (uint32_t)(ks != 0));
+          }
+          tc_commit(bar_o + 8 * (j & 1));               // O(j) complete
+          tc_commit(bar_empty + 8 * (j % TCF_STAGES));  // ... and stage j's tiles are no longer read
+        }
+        __syncwarp();
         if (j + 2 < N) issue_s(j + 2);                  // its S buffer was read before P(j) was announced
       }
     }
@@ -395,7 +408,7 @@ tri_attn_bwd_tc(const tgt_triplet_attn_desc D, const __grid_constant__ CUtensorM
   extern __shared__ unsigned char smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int N = D.N, H = D.H;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform
   const int total_items = D.B * 2 * H;
   const uint32_t bars = sbase + 2 * TCB_WG_BYTES;
   const uint32_t tmem_slot = bars + 288;
@@ -513,15 +526,20 @@ tri_attn_bwd_tc(const tgt_triplet_attn_desc D, const __grid_constant__ CUtensorM
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TCB_REGS_CTRL));
     const int w = warp & 1;                                  // the compute warpgroup this control warp serves
     const uint32_t wg_smem = sbase + w * TCB_WG_BYTES;
-    if (warp < 10 && lane == 0) {
+    if (warp < 10) {
       // ------------------------------------------------------------------------------------------ TMA producer
-      int n = 0, t_next = atomicAdd(item_counter, 1);
+      // (the whole warp walks the loops with warp-uniform values; lane 0 draws the work items, one elected lane issues)
+      auto draw = [&]() { return __shfl_sync(0xffffffffu, lane == 0 ? atomicAdd(item_counter, 1) : 0, 0); };
+      int n = 0, t_next = draw();
       for (int k = 0;; ++k) {
         const int t = t_next < total_items ? t_next : -1;
-        *q_item(w, k) = t;
-        mbar_arrive(q_full(w, k));                           // release: the id is visible to whoever waits on the slot
+        if (elect_one()) {
+          *q_item(w, k) = t;
+          mbar_arrive(q_full(w, k));                         // release: the id is visible to whoever waits on the slot
+        }
+        __syncwarp();
         if (t < 0) break;
-        t_next = atomicAdd(item_counter, 1);                 // next id: its latency hides behind this item's loads
+        t_next = draw();                                     // next id: its latency hides behind this item's loads
         const int b = t / (2 * H), r = t - b * 2 * H, dir = r / H, h = r - dir * H;
         const int cq = (dir ? oq1 : oq0) + h * HD, ck = (dir ? ok1 : ok0) + h * HD, cv = (dir ? ov1 : ov0) + h * HD;
         const int co = dir * H * HD + h * HD;
@@ -529,20 +547,23 @@ tri_attn_bwd_tc(const tgt_triplet_attn_desc D, const __grid_constant__ CUtensorM
           const int s = n % TCB_STAGES;
           mbar_wait_polite(bar_empty(w, s), (uint32_t)(((n / TCB_STAGES) & 1) ^ 1));
           const uint32_t st = wg_smem + s * TCB_STAGE_BYTES, bar = bar_full(w, s);
-          mbar_expect_tx(bar, TCB_STAGE_BYTES);
-          tma_load_4d(&mPcol, bar, st, cq, j, 0, b);
-          if (dir == 0) {
-            tma_load_4d(&mProw, bar, st + TCF_TILE, ck, 0, j, b);
-            tma_load_4d(&mProw, bar, st + 2 * TCF_TILE, cv, 0, j, b);
-          } else {
-            tma_load_4d(&mPcol, bar, st + TCF_TILE, ck, j, 0, b);
-            tma_load_4d(&mPcol, bar, st + 2 * TCF_TILE, cv, j, 0, b);
+          if (elect_one()) {
+            mbar_expect_tx(bar, TCB_STAGE_BYTES);
+            tma_load_4d(&mPcol, bar, st, cq, j, 0, b);
+            if (dir == 0) {
+              tma_load_4d(&mProw, bar, st + TCF_TILE, ck, 0, j, b);
+              tma_load_4d(&mProw, bar, st + 2 * TCF_TILE, cv, 0, j, b);
+            } else {
+              tma_load_4d(&mPcol, bar, st + TCF_TILE, ck, j, 0, b);
+              tma_load_4d(&mPcol, bar, st + 2 * TCF_TILE, cv, j, 0, b);
+            }
+            tma_load_4d(&mDVA, bar, st + 3 * TCF_TILE, co, j, 0, b);
+            tma_load_4d(&mVA, bar, st + 4 * TCF_TILE, co, j, 0, b);
           }
-          tma_load_4d(&mDVA, bar, st + 3 * TCF_TILE, co, j, 0, b);
-          tma_load_4d(&mVA, bar, st + 4 * TCF_TILE, co, j, 0, b);
+          __syncwarp();
         }
       }
-    } else if (warp >= 10 && lane == 0) {
+    } else if (warp >= 10) {
       // ------------------------------------------------------------------------------------------ MMA issuer
       const uint32_t tw = tmem + (uint32_t)w * TCB_COLS_WG;
       const uint32_t sX16 = (wg_smem + TCB_STAGES * TCB_STAGE_BYTES) >> 4;       // [buf][dS | A], address >> 4
@@ -564,12 +585,15 @@ tri_attn_bwd_tc(const tgt_triplet_attn_desc D, const __grid_constant__ CUtensorM
         const uint32_t st16 = (wg_smem + s * TCB_STAGE_BYTES) >> 4;
         const uint32_t tSA = tw + (uint32_t)(ns & 1) * 64u;
         const uint64_t dQ_ = umma_desc_at(st16, 0, HI32), dO_ = umma_desc_at(st16, 3 * TCF_TILE, HI32);
+        if (elect_one()) {
 #pragma unroll
-        for (int kh = 0; kh < 2; ++kh) {                     // keys 32 kh .. 32 kh + 31 -> lane offset 16 kh
-          tc_mma(tSA + kh * TC_LANE16, dQ_, umma_desc_at(st16, TCF_TILE + kh * 1024, HI32), id_sa, 0u);
-          tc_mma(tSA + 32u + kh * TC_LANE16, dO_, umma_desc_at(st16, 2 * TCF_TILE + kh * 1024, HI32), id_sa, 0u);
+          for (int kh = 0; kh < 2; ++kh) {                   // keys 32 kh .. 32 kh + 31 -> lane offset 16 kh
+            tc_mma(tSA + kh * TC_LANE16, dQ_, umma_desc_at(st16, TCF_TILE + kh * 1024, HI32), id_sa, 0u);
+            tc_mma(tSA + 32u + kh * TC_LANE16, dO_, umma_desc_at(st16, 2 * TCF_TILE + kh * 1024, HI32), id_sa, 0u);
+          }
+          tc_commit(bar_s(w, ns & 1));
         }
-        tc_commit(bar_s(w, ns & 1));
+        __syncwarp();
         ++ns;
         if (++js == N) { js = 0; ++ks; }
       };
@@ -582,6 +606,7 @@ tri_attn_bwd_tc(const tgt_triplet_attn_desc D, const __grid_constant__ CUtensorM
         const uint32_t st16 = (wg_smem + (n % TCB_STAGES) * TCB_STAGE_BYTES) >> 4;
         const uint32_t dS16 = sX16 + (uint32_t)(n & 1) * (2 * TCB_XT >> 4), a16 = dS16 + (TCB_XT >> 4);
         const uint32_t tOut = tw + TCB_COL_OUT + (uint32_t)(n & 1) * 32u;
+        if (elect_one()) {
 #pragma unroll
         for (int ks_ = 0; ks_ < 4; ++ks_) {
           // dQ[i, d] += dS[i, 16ks..] K[16ks.., d]        A: dS K-major (32 B per step), B: K tile MN-major
@@ -596,6 +621,8 @@ tri_attn_bwd_tc(const tgt_triplet_attn_desc D, const __grid_constant__ CUtensorM
         }
         tc_commit(bar_o(w, n & 1));
         tc_commit(bar_empty(w, n % TCB_STAGES));
+        }
+        __syncwarp();
         try_issue_sa();
       }
     }

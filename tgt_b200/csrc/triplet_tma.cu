@@ -205,7 +205,8 @@ tri_attn_bwd_tma_pipe(const tgt_triplet_attn_desc D, const __grid_constant__ CUt
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int N = D.N, H = D.H;
   const int h = blockIdx.x, dir = blockIdx.y, b = blockIdx.z;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // (warp index through a shuffle: warp-uniform, so the elected lane of warp 0 issues TMA with uniform-register operands)
+  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int g = lane >> 2, q = lane & 3;
   const int m0 = warp * 16;
   const uint32_t xbase = sbase + TP_STAGES * TB_STAGE_BYTES;
@@ -289,9 +290,12 @@ tri_attn_bwd_tma_pipe(const tgt_triplet_attn_desc D, const __grid_constant__ CUt
   };
 
   __syncthreads();
-  if (tid == 0) {
-    issue(0);
-    issue(1);
+  if (warp == 0) {
+    if (elect_one()) {
+      issue(0);
+      issue(1);
+    }
+    __syncwarp();
   }
   float sa0, sa1, sb0, sb1;                  // lse of the next two junctions (fetched two iterations ahead)
   load_stats(0, sa0, sa1);
@@ -305,9 +309,12 @@ tri_attn_bwd_tma_pipe(const tgt_triplet_attn_desc D, const __grid_constant__ CUt
   // from "exchange tiles read" (the exchange and staging tiles are double-buffered), and each warp has two independent
   // instruction streams between barriers.
   for (int it = 0; it <= N; ++it) {
-    if (tid == 0) {
-      issue(it + 2);                                   // slot of junction it-2: its key pass ended before the last barrier
-      if (it > 0) store_group(it - 1);
+    if (warp == 0) {
+      if (elect_one()) {
+        issue(it + 2);                                 // slot of junction it-2: its key pass ended before the last barrier
+        if (it > 0) store_group(it - 1);
+      }
+      __syncwarp();
     }
     const uint32_t sOut = sOut0 + (it & 1) * 3 * TILE_BYTES;
     if (it > 0) {
@@ -456,12 +463,18 @@ tri_attn_bwd_tma_pipe(const tgt_triplet_attn_desc D, const __grid_constant__ CUt
 
     }
     fence_proxy_async();
-    if (tid == 0) tma_store_wait_read();               // the group issued at the top of this iteration has left its buffer
+    if (warp == 0) {
+      if (elect_one()) tma_store_wait_read();          // the group issued at the top of this iteration has left its buffer
+      __syncwarp();
+    }
     __syncthreads();
   }
-  if (tid == 0) {
-    store_group(N);
-    tma_store_wait_all();
+  if (warp == 0) {
+    if (elect_one()) {
+      store_group(N);
+      tma_store_wait_all();
+    }
+    __syncwarp();
   }
   // dE = sum_j dS ; dG = g (1 - g) sum_j dA P
 #pragma unroll

@@ -33,7 +33,7 @@ tri_attn_fwd_tma(const tgt_triplet_attn_desc D, const __grid_constant__ CUtensor
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int N = D.N, H = D.H;
   const int h = blockIdx.x, dir = blockIdx.y, b = blockIdx.z;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform
   const int g = lane >> 2, q = lane & 3;
   const int m0 = warp * 16;
   const uint32_t sOut = sbase + TF_STAGES * TF_STAGE_BYTES;
@@ -82,21 +82,30 @@ tri_attn_fwd_tma(const tgt_triplet_attn_desc D, const __grid_constant__ CUtensor
     }
   };
   __syncthreads();
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < TF_STAGES - 1; ++s) issue(s);
+  if (warp == 0) {
+    if (elect_one()) {
+  #pragma unroll
+      for (int s = 0; s < TF_STAGES - 1; ++s) issue(s);
+    }
+    __syncwarp();
   }
 
   for (int j = 0; j < N; ++j) {
-    if (tid == 0) tma_store_wait_read();            // the output tile written two iterations ago has left smem
+    if (warp == 0) {            // the output tile written two iterations ago has left smem
+      if (elect_one()) tma_store_wait_read();
+      __syncwarp();
+    }
     mbar_wait(bar_full + (j % TF_STAGES) * 8, (uint32_t)((j / TF_STAGES) & 1));
     __syncthreads();                                // stage j landed; everyone is done with iteration j-1
-    if (tid == 0) {
-      issue(j + TF_STAGES - 1);
-      if (j > 0) {
-        tma_store_4d(&mVA, sOut + ((j - 1) & 1) * TILE_BYTES, co, j - 1, 0, b);
-        tma_store_commit();
+    if (warp == 0) {
+      if (elect_one()) {
+        issue(j + TF_STAGES - 1);
+        if (j > 0) {
+          tma_store_4d(&mVA, sOut + ((j - 1) & 1) * TILE_BYTES, co, j - 1, 0, b);
+          tma_store_commit();
+        }
       }
+      __syncwarp();
     }
     const uint32_t st = sbase + (j % TF_STAGES) * TF_STAGE_BYTES;
     const uint32_t sQ = st, sK = st + TILE_BYTES, sV = st + 2 * TILE_BYTES;
@@ -172,10 +181,13 @@ tri_attn_fwd_tma(const tgt_triplet_attn_desc D, const __grid_constant__ CUtensor
     }
   }
   __syncthreads();
-  if (tid == 0) {
-    tma_store_4d(&mVA, sOut + ((N - 1) & 1) * TILE_BYTES, co, N - 1, 0, b);
-    tma_store_commit();
-    tma_store_wait_all();
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_store_4d(&mVA, sOut + ((N - 1) & 1) * TILE_BYTES, co, N - 1, 0, b);
+      tma_store_commit();
+      tma_store_wait_all();
+    }
+    __syncwarp();
   }
 }
 
@@ -629,7 +641,7 @@ tri_aggr_fwd_tma(const tgt_triplet_aggr_desc D, const __grid_constant__ CUtensor
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int N = D.N, H = D.H;
   const int h = blockIdx.x, dir = blockIdx.y, b = blockIdx.z;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform
   const int g = lane >> 2, q = lane & 3;
   const int m0 = warp * 16;
   const uint32_t sOut = sbase + TA_STAGES * TILE_BYTES;
@@ -653,20 +665,29 @@ tri_aggr_fwd_tma(const tgt_triplet_aggr_desc D, const __grid_constant__ CUtensor
     }
   };
   __syncthreads();
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < TA_STAGES - 1; ++s) issue(s);
+  if (warp == 0) {
+    if (elect_one()) {
+  #pragma unroll
+      for (int s = 0; s < TA_STAGES - 1; ++s) issue(s);
+    }
+    __syncwarp();
   }
   for (int j = 0; j < N; ++j) {
-    if (tid == 0) tma_store_wait_read();            // the output tile written two iterations ago has left smem
+    if (warp == 0) {            // the output tile written two iterations ago has left smem
+      if (elect_one()) tma_store_wait_read();
+      __syncwarp();
+    }
     mbar_wait(bar_full + (j % TA_STAGES) * 8, (uint32_t)((j / TA_STAGES) & 1));
     __syncthreads();                                // stage j landed; everyone is done with iteration j-1
-    if (tid == 0) {
-      issue(j + TA_STAGES - 1);
-      if (j > 0) {
-        tma_store_4d(&mVA, sOut + ((j - 1) & 1) * TILE_BYTES, co, j - 1, 0, b);
-        tma_store_commit();
+    if (warp == 0) {
+      if (elect_one()) {
+        issue(j + TA_STAGES - 1);
+        if (j > 0) {
+          tma_store_4d(&mVA, sOut + ((j - 1) & 1) * TILE_BYTES, co, j - 1, 0, b);
+          tma_store_commit();
+        }
       }
+      __syncwarp();
     }
     const uint32_t sV = sbase + (j % TA_STAGES) * TILE_BYTES;
     float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
@@ -681,10 +702,13 @@ tri_aggr_fwd_tma(const tgt_triplet_aggr_desc D, const __grid_constant__ CUtensor
     fence_proxy_async();
   }
   __syncthreads();
-  if (tid == 0) {
-    tma_store_4d(&mVA, sOut + ((N - 1) & 1) * TILE_BYTES, co, N - 1, 0, b);
-    tma_store_commit();
-    tma_store_wait_all();
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_store_4d(&mVA, sOut + ((N - 1) & 1) * TILE_BYTES, co, N - 1, 0, b);
+      tma_store_commit();
+      tma_store_wait_all();
+    }
+    __syncwarp();
   }
 }
 
@@ -702,7 +726,7 @@ tri_aggr_bwd_tma(const tgt_triplet_aggr_desc D, const __grid_constant__ CUtensor
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int N = D.N, H = D.H;
   const int h = blockIdx.x, dir = blockIdx.y, b = blockIdx.z;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform
   const int g = lane >> 2, q = lane & 3;
   const int m0 = warp * 16;
   const uint32_t sOut = sbase + TAB_STAGES * TAB_STAGE_BYTES;
@@ -738,17 +762,26 @@ tri_aggr_bwd_tma(const tgt_triplet_aggr_desc D, const __grid_constant__ CUtensor
     tma_store_commit();
   };
   __syncthreads();
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < TAB_STAGES - 1; ++s) issue(s);
+  if (warp == 0) {
+    if (elect_one()) {
+  #pragma unroll
+      for (int s = 0; s < TAB_STAGES - 1; ++s) issue(s);
+    }
+    __syncwarp();
   }
   for (int j = 0; j < N; ++j) {
-    if (tid == 0) tma_store_wait_read();
+    if (warp == 0) {
+      if (elect_one()) tma_store_wait_read();
+      __syncwarp();
+    }
     mbar_wait(bar_full + (j % TAB_STAGES) * 8, (uint32_t)((j / TAB_STAGES) & 1));
     __syncthreads();
-    if (tid == 0) {
-      issue(j + TAB_STAGES - 1);
-      if (j > 0) store_dv(j - 1);
+    if (warp == 0) {
+      if (elect_one()) {
+        issue(j + TAB_STAGES - 1);
+        if (j > 0) store_dv(j - 1);
+      }
+      __syncwarp();
     }
     const uint32_t sV = sbase + (j % TAB_STAGES) * TAB_STAGE_BYTES, sO = sV + TILE_BYTES;
     // dA += dO_j V_j^T   (rows of this warp x all 64 keys)
@@ -774,9 +807,12 @@ tri_aggr_bwd_tma(const tgt_triplet_aggr_desc D, const __grid_constant__ CUtensor
     fence_proxy_async();
   }
   __syncthreads();
-  if (tid == 0) {
-    store_dv(N - 1);
-    tma_store_wait_all();
+  if (warp == 0) {
+    if (elect_one()) {
+      store_dv(N - 1);
+      tma_store_wait_all();
+    }
+    __syncwarp();
   }
   float *o = daw + abase;
 #pragma unroll

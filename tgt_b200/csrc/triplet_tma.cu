@@ -33,7 +33,7 @@ tri_attn_fwd_tma(const tgt_triplet_attn_desc D, const __grid_constant__ CUtensor
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int N = D.N, H = D.H;
   const int h = blockIdx.x, dir = blockIdx.y, b = blockIdx.z;
-  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, q = lane & 3;
   const int m0 = warp * 16;
   const uint32_t sOut = sbase + TF_STAGES * TF_STAGE_BYTES;
@@ -82,30 +82,21 @@ tri_attn_fwd_tma(const tgt_triplet_attn_desc D, const __grid_constant__ CUtensor
     }
   };
   __syncthreads();
-  if (warp == 0) {
-    if (elect_one()) {
-  #pragma unroll
-      for (int s = 0; s < TF_STAGES - 1; ++s) issue(s);
-    }
-    __syncwarp();
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < TF_STAGES - 1; ++s) issue(s);
   }
 
   for (int j = 0; j < N; ++j) {
-    if (warp == 0) {            // the output tile written two iterations ago has left smem
-      if (elect_one()) tma_store_wait_read();
-      __syncwarp();
-    }
+    if (tid == 0) tma_store_wait_read();            // the output tile written two iterations ago has left smem
     mbar_wait(bar_full + (j % TF_STAGES) * 8, (uint32_t)((j / TF_STAGES) & 1));
     __syncthreads();                                // stage j landed; everyone is done with iteration j-1
-    if (warp == 0) {
-      if (elect_one()) {
-        issue(j + TF_STAGES - 1);
-        if (j > 0) {
-          tma_store_4d(&mVA, sOut + ((j - 1) & 1) * TILE_BYTES, co, j - 1, 0, b);
-          tma_store_commit();
-        }
+    if (tid == 0) {
+      issue(j + TF_STAGES - 1);
+      if (j > 0) {
+        tma_store_4d(&mVA, sOut + ((j - 1) & 1) * TILE_BYTES, co, j - 1, 0, b);
+        tma_store_commit();
       }
-      __syncwarp();
     }
     const uint32_t st = sbase + (j % TF_STAGES) * TF_STAGE_BYTES;
     const uint32_t sQ = st, sK = st + TILE_BYTES, sV = st + 2 * TILE_BYTES;
@@ -181,13 +172,10 @@ tri_attn_fwd_tma(const tgt_triplet_attn_desc D, const __grid_constant__ CUtensor
     }
   }
   __syncthreads();
-  if (warp == 0) {
-    if (elect_one()) {
-      tma_store_4d(&mVA, sOut + ((N - 1) & 1) * TILE_BYTES, co, N - 1, 0, b);
-      tma_store_commit();
-      tma_store_wait_all();
-    }
-    __syncwarp();
+  if (tid == 0) {
+    tma_store_4d(&mVA, sOut + ((N - 1) & 1) * TILE_BYTES, co, N - 1, 0, b);
+    tma_store_commit();
+    tma_store_wait_all();
   }
 }
 
@@ -217,8 +205,7 @@ tri_attn_bwd_tma_pipe(const tgt_triplet_attn_desc D, const __grid_constant__ CUt
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int N = D.N, H = D.H;
   const int h = blockIdx.x, dir = blockIdx.y, b = blockIdx.z;
-  // (warp index through a shuffle: warp-uniform, so the elected lane of warp 0 issues TMA with uniform-register operands)
-  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, q = lane & 3;
   const int m0 = warp * 16;
   const uint32_t xbase = sbase + TP_STAGES * TB_STAGE_BYTES;
@@ -302,12 +289,9 @@ tri_attn_bwd_tma_pipe(const tgt_triplet_attn_desc D, const __grid_constant__ CUt
   };
 
   __syncthreads();
-  if (warp == 0) {
-    if (elect_one()) {
-      issue(0);
-      issue(1);
-    }
-    __syncwarp();
+  if (tid == 0) {
+    issue(0);
+    issue(1);
   }
   float sa0, sa1, sb0, sb1;                  // lse of the next two junctions (fetched two iterations ahead)
   load_stats(0, sa0, sa1);
@@ -321,12 +305,9 @@ tri_attn_bwd_tma_pipe(const tgt_triplet_attn_desc D, const __grid_constant__ CUt
   // from "exchange tiles read" (the exchange and staging tiles are double-buffered), and each warp has two independent
   // instruction streams between barriers.
   for (int it = 0; it <= N; ++it) {
-    if (warp == 0) {
-      if (elect_one()) {
-        issue(it + 2);                                 // slot of junction it-2: its key pass ended before the last barrier
-        if (it > 0) store_group(it - 1);
-      }
-      __syncwarp();
+    if (tid == 0) {
+      issue(it + 2);                                   // slot of junction it-2: its key pass ended before the last barrier
+      if (it > 0) store_group(it - 1);
     }
     const uint32_t sOut = sOut0 + (it & 1) * 3 * TILE_BYTES;
     if (it > 0) {
@@ -475,18 +456,12 @@ tri_attn_bwd_tma_pipe(const tgt_triplet_attn_desc D, const __grid_constant__ CUt
 
     }
     fence_proxy_async();
-    if (warp == 0) {
-      if (elect_one()) tma_store_wait_read();          // the group issued at the top of this iteration has left its buffer
-      __syncwarp();
-    }
+    if (tid == 0) tma_store_wait_read();               // the group issued at the top of this iteration has left its buffer
     __syncthreads();
   }
-  if (warp == 0) {
-    if (elect_one()) {
-      store_group(N);
-      tma_store_wait_all();
-    }
-    __syncwarp();
+  if (tid == 0) {
+    store_group(N);
+    tma_store_wait_all();
   }
   // dE = sum_j dS ; dG = g (1 - g) sum_j dA P
 #pragma unroll
@@ -641,7 +616,7 @@ tri_aggr_fwd_tma(const tgt_triplet_aggr_desc D, const __grid_constant__ CUtensor
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int N = D.N, H = D.H;
   const int h = blockIdx.x, dir = blockIdx.y, b = blockIdx.z;
-  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, q = lane & 3;
   const int m0 = warp * 16;
   const uint32_t sOut = sbase + TA_STAGES * TILE_BYTES;
@@ -665,29 +640,20 @@ tri_aggr_fwd_tma(const tgt_triplet_aggr_desc D, const __grid_constant__ CUtensor
     }
   };
   __syncthreads();
-  if (warp == 0) {
-    if (elect_one()) {
-  #pragma unroll
-      for (int s = 0; s < TA_STAGES - 1; ++s) issue(s);
-    }
-    __syncwarp();
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < TA_STAGES - 1; ++s) issue(s);
   }
   for (int j = 0; j < N; ++j) {
-    if (warp == 0) {            // the output tile written two iterations ago has left smem
-      if (elect_one()) tma_store_wait_read();
-      __syncwarp();
-    }
+    if (tid == 0) tma_store_wait_read();            // the output tile written two iterations ago has left smem
     mbar_wait(bar_full + (j % TA_STAGES) * 8, (uint32_t)((j / TA_STAGES) & 1));
     __syncthreads();                                // stage j landed; everyone is done with iteration j-1
-    if (warp == 0) {
-      if (elect_one()) {
-        issue(j + TA_STAGES - 1);
-        if (j > 0) {
-          tma_store_4d(&mVA, sOut + ((j - 1) & 1) * TILE_BYTES, co, j - 1, 0, b);
-          tma_store_commit();
-        }
+    if (tid == 0) {
+      issue(j + TA_STAGES - 1);
+      if (j > 0) {
+        tma_store_4d(&mVA, sOut + ((j - 1) & 1) * TILE_BYTES, co, j - 1, 0, b);
+        tma_store_commit();
       }
-      __syncwarp();
     }
     const uint32_t sV = sbase + (j % TA_STAGES) * TILE_BYTES;
     float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
@@ -702,13 +668,10 @@ tri_aggr_fwd_tma(const tgt_triplet_aggr_desc D, const __grid_constant__ CUtensor
     fence_proxy_async();
   }
   __syncthreads();
-  if (warp == 0) {
-    if (elect_one()) {
-      tma_store_4d(&mVA, sOut + ((N - 1) & 1) * TILE_BYTES, co, N - 1, 0, b);
-      tma_store_commit();
-      tma_store_wait_all();
-    }
-    __syncwarp();
+  if (tid == 0) {
+    tma_store_4d(&mVA, sOut + ((N - 1) & 1) * TILE_BYTES, co, N - 1, 0, b);
+    tma_store_commit();
+    tma_store_wait_all();
   }
 }
 
@@ -726,7 +689,7 @@ tri_aggr_bwd_tma(const tgt_triplet_aggr_desc D, const __grid_constant__ CUtensor
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int N = D.N, H = D.H;
   const int h = blockIdx.x, dir = blockIdx.y, b = blockIdx.z;
-  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, q = lane & 3;
   const int m0 = warp * 16;
   const uint32_t sOut = sbase + TAB_STAGES * TAB_STAGE_BYTES;
@@ -762,26 +725,17 @@ tri_aggr_bwd_tma(const tgt_triplet_aggr_desc D, const __grid_constant__ CUtensor
     tma_store_commit();
   };
   __syncthreads();
-  if (warp == 0) {
-    if (elect_one()) {
-  #pragma unroll
-      for (int s = 0; s < TAB_STAGES - 1; ++s) issue(s);
-    }
-    __syncwarp();
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < TAB_STAGES - 1; ++s) issue(s);
   }
   for (int j = 0; j < N; ++j) {
-    if (warp == 0) {
-      if (elect_one()) tma_store_wait_read();
-      __syncwarp();
-    }
+    if (tid == 0) tma_store_wait_read();
     mbar_wait(bar_full + (j % TAB_STAGES) * 8, (uint32_t)((j / TAB_STAGES) & 1));
     __syncthreads();
-    if (warp == 0) {
-      if (elect_one()) {
-        issue(j + TAB_STAGES - 1);
-        if (j > 0) store_dv(j - 1);
-      }
-      __syncwarp();
+    if (tid == 0) {
+      issue(j + TAB_STAGES - 1);
+      if (j > 0) store_dv(j - 1);
     }
     const uint32_t sV = sbase + (j % TAB_STAGES) * TAB_STAGE_BYTES, sO = sV + TILE_BYTES;
     // dA += dO_j V_j^T   (rows of this warp x all 64 keys)
@@ -807,12 +761,9 @@ tri_aggr_bwd_tma(const tgt_triplet_aggr_desc D, const __grid_constant__ CUtensor
     fence_proxy_async();
   }
   __syncthreads();
-  if (warp == 0) {
-    if (elect_one()) {
-      store_dv(N - 1);
-      tma_store_wait_all();
-    }
-    __syncwarp();
+  if (tid == 0) {
+    store_dv(N - 1);
+    tma_store_wait_all();
   }
   float *o = daw + abase;
 #pragma unroll

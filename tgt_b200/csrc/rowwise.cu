@@ -2,6 +2,7 @@
 // All are one-pass streaming kernels: 16-byte vector loads/stores, one warp per row for LN
 // (W = 256 bf16 -> exactly one 16B vector per lane), grid-stride over rows so the grid can be
 // sized to the 148 SMs.
+#include <mutex>
 #include "common.cuh"
 #include <type_traits>
 
@@ -298,6 +299,18 @@ ln_fwd_w256(const XT *__restrict__ x, const float *__restrict__ gamma, const flo
 // COLSUM: also accumulate  dres_colsum[c] += sum_r w_r * dres[r, c],  w_r = res_row_scale[r / rows_per_scale] (1 if null):
 // the residual gradient dres IS the upstream gradient of the module whose LayerNorm this is, so this is the bias gradient
 // of the module's output projection (DropPath-weighted) -- it costs no pass of its own.
+//
+// The kernel moves up to five edge-sized streams (dy, x, dres in; dx, y out) and nothing else, so what matters is bytes in
+// flight: each warp owns a private shared-memory ring of LNB_STAGES stages x RU rows x (x | dy | dres) filled by cp.async
+// (every lane copies and later reads back its own 16-byte pieces, so no barrier is needed), i.e. ~9 KB per warp and
+// ~144 KB per SM requested ahead of the arithmetic instead of the 48 KB that register staging allowed.
+constexpr int LNB_STAGES = 3;
+template <typename XT> __host__ __device__ constexpr int lnb_stage_bytes(int ru) { return ru * (2 * 256 * (int)sizeof(XT) + 512); }
+
+__device__ __forceinline__ void lnb_cp16(uint32_t dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src));
+}
+
 template <typename XT, typename T, int RU, bool EMIT_Y = false, bool COLSUM = false>
 __global__ void __launch_bounds__(256)
 ln_bwd_w256(const T *__restrict__ dy, const XT *__restrict__ x, const float *__restrict__ gamma,
@@ -307,9 +320,16 @@ ln_bwd_w256(const T *__restrict__ dy, const XT *__restrict__ x, const float *__r
             const float *__restrict__ res_row_scale = nullptr, int64_t rows_per_scale = 1,
             float *__restrict__ dres_colsum = nullptr) {
   __shared__ float sm[(COLSUM ? 3 : 2) * 256];
-  const int lane = threadIdx.x & 31;
-  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  extern __shared__ __align__(16) unsigned char ring_raw[];
+  constexpr int XB = 256 * (int)sizeof(XT);                   // bytes of an x / dres row
+  constexpr int XV = XB / 512;                                // 16-byte pieces per lane of such a row (1 or 2)
+  constexpr int ROWB = 2 * XB + 512;                          // x | dres | dy of one row
+  constexpr int STAGE = RU * ROWB;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(ring_raw) + (uint32_t)wib * (LNB_STAGES * STAGE);
+  unsigned char *ring_gen = ring_raw + wib * (LNB_STAGES * STAGE);
   for (int c = threadIdx.x; c < (COLSUM ? 768 : 512); c += blockDim.x) sm[c] = 0.f;
   __syncthreads();
   float g[8], ag[8], ab[8], ar[COLSUM ? 8 : 1];
@@ -328,16 +348,40 @@ ln_bwd_w256(const T *__restrict__ dy, const XT *__restrict__ x, const float *__r
     const float4 b0 = *reinterpret_cast<const float4 *>(beta + lane * 8), b1 = *reinterpret_cast<const float4 *>(beta + lane * 8 + 4);
     bt[0] = b0.x; bt[1] = b0.y; bt[2] = b0.z; bt[3] = b0.w; bt[4] = b1.x; bt[5] = b1.y; bt[6] = b1.z; bt[7] = b1.w;
   }
-  for (int64_t r0 = warp0 * RU; r0 < rows; r0 += nwarps * RU) {
-    typename V8<XT>::Raw rx[RU], rr[RU];
-    uint4 rd[RU];
+  // stage `slot` <- rows r0 .. r0+RU-1: this lane's 8 channels of x, dres and dy (lane * 8 elements into each row)
+  auto issue = [&](int64_t r0, int slot) {
+    if (r0 < rows) {
+#pragma unroll
+      for (int u = 0; u < RU; ++u) {
+        if (r0 + u < rows) {
+          const uint32_t d = ring + slot * STAGE + u * ROWB;
+          const unsigned char *xs = reinterpret_cast<const unsigned char *>(x + (r0 + u) * 256 + lane * 8);
+#pragma unroll
+          for (int v = 0; v < XV; ++v) lnb_cp16(d + lane * (16 * XV) + v * 16, xs + v * 16);
+          if (dres) {
+            const unsigned char *rs_ = reinterpret_cast<const unsigned char *>(dres + (r0 + u) * 256 + lane * 8);
+#pragma unroll
+            for (int v = 0; v < XV; ++v) lnb_cp16(d + XB + lane * (16 * XV) + v * 16, rs_ + v * 16);
+          }
+          lnb_cp16(d + 2 * XB + lane * 16, dy + (r0 + u) * 256 + lane * 8);
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+  const int64_t step = nwarps * RU;
+#pragma unroll
+  for (int s = 0; s < LNB_STAGES - 1; ++s) issue(warp0 * RU + s * step, s);
+  int slot = 0;
+  for (int64_t r0 = warp0 * RU; r0 < rows; r0 += step) {
+    int nslot = slot + LNB_STAGES - 1;
+    if (nslot >= LNB_STAGES) nslot -= LNB_STAGES;
+    issue(r0 + (LNB_STAGES - 1) * step, nslot);               // (the slot processed in the previous iteration)
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(LNB_STAGES - 1));
     float mu[RU], rs[RU];
 #pragma unroll
     for (int u = 0; u < RU; ++u) {
       if (r0 + u < rows) {
-        rx[u] = V8<XT>::load(x + (r0 + u) * 256 + lane * 8);
-        rd[u] = *reinterpret_cast<const uint4 *>(dy + (r0 + u) * 256 + lane * 8);
-        if (dres) rr[u] = V8<XT>::load(dres + (r0 + u) * 256 + lane * 8);
         mu[u] = mean[r0 + u];
         rs[u] = rstd[r0 + u];
       }
@@ -345,9 +389,10 @@ ln_bwd_w256(const T *__restrict__ dy, const XT *__restrict__ x, const float *__r
 #pragma unroll
     for (int u = 0; u < RU; ++u) {
       if (r0 + u >= rows) continue;
+      const unsigned char *st = ring_gen + slot * STAGE + u * ROWB;
       float xv[8], dv[8];
-      V8<XT>::unpack(rx[u], xv);
-      V8<T>::unpack(rd[u], dv);
+      V8<XT>::unpack(V8<XT>::load(reinterpret_cast<const XT *>(st + lane * (16 * XV))), xv);
+      V8<T>::unpack(*reinterpret_cast<const uint4 *>(st + 2 * XB + lane * 16), dv);
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
@@ -375,7 +420,7 @@ ln_bwd_w256(const T *__restrict__ dy, const XT *__restrict__ x, const float *__r
       for (int q = 0; q < 8; ++q) o[q] = rs[u] * (dv[q] - s1 - xv[q] * s2);
       if (dres) {
         float rv[8];
-        V8<XT>::unpack(rr[u], rv);
+        V8<XT>::unpack(V8<XT>::load(reinterpret_cast<const XT *>(st + XB + lane * (16 * XV))), rv);
 #pragma unroll
         for (int q = 0; q < 8; ++q) o[q] += rv[q];
         if constexpr (COLSUM) {
@@ -386,7 +431,9 @@ ln_bwd_w256(const T *__restrict__ dy, const XT *__restrict__ x, const float *__r
       }
       V8<XT>::store(dx + (r0 + u) * 256 + lane * 8, o);
     }
+    slot = slot + 1 == LNB_STAGES ? 0 : slot + 1;
   }
+  asm volatile("cp.async.wait_group 0;\n" ::);
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     atomicAdd(&sm[lane * 8 + q], ag[q]);
@@ -819,26 +866,33 @@ static int ln_bwd_launch(const void *dy, const void *x, const float *gamma, cons
     if (W == 256 && (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx | (uintptr_t)dres | (uintptr_t)y) & 15) == 0) {
       int g = grid_for(rows, 8 * 2 * 8);
       if (g > 148 * 8) g = 148 * 8;
+      constexpr int RING = 8 * LNB_STAGES * lnb_stage_bytes<XT>(2);       // 8 warps x 3 stages x 2 rows: 72 KB (16-bit x)
+#define LNB_LAUNCH(EY, CS, ...)                                                                                          \
+  do {                                                                                                                   \
+    static std::once_flag once;                                                                                          \
+    std::call_once(once, [] {                                                                                            \
+      cudaFuncSetAttribute(ln_bwd_w256<XT, YT, 2, EY, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, RING);              \
+    });                                                                                                                  \
+    ln_bwd_w256<XT, YT, 2, EY, CS><<<g, 256, RING, st>>>(__VA_ARGS__);                                                    \
+  } while (0)
       if (dres_colsum && (!dres || rows_per_scale <= 0)) return fail("layernorm_bwd_y: dres_colsum needs dres and rows_per_scale > 0");
       if (y) {
         if (!beta || (ldy != 256 && ldy != 264)) return fail("layernorm_bwd_y: beta is required and ldy must be 256 or 264");
         if (dres_colsum)
-          ln_bwd_w256<XT, YT, 2, true, true><<<g, 256, 0, st>>>((const YT *)dy, (const XT *)x, gamma, mean, rstd,
-                                                                (const XT *)dres, (XT *)dx, dgamma, dbeta, rows, beta, (YT *)y,
-                                                                ldy, res_row_scale, rows_per_scale, dres_colsum);
+          LNB_LAUNCH(true, true, (const YT *)dy, (const XT *)x, gamma, mean, rstd, (const XT *)dres, (XT *)dx, dgamma, dbeta, rows,
+                     beta, (YT *)y, ldy, res_row_scale, rows_per_scale, dres_colsum);
         else
-          ln_bwd_w256<XT, YT, 2, true><<<g, 256, 0, st>>>((const YT *)dy, (const XT *)x, gamma, mean, rstd, (const XT *)dres,
-                                                          (XT *)dx, dgamma, dbeta, rows, beta, (YT *)y, ldy);
+          LNB_LAUNCH(true, false, (const YT *)dy, (const XT *)x, gamma, mean, rstd, (const XT *)dres, (XT *)dx, dgamma, dbeta, rows,
+                     beta, (YT *)y, ldy);
         return check_launch("ln_bwd_w256_y");
       }
       if (dres_colsum) {
-        ln_bwd_w256<XT, YT, 2, false, true><<<g, 256, 0, st>>>((const YT *)dy, (const XT *)x, gamma, mean, rstd,
-                                                               (const XT *)dres, (XT *)dx, dgamma, dbeta, rows, nullptr, nullptr, 0,
-                                                               res_row_scale, rows_per_scale, dres_colsum);
+        LNB_LAUNCH(false, true, (const YT *)dy, (const XT *)x, gamma, mean, rstd, (const XT *)dres, (XT *)dx, dgamma, dbeta, rows,
+                   nullptr, nullptr, 0, res_row_scale, rows_per_scale, dres_colsum);
         return check_launch("ln_bwd_w256_cs");
       }
-      ln_bwd_w256<XT, YT, 2><<<g, 256, 0, st>>>((const YT *)dy, (const XT *)x, gamma, mean, rstd, (const XT *)dres, (XT *)dx,
-                                            dgamma, dbeta, rows);
+      LNB_LAUNCH(false, false, (const YT *)dy, (const XT *)x, gamma, mean, rstd, (const XT *)dres, (XT *)dx, dgamma, dbeta, rows);
+#undef LNB_LAUNCH
       return check_launch("ln_bwd_w256");
     }
   }
